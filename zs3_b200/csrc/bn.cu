@@ -1,0 +1,459 @@
+// BatchNorm2d training/eval passes fused with ReLU, residual add and Dropout (NHWC bf16, fp32 math).
+// HBM-bound kernels: 16-byte vector accesses, one pass over each tensor, per-channel reductions kept in
+// registers/shared memory and flushed with one fp64 atomic per channel per CTA.
+//
+// Reference semantics: F.batch_norm as called from zs3/modeling/sync_batchnorm/batchnorm.py:48-58
+// (biased variance for normalisation, unbiased for running_var, momentum 0.1, eps 1e-5),
+// nn.ReLU, `out += residual` (zs3/modeling/backbone/resnet.py:50), nn.Dropout (aspp.py:101, decoder.py:19,23).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace zs3 {
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// keep decisions for 8 consecutive logical elements starting at linear index `idx` (multiple of 8)
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t idx, uint32_t thresh16) {
+  const uint64_t h0 = splitmix64(seed ^ splitmix64(offset + idx));
+  const uint64_t h1 = splitmix64(h0 ^ 0xD1B54A32D192ED03ull);
+  uint32_t keep = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    keep |= (uint32_t)(((h0 >> (16 * j)) & 0xFFFF) >= thresh16) << j;
+    keep |= (uint32_t)(((h1 >> (16 * j)) & 0xFFFF) >= thresh16) << (4 + j);
+  }
+  return keep;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------- finalize
+__global__ void bn_finalize_kernel(double* sum, double* sqsum, long long count, const float* gamma, const float* beta,
+                                   float eps, float momentum, float* rmean, float* rvar, float* scale, float* shift,
+                                   float* mean_out, float* invstd_out, int C, int Cpad, int reset) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cpad) return;
+  if (c < C) {
+    const double n = (double)count;
+    const double m = sum[c] / n;
+    double var = sqsum[c] / n - m * m;  // biased
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f;
+    const float b = beta ? beta[c] : 0.f;
+    const float sc = g * invstd;
+    scale[c] = sc;
+    shift[c] = b - (float)m * sc;
+    if (mean_out) mean_out[c] = (float)m;
+    if (invstd_out) invstd_out[c] = invstd;
+    if (rmean) {
+      const double unbiased = count > 1 ? var * n / (n - 1.0) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    }
+  } else {
+    scale[c] = 0.f;
+    shift[c] = 0.f;
+    if (mean_out) mean_out[c] = 0.f;
+    if (invstd_out) invstd_out[c] = 0.f;
+  }
+  if (reset) {
+    sum[c] = 0.0;
+    sqsum[c] = 0.0;
+  }
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar,
+                                      float eps, float* scale, float* shift, float* mean_out, float* invstd_out, int C,
+                                      int Cpad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cpad) return;
+  float sc = 0.f, sh = 0.f, m = 0.f, is = 0.f;
+  if (c < C) {
+    m = rmean[c];
+    is = 1.f / sqrtf(rvar[c] + eps);
+    sc = (gamma ? gamma[c] : 1.f) * is;
+    sh = (beta ? beta[c] : 0.f) - m * sc;
+  }
+  scale[c] = sc;
+  shift[c] = sh;
+  if (mean_out) mean_out[c] = m;
+  if (invstd_out) invstd_out[c] = is;
+}
+
+// ---------------------------------------------------------------------------------- apply
+struct ApplyP {
+  const __nv_bfloat16* y; long long y_cs;
+  const __nv_bfloat16* res; long long res_cs;
+  __nv_bfloat16* out; long long out_cs;
+  const float* scale; const float* shift;
+  long long M; int C; int relu; int drop_mode; uint32_t thresh16; float keep_scale;
+  uint64_t seed, offset; const unsigned char* mask;
+};
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyP p) {
+  const int vpc = p.C >> 3;  // 16-byte vectors per pixel
+  const long long total = p.M * vpc;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
+       v += (long long)gridDim.x * blockDim.x) {
+    const long long m = v / vpc;
+    const int c = (int)(v - m * vpc) << 3;
+    float f[8], sc[8], sh[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), f);
+    load8f(p.scale + c, sc);
+    load8f(p.shift + c, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+    if (p.res) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.res + m * p.res_cs + c), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (p.drop_mode == 1) {
+      const uint32_t keep = dropout_keep8(p.seed, p.offset, (uint64_t)(m * p.C + c), p.thresh16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1) ? f[j] * p.keep_scale : 0.f;
+    } else if (p.drop_mode == 2) {
+      const uint2 mk = *reinterpret_cast<const uint2*>(p.mask + m * p.C + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t b = ((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xFF;
+        f[j] = b ? f[j] * p.keep_scale : 0.f;
+      }
+    }
+    *reinterpret_cast<uint4*>(p.out + m * p.out_cs + c) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------- backward
+struct BwdP {
+  const __nv_bfloat16* dout; long long dout_cs;
+  const __nv_bfloat16* out; long long out_cs;
+  const __nv_bfloat16* y; long long y_cs;
+  const float* mean; const float* invstd; const float* scale;
+  long long M; int C; int relu; float grad_scale; int training;
+  double* sum_dz; double* sum_dzx;
+  __nv_bfloat16* dy; long long dy_cs;
+  int sp_stride, sp_HoWo, sp_Wo; long long dy_img, dy_row;
+  __nv_bfloat16* dres; long long dres_cs; int dres_acc;
+  float* dgamma; float* dbeta; int C_real; int param_acc;
+  int rows_per_block;  // reduce kernel: pixel rows handled concurrently by one CTA
+};
+
+// dz for 8 channels of pixel m
+__device__ __forceinline__ void load_dz(const BwdP& p, long long m, int c, float (&dz)[8]) {
+  unpack8(*reinterpret_cast<const uint4*>(p.dout + m * p.dout_cs + c), dz);
+  if (p.relu) {
+    float o[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.out + m * p.out_cs + c), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = o[j] > 0.f ? dz[j] * p.grad_scale : 0.f;
+  } else if (p.grad_scale != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] *= p.grad_scale;
+  }
+}
+
+// grid-stride over pixel rows; thread (vc, rl) owns 8 channels and every rows_per_block-th row.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdP p) {
+  extern __shared__ float red[];  // [rows_per_block][C] x 2
+  const int vpc = p.C >> 3;
+  const int vc = threadIdx.x % vpc;
+  const int rl = threadIdx.x / vpc;
+  const int c = vc << 3;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  if (rl < p.rows_per_block) {
+    float mu[8], is[8];
+    load8f(p.mean + c, mu);
+    load8f(p.invstd + c, is);
+    for (long long m = (long long)blockIdx.x * p.rows_per_block + rl; m < p.M;
+         m += (long long)gridDim.x * p.rows_per_block) {
+      float dz[8], yv[8];
+      load_dz(p, m, c, dz);
+      unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += dz[j];
+        a2[j] += dz[j] * ((yv[j] - mu[j]) * is[j]);
+      }
+    }
+    float* r1 = red + (size_t)rl * p.C + c;
+    float* r2 = red + (size_t)p.rows_per_block * p.C + (size_t)rl * p.C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r1[j] = a1[j];
+      r2[j] = a2[j];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < p.rows_per_block; ++r) {
+      s1 += red[(size_t)r * p.C + ch];
+      s2 += red[(size_t)p.rows_per_block * p.C + (size_t)r * p.C + ch];
+    }
+    atomicAdd(p.sum_dz + ch, (double)s1);
+    atomicAdd(p.sum_dzx + ch, (double)s2);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
+  const int vpc = p.C >> 3;
+  const long long total = p.M * vpc;
+  const float inv_m = 1.f / (float)p.M;
+  if (blockIdx.x == 0 && p.dgamma != nullptr) {
+    for (int ch = threadIdx.x; ch < p.C_real; ch += blockDim.x) {
+      const float dg = (float)p.sum_dzx[ch], db = (float)p.sum_dz[ch];
+      p.dgamma[ch] = p.param_acc ? p.dgamma[ch] + dg : dg;
+      p.dbeta[ch] = p.param_acc ? p.dbeta[ch] + db : db;
+    }
+  }
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
+       v += (long long)gridDim.x * blockDim.x) {
+    const long long m = v / vpc;
+    const int c = (int)(v - m * vpc) << 3;
+    float dz[8];
+    load_dz(p, m, c, dz);
+    if (p.dres) {
+      float r[8];
+      uint4* dst = reinterpret_cast<uint4*>(p.dres + m * p.dres_cs + c);
+      if (p.dres_acc) {
+        unpack8(*dst, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += dz[j];
+        *dst = pack8(r);
+      } else {
+        *dst = pack8(dz);
+      }
+    }
+    float sc[8], g[8];
+    load8f(p.scale + c, sc);
+    if (p.training) {
+      float mu[8], is[8], yv[8];
+      load8f(p.mean + c, mu);
+      load8f(p.invstd + c, is);
+      unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (yv[j] - mu[j]) * is[j];
+        const float m1 = (float)p.sum_dz[c + j] * inv_m;
+        const float m2 = (float)p.sum_dzx[c + j] * inv_m;
+        g[j] = sc[j] * (dz[j] - m1 - xh * m2);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = sc[j] * dz[j];
+    }
+    long long pix = m;
+    if (p.sp_stride > 1) {
+      const long long img = m / p.sp_HoWo;
+      const int rem = (int)(m - img * p.sp_HoWo);
+      const int op = rem / p.sp_Wo;
+      const int oq = rem - op * p.sp_Wo;
+      pix = img * p.dy_img + (long long)op * p.dy_row + (long long)oq * p.sp_stride;
+    }
+    *reinterpret_cast<uint4*>(p.dy + pix * p.dy_cs + c) = pack8(g);
+  }
+}
+
+// ------------------------------------------------------------------------- layout changes
+// NCHW fp32 -> NHWC bf16 through a 32x32 shared-memory transpose (coalesced on both sides).
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, long long HW,
+                                    int cs) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long hw0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long hw = hw0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && hw < HW) ? src[((long long)n * C + c) * HW + hw] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long hw = hw0 + i;
+    const int c = c0 + threadIdx.x;
+    if (hw < HW && c < cs) dst[((long long)n * HW + hw) * cs + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, long long HW,
+                                    int cs) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long hw0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long hw = hw0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (hw < HW && c < C) ? __bfloat162float(src[((long long)n * HW + hw) * cs + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long hw = hw0 + threadIdx.x;
+    if (c < C && hw < HW) dst[((long long)n * C + c) * HW + hw] = tile[threadIdx.x][i];
+  }
+}
+
+static int ew_grid(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = 148ll * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace zs3
+
+using namespace zs3;
+
+extern "C" int zs3_bn_finalize(double* stat_sum, double* stat_sqsum, long long count, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                               float* scale, float* shift, float* mean, float* invstd, int C, int Cpad,
+                               int reset_stats, void* stream) {
+  ZS3_CHECK_ARG(stat_sum && stat_sqsum && scale && shift, "bn_finalize: null pointer");
+  ZS3_CHECK_ARG(count > 0 && C > 0 && Cpad >= C, "bn_finalize: bad sizes count=%lld C=%d Cpad=%d", count, C, Cpad);
+  ZS3_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats mismatch");
+  bn_finalize_kernel<<<ceil_div(Cpad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stat_sum, stat_sqsum, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd,
+      C, Cpad, reset_stats);
+  ZS3_CHECK_LAUNCH("bn_finalize");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, float* scale, float* shift, float* mean,
+                                  float* invstd, int C, int Cpad, void* stream) {
+  ZS3_CHECK_ARG(running_mean && running_var && scale && shift, "bn_eval_coeffs: null pointer");
+  ZS3_CHECK_ARG(C > 0 && Cpad >= C, "bn_eval_coeffs: bad sizes");
+  bn_eval_coeffs_kernel<<<ceil_div(Cpad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      gamma, beta, running_mean, running_var, eps, scale, shift, mean, invstd, C, Cpad);
+  ZS3_CHECK_LAUNCH("bn_eval_coeffs");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
+  ZS3_CHECK_ARG(a && a->y && a->out && a->scale && a->shift, "bn_apply: null pointer");
+  ZS3_CHECK_ARG(a->C > 0 && a->C % 8 == 0 && a->y_cstride % 8 == 0 && a->out_cstride % 8 == 0 &&
+                    a->y_cstride >= a->C && a->out_cstride >= a->C,
+                "bn_apply: C=%d strides %d/%d must be multiples of 8", a->C, a->y_cstride, a->out_cstride);
+  ZS3_CHECK_ARG(a->residual == nullptr || (a->res_cstride % 8 == 0 && a->res_cstride >= a->C),
+                "bn_apply: residual stride");
+  ZS3_CHECK_ARG(a->drop_mode >= 0 && a->drop_mode <= 2 && a->drop_p >= 0.f && a->drop_p < 1.f, "bn_apply: dropout");
+  ZS3_CHECK_ARG(a->drop_mode != 2 || a->keep_mask != nullptr, "bn_apply: drop_mode 2 needs keep_mask");
+  if (a->M <= 0) return ZS3_OK;
+  ApplyP p;
+  p.y = static_cast<const __nv_bfloat16*>(a->y); p.y_cs = a->y_cstride;
+  p.res = static_cast<const __nv_bfloat16*>(a->residual); p.res_cs = a->res_cstride;
+  p.out = static_cast<__nv_bfloat16*>(a->out); p.out_cs = a->out_cstride;
+  p.scale = a->scale; p.shift = a->shift;
+  p.M = a->M; p.C = a->C; p.relu = a->relu;
+  p.drop_mode = (a->drop_p > 0.f) ? a->drop_mode : 0;
+  p.thresh16 = (uint32_t)(a->drop_p * 65536.0f + 0.5f);
+  p.keep_scale = 1.f / (1.f - a->drop_p);
+  p.seed = a->seed; p.offset = a->offset; p.mask = a->keep_mask;
+  bn_apply_kernel<<<ew_grid(a->M * (a->C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ZS3_CHECK_LAUNCH("bn_apply");
+  return ZS3_OK;
+}
+
+static int fill_bwd(const zs3_bn_bwd_args* a, BwdP& p, const char* who) {
+  ZS3_CHECK_ARG(a && a->dout && a->y && a->mean && a->invstd && a->scale && a->sum_dz && a->sum_dzx,
+                "%s: null pointer", who);
+  ZS3_CHECK_ARG(a->C > 0 && a->C % 8 == 0 && a->C <= 2048 && a->dout_cstride % 8 == 0 && a->y_cstride % 8 == 0,
+                "%s: C=%d must be a multiple of 8 and <= 2048", who, a->C);
+  ZS3_CHECK_ARG(!a->relu || (a->out && a->out_cstride % 8 == 0), "%s: relu needs the forward output", who);
+  p.dout = static_cast<const __nv_bfloat16*>(a->dout); p.dout_cs = a->dout_cstride;
+  p.out = static_cast<const __nv_bfloat16*>(a->out); p.out_cs = a->out_cstride;
+  p.y = static_cast<const __nv_bfloat16*>(a->y); p.y_cs = a->y_cstride;
+  p.mean = a->mean; p.invstd = a->invstd; p.scale = a->scale;
+  p.M = a->M; p.C = a->C; p.relu = a->relu; p.grad_scale = a->grad_scale; p.training = a->training;
+  p.sum_dz = a->sum_dz; p.sum_dzx = a->sum_dzx;
+  p.dy = static_cast<__nv_bfloat16*>(a->dy); p.dy_cs = a->dy_cstride;
+  p.sp_stride = a->dy_sp_stride; p.sp_HoWo = a->sp_Ho * a->sp_Wo; p.sp_Wo = a->sp_Wo;
+  p.dy_img = (long long)a->dy_H * a->dy_W; p.dy_row = (long long)a->dy_W * a->dy_sp_stride;
+  p.dres = static_cast<__nv_bfloat16*>(a->dres); p.dres_cs = a->dres_cstride; p.dres_acc = a->dres_accumulate;
+  p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.C_real = a->C_real; p.param_acc = a->param_accumulate;
+  p.rows_per_block = 1;
+  return ZS3_OK;
+}
+
+extern "C" int zs3_bn_bwd_reduce(const zs3_bn_bwd_args* a, void* stream) {
+  BwdP p;
+  int rc = fill_bwd(a, p, "bn_bwd_reduce");
+  if (rc) return rc;
+  if (a->M <= 0) return ZS3_OK;
+  const int vpc = a->C / 8;
+  p.rows_per_block = 256 / vpc;  // C <= 2048 -> vpc <= 256
+  if (p.rows_per_block < 1) p.rows_per_block = 1;
+  const size_t smem = (size_t)2 * p.rows_per_block * a->C * sizeof(float);
+  long long blocks = (a->M + p.rows_per_block - 1) / p.rows_per_block;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  bn_bwd_reduce_kernel<<<(int)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  ZS3_CHECK_LAUNCH("bn_bwd_reduce");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_bn_bwd_apply(const zs3_bn_bwd_args* a, void* stream) {
+  BwdP p;
+  int rc = fill_bwd(a, p, "bn_bwd_apply");
+  if (rc) return rc;
+  ZS3_CHECK_ARG(a->dy && a->dy_cstride % 8 == 0 && a->dy_cstride >= a->C, "bn_bwd_apply: bad dy");
+  ZS3_CHECK_ARG(a->dres == nullptr || (a->dres_cstride % 8 == 0 && a->dres_cstride >= a->C), "bn_bwd_apply: bad dres");
+  ZS3_CHECK_ARG(a->dy_sp_stride <= 1 || (a->sp_Ho > 0 && a->sp_Wo > 0 && a->dy_H >= (a->sp_Ho - 1) * a->dy_sp_stride + 1 &&
+                                         a->dy_W >= (a->sp_Wo - 1) * a->dy_sp_stride + 1),
+                "bn_bwd_apply: bad scatter geometry");
+  ZS3_CHECK_ARG((a->dgamma == nullptr) == (a->dbeta == nullptr) && (a->dgamma == nullptr || a->C_real <= a->C),
+                "bn_bwd_apply: bad parameter gradient buffers");
+  if (a->M <= 0) return ZS3_OK;
+  bn_bwd_apply_kernel<<<ew_grid(a->M * (a->C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ZS3_CHECK_LAUNCH("bn_bwd_apply");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, long long HW, int cs,
+                                         void* stream) {
+  ZS3_CHECK_ARG(src && dst && N > 0 && C > 0 && HW > 0 && cs >= C, "nchw_to_nhwc: bad args");
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((cs + 31) / 32), (unsigned)N);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), C, HW, cs);
+  ZS3_CHECK_LAUNCH("nchw_to_nhwc");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, long long HW, int cs,
+                                         void* stream) {
+  ZS3_CHECK_ARG(src && dst && N > 0 && C > 0 && HW > 0 && cs >= C, "nhwc_to_nchw: bad args");
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, C, HW, cs);
+  ZS3_CHECK_LAUNCH("nhwc_to_nchw");
+  return ZS3_OK;
+}

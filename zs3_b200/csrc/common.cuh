@@ -1,0 +1,46 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, launch checks,
+// TMA tensor-map encoding through the driver entry points (no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/zs3b200.h"
+
+namespace zs3 {
+
+void set_error(const char* fmt, ...);
+
+#define ZS3_CHECK_ARG(cond, ...)           \
+  do {                                     \
+    if (!(cond)) {                         \
+      zs3::set_error(__VA_ARGS__);         \
+      return ZS3_ERR_INVALID_ARG;          \
+    }                                      \
+  } while (0)
+
+#define ZS3_CHECK_LAUNCH(name)                                                  \
+  do {                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      zs3::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+      return ZS3_ERR_LAUNCH;                                                    \
+    }                                                                           \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// bf16, SWIZZLE_128B tensor maps.  All return 0 on success.
+// im2col map over an NHWC activation tensor [N][H][W][C] (C = channel stride, elements).
+int encode_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C, int pad_lo, int upper_corner,
+                       int stride, int channels_per_pixel, int pixels_per_column);
+// tiled 2-D map over a row-major [rows][cols] bf16 matrix with row stride ld (elements); box = [box_rows][box_cols].
+int encode_tiled2d_bf16(CUtensorMap* out, const void* base, long long rows, int cols, long long ld, int box_rows,
+                        int box_cols);
+// tiled 3-D map over [d2][d1][d0] bf16 (d0 contiguous); box = [b2][b1][b0].
+int encode_tiled3d_bf16(CUtensorMap* out, const void* base, int d2, int d1, int d0, int b2, int b1, int b0);
+
+}  // namespace zs3

@@ -1,0 +1,698 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a).
+//
+//   fprop / dgrad :  Y[m][n]  = sum_k A[m][k] * Wt[n][k]     m = output pixel, n = output channel,
+//                                                            k = (segment, tap, input channel)
+//   wgrad         :  dW[n][c] = sum_p dY[p][n] * X[p@tap][c] p = output pixel (the reduction)
+//
+// Data movement: A tiles are fetched by TMA in im2col mode straight from the NHWC activation tensor
+// (zero padding, stride and dilation are resolved by the TMA unit: no index math in the SM), weight
+// tiles by tiled TMA; both land in 128B-swizzled shared memory that tcgen05.mma consumes through
+// shared-memory descriptors.  Accumulators live in TMEM (double buffered), epilogue warps read them back
+// with tcgen05.ld, fuse bias / BatchNorm batch statistics / accumulate, and store NHWC.
+//
+// Warp roles (256 threads, 1 persistent CTA per SM):
+//   warp 0: TMA producer (one elected lane)      warp 1: MMA issuer (one elected lane)
+//   warp 2: TMEM allocator                       warps 4-7: epilogue (one TMEM lane quarter each)
+//
+// Reference call sites replaced: every nn.Conv2d on the DeepLab path (see include/zs3b200.h).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace zs3 {
+
+constexpr int BLOCK_M = 128;      // output pixels per tile (= TMEM lanes)
+constexpr int BLOCK_K = 64;       // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+struct alignas(64) FpropSegment {
+  CUtensorMap a;  // im2col map over the segment's activation tensor
+  CUtensorMap b;  // tiled 3-D map over the segment's packed weights [cout_pad][taps][cin_pad]
+  int num_cblk;   // cin_pad / 64
+};
+
+struct FpropParams {
+  FpropSegment seg[ZS3_MAX_SEGMENTS];
+  int num_segments;
+  int M;          // N*Ho*Wo
+  int HoWo, Wo;
+  int stride, pad, dil, R, S;
+  int cout_pad;
+  int num_m_tiles, num_n_tiles;
+  int kb_per_tile;  // total k-blocks per output tile
+  void* y;
+  long long y_cstride;
+  // output pixel (n,p,q) is stored at pixel index n*y_img + p*y_row + q*y_pix of y
+  long long y_img, y_row, y_pix;
+  int y_is_f32;
+  int accumulate;
+  const float* bias;
+  double* stat_sum;
+  double* stat_sqsum;
+};
+
+template <int BN, int STAGES>
+struct FpropSmem {
+  static constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
+};
+
+// Column sums over the 32 lanes of a warp: lane j ends up with sum over lanes of v[j].
+// Recursive halving: 31 shuffles instead of 32*5.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float keep = upper ? v[i + off] : v[i];
+      float send = upper ? v[i] : v[i + off];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid_constant__ FpropParams p) {
+  using L = FpropSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_segments; ++s) {
+      tma_prefetch_desc(&p.seg[s].a);
+      tma_prefetch_desc(&p.seg[s].b);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        const int m0 = m_tile * BLOCK_M;
+        const int img = m0 / p.HoWo;
+        const int rem = m0 - img * p.HoWo;
+        const int op = rem / p.Wo;
+        const int oq = rem - op * p.Wo;
+        const int base_w = oq * p.stride - p.pad;
+        const int base_h = op * p.stride - p.pad;
+        for (int s = 0; s < p.num_segments; ++s) {
+          const FpropSegment& sg = p.seg[s];
+          for (int r = 0; r < p.R; ++r) {
+            for (int q = 0; q < p.S; ++q) {
+              const int tap = r * p.S + q;
+              for (int cb = 0; cb < sg.num_cblk; ++cb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                uint8_t* sb = sa + A_TILE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                tma_load_im2col_4d(sa, &sg.a, &full_bar[stage], cb * BLOCK_K, base_w, base_h, img,
+                                   (uint16_t)(q * p.dil), (uint16_t)(r * p.dil));
+                tma_load_3d(sb, &sg.b, &full_bar[stage], cb * BLOCK_K, tap, n_tile * BN);
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================= MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[as], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < p.kb_per_tile; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + A_TILE_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ========================================================================= epilogue
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int as = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m = m_tile * BLOCK_M + row;
+      const bool valid = m < p.M;
+      long long pix = 0;
+      if (valid) {
+        const int img = m / p.HoWo;
+        const int rem = m - img * p.HoWo;
+        const int op = rem / p.Wo;
+        const int oq = rem - op * p.Wo;
+        pix = img * p.y_img + op * p.y_row + oq * p.y_pix;
+      }
+      mbar_wait(&acc_full[as], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        const int n = n_tile * BN + chunk * 32;
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + chunk * 32, raw);
+        tmem_ld_wait();
+        if (n >= p.cout_pad) continue;  // warp-uniform
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(raw[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n + j);
+        }
+        if (valid) {
+          if (p.y_is_f32) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.y) + pix * p.y_cstride + n);
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o = dst[j];
+                f[4 * j + 0] += o.x;
+                f[4 * j + 1] += o.y;
+                f[4 * j + 2] += o.z;
+                f[4 * j + 3] += o.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + pix * p.y_cstride + n);
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o = dst[j];
+                f[8 * j + 0] += bf16_lo(o.x);
+                f[8 * j + 1] += bf16_hi(o.x);
+                f[8 * j + 2] += bf16_lo(o.y);
+                f[8 * j + 3] += bf16_hi(o.y);
+                f[8 * j + 4] += bf16_lo(o.z);
+                f[8 * j + 5] += bf16_hi(o.z);
+                f[8 * j + 6] += bf16_lo(o.w);
+                f[8 * j + 7] += bf16_hi(o.w);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              dst[j] = o;
+            }
+          }
+        }
+        if (p.stat_sum != nullptr) {
+          // BatchNorm batch statistics of the fp32 conv output (F.batch_norm training path,
+          // zs3/modeling/sync_batchnorm/batchnorm.py:48-58): per-channel sum and sum of squares.
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (!valid) f[j] = 0.f;
+            sq[j] = f[j] * f[j];
+          }
+          const float s1 = warp_column_sums(f, lane);
+          const float s2 = warp_column_sums(sq, lane);
+          atomicAdd(p.stat_sum + n + lane, (double)s1);
+          atomicAdd(p.stat_sqsum + n + lane, (double)s2);
+        }
+      }
+      // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+// dW[co][tap][ci] += sum_p dY[p][co] * X[p@tap][ci]; both operands are MN-major for the MMA
+// (the reduction index p runs over 128-byte rows of the TMA tiles).
+constexpr int WG_BLOCK_P = 64;  // pixels (reduction) per k-block
+constexpr int WG_CHUNK_BYTES = WG_BLOCK_P * 128;  // one [64 pixels][64 channels] bf16 sub-tile = 8 KiB
+
+struct WgradParams {
+  CUtensorMap dy;  // tiled 2-D over [M][dy_cstride], box [64 pixels][64 channels]
+  CUtensorMap x;   // im2col over the input activation, 64 pixels x 64 channels
+  int M, HoWo, Wo;
+  int stride, pad, dil, R, S;
+  int cout_pad, cin_pad;
+  int num_co_tiles, num_ci_tiles;
+  int k_splits;
+  int pblocks_total;  // ceil(M / 64)
+  float* dw;
+};
+
+template <int CN, int STAGES>
+struct WgradSmem {
+  static constexpr int A_BYTES = 2 * WG_CHUNK_BYTES;          // 128 output channels
+  static constexpr int B_BYTES = (CN / 64) * WG_CHUNK_BYTES;  // CN input channels
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int CN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using L = WgradSmem<CN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // blockIdx.x -> (ci_tile, co_tile, tap); blockIdx.y -> pixel split
+  int t = blockIdx.x;
+  const int ci_tile = t % p.num_ci_tiles;
+  t /= p.num_ci_tiles;
+  const int co_tile = t % p.num_co_tiles;
+  const int tap = t / p.num_co_tiles;
+  const int tap_r = tap / p.S;
+  const int tap_s = tap - tap_r * p.S;
+  const int pb_per_split = (p.pblocks_total + p.k_splits - 1) / p.k_splits;
+  const int pb_begin = blockIdx.y * pb_per_split;
+  const int pb_end = min(p.pblocks_total, pb_begin + pb_per_split);
+  const int num_kb = pb_end - pb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, CN < 32 ? 32 : CN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int p0 = (pb_begin + kb) * WG_BLOCK_P;
+          const int img = p0 / p.HoWo;
+          const int rem = p0 - img * p.HoWo;
+          const int op = rem / p.Wo;
+          const int oq = rem - op * p.Wo;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d(sa + c * WG_CHUNK_BYTES, &p.dy, &full_bar[stage], co_tile * 128 + c * 64, p0);
+#pragma unroll
+          for (int c = 0; c < CN / 64; ++c)
+            tma_load_im2col_4d(sb + c * WG_CHUNK_BYTES, &p.x, &full_bar[stage], ci_tile * CN + c * 64,
+                               oq * p.stride - p.pad, op * p.stride - p.pad, img, (uint16_t)(tap_s * p.dil),
+                               (uint16_t)(tap_r * p.dil));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, CN, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < WG_BLOCK_P / 16; ++k) {
+            // MN-major SW128: LBO = byte distance between 64-channel sub-tiles, SBO = 8 pixel rows = 1024 B;
+            // one UMMA_K step = 16 pixel rows = 2048 B.
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * 2048, WG_CHUNK_BYTES, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * 2048, WG_CHUNK_BYTES, 1024);
+            umma_f16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(acc_full);
+      }
+    } else if (warp >= EPI_WARP0) {
+      const int quarter = warp & 3;
+      const int co = co_tile * 128 + quarter * 32 + lane;
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const int taps = p.R * p.S;
+#pragma unroll 1
+      for (int chunk = 0; chunk < CN / 32; ++chunk) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + chunk * 32, raw);
+        tmem_ld_wait();
+        const int ci = ci_tile * CN + chunk * 32;
+        if (co < p.cout_pad && ci < p.cin_pad) {
+          float* dst = p.dw + ((long long)co * taps + tap) * p.cin_pad + ci;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(raw[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, CN < 32 ? 32 : CN);
+}
+
+// ---------------------------------------------------------------------------- weight packing
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, int ci_begin,
+                                   int ci_count, __nv_bfloat16* __restrict__ dst, int cout_pad, int cin_pad,
+                                   int mode) {
+  const int taps = R * S;
+  const long long total = (long long)cout_pad * taps * cin_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int co, ci, tap;
+    if (mode == 0) {  // [cout_pad][taps][cin_pad]
+      ci = (int)(i % cin_pad);
+      tap = (int)((i / cin_pad) % taps);
+      co = (int)(i / ((long long)cin_pad * taps));
+    } else {  // [cin_pad][taps][cout_pad], spatially flipped taps
+      co = (int)(i % cout_pad);
+      int tflip = (int)((i / cout_pad) % taps);
+      ci = (int)(i / ((long long)cout_pad * taps));
+      tap = taps - 1 - tflip;
+    }
+    float v = 0.f;
+    if (co < Cout && ci < ci_count) {
+      const int r = tap / S, s = tap - r * S;
+      v = w[(((long long)co * Cin + (ci_begin + ci)) * R + r) * S + s];
+    }
+    dst[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int cout_pad, int cin_pad, float* __restrict__ g,
+                                    int Cout, int Cin, int R, int S, int ci_begin, int ci_count, int accumulate) {
+  const int taps = R * S;
+  const long long total = (long long)Cout * ci_count * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % ci_count);
+    const int co = (int)(i / ((long long)taps * ci_count));
+    const float v = dw[((long long)co * taps + tap) * cin_pad + ci];
+    float* d = g + ((long long)co * Cin + ci_begin + ci) * taps + tap;
+    *d = accumulate ? (*d + v) : v;
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int STAGES>
+static int launch_fprop(const FpropParams& p, cudaStream_t st) {
+  using L = FpropSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("conv_fprop: cudaFuncSetAttribute(%d bytes) failed: %s", L::TOTAL, cudaGetErrorString(e));
+      return ZS3_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_fprop_kernel<BN, STAGES><<<grid, NUM_THREADS, L::TOTAL, st>>>(p);
+  ZS3_CHECK_LAUNCH("conv_fprop");
+  return ZS3_OK;
+}
+
+template <int CN, int STAGES>
+static int launch_wgrad(const WgradParams& p, cudaStream_t st) {
+  using L = WgradSmem<CN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<CN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("conv_wgrad: cudaFuncSetAttribute(%d bytes) failed: %s", L::TOTAL, cudaGetErrorString(e));
+      return ZS3_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  dim3 grid(p.num_ci_tiles * p.num_co_tiles * p.R * p.S, p.k_splits);
+  conv_wgrad_kernel<CN, STAGES><<<grid, NUM_THREADS, L::TOTAL, st>>>(p);
+  ZS3_CHECK_LAUNCH("conv_wgrad");
+  return ZS3_OK;
+}
+
+}  // namespace zs3
+
+using namespace zs3;
+
+extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
+  ZS3_CHECK_ARG(a != nullptr, "conv_fprop: null args");
+  ZS3_CHECK_ARG(a->num_segments >= 1 && a->num_segments <= ZS3_MAX_SEGMENTS, "conv_fprop: num_segments=%d",
+                a->num_segments);
+  ZS3_CHECK_ARG(a->cout_pad > 0 && a->cout_pad % 64 == 0, "conv_fprop: cout_pad=%d must be a multiple of 64",
+                a->cout_pad);
+  ZS3_CHECK_ARG(a->N > 0 && a->H > 0 && a->W > 0 && a->Ho > 0 && a->Wo > 0, "conv_fprop: bad spatial dims");
+  ZS3_CHECK_ARG(a->R >= 1 && a->S >= 1 && a->stride >= 1 && a->stride <= 8 && a->dil >= 1 && a->pad >= 0,
+                "conv_fprop: bad filter geometry");
+  ZS3_CHECK_ARG(a->pad <= 128 && (a->R - 1) * a->dil <= 255 && (a->S - 1) * a->dil <= 255,
+                "conv_fprop: pad/dilation outside the TMA im2col range");
+  ZS3_CHECK_ARG(a->y != nullptr && a->y_cstride >= a->cout_pad, "conv_fprop: bad output");
+  ZS3_CHECK_ARG((a->stat_sum == nullptr) == (a->stat_sqsum == nullptr), "conv_fprop: stat_sum/stat_sqsum mismatch");
+  const long long M = (long long)a->N * a->Ho * a->Wo;
+  ZS3_CHECK_ARG(M < (1ll << 31), "conv_fprop: too many output pixels");
+
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  const int BN = a->cout_pad >= 256 ? 256 : (a->cout_pad >= 128 ? 128 : 64);
+  int kb = 0;
+  for (int s = 0; s < a->num_segments; ++s) {
+    const zs3_conv_segment& sg = a->seg[s];
+    ZS3_CHECK_ARG(sg.x != nullptr && sg.w != nullptr, "conv_fprop: segment %d null pointer", s);
+    ZS3_CHECK_ARG(sg.cin_pad > 0 && sg.cin_pad % 64 == 0 && sg.x_cstride >= sg.cin_pad && sg.x_cstride % 8 == 0,
+                  "conv_fprop: segment %d cin_pad=%d x_cstride=%d", s, sg.cin_pad, sg.x_cstride);
+    // bounding box of filter base positions: [-pad, W-1 + pad - (S-1)*dil]
+    const int upper_w = a->pad - (a->S - 1) * a->dil;
+    const int upper_h = a->pad - (a->R - 1) * a->dil;
+    ZS3_CHECK_ARG(upper_w == upper_h || a->H == a->W, "conv_fprop: non-square filters need square geometry");
+    int rc = encode_im2col_bf16(&p.seg[s].a, sg.x, a->N, a->H, a->W, sg.x_cstride, a->pad, upper_w, a->stride, BLOCK_K,
+                                BLOCK_M);
+    if (rc) return rc;
+    rc = encode_tiled3d_bf16(&p.seg[s].b, sg.w, a->cout_pad, a->R * a->S, sg.cin_pad, BN, 1, BLOCK_K);
+    if (rc) return rc;
+    p.seg[s].num_cblk = sg.cin_pad / BLOCK_K;
+    kb += a->R * a->S * p.seg[s].num_cblk;
+  }
+  p.num_segments = a->num_segments;
+  p.M = (int)M;
+  p.HoWo = a->Ho * a->Wo;
+  p.Wo = a->Wo;
+  p.stride = a->stride;
+  p.pad = a->pad;
+  p.dil = a->dil;
+  p.R = a->R;
+  p.S = a->S;
+  p.cout_pad = a->cout_pad;
+  p.num_m_tiles = (int)ceil_div_ll(M, BLOCK_M);
+  p.num_n_tiles = ceil_div(a->cout_pad, BN);
+  p.kb_per_tile = kb;
+  p.y = a->y;
+  p.y_cstride = a->y_cstride;
+  if (a->y_sp_stride > 1) {
+    ZS3_CHECK_ARG(a->y_H >= (a->Ho - 1) * a->y_sp_stride + 1 && a->y_W >= (a->Wo - 1) * a->y_sp_stride + 1,
+                  "conv_fprop: scatter target %dx%d too small", a->y_H, a->y_W);
+    p.y_img = (long long)a->y_H * a->y_W;
+    p.y_row = (long long)a->y_W * a->y_sp_stride;
+    p.y_pix = a->y_sp_stride;
+  } else {
+    p.y_img = (long long)a->Ho * a->Wo;
+    p.y_row = a->Wo;
+    p.y_pix = 1;
+  }
+  p.y_is_f32 = a->y_is_f32;
+  p.accumulate = a->accumulate;
+  p.bias = a->bias;
+  p.stat_sum = a->stat_sum;
+  p.stat_sqsum = a->stat_sqsum;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (BN == 256) return launch_fprop<256, 4>(p, st);
+  if (BN == 128) return launch_fprop<128, 6>(p, st);
+  return launch_fprop<64, 8>(p, st);
+}
+
+extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
+  ZS3_CHECK_ARG(a != nullptr, "conv_wgrad: null args");
+  ZS3_CHECK_ARG(a->cout_pad > 0 && a->cout_pad % 64 == 0 && a->cin_pad > 0 && a->cin_pad % 64 == 0,
+                "conv_wgrad: cout_pad=%d cin_pad=%d must be multiples of 64", a->cout_pad, a->cin_pad);
+  ZS3_CHECK_ARG(a->x && a->dy && a->dw, "conv_wgrad: null pointer");
+  ZS3_CHECK_ARG(a->x_cstride >= a->cin_pad && a->x_cstride % 8 == 0 && a->dy_cstride >= a->cout_pad &&
+                    a->dy_cstride % 8 == 0,
+                "conv_wgrad: bad channel strides");
+  ZS3_CHECK_ARG(a->pad <= 128 && (a->R - 1) * a->dil <= 255 && (a->S - 1) * a->dil <= 255,
+                "conv_wgrad: pad/dilation outside the TMA im2col range");
+  const long long M = (long long)a->N * a->Ho * a->Wo;
+  ZS3_CHECK_ARG(M > 0 && M < (1ll << 31), "conv_wgrad: bad pixel count");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  const int CN = a->cin_pad >= 256 ? 256 : (a->cin_pad >= 128 ? 128 : 64);
+  int rc = encode_tiled2d_bf16(&p.dy, a->dy, M, a->cout_pad, a->dy_cstride, WG_BLOCK_P, 64);
+  if (rc) return rc;
+  rc = encode_im2col_bf16(&p.x, a->x, a->N, a->H, a->W, a->x_cstride, a->pad, a->pad - (a->S - 1) * a->dil, a->stride,
+                          64, WG_BLOCK_P);
+  if (rc) return rc;
+  p.M = (int)M;
+  p.HoWo = a->Ho * a->Wo;
+  p.Wo = a->Wo;
+  p.stride = a->stride;
+  p.pad = a->pad;
+  p.dil = a->dil;
+  p.R = a->R;
+  p.S = a->S;
+  p.cout_pad = a->cout_pad;
+  p.cin_pad = a->cin_pad;
+  p.num_co_tiles = ceil_div(a->cout_pad, 128);
+  p.num_ci_tiles = ceil_div(a->cin_pad, CN);
+  p.pblocks_total = (int)ceil_div_ll(M, WG_BLOCK_P);
+  const int out_tiles = p.num_co_tiles * p.num_ci_tiles * a->R * a->S;
+  int ks = a->k_splits;
+  if (ks <= 0) {
+    // fill the machine about twice over, but keep at least 8 k-blocks per CTA
+    ks = ceil_div(2 * num_sms(), out_tiles);
+    const int max_ks = p.pblocks_total / 8 > 0 ? p.pblocks_total / 8 : 1;
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+  }
+  if (ks > p.pblocks_total) ks = p.pblocks_total;
+  p.k_splits = ks;
+  p.dw = a->dw;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (CN == 256) return launch_wgrad<256, 4>(p, st);
+  if (CN == 128) return launch_wgrad<128, 6>(p, st);
+  return launch_wgrad<64, 8>(p, st);
+}
+
+extern "C" int zs3_pack_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int ci_begin, int ci_count,
+                               void* dst_bf16, int cout_pad, int cin_pad, int mode, void* stream) {
+  ZS3_CHECK_ARG(w_oihw && dst_bf16, "pack_weight: null pointer");
+  ZS3_CHECK_ARG(Cout <= cout_pad && ci_count <= cin_pad && ci_begin >= 0 && ci_begin + ci_count <= Cin,
+                "pack_weight: bad channel ranges");
+  ZS3_CHECK_ARG(mode == 0 || mode == 1, "pack_weight: mode=%d", mode);
+  const long long total = (long long)cout_pad * cin_pad * R * S;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, Cout, Cin, R, S, ci_begin, ci_count, static_cast<__nv_bfloat16*>(dst_bf16), cout_pad, cin_pad, mode);
+  ZS3_CHECK_LAUNCH("pack_weight");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_unpack_wgrad(const float* dw, int cout_pad, int cin_pad, float* grad_oihw, int Cout, int Cin, int R,
+                                int S, int ci_begin, int ci_count, int accumulate, void* stream) {
+  ZS3_CHECK_ARG(dw && grad_oihw, "unpack_wgrad: null pointer");
+  ZS3_CHECK_ARG(Cout <= cout_pad && ci_count <= cin_pad && ci_begin >= 0 && ci_begin + ci_count <= Cin,
+                "unpack_wgrad: bad channel ranges");
+  const long long total = (long long)Cout * ci_count * R * S;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_wgrad_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dw, cout_pad, cin_pad, grad_oihw, Cout,
+                                                                             Cin, R, S, ci_begin, ci_count, accumulate);
+  ZS3_CHECK_LAUNCH("unpack_wgrad");
+  return ZS3_OK;
+}

@@ -1,0 +1,229 @@
+"""Thin torch-tensor wrappers over the C ABI (include/zs3b200.h).
+
+Everything here works on CUDA tensors only and launches on torch's current stream.  Activations are
+NHWC bf16 tensors of shape [N, H, W, Cs] with Cs (the channel stride) a multiple of 64; channels beyond
+the logical channel count are zero.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def cpad(c, to=64):
+    return (c + to - 1) // to * to
+
+
+def _chk_act(t, name):
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4 and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous CUDA bf16 NHWC tensor, got {t.dtype} {tuple(t.shape)}")
+
+
+def conv_out_size(h, k, stride, pad, dil):
+    return (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def pack_weight(w, cout_pad, cin_pad, ci_begin=0, ci_count=None, mode=0):
+    """OIHW fp32 -> packed bf16.  mode 0: [cout_pad][R*S][cin_pad]; mode 1 (dgrad): [cin_pad][R*S][cout_pad]
+    with spatially flipped taps."""
+    cout, cin, r, s = w.shape
+    if ci_count is None:
+        ci_count = cin - ci_begin
+    w = w.detach().contiguous().float()
+    shape = (cout_pad, r * s, cin_pad) if mode == 0 else (cin_pad, r * s, cout_pad)
+    dst = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    L.check(L.lib().zs3_pack_weight(L.ptr(w), cout, cin, r, s, ci_begin, ci_count, L.ptr(dst), cout_pad, cin_pad, mode,
+                                    L.stream_ptr()), "zs3_pack_weight")
+    return dst
+
+
+def unpack_wgrad(dw, grad_oihw, ci_begin=0, ci_count=None, accumulate=False):
+    cout, cin, r, s = grad_oihw.shape
+    if ci_count is None:
+        ci_count = cin - ci_begin
+    cout_pad, taps, cin_pad = dw.shape
+    L.check(L.lib().zs3_unpack_wgrad(L.ptr(dw), cout_pad, cin_pad, L.ptr(grad_oihw), cout, cin, r, s, ci_begin,
+                                     ci_count, int(accumulate), L.stream_ptr()), "zs3_unpack_wgrad")
+
+
+def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=False, accumulate=False, bias=None,
+               stats=None, scatter=None):
+    """segments: list of (x [N,H,W,Cs] bf16, w_packed [cout_pad, R*S, cin_pad] bf16).
+    stats: optional (sum, sqsum) fp64 [cout_pad] accumulators.  scatter: optional (sp_stride, y_H, y_W).
+    Returns y [N,Ho,Wo,cout_pad] (or the provided `out`)."""
+    x0 = segments[0][0]
+    _chk_act(x0, "conv_fprop x")
+    n, h, w_, _ = x0.shape
+    ho = conv_out_size(h, R, stride, pad, dil)
+    wo = conv_out_size(w_, S, stride, pad, dil)
+    a = L.ConvArgs()
+    a.N, a.H, a.W, a.Ho, a.Wo = n, h, w_, ho, wo
+    a.R, a.S, a.stride, a.pad, a.dil = R, S, stride, pad, dil
+    a.cout_pad = cout_pad
+    a.num_segments = len(segments)
+    for i, (x, wp) in enumerate(segments):
+        _chk_act(x, f"conv_fprop seg{i}")
+        if tuple(x.shape[:3]) != (n, h, w_):
+            raise ValueError("conv_fprop: segments disagree on N/H/W")
+        if wp.dtype != torch.bfloat16 or wp.shape[0] != cout_pad or wp.shape[1] != R * S:
+            raise ValueError(f"conv_fprop: packed weight shape {tuple(wp.shape)} does not match")
+        a.seg[i].x = x.data_ptr()
+        a.seg[i].x_cstride = x.shape[3]
+        a.seg[i].w = wp.data_ptr()
+        a.seg[i].cin_pad = wp.shape[2]
+    if out is None:
+        if scatter is not None:
+            raise ValueError("scatter needs an explicit output tensor")
+        out = torch.empty((n, ho, wo, cout_pad), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x0.device)
+    a.y = out.data_ptr()
+    a.y_cstride = out.shape[-1]
+    a.y_is_f32 = int(out.dtype == torch.float32)
+    if scatter is not None:
+        a.y_sp_stride, a.y_H, a.y_W = scatter
+    a.accumulate = int(accumulate)
+    a.bias = None if bias is None else bias.data_ptr()
+    if stats is not None:
+        a.stat_sum = stats[0].data_ptr()
+        a.stat_sqsum = stats[1].data_ptr()
+    L.check(L.lib().zs3_conv_fprop(C.byref(a), L.stream_ptr()), "zs3_conv_fprop")
+    return out
+
+
+def conv_wgrad(x, dy, R, S, stride, pad, dil, cin_pad, cout_pad, dw=None, k_splits=0):
+    """dw[cout_pad][R*S][cin_pad] fp32 (+)= sum_p dy[p] (x) x[p@tap].  Returns dw."""
+    _chk_act(x, "conv_wgrad x")
+    _chk_act(dy, "conv_wgrad dy")
+    n, h, w_, _ = x.shape
+    ho, wo = dy.shape[1], dy.shape[2]
+    if dw is None:
+        dw = torch.zeros((cout_pad, R * S, cin_pad), dtype=torch.float32, device=x.device)
+    a = L.WgradArgs()
+    a.N, a.H, a.W, a.Ho, a.Wo = n, h, w_, ho, wo
+    a.R, a.S, a.stride, a.pad, a.dil = R, S, stride, pad, dil
+    a.x = x.data_ptr()
+    a.x_cstride = x.shape[3]
+    a.cin_pad = cin_pad
+    a.dy = dy.data_ptr()
+    a.dy_cstride = dy.shape[3]
+    a.cout_pad = cout_pad
+    a.dw = dw.data_ptr()
+    a.k_splits = k_splits
+    L.check(L.lib().zs3_conv_wgrad(C.byref(a), L.stream_ptr()), "zs3_conv_wgrad")
+    return dw
+
+
+def nchw_to_nhwc(x, cs=None):
+    """fp32 NCHW -> bf16 NHWC with channel stride cs (zero padded)."""
+    n, c, h, w = x.shape
+    cs = cpad(c) if cs is None else cs
+    x = x.contiguous().float()
+    out = torch.empty((n, h, w, cs), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().zs3_nchw_f32_to_nhwc_bf16(L.ptr(x), L.ptr(out), n, c, h * w, cs, L.stream_ptr()),
+            "zs3_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_to_nchw(x, c):
+    """bf16 NHWC [N,H,W,Cs] -> fp32 NCHW [N,c,H,W]."""
+    _chk_act(x, "nhwc_to_nchw")
+    n, h, w, cs = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    L.check(L.lib().zs3_nhwc_bf16_to_nchw_f32(L.ptr(x), L.ptr(out), n, c, h * w, cs, L.stream_ptr()),
+            "zs3_nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, cpad_, reset=True):
+    """Returns (scale, shift, mean, invstd), each fp32 [cpad_]."""
+    dev = stats[0].device
+    c = gamma.numel()
+    coef = torch.empty((4, cpad_), dtype=torch.float32, device=dev)
+    L.check(L.lib().zs3_bn_finalize(L.ptr(stats[0]), L.ptr(stats[1]), int(count), L.ptr(gamma), L.ptr(beta),
+                                    float(eps), float(momentum), L.ptr(running_mean), L.ptr(running_var),
+                                    L.ptr(coef[0]), L.ptr(coef[1]), L.ptr(coef[2]), L.ptr(coef[3]), c, cpad_,
+                                    int(reset), L.stream_ptr()), "zs3_bn_finalize")
+    return coef[0], coef[1], coef[2], coef[3]
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, cpad_):
+    dev = running_mean.device
+    c = running_mean.numel()
+    coef = torch.empty((4, cpad_), dtype=torch.float32, device=dev)
+    L.check(L.lib().zs3_bn_eval_coeffs(L.ptr(gamma), L.ptr(beta), L.ptr(running_mean), L.ptr(running_var), float(eps),
+                                       L.ptr(coef[0]), L.ptr(coef[1]), L.ptr(coef[2]), L.ptr(coef[3]), c, cpad_,
+                                       L.stream_ptr()), "zs3_bn_eval_coeffs")
+    return coef[0], coef[1], coef[2], coef[3]
+
+
+def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0, offset=0, keep_mask=None):
+    _chk_act(y, "bn_apply y")
+    n, h, w, cs = y.shape
+    if out is None:
+        out = torch.empty_like(y)
+    a = L.BnApplyArgs()
+    a.y, a.y_cstride = y.data_ptr(), cs
+    if residual is not None:
+        _chk_act(residual, "bn_apply residual")
+        a.residual, a.res_cstride = residual.data_ptr(), residual.shape[3]
+    a.out, a.out_cstride = out.data_ptr(), out.shape[3]
+    a.scale, a.shift = scale.data_ptr(), shift.data_ptr()
+    a.M, a.C = n * h * w, cs
+    a.relu = int(relu)
+    a.drop_p = float(drop_p)
+    if keep_mask is not None:
+        a.drop_mode = 2
+        a.keep_mask = keep_mask.data_ptr()
+    elif drop_p > 0:
+        a.drop_mode = 1
+    a.seed, a.offset = int(seed), int(offset)
+    L.check(L.lib().zs3_bn_apply(C.byref(a), L.stream_ptr()), "zs3_bn_apply")
+    return out
+
+
+def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, training=True, dres=None,
+                dres_accumulate=False, dgamma=None, dbeta=None, param_accumulate=False, scatter=None, dy=None,
+                scratch=None):
+    """Two-phase BatchNorm(+ReLU/+Dropout) backward.  Returns dy (bf16, same layout as y unless scatter)."""
+    _chk_act(dout, "bn_backward dout")
+    n, h, w, cs = y.shape
+    if scratch is None:
+        scratch = torch.zeros((2, cs), dtype=torch.float64, device=y.device)
+    else:
+        scratch.zero_()
+    a = L.BnBwdArgs()
+    a.dout, a.dout_cstride = dout.data_ptr(), dout.shape[3]
+    if relu:
+        a.out, a.out_cstride = out.data_ptr(), out.shape[3]
+    a.y, a.y_cstride = y.data_ptr(), cs
+    a.mean, a.invstd, a.scale = mean.data_ptr(), invstd.data_ptr(), scale.data_ptr()
+    a.M, a.C = n * h * w, cs
+    a.relu, a.grad_scale, a.training = int(relu), float(grad_scale), int(training)
+    a.sum_dz, a.sum_dzx = scratch[0].data_ptr(), scratch[1].data_ptr()
+    if scatter is not None:
+        sp, hy, wy = scatter
+        if dy is None:
+            dy = torch.zeros((n, hy, wy, cs), dtype=torch.bfloat16, device=y.device)
+        a.dy_sp_stride, a.sp_Ho, a.sp_Wo, a.dy_H, a.dy_W = sp, h, w, hy, wy
+    elif dy is None:
+        dy = torch.empty_like(y)
+    a.dy, a.dy_cstride = dy.data_ptr(), dy.shape[3]
+    if dres is not None:
+        a.dres, a.dres_cstride, a.dres_accumulate = dres.data_ptr(), dres.shape[3], int(dres_accumulate)
+    if dgamma is not None:
+        a.dgamma, a.dbeta, a.C_real = dgamma.data_ptr(), dbeta.data_ptr(), dgamma.numel()
+        a.param_accumulate = int(param_accumulate)
+    st = L.stream_ptr()
+    L.check(L.lib().zs3_bn_bwd_reduce(C.byref(a), st), "zs3_bn_bwd_reduce")
+    L.check(L.lib().zs3_bn_bwd_apply(C.byref(a), st), "zs3_bn_bwd_apply")
+    return dy
+
+
+def im2col_probe(x, pad, upper, stride, cpp, ppc, c, w, h, n, off_w, off_h):
+    """Raw (swizzled) shared-memory image of one im2col TMA load: uint8 [ppc*cpp*2]."""
+    _chk_act(x, "im2col_probe x")
+    nn, hh, ww, cc = x.shape
+    out = torch.empty(ppc * cpp * 2, dtype=torch.uint8, device=x.device)
+    L.check(L.lib().zs3_debug_im2col_probe(L.ptr(x), nn, hh, ww, cc, pad, upper, stride, cpp, ppc, c, w, h, n, off_w,
+                                           off_h, L.ptr(out), L.stream_ptr()), "zs3_debug_im2col_probe")
+    return out
