@@ -1,0 +1,153 @@
+"""CPU: the oracle restatement (oracle/zs3_oracle.py) against golden vectors produced by the REAL reference
+(tests/golden/make_golden.py).  This is what pins the oracle; the GPU parity tests then compare the CUDA
+path with the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+import zs3_oracle as O  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+def _sub(t, step=4):
+    return t.detach()[..., ::step, ::step].numpy()
+
+
+def test_state_dict_layout():
+    shapes = O.deeplab_param_shapes(21)
+    assert len(shapes) == 680
+    n_params = sum(int(np.prod(s)) for k, s in shapes.items()
+                   if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
+    assert n_params == 59344309  # parameter count of the reference model
+    assert shapes["decoder.last_conv.0.weight"] == (256, 304, 3, 3)
+    assert shapes["backbone.layer4.2.conv2.weight"] == (512, 512, 3, 3)
+    assert len(O.resnet101_blocks(16)) == 33
+    with pytest.raises(NotImplementedError):
+        O.resnet101_blocks(32)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "deeplab_small.npz"))
+
+
+def test_deeplab_eval_matches_reference(gold):
+    torch.set_num_threads(8)
+    st = O.init_deeplab_state(seed=1, randomize_bn=True)
+    x = torch.randn(2, 3, 65, 65, generator=torch.Generator().manual_seed(int(gold["x_seed"])))
+    taps = {}
+    with torch.no_grad():
+        logits = O.deeplab_forward(st, x, training=False, taps=taps)
+    assert _rel(_sub(logits), gold["eval_logits"]) < 1e-5
+    for k in ("low_level", "backbone", "aspp", "features"):
+        assert _rel(_sub(taps[k], 2)[:, ::8], gold[f"eval_{k}"]) < 1e-5, k
+    assert _rel(_sub(taps["backbone.layer2.3"], 2)[:, ::8], gold["eval_layer2"]) < 1e-5
+    assert _rel(_sub(taps["backbone.layer3.22"], 2)[:, ::8], gold["eval_layer3"]) < 1e-5
+
+
+def test_deeplab_train_step_matches_reference(gold):
+    torch.set_num_threads(8)
+    st = O.init_deeplab_state(seed=1)
+    for k, v in st.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    x = torch.randn(2, 3, 65, 65, generator=torch.Generator().manual_seed(int(gold["x_seed"])))
+    target = torch.from_numpy(gold["target"])
+    taps = {}
+    logits = O.deeplab_forward(st, x, training=True, drop_p=(0.0, 0.0, 0.0), taps=taps)
+    # train-mode BN at random init amplifies rounding ~1e3x: same math, looser bound
+    assert _rel(_sub(logits), gold["train_logits"]) < 2e-3
+    assert _rel(_sub(taps["low_level"], 2)[:, ::8], gold["train_low_level"]) < 1e-4
+    loss = O.cross_entropy(logits, target)
+    assert abs(loss.item() - float(gold["train_loss"])) < 2e-4 * abs(float(gold["train_loss"]))
+    w = torch.ones(21)
+    w[[15, 16, 17, 18, 19]] = 100.0
+    lw = O.cross_entropy(logits.detach(), target, weight=w)
+    assert abs(lw.item() - float(gold["train_loss_weighted"])) < 2e-4 * abs(float(gold["train_loss_weighted"]))
+    loss.backward()
+    for key in [k for k in gold.files if k.startswith("gradnorm/")]:
+        name = key.split("/", 1)[1]
+        g = st[name].grad.reshape(-1)
+        # well-conditioned layers (decoder) are tight; deep backbone layers inherit the chaotic gain
+        tol = 5e-3 if name.startswith("decoder") else 5e-2
+        assert abs(g.double().norm().item() - float(gold[key])) < tol * float(gold[key]), name
+        samp = g[:: max(1, g.numel() // 512)][:512].detach().numpy()
+        assert _rel(samp, gold["grad/" + name]) < (2e-2 if name.startswith("decoder") else 0.5), name
+    assert _rel(st["backbone.bn1.running_mean"].numpy(), gold["train_running_mean/backbone.bn1"]) < 1e-5
+
+
+def _gmmn_inputs():
+    g = torch.Generator().manual_seed(21)
+    emb = torch.randn(200, 300, generator=g) * 0.06
+    z = torch.rand(200, 300, generator=g)
+    real = torch.relu(torch.randn(200, 256, generator=g))
+    idx = torch.randint(0, 200, (128,), generator=g)
+    return emb, z, real, idx
+
+
+def test_gmmn_and_mmd_match_reference():
+    gold = np.load(os.path.join(GOLD, "gmmn.npz"))
+    emb, z, real, idx = _gmmn_inputs()
+    chk = gold["input_checksum"]
+    assert abs(emb.double().sum().item() - chk[0]) < 1e-6 and abs(real.double().sum().item() - chk[2]) < 1e-6
+    assert np.array_equal(idx.numpy(), gold["idx"])
+    st = O.init_gmmn_state(seed=3)
+    for v in st.values():
+        v.requires_grad_(True)
+    fake = O.gmmn_forward(st, emb, z, training=False)
+    assert _rel(fake.detach().numpy()[::2], gold["fake_eval"]) < 1e-6
+    fk = fake[idx].detach().requires_grad_(True)
+    loss = O.moment_loss(fk, real[idx])
+    assert abs(loss.item() - float(gold["mmd_loss"])) < 1e-6 * float(gold["mmd_loss"])
+    loss.backward()
+    assert _rel(fk.grad.numpy(), gold["mmd_grad_fake"]) < 1e-5
+    O.moment_loss(fake[idx], real[idx]).backward()
+    for k, v in st.items():
+        g = v.grad.reshape(-1)
+        assert abs(g.double().norm().item() - float(gold["gen_gradnorm/" + k])) < 1e-5 * float(gold["gen_gradnorm/" + k])
+        assert _rel(g[:: max(1, g.numel() // 2048)][:2048].numpy(), gold["gen_grad/" + k]) < 1e-5
+    st0 = O.init_gmmn_state(seed=4, hidden=0)
+    assert _rel(O.gmmn_forward(st0, emb, z).numpy()[::4], gold["fake_linear"]) < 1e-6
+
+
+def test_mmd_edge_cases():
+    """identical samples -> loss 0 (sqrt(0), NaN gradient like the reference); M != N keeps the scale-matrix quirk."""
+    x = torch.randn(8, 16)
+    assert O.moment_loss(x, x).item() < 1e-3
+    a, b = torch.randn(5, 16), torch.randn(7, 16)
+    assert torch.isfinite(O.moment_loss(a, b))
+
+
+def test_optimizer_restatements():
+    torch.manual_seed(0)
+    p = torch.randn(50, requires_grad=True)
+    q = p.detach().clone()
+    opt = torch.optim.SGD([p], lr=0.07, momentum=0.9, weight_decay=5e-4)
+    bufs = [None]
+    for _ in range(3):
+        g = torch.randn(50)
+        p.grad = g.clone()
+        opt.step()
+        O.sgd_step([q], [g], bufs, 0.07)
+    assert torch.allclose(p.detach(), q, atol=1e-6)
+    p = torch.randn(50, requires_grad=True)
+    q = p.detach().clone()
+    m, v = torch.zeros(50), torch.zeros(50)
+    opt = torch.optim.Adam([p], lr=2e-4)
+    for step in range(1, 4):
+        g = torch.randn(50)
+        p.grad = g.clone()
+        opt.step()
+        O.adam_step(q, g, m, v, step)
+    assert torch.allclose(p.detach(), q, atol=1e-6)
