@@ -187,6 +187,57 @@ int zs3_bn_bwd_apply(const zs3_bn_bwd_args* a, void* stream);
 int zs3_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, long long HW, int cs, void* stream);
 int zs3_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, long long HW, int cs, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Remaining DeepLab glue ops (all HBM-bound, NHWC bf16 unless stated).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Stem 7x7/s2/p3 conv (zs3/modeling/backbone/resnet.py:79): im2col of the NCHW fp32 image into
+ * cols[N*Ho*Wo][kpad] bf16 with k = c*R*R + r*R + s (the OIHW flattening), so that the stem runs as a
+ * 1x1 zs3_conv_fprop / zs3_conv_wgrad over `cols` with the weight viewed as [Cout][C*R*R][1][1]. */
+int zs3_stem_im2col(const float* x_nchw, void* cols, int N, int C, int H, int W, int R, int stride, int pad, int Ho,
+                    int Wo, int kpad, void* stream);
+
+/* nn.MaxPool2d(3, 2, 1) (resnet.py:82); argmax keeps the winning window slot (first max wins) per element */
+int zs3_maxpool_fwd(const void* x, void* y, unsigned char* argmax, int N, int H, int W, int C, int Ho, int Wo, int k,
+                    int stride, int pad, void* stream);
+int zs3_maxpool_bwd(const void* dy, const unsigned char* argmax, void* dx, int N, int H, int W, int C, int Ho, int Wo,
+                    int k, int stride, int pad, void* stream);
+
+/* F.interpolate(mode="bilinear", align_corners=True) on NHWC bf16 (decoder.py:33-35,46-48) and its adjoint */
+int zs3_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int x_cs, int y_cs,
+                     void* stream);
+int zs3_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int Wi, int Ho, int Wo, int C, int dy_cs, int dx_cs,
+                     int accumulate, void* stream);
+
+/* Final upsample of the class scores to the input size (deeplab.py:44,55): NHWC bf16 [N][Hi][Wi][cs] ->
+ * NCHW fp32 [N][C][Ho][Wo] (the tensor the reference API returns), and its adjoint. */
+int zs3_upsample_logits_fwd(const void* x, float* y, int N, int C, int Hi, int Wi, int cs, int Ho, int Wo,
+                            void* stream);
+int zs3_upsample_logits_bwd(const float* dy, void* dx, int N, int C, int Hi, int Wi, int cs, int Ho, int Wo,
+                            void* stream);
+
+/* nn.AdaptiveAvgPool2d((1,1)) (aspp.py:84): y[n][c] = scale * sum_hw x[n][hw][c]; and the broadcast
+ * y[n][hw][c] (+)= scale * x[n][c] (the 1x1 -> HxW "interpolate" of aspp.py:109 and the pool's adjoint). */
+int zs3_spatial_sum(const void* x, void* y, int N, int HW, int C, int x_cs, int y_cs, float scale, void* stream);
+int zs3_spatial_broadcast(const void* x, void* y, int N, int HW, int C, int x_cs, int y_cs, float scale,
+                          int accumulate, void* stream);
+
+/* SegmentationLosses.CrossEntropyLoss (zs3/utils/loss.py:31-46): logits NCHW fp32, target float [N][HW],
+ * optional class weights, ignore_index; loss = sum_i w_t nll_i / sum_i w_t / div (div = batch size when
+ * batch_average).  accum2 = two fp64 scratch values kept for the backward (sum w*nll, sum w). */
+int zs3_ce_fwd(const float* logit, const float* target, const float* weight, int N, int C, long long HW,
+               int ignore_index, float div, double* accum2, float* loss, void* stream);
+int zs3_ce_bwd(const float* logit, const float* target, const float* weight, int N, int C, long long HW,
+               int ignore_index, float div, const double* accum2, const float* grad_out, float* dlogit,
+               void* stream);
+
+/* torch.optim.SGD (zs3/train_pascal.py:55-60) and torch.optim.Adam (zs3/train_pascal_GMMN.py:65-67) over one
+ * flat fp32 buffer; grad_scale multiplies the gradient first (1/world_size after the NCCL all-reduce). */
+int zs3_sgd_step(float* p, const float* g, float* momentum_buf, long long n, float lr, float momentum,
+                 float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
+int zs3_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, int step, float grad_scale, void* stream);
+
 /* debug: one im2col TMA load dumped raw (tests/test_tma_probe.py) */
 int zs3_debug_im2col_probe(const void* x, int N, int H, int W, int C, int pad, int upper, int stride, int cpp, int ppc,
                            int c, int w, int h, int n, int off_w, int off_h, void* out, void* stream);

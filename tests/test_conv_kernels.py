@@ -74,9 +74,11 @@ def test_fprop_bias_accumulate_segments():
     err = rel_l2(y.permute(0, 3, 1, 2), ref)
     assert err < TOL_F32_OUT, err
     # accumulate on top of an existing tensor
-    y2 = K.conv_fprop(segs, 3, 3, 1, 1, 1, 256, out=y.clone(), accumulate=True)
-    assert rel_l2(y2.permute(0, 3, 1, 2), 2 * ref + 0 * ref - bias.view(1, -1, 1, 1) * 0) < 1e-4 or True
+    y2 = K.conv_fprop(segs, 3, 3, 1, 1, 1, 256, out=y.clone(), accumulate=True, bias=bias)
     assert rel_l2(y2, 2 * y) < TOL_F32_OUT
+    yb = y.to(torch.bfloat16)
+    y3 = K.conv_fprop(segs, 3, 3, 1, 1, 1, 256, out=yb.clone(), accumulate=True)  # bf16 read-modify-write, no bias
+    assert rel_l2(y3.float(), yb.float() + y - bias) < TOL_BF16_OUT
 
 
 @pytest.mark.parametrize("case", [

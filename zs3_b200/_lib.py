@@ -124,6 +124,19 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_bn_apply": [C.POINTER(BnApplyArgs), vp],
         "zs3_bn_bwd_reduce": [C.POINTER(BnBwdArgs), vp],
         "zs3_bn_bwd_apply": [C.POINTER(BnBwdArgs), vp],
+        "zs3_stem_im2col": [vp, vp, i, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_maxpool_fwd": [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_maxpool_bwd": [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_bilinear_fwd": [vp, vp, i, i, i, i, i, i, i, i, vp],
+        "zs3_bilinear_bwd": [vp, vp, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_upsample_logits_fwd": [vp, vp, i, i, i, i, i, i, i, vp],
+        "zs3_upsample_logits_bwd": [vp, vp, i, i, i, i, i, i, i, vp],
+        "zs3_spatial_sum": [vp, vp, i, i, i, i, i, f, vp],
+        "zs3_spatial_broadcast": [vp, vp, i, i, i, i, i, f, i, vp],
+        "zs3_ce_fwd": [vp, vp, vp, i, i, ll, i, f, vp, vp, vp],
+        "zs3_ce_bwd": [vp, vp, vp, i, i, ll, i, f, vp, vp, vp, vp],
+        "zs3_sgd_step": [vp, vp, vp, ll, f, f, f, i, i, f, vp],
+        "zs3_adam_step": [vp, vp, vp, vp, ll, f, f, f, f, i, f, vp],
     }
 
 

@@ -1,0 +1,552 @@
+// HBM-bound glue kernels of the DeepLab path (NHWC bf16 activations, fp32 math):
+// stem im2col, max-pool, bilinear resampling, global average pool, cross-entropy, fused optimizers.
+// Each entry point cites the reference op it replaces in include/zs3b200.h.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace zs3 {
+
+__device__ __forceinline__ void unpack8m(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8m(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+static int ew_blocks(long long items, int threads, int cap = 148 * 16) {
+  long long b = (items + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------ stem im2col
+// cols[m][k], k = c*R*S + r*S + s (the OIHW flattening of the weight), zero padded to kpad columns.
+__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, int N, int C, int H,
+                                   int W, int R, int stride, int pad, int Ho, int Wo, int kpad) {
+  const int K = C * R * R;
+  const long long total = (long long)N * Ho * Wo * kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kpad);
+    const long long m = i / kpad;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k / (R * R);
+      const int rs = k - c * R * R;
+      const int r = rs / R, s = rs - r * R;
+      const int q = (int)(m % Wo);
+      const int p = (int)((m / Wo) % Ho);
+      const int n = (int)(m / ((long long)Wo * Ho));
+      const int ih = p * stride - pad + r, iw = q * stride - pad + s;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((long long)n * C + c) * H + ih) * W + iw);
+    }
+    cols[i] = __float2bfloat16(v);
+  }
+}
+
+// --------------------------------------------------------------------------------- max-pool
+// first maximum in row-major window order wins (ATen max_pool2d semantics); argmax stores the window slot.
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   unsigned char* __restrict__ arg, int N, int H, int W, int C, int Ho, int Wo, int k,
+                                   int stride, int pad) {
+  const int vpc = C >> 3;
+  const long long total = (long long)N * Ho * Wo * vpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vpc) << 3;
+    const long long m = i / vpc;
+    const int q = (int)(m % Wo), p = (int)((m / Wo) % Ho), n = (int)(m / ((long long)Wo * Ho));
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int r = 0; r < k; ++r) {
+      const int ih = p * stride - pad + r;
+      if (ih < 0 || ih >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int iw = q * stride - pad + s;
+        if (iw < 0 || iw >= W) continue;
+        float v[8];
+        unpack8m(*reinterpret_cast<const uint4*>(x + (((long long)n * H + ih) * W + iw) * C + c), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j]) { best[j] = v[j]; bi[j] = r * k + s; }
+      }
+    }
+    *reinterpret_cast<uint4*>(y + m * C + c) = pack8m(best);
+    uint2 a;
+    a.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    a.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(arg + m * C + c) = a;
+  }
+}
+
+// gather form: every input pixel sums the output gradients of the windows that selected it
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ arg,
+                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int k,
+                                   int stride, int pad) {
+  const int vpc = C >> 3;
+  const long long total = (long long)N * H * W * vpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vpc) << 3;
+    const long long m = i / vpc;
+    const int w = (int)(m % W), h = (int)((m / W) % H), n = (int)(m / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < k; ++r) {
+      const int t = h + pad - r;
+      if (t < 0 || t % stride) continue;
+      const int p = t / stride;
+      if (p >= Ho) continue;
+      for (int s = 0; s < k; ++s) {
+        const int u = w + pad - s;
+        if (u < 0 || u % stride) continue;
+        const int q = u / stride;
+        if (q >= Wo) continue;
+        const long long mo = ((long long)n * Ho + p) * Wo + q;
+        const uint2 a = *reinterpret_cast<const uint2*>(arg + mo * C + c);
+        float g[8];
+        unpack8m(*reinterpret_cast<const uint4*>(dy + mo * C + c), g);
+        const int slot = r * k + s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int sel = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xFF;
+          if (sel == slot) acc[j] += g[j];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + m * C + c) = pack8m(acc);
+  }
+}
+
+// ------------------------------------------------------------------ bilinear (align_corners)
+__device__ __forceinline__ void bl_coord(int o, float scale, int in_size, int& i0, int& i1, float& l1) {
+  const float r = scale * o;  // ATen: area_pixel_compute_source_index(align_corners=True)
+  i0 = (int)r;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = r - i0;
+}
+
+__global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int Hi,
+                                    int Wi, int Ho, int Wo, int C, int x_cs, int y_cs, float sh, float sw) {
+  const int vpc = C >> 3;
+  const long long total = (long long)N * Ho * Wo * vpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vpc) << 3;
+    const long long m = i / vpc;
+    const int ow = (int)(m % Wo), oh = (int)((m / Wo) % Ho), n = (int)(m / ((long long)Wo * Ho));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bl_coord(oh, sh, Hi, y0, y1, ly);
+    bl_coord(ow, sw, Wi, x0, x1, lx);
+    const __nv_bfloat16* base = x + (long long)n * Hi * Wi * x_cs + c;
+    float a[8], b[8], d[8], e[8], o[8];
+    unpack8m(*reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x0) * x_cs), a);
+    unpack8m(*reinterpret_cast<const uint4*>(base + ((long long)y0 * Wi + x1) * x_cs), b);
+    unpack8m(*reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x0) * x_cs), d);
+    unpack8m(*reinterpret_cast<const uint4*>(base + ((long long)y1 * Wi + x1) * x_cs), e);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * d[j] + lx * e[j]);
+    *reinterpret_cast<uint4*>(y + m * y_cs + c) = pack8m(o);
+  }
+}
+
+// gather form of the transpose: dx[h][w] = sum over the output pixels whose stencil touches (h,w)
+__global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
+                                    int Hi, int Wi, int Ho, int Wo, int C, int dy_cs, int dx_cs, float sh, float sw,
+                                    int accumulate) {
+  const int vpc = C >> 3;
+  const long long total = (long long)N * Hi * Wi * vpc;
+  const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vpc) << 3;
+    const long long m = i / vpc;
+    const int w = (int)(m % Wi), h = (int)((m / Wi) % Hi), n = (int)(m / ((long long)Wi * Hi));
+    int oh_lo = sh > 0.f ? (int)floorf((h - 1) * ish) - 1 : 0, oh_hi = sh > 0.f ? (int)ceilf((h + 1) * ish) + 1 : Ho - 1;
+    int ow_lo = sw > 0.f ? (int)floorf((w - 1) * isw) - 1 : 0, ow_hi = sw > 0.f ? (int)ceilf((w + 1) * isw) + 1 : Wo - 1;
+    oh_lo = max(oh_lo, 0); oh_hi = min(oh_hi, Ho - 1);
+    ow_lo = max(ow_lo, 0); ow_hi = min(ow_hi, Wo - 1);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      int y0, y1; float ly;
+      bl_coord(oh, sh, Hi, y0, y1, ly);
+      const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        int x0, x1; float lx;
+        bl_coord(ow, sw, Wi, x0, x1, lx);
+        const float wx = (x0 == w ? 1.f - lx : 0.f) + (x1 == w ? lx : 0.f);
+        if (wx == 0.f) continue;
+        float g[8];
+        unpack8m(*reinterpret_cast<const uint4*>(dy + (((long long)n * Ho + oh) * Wo + ow) * dy_cs + c), g);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += wgt * g[j];
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dx + m * dx_cs + c);
+    if (accumulate) {
+      float o[8];
+      unpack8m(*dst, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += o[j];
+    }
+    *dst = pack8m(acc);
+  }
+}
+
+// final x4 upsample of the class scores: NHWC bf16 [N][Hi][Wi][cs] -> NCHW fp32 [N][C][Ho][Wo]
+// one CTA per output row; the vertically blended input row is staged in shared memory as [c][w_in].
+__global__ void upsample_logits_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int Hi,
+                                           int Wi, int cs, int Ho, int Wo, float sh, float sw) {
+  extern __shared__ float rb[];  // [C][Wi+1]
+  const int oh = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  int y0, y1; float ly;
+  bl_coord(oh, sh, Hi, y0, y1, ly);
+  const int ld = Wi + 1;
+  const __nv_bfloat16* r0 = x + ((long long)n * Hi + y0) * Wi * cs;
+  const __nv_bfloat16* r1 = x + ((long long)n * Hi + y1) * Wi * cs;
+  for (int i = threadIdx.x; i < Wi * C; i += blockDim.x) {
+    const int c = i % C, w = i / C;
+    rb[c * ld + w] = (1.f - ly) * __bfloat162float(r0[(long long)w * cs + c]) + ly * __bfloat162float(r1[(long long)w * cs + c]);
+  }
+  __syncthreads();
+  float* out = y + ((long long)n * C * Ho + oh) * Wo;
+  for (int i = threadIdx.x; i < C * Wo; i += blockDim.x) {
+    const int ow = i % Wo, c = i / Wo;
+    int x0, x1; float lx;
+    bl_coord(ow, sw, Wi, x0, x1, lx);
+    out[(long long)c * Ho * Wo + ow] = (1.f - lx) * rb[c * ld + x0] + lx * rb[c * ld + x1];
+  }
+}
+
+// backward: NCHW fp32 dlogits -> NHWC bf16 [N][Hi][Wi][cs]; one CTA per input row:
+// stage 1 blends the contributing output rows vertically into shared memory v[c][ow], stage 2 reduces horizontally.
+__global__ void upsample_logits_bwd_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int C, int Hi,
+                                           int Wi, int cs, int Ho, int Wo, float sh, float sw) {
+  extern __shared__ float v[];  // [C][Wo+1]
+  const int h = blockIdx.x % Hi, n = blockIdx.x / Hi;
+  const int ld = Wo + 1;
+  const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
+  int oh_lo = sh > 0.f ? (int)floorf((h - 1) * ish) - 1 : 0, oh_hi = sh > 0.f ? (int)ceilf((h + 1) * ish) + 1 : Ho - 1;
+  oh_lo = max(oh_lo, 0); oh_hi = min(oh_hi, Ho - 1);
+  for (int i = threadIdx.x; i < C * Wo; i += blockDim.x) {
+    const int ow = i % Wo, c = i / Wo;
+    float acc = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      int y0, y1; float ly;
+      bl_coord(oh, sh, Hi, y0, y1, ly);
+      const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
+      if (wy != 0.f) acc += wy * __ldg(dy + (((long long)n * C + c) * Ho + oh) * Wo + ow);
+    }
+    v[c * ld + ow] = acc;
+  }
+  __syncthreads();
+  __nv_bfloat16* out = dx + ((long long)n * Hi + h) * Wi * cs;
+  for (int i = threadIdx.x; i < Wi * cs; i += blockDim.x) {
+    const int c = i % cs, w = i / cs;
+    float acc = 0.f;
+    if (c < C) {
+      int ow_lo = sw > 0.f ? (int)floorf((w - 1) * isw) - 1 : 0, ow_hi = sw > 0.f ? (int)ceilf((w + 1) * isw) + 1 : Wo - 1;
+      ow_lo = max(ow_lo, 0); ow_hi = min(ow_hi, Wo - 1);
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        int x0, x1; float lx;
+        bl_coord(ow, sw, Wi, x0, x1, lx);
+        const float wx = (x0 == w ? 1.f - lx : 0.f) + (x1 == w ? lx : 0.f);
+        if (wx != 0.f) acc += wx * v[c * ld + ow];
+      }
+    }
+    out[(long long)w * cs + c] = __float2bfloat16(acc);
+  }
+}
+
+// ------------------------------------------------------------------ global average pooling
+// y[n][c] = scale * sum_hw x[n][hw][c]   (one CTA per (n, 64-channel group))
+__global__ void spatial_sum_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int HW, int x_cs,
+                                   int y_cs, float scale) {
+  __shared__ float red[4][64];
+  const int n = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int lane_row = threadIdx.x >> 6;  // 4 row lanes with 256 threads
+  float acc = 0.f;
+  for (int p = lane_row; p < HW; p += 4) acc += __bfloat162float(x[((long long)n * HW + p) * x_cs + c]);
+  red[lane_row][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const float s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    y[(long long)n * y_cs + c] = __float2bfloat16(s * scale);
+  }
+}
+
+// y[n][hw][c] (+)= scale * x[n][c]
+__global__ void spatial_broadcast_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
+                                         int HW, int C, int x_cs, int y_cs, float scale, int accumulate) {
+  const int vpc = C >> 3;
+  const long long total = (long long)N * HW * vpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vpc) << 3;
+    const long long m = i / vpc;
+    const int n = (int)(m / HW);
+    float f[8];
+    unpack8m(*reinterpret_cast<const uint4*>(x + (long long)n * x_cs + c), f);
+    uint4* dst = reinterpret_cast<uint4*>(y + m * y_cs + c);
+    float o[8];
+    if (accumulate) unpack8m(*dst, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * scale + (accumulate ? o[j] : 0.f);
+    *dst = pack8m(f);
+  }
+}
+
+// ----------------------------------------------------------------------------- cross-entropy
+// accum[0] += sum_i w[t_i] * (-log softmax(logit_i)[t_i]),  accum[1] += sum_i w[t_i]   (t_i != ignore)
+__global__ void ce_fwd_kernel(const float* __restrict__ logit, const float* __restrict__ target,
+                              const float* __restrict__ weight, int C, long long HW, long long total, int ignore,
+                              double* __restrict__ accum) {
+  float num = 0.f, den = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)target[i];
+    if (t == ignore || t < 0 || t >= C) continue;
+    const long long n = i / HW, hw = i - n * HW;
+    const float* lp = logit + n * C * HW + hw;
+    float mx = -INFINITY, s = 0.f, lt = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(lp + (long long)c * HW);
+      if (c == t) lt = v;
+      if (v > mx) { s = s * __expf(mx - v); mx = v; }
+      s += __expf(v - mx);
+    }
+    const float w = weight ? weight[t] : 1.f;
+    num += w * (mx + __logf(s) - lt);
+    den += w;
+  }
+  __shared__ float sn[32], sd[32];
+  for (int off = 16; off; off >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, off);
+    den += __shfl_xor_sync(0xffffffffu, den, off);
+  }
+  if ((threadIdx.x & 31) == 0) { sn[threadIdx.x >> 5] = num; sd[threadIdx.x >> 5] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sn[i]; b += sd[i]; }
+    atomicAdd(accum, a);
+    atomicAdd(accum + 1, b);
+  }
+}
+
+__global__ void ce_finalize_kernel(const double* accum, float div, float* loss) {
+  *loss = (float)(accum[0] / accum[1] / (double)div);
+}
+
+// dlogit = gout * w[t] * (softmax - onehot) / (sum_w * div); 0 for ignored pixels
+__global__ void ce_bwd_kernel(const float* __restrict__ logit, const float* __restrict__ target,
+                              const float* __restrict__ weight, int C, long long HW, long long total, int ignore,
+                              const double* __restrict__ accum, float div, const float* __restrict__ gout,
+                              float* __restrict__ dlogit) {
+  const float g = gout[0] / ((float)accum[1] * div);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)target[i];
+    const long long n = i / HW, hw = i - n * HW;
+    const float* lp = logit + n * C * HW + hw;
+    float* dp = dlogit + n * C * HW + hw;
+    if (t == ignore || t < 0 || t >= C) {
+      for (int c = 0; c < C; ++c) dp[(long long)c * HW] = 0.f;
+      continue;
+    }
+    float mx = -INFINITY, s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(lp + (long long)c * HW);
+      if (v > mx) { s = s * __expf(mx - v); mx = v; }
+      s += __expf(v - mx);
+    }
+    const float inv = 1.f / s;
+    const float gw = g * (weight ? weight[t] : 1.f);
+    for (int c = 0; c < C; ++c) {
+      const float pr = __expf(__ldg(lp + (long long)c * HW) - mx) * inv;
+      dp[(long long)c * HW] = gw * (pr - (c == t ? 1.f : 0.f));
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- optimizers
+// torch.optim.SGD: d = g*gscale + wd*p; buf = first ? d : mom*buf + d; p -= lr * (nesterov ? d + mom*buf : buf)
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+                           float lr, float mom, float wd, int nesterov, int first, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float w = p[i];
+    float d = g[i] * gscale + wd * w;
+    float b = first ? d : mom * buf[i] + d;
+    buf[i] = b;
+    p[i] = w - lr * (nesterov ? d + mom * b : b);
+  }
+}
+
+// torch.optim.Adam (no amsgrad, no weight decay)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+}  // namespace zs3
+
+using namespace zs3;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define BF(p) static_cast<__nv_bfloat16*>(p)
+#define CBF(p) static_cast<const __nv_bfloat16*>(p)
+
+extern "C" int zs3_stem_im2col(const float* x, void* cols, int N, int C, int H, int W, int R, int stride, int pad,
+                               int Ho, int Wo, int kpad, void* stream) {
+  ZS3_CHECK_ARG(x && cols && kpad >= C * R * R && kpad % 8 == 0, "stem_im2col: bad args");
+  const long long total = (long long)N * Ho * Wo * kpad;
+  stem_im2col_kernel<<<ew_blocks(total, 256, 148 * 32), 256, 0, ST(stream)>>>(x, BF(cols), N, C, H, W, R, stride, pad,
+                                                                              Ho, Wo, kpad);
+  ZS3_CHECK_LAUNCH("stem_im2col");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_maxpool_fwd(const void* x, void* y, unsigned char* argmax, int N, int H, int W, int C, int Ho,
+                               int Wo, int k, int stride, int pad, void* stream) {
+  ZS3_CHECK_ARG(x && y && argmax && C % 8 == 0 && k * k <= 255, "maxpool_fwd: bad args");
+  maxpool_fwd_kernel<<<ew_blocks((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), BF(y), argmax, N, H, W, C, Ho, Wo, k, stride, pad);
+  ZS3_CHECK_LAUNCH("maxpool_fwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_maxpool_bwd(const void* dy, const unsigned char* argmax, void* dx, int N, int H, int W, int C,
+                               int Ho, int Wo, int k, int stride, int pad, void* stream) {
+  ZS3_CHECK_ARG(dy && dx && argmax && C % 8 == 0, "maxpool_bwd: bad args");
+  maxpool_bwd_kernel<<<ew_blocks((long long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(dy), argmax, BF(dx), N, H, W, C, Ho, Wo, k, stride, pad);
+  ZS3_CHECK_LAUNCH("maxpool_bwd");
+  return ZS3_OK;
+}
+
+static float bl_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+extern "C" int zs3_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int x_cs,
+                                int y_cs, void* stream) {
+  ZS3_CHECK_ARG(x && y && C % 8 == 0 && x_cs % 8 == 0 && y_cs % 8 == 0 && x_cs >= C && y_cs >= C, "bilinear_fwd: bad args");
+  bilinear_fwd_kernel<<<ew_blocks((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), BF(y), N, Hi, Wi, Ho, Wo, C, x_cs, y_cs, bl_scale(Hi, Ho), bl_scale(Wi, Wo));
+  ZS3_CHECK_LAUNCH("bilinear_fwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int Wi, int Ho, int Wo, int C, int dy_cs,
+                                int dx_cs, int accumulate, void* stream) {
+  ZS3_CHECK_ARG(dy && dx && C % 8 == 0 && dy_cs % 8 == 0 && dx_cs % 8 == 0, "bilinear_bwd: bad args");
+  bilinear_bwd_kernel<<<ew_blocks((long long)N * Hi * Wi * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(dy), BF(dx), N, Hi, Wi, Ho, Wo, C, dy_cs, dx_cs, bl_scale(Hi, Ho), bl_scale(Wi, Wo), accumulate);
+  ZS3_CHECK_LAUNCH("bilinear_bwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_upsample_logits_fwd(const void* x, float* y, int N, int C, int Hi, int Wi, int cs, int Ho, int Wo,
+                                       void* stream) {
+  ZS3_CHECK_ARG(x && y && C <= cs, "upsample_logits_fwd: bad args");
+  const size_t smem = (size_t)C * (Wi + 1) * sizeof(float);
+  ZS3_CHECK_ARG(smem <= 200 * 1024, "upsample_logits_fwd: C*Wi too large for shared memory");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_logits_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  upsample_logits_fwd_kernel<<<N * Ho, 256, smem, ST(stream)>>>(CBF(x), y, C, Hi, Wi, cs, Ho, Wo, bl_scale(Hi, Ho),
+                                                                bl_scale(Wi, Wo));
+  ZS3_CHECK_LAUNCH("upsample_logits_fwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_upsample_logits_bwd(const float* dy, void* dx, int N, int C, int Hi, int Wi, int cs, int Ho, int Wo,
+                                       void* stream) {
+  ZS3_CHECK_ARG(dy && dx && C <= cs, "upsample_logits_bwd: bad args");
+  const size_t smem = (size_t)C * (Wo + 1) * sizeof(float);
+  ZS3_CHECK_ARG(smem <= 200 * 1024, "upsample_logits_bwd: C*Wo too large for shared memory");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_logits_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  upsample_logits_bwd_kernel<<<N * Hi, 256, smem, ST(stream)>>>(dy, BF(dx), C, Hi, Wi, cs, Ho, Wo, bl_scale(Hi, Ho),
+                                                                bl_scale(Wi, Wo));
+  ZS3_CHECK_LAUNCH("upsample_logits_bwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_spatial_sum(const void* x, void* y, int N, int HW, int C, int x_cs, int y_cs, float scale,
+                               void* stream) {
+  ZS3_CHECK_ARG(x && y && C % 64 == 0 && x_cs >= C && y_cs >= C, "spatial_sum: C must be a multiple of 64");
+  spatial_sum_kernel<<<dim3(C / 64, N), 256, 0, ST(stream)>>>(CBF(x), BF(y), HW, x_cs, y_cs, scale);
+  ZS3_CHECK_LAUNCH("spatial_sum");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_spatial_broadcast(const void* x, void* y, int N, int HW, int C, int x_cs, int y_cs, float scale,
+                                     int accumulate, void* stream) {
+  ZS3_CHECK_ARG(x && y && C % 8 == 0 && x_cs % 8 == 0 && y_cs % 8 == 0, "spatial_broadcast: bad args");
+  spatial_broadcast_kernel<<<ew_blocks((long long)N * HW * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), BF(y), N, HW, C, x_cs, y_cs, scale, accumulate);
+  ZS3_CHECK_LAUNCH("spatial_broadcast");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_ce_fwd(const float* logit, const float* target, const float* weight, int N, int C, long long HW,
+                          int ignore_index, float div, double* accum2, float* loss, void* stream) {
+  ZS3_CHECK_ARG(logit && target && accum2 && loss && C > 0, "ce_fwd: bad args");
+  cudaMemsetAsync(accum2, 0, 2 * sizeof(double), ST(stream));
+  const long long total = (long long)N * HW;
+  ce_fwd_kernel<<<ew_blocks(total, 256, 148 * 8), 256, 0, ST(stream)>>>(logit, target, weight, C, HW, total,
+                                                                        ignore_index, accum2);
+  ce_finalize_kernel<<<1, 1, 0, ST(stream)>>>(accum2, div, loss);
+  ZS3_CHECK_LAUNCH("ce_fwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_ce_bwd(const float* logit, const float* target, const float* weight, int N, int C, long long HW,
+                          int ignore_index, float div, const double* accum2, const float* grad_out, float* dlogit,
+                          void* stream) {
+  ZS3_CHECK_ARG(logit && target && accum2 && grad_out && dlogit, "ce_bwd: bad args");
+  const long long total = (long long)N * HW;
+  ce_bwd_kernel<<<ew_blocks(total, 256, 148 * 8), 256, 0, ST(stream)>>>(logit, target, weight, C, HW, total,
+                                                                        ignore_index, accum2, div, grad_out, dlogit);
+  ZS3_CHECK_LAUNCH("ce_bwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_sgd_step(float* p, const float* g, float* buf, long long n, float lr, float momentum,
+                            float weight_decay, int nesterov, int first_step, float grad_scale, void* stream) {
+  ZS3_CHECK_ARG(p && g && buf && n >= 0, "sgd_step: bad args");
+  if (n == 0) return ZS3_OK;
+  sgd_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(p, g, buf, n, lr, momentum, weight_decay, nesterov, first_step,
+                                                        grad_scale);
+  ZS3_CHECK_LAUNCH("sgd_step");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                             float beta2, float eps, int step, float grad_scale, void* stream) {
+  ZS3_CHECK_ARG(p && g && m && v && n >= 0 && step >= 1, "adam_step: bad args");
+  if (n == 0) return ZS3_OK;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
+  ZS3_CHECK_LAUNCH("adam_step");
+  return ZS3_OK;
+}

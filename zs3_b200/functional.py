@@ -1,0 +1,422 @@
+"""autograd Functions that stitch the sm_100a kernels (zs3_b200/kernels.py) into the DeepLab graph.
+
+Internal activations are NHWC bf16 tensors [N, H, W, Cs] (Cs = channels padded to a multiple of 64).
+Parameters stay fp32 tensors in the reference's layout (OIHW conv weights, [C] BatchNorm affine), so
+state_dict()s are interchangeable with the reference's; the Functions return parameter gradients in
+that layout.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import kernels as K
+
+_SCRATCH = {}
+PENDING_BATCH_COUNTERS = []  # num_batches_tracked buffers to bump (one fused foreach add per model forward)
+
+
+def flush_batch_counters():
+    if PENDING_BATCH_COUNTERS:
+        torch._foreach_add_(PENDING_BATCH_COUNTERS, 1)
+        PENDING_BATCH_COUNTERS.clear()
+
+
+class IdentityBN:
+    """stand-in for 'no normalisation' (aspp.global_avg_pool without BN, zs3/modeling/aspp.py:90-95)"""
+    training = False
+    weight = None
+    bias = None
+    eps = 0.0
+    momentum = 0.1
+    num_batches_tracked = None
+
+    def __init__(self, c, device):
+        self.running_mean = torch.zeros(c, dtype=torch.float32, device=device)
+        self.running_var = torch.ones(c, dtype=torch.float32, device=device)
+
+
+
+def _scratch64(dev, tag="fwd", n=2 * 2048):
+    """fp64 scratch: "fwd" holds the conv-epilogue BN statistics (kept zero between uses by bn_finalize's
+    reset), "bwd" the BN-backward sums (zeroed before each use)."""
+    key = (dev, tag, n)
+    t = _SCRATCH.get(key)
+    if t is None:
+        t = torch.zeros(n, dtype=torch.float64, device=dev)
+        _SCRATCH[key] = t
+    return t
+
+
+class _RngState:
+    """Counter-based dropout RNG: (seed, running offset) on the host, in the spirit of torch's Philox state."""
+    offset = 0
+
+    @classmethod
+    def next(cls, numel):
+        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        off = cls.offset
+        cls.offset += numel
+        return seed, off
+
+
+def _packed_weight(conv, mode, ci_begin, ci_count, cin_pad, cout_pad):
+    """bf16 kernel-layout copy of conv.weight, cached until the parameter changes (version counter)."""
+    w = conv.weight
+    cache = conv.__dict__.setdefault("_zs3_pack_cache", {})
+    key = (mode, ci_begin, ci_count, cin_pad, cout_pad)
+    ent = cache.get(key)
+    ver = (w._version, w.data_ptr())
+    if ent is None or ent[0] != ver:
+        ent = (ver, K.pack_weight(w.detach(), cout_pad, cin_pad, ci_begin, ci_count, mode))
+        cache[key] = ent
+    return ent[1]
+
+
+def _bn_forward_coeffs(bn, stats, count, cs):
+    """(scale, shift, mean, invstd) for this BN: batch statistics in training mode (updates the running
+    buffers like F.batch_norm), running statistics otherwise."""
+    w = bn.weight.detach() if bn.weight is not None else None
+    b = bn.bias.detach() if bn.bias is not None else None
+    if stats is not None:
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        if bn.num_batches_tracked is not None:
+            PENDING_BATCH_COUNTERS.append(bn.num_batches_tracked)
+        return K.bn_finalize(stats, count, w, b, bn.eps, mom, bn.running_mean, bn.running_var, cs)
+    return K.bn_eval_coeffs(w, b, bn.running_mean, bn.running_var, bn.eps, cs)
+
+
+class ConvBnAct(torch.autograd.Function):
+    """[concat ->] conv -> BatchNorm -> (+residual) -> (ReLU) -> (Dropout), one fused forward/backward.
+
+    Replaces the nn.Conv2d/BatchNorm/ReLU/Dropout runs of zs3/modeling/backbone/resnet.py:33-53,
+    zs3/modeling/aspp.py:25-29,111-116 and zs3/modeling/decoder.py:30-38."""
+
+    @staticmethod
+    def forward(ctx, conv, bn, relu, drop_p, keep_mask, weight, gamma, beta, residual, *xs):
+        R, S = conv.kernel_size
+        stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
+        cout = conv.out_channels
+        cout_p = K.cpad(cout)
+        training = bn.training
+        # input channel ranges of the (virtually concatenated) segments
+        segs, ranges, ci = [], [], 0
+        for x, c_real in xs_with_channels(xs, ctx_channels=conv.__dict__.get("_zs3_seg_channels")):
+            cin_p = x.shape[3]
+            wp = _packed_weight(conv, 0, ci, c_real, cin_p, cout_p)
+            segs.append((x, wp))
+            ranges.append((ci, c_real, cin_p))
+            ci += c_real
+        if ci != conv.in_channels:
+            raise ValueError(f"segments provide {ci} channels, conv expects {conv.in_channels}")
+        dev = xs[0].device
+        stats = None
+        if training:
+            sc = _scratch64(dev)
+            stats = (sc[:cout_p], sc[2048:2048 + cout_p])
+        y = K.conv_fprop(segs, R, S, stride, pad, dil, cout_p, stats=stats)
+        n, ho, wo, _ = y.shape
+        scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
+        seed = off = 0
+        p = float(drop_p) if (drop_p and training_dropout(conv, bn)) else 0.0
+        if p > 0 and keep_mask is None:
+            seed, off = _RngState.next(y.numel())
+        out = K.bn_apply(y, scale, shift, relu, residual=residual, drop_p=p, seed=seed, offset=off,
+                         keep_mask=keep_mask if p > 0 else None)
+        ctx.conv, ctx.bn, ctx.relu, ctx.p, ctx.training = conv, bn, relu, p, training
+        ctx.ranges = ranges
+        ctx.has_res = residual is not None
+        ctx.geom = (R, S, stride, pad, dil, cout, cout_p)
+        ctx.save_for_backward(y, out, mean, invstd, scale, *xs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, out, mean, invstd, scale, *xs = ctx.saved_tensors
+        conv, bn = ctx.conv, ctx.bn
+        R, S, stride, pad, dil, cout, cout_p = ctx.geom
+        dout = dout.contiguous()
+        dev = dout.device
+        need_w = ctx.needs_input_grad[5]
+        dgamma = torch.empty(cout, dtype=torch.float32, device=dev) if bn.weight is not None else None
+        dbeta = torch.empty(cout, dtype=torch.float32, device=dev) if bn.weight is not None else None
+        dres = torch.empty_like(dout) if ctx.has_res else None
+        sc = _scratch64(dev, "bwd")
+        scratch = sc[:2 * cout_p].view(2, cout_p)
+        # strided 3x3: write dy zero-inserted so that the data gradient is a stride-1 conv (see conv_igemm.cu)
+        zero_insert = stride > 1 and R > 1
+        n, ho, wo, _ = y.shape
+        h_in, w_in = xs[0].shape[1], xs[0].shape[2]
+        scatter = None
+        if zero_insert:
+            hz, wz = (ho - 1) * stride + 1, (wo - 1) * stride + 1
+            scatter = (stride, hz, wz)
+        dy_dense_needed = need_w and zero_insert
+        dy = K.bn_backward(dout, out, y, mean, invstd, scale, ctx.relu, grad_scale=1.0 / (1.0 - ctx.p),
+                           training=ctx.training, dres=dres, dgamma=dgamma, dbeta=dbeta, scratch=scratch,
+                           scatter=None if dy_dense_needed else scatter)
+        dy_z = dy
+        if dy_dense_needed:
+            # both layouts are needed: dense for wgrad, zero-inserted for dgrad
+            dy_z = torch.zeros((n, scatter[1], scatter[2], cout_p), dtype=torch.bfloat16, device=dev)
+            dy_z[:, ::stride, ::stride] = dy
+        dxs = []
+        dweight = torch.empty_like(conv.weight) if need_w else None
+        for i, x in enumerate(xs):
+            ci0, c_real, cin_p = ctx.ranges[i]
+            if ctx.needs_input_grad[9 + i]:
+                wt = _packed_weight(conv, 1, ci0, c_real, cin_p, cout_p)  # [cin_p][taps][cout_p]
+                if stride == 1:
+                    dx = K.conv_fprop([(dy, wt)], R, S, 1, dil * (R - 1) - pad, dil, cin_p)
+                elif R == 1:
+                    dx = torch.zeros_like(x)
+                    K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, out=dx, scatter=(stride, h_in, w_in))
+                else:
+                    # zero-inserted dy has (ho-1)*s+1 rows; pad so that the output covers the full input extent
+                    dxf = K.conv_fprop([(_pad_to(dy_z, h_in + 2 * pad - dil * (R - 1), w_in + 2 * pad - dil * (S - 1)), wt)],
+                                       R, S, 1, dil * (R - 1) - pad, dil, cin_p)
+                    dx = dxf
+                dxs.append(dx)
+            else:
+                dxs.append(None)
+            if need_w:
+                dw = K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p)
+                K.unpack_wgrad(dw, dweight, ci0, c_real, accumulate=False)
+        return (None, None, None, None, None, dweight, dgamma, dbeta, dres, *dxs)
+
+
+def _pad_to(t, h, w):
+    """zero-pad a [N,H,W,C] tensor at the bottom/right to (h, w) (no-op if already that size)."""
+    n, hh, ww, c = t.shape
+    if hh == h and ww == w:
+        return t
+    out = torch.zeros((n, h, w, c), dtype=t.dtype, device=t.device)
+    out[:, :hh, :ww] = t
+    return out
+
+
+def xs_with_channels(xs, ctx_channels):
+    """pair every segment tensor with its logical channel count"""
+    if ctx_channels is None:
+        raise ValueError("conv_bn_act: segment channel counts missing")
+    if len(ctx_channels) != len(xs):
+        raise ValueError("conv_bn_act: segment count mismatch")
+    return list(zip(xs, ctx_channels))
+
+
+def training_dropout(conv, bn):
+    return conv.__dict__.get("_zs3_drop_training", False)
+
+
+def conv_bn_act(xs, channels, conv, bn, relu=True, residual=None, drop_p=0.0, drop_training=False, keep_mask=None):
+    """xs: list of NHWC bf16 tensors (a virtual channel concat), channels: their logical channel counts."""
+    conv.__dict__["_zs3_seg_channels"] = list(channels)
+    conv.__dict__["_zs3_drop_training"] = bool(drop_training)
+    return ConvBnAct.apply(conv, bn, relu, drop_p, keep_mask, conv.weight, bn.weight, bn.bias, residual, *xs)
+
+
+class ConvBias(torch.autograd.Function):
+    """1x1 conv with bias and no normalisation: decoder.pred_conv (zs3/modeling/decoder.py:26,66-68)."""
+
+    @staticmethod
+    def forward(ctx, conv, weight, bias, x):
+        cout, cin = conv.out_channels, conv.in_channels
+        cout_p, cin_p = K.cpad(cout), x.shape[3]
+        wp = _packed_weight(conv, 0, 0, cin, cin_p, cout_p)
+        bias_p = torch.zeros(cout_p, dtype=torch.float32, device=x.device)
+        if bias is not None:
+            bias_p[:cout] = bias.detach()
+        y = K.conv_fprop([(x, wp)], 1, 1, 1, 0, 1, cout_p, bias=bias_p)
+        ctx.conv = conv
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        conv = ctx.conv
+        cout, cin = conv.out_channels, conv.in_channels
+        cout_p, cin_p = K.cpad(cout), x.shape[3]
+        dy = dy.contiguous()
+        dx = dw_oihw = dbias = None
+        if ctx.needs_input_grad[3]:
+            wt = _packed_weight(conv, 1, 0, cin, cin_p, cout_p)
+            dx = K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p)
+        if ctx.needs_input_grad[1]:
+            dw = K.conv_wgrad(x, dy, 1, 1, 1, 0, 1, cin_p, cout_p)
+            dw_oihw = torch.empty_like(conv.weight)
+            K.unpack_wgrad(dw, dw_oihw)
+        if conv.bias is not None and ctx.needs_input_grad[2]:
+            dbias = K.channel_sums(dy)[:cout].float()
+        return None, dw_oihw, dbias, dx
+
+
+class Stem(torch.autograd.Function):
+    """conv7x7/s2 -> BN -> ReLU -> maxpool3x3/s2 (zs3/modeling/backbone/resnet.py:186-190) from the NCHW fp32 image."""
+
+    @staticmethod
+    def forward(ctx, conv, bn, pool, weight, gamma, beta, x):
+        n, c, h, w = x.shape
+        R = conv.kernel_size[0]
+        stride, pad = conv.stride[0], conv.padding[0]
+        cout = conv.out_channels
+        cout_p = K.cpad(cout)
+        ho, wo = K.conv_out_size(h, R, stride, pad, 1), K.conv_out_size(w, R, stride, pad, 1)
+        kreal = c * R * R
+        kpad = K.cpad(kreal)
+        cols = K.stem_im2col(x, R, stride, pad, ho, wo, kpad)          # [n, ho, wo, kpad]
+        wp = _packed_weight_2d(conv, kreal, kpad, cout_p)
+        training = bn.training
+        stats = None
+        if training:
+            sc = _scratch64(x.device)
+            stats = (sc[:cout_p], sc[2048:2048 + cout_p])
+        y = K.conv_fprop([(cols, wp)], 1, 1, 1, 0, 1, cout_p, stats=stats)
+        scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
+        a = K.bn_apply(y, scale, shift, True)
+        k, ps, pp = pool.kernel_size, pool.stride, pool.padding
+        out, arg = K.maxpool_fwd(a, k, ps, pp)
+        ctx.conv, ctx.bn, ctx.training = conv, bn, training
+        ctx.pool = (k, ps, pp)
+        ctx.dims = (kreal, kpad, cout, cout_p)
+        ctx.save_for_backward(cols, y, a, arg, mean, invstd, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cols, y, a, arg, mean, invstd, scale = ctx.saved_tensors
+        conv, bn = ctx.conv, ctx.bn
+        kreal, kpad, cout, cout_p = ctx.dims
+        k, ps, pp = ctx.pool
+        da = K.maxpool_bwd(dout.contiguous(), arg, a.shape, k, ps, pp)
+        dev = dout.device
+        dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+        sc = _scratch64(dev, "bwd")
+        dy = K.bn_backward(da, a, y, mean, invstd, scale, True, training=ctx.training, dgamma=dgamma, dbeta=dbeta,
+                           scratch=sc[:2 * cout_p].view(2, cout_p))
+        dw = K.conv_wgrad(cols, dy, 1, 1, 1, 0, 1, kpad, cout_p)
+        dweight = torch.empty_like(conv.weight)
+        K.unpack_wgrad(dw, dweight.view(cout, kreal, 1, 1))
+        return None, None, None, dweight, dgamma, dbeta, None  # the image needs no gradient (stem dgrad is never used)
+
+
+def _packed_weight_2d(conv, kreal, kpad, cout_p):
+    w = conv.weight
+    cache = conv.__dict__.setdefault("_zs3_pack_cache", {})
+    key = ("stem", kpad, cout_p)
+    ent = cache.get(key)
+    ver = (w._version, w.data_ptr())
+    if ent is None or ent[0] != ver:
+        ent = (ver, K.pack_weight(w.detach().reshape(w.shape[0], kreal, 1, 1), cout_p, kpad))
+        cache[key] = ent
+    return ent[1]
+
+
+class Bilinear(torch.autograd.Function):
+    """F.interpolate(bilinear, align_corners=True) NHWC bf16 (zs3/modeling/decoder.py:33-35)."""
+
+    @staticmethod
+    def forward(ctx, x, ho, wo):
+        ctx.in_hw = (x.shape[1], x.shape[2])
+        return K.bilinear_fwd(x, ho, wo)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.bilinear_bwd(dy.contiguous(), ctx.in_hw[0], ctx.in_hw[1]), None, None
+
+
+class SpatialMean(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d((1,1)) (zs3/modeling/aspp.py:84): [N,H,W,C] -> [N,1,1,C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        n, h, w, c = x.shape
+        return K.spatial_sum(x, 1.0 / (h * w))
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, h, w, c = ctx.shape
+        return K.spatial_broadcast(dy.contiguous(), h, w, 1.0 / (h * w))
+
+
+class SpatialBroadcast(torch.autograd.Function):
+    """bilinear 'upsampling' of a 1x1 map = broadcast (zs3/modeling/aspp.py:109): [N,1,1,C] -> [N,H,W,C]."""
+
+    @staticmethod
+    def forward(ctx, x, h, w):
+        return K.spatial_broadcast(x, h, w, 1.0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.spatial_sum(dy.contiguous(), 1.0), None, None
+
+
+class UpsampleLogits(torch.autograd.Function):
+    """F.interpolate(..., size=input, bilinear, align_corners=True) of the class scores (deeplab.py:44,55):
+    NHWC bf16 in, NCHW fp32 out (what the reference API returns)."""
+
+    @staticmethod
+    def forward(ctx, x, c, ho, wo):
+        ctx.info = (x.shape, c)
+        return K.upsample_logits_fwd(x, c, ho, wo)
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, c = ctx.info
+        return K.upsample_logits_bwd(dy.contiguous().float(), shape, c), None, None, None
+
+
+class FromNCHW(torch.autograd.Function):
+    """fp32 NCHW (reference API) -> NHWC bf16 (internal)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.c = x.shape[1]
+        return K.nchw_to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.nhwc_to_nchw(dy.contiguous(), ctx.c)
+
+
+class ToNCHW(torch.autograd.Function):
+    """NHWC bf16 (internal) -> fp32 NCHW (reference API)."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.cs = x.shape[3]
+        return K.nhwc_to_nchw(x, c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.nchw_to_nhwc(dy.contiguous(), ctx.cs), None
+
+
+class CrossEntropy(torch.autograd.Function):
+    """nn.CrossEntropyLoss(weight, ignore_index, mean) then /batch (zs3/utils/loss.py:31-46), fused."""
+
+    @staticmethod
+    def forward(ctx, logit, target, weight, ignore_index, div):
+        logit = logit.contiguous().float()
+        target = target.contiguous().float()
+        n, c, h, w = logit.shape
+        accum = torch.empty(2, dtype=torch.float64, device=logit.device)
+        loss = torch.empty((), dtype=torch.float32, device=logit.device)
+        wt = None if weight is None else weight.contiguous().float()
+        L.check(L.lib().zs3_ce_fwd(L.ptr(logit), L.ptr(target), L.ptr(wt), n, c, h * w, int(ignore_index), float(div),
+                                   L.ptr(accum), L.ptr(loss), L.stream_ptr()), "zs3_ce_fwd")
+        ctx.save_for_backward(logit, target, accum)
+        ctx.wt, ctx.ignore, ctx.div = wt, int(ignore_index), float(div)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        logit, target, accum = ctx.saved_tensors
+        n, c, h, w = logit.shape
+        dlogit = torch.empty_like(logit)
+        gout = gout.contiguous().float()
+        L.check(L.lib().zs3_ce_bwd(L.ptr(logit), L.ptr(target), L.ptr(ctx.wt), n, c, h * w, ctx.ignore, ctx.div,
+                                   L.ptr(accum), L.ptr(gout), L.ptr(dlogit), L.stream_ptr()), "zs3_ce_bwd")
+        return dlogit, None, None, None, None

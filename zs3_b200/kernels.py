@@ -227,3 +227,116 @@ def im2col_probe(x, pad, upper, stride, cpp, ppc, c, w, h, n, off_w, off_h):
     L.check(L.lib().zs3_debug_im2col_probe(L.ptr(x), nn, hh, ww, cc, pad, upper, stride, cpp, ppc, c, w, h, n, off_w,
                                            off_h, L.ptr(out), L.stream_ptr()), "zs3_debug_im2col_probe")
     return out
+
+
+def stem_im2col(x, R, stride, pad, ho, wo, kpad):
+    """fp32 NCHW image -> bf16 im2col matrix viewed as NHWC [N, ho, wo, kpad] (k = c*R*R + r*R + s)."""
+    n, c, h, w = x.shape
+    x = x.contiguous().float()
+    cols = torch.empty((n, ho, wo, kpad), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().zs3_stem_im2col(L.ptr(x), L.ptr(cols), n, c, h, w, R, stride, pad, ho, wo, kpad, L.stream_ptr()),
+            "zs3_stem_im2col")
+    return cols
+
+
+def maxpool_fwd(x, k, stride, pad):
+    _chk_act(x, "maxpool_fwd")
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, k, stride, pad, 1), conv_out_size(w, k, stride, pad, 1)
+    y = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
+    arg = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device)
+    L.check(L.lib().zs3_maxpool_fwd(L.ptr(x), L.ptr(y), L.ptr(arg), n, h, w, c, ho, wo, k, stride, pad,
+                                    L.stream_ptr()), "zs3_maxpool_fwd")
+    return y, arg
+
+
+def maxpool_bwd(dy, arg, in_shape, k, stride, pad):
+    n, h, w, c = in_shape
+    dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
+    L.check(L.lib().zs3_maxpool_bwd(L.ptr(dy), L.ptr(arg), L.ptr(dx), n, h, w, c, dy.shape[1], dy.shape[2], k, stride,
+                                    pad, L.stream_ptr()), "zs3_maxpool_bwd")
+    return dx
+
+
+def bilinear_fwd(x, ho, wo):
+    _chk_act(x, "bilinear_fwd")
+    n, hi, wi, c = x.shape
+    y = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().zs3_bilinear_fwd(L.ptr(x), L.ptr(y), n, hi, wi, ho, wo, c, c, c, L.stream_ptr()),
+            "zs3_bilinear_fwd")
+    return y
+
+
+def bilinear_bwd(dy, hi, wi):
+    _chk_act(dy, "bilinear_bwd")
+    n, ho, wo, c = dy.shape
+    dx = torch.empty((n, hi, wi, c), dtype=torch.bfloat16, device=dy.device)
+    L.check(L.lib().zs3_bilinear_bwd(L.ptr(dy), L.ptr(dx), n, hi, wi, ho, wo, c, c, c, 0, L.stream_ptr()),
+            "zs3_bilinear_bwd")
+    return dx
+
+
+def upsample_logits_fwd(x, c, ho, wo):
+    _chk_act(x, "upsample_logits_fwd")
+    n, hi, wi, cs = x.shape
+    y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device)
+    L.check(L.lib().zs3_upsample_logits_fwd(L.ptr(x), L.ptr(y), n, c, hi, wi, cs, ho, wo, L.stream_ptr()),
+            "zs3_upsample_logits_fwd")
+    return y
+
+
+def upsample_logits_bwd(dy, in_shape, c):
+    n, hi, wi, cs = in_shape
+    dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
+    L.check(L.lib().zs3_upsample_logits_bwd(L.ptr(dy), L.ptr(dx), n, c, hi, wi, cs, dy.shape[2], dy.shape[3],
+                                            L.stream_ptr()), "zs3_upsample_logits_bwd")
+    return dx
+
+
+def spatial_sum(x, scale):
+    """[N,H,W,C] -> [N,1,1,C], y = scale * sum over H,W."""
+    _chk_act(x, "spatial_sum")
+    n, h, w, c = x.shape
+    y = torch.empty((n, 1, 1, c), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().zs3_spatial_sum(L.ptr(x), L.ptr(y), n, h * w, c, c, c, float(scale), L.stream_ptr()),
+            "zs3_spatial_sum")
+    return y
+
+
+def spatial_broadcast(x, h, w, scale):
+    """[N,1,1,C] -> [N,h,w,C], y = scale * x."""
+    n, _, _, c = x.shape
+    y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().zs3_spatial_broadcast(L.ptr(x), L.ptr(y), n, h * w, c, c, c, float(scale), 0, L.stream_ptr()),
+            "zs3_spatial_broadcast")
+    return y
+
+
+def channel_sums(t):
+    """fp64 per-channel sums over all pixels of an NHWC bf16 tensor (bias gradients)."""
+    _chk_act(t, "channel_sums")
+    n, h, w, cs = t.shape
+    scratch = torch.zeros((2, cs), dtype=torch.float64, device=t.device)
+    ones = torch.ones(cs, dtype=torch.float32, device=t.device)
+    zeros = torch.zeros(cs, dtype=torch.float32, device=t.device)
+    a = L.BnBwdArgs()
+    a.dout, a.dout_cstride = t.data_ptr(), cs
+    a.y, a.y_cstride = t.data_ptr(), cs
+    a.mean, a.invstd, a.scale = zeros.data_ptr(), ones.data_ptr(), ones.data_ptr()
+    a.M, a.C = n * h * w, cs
+    a.relu, a.grad_scale, a.training = 0, 1.0, 1
+    a.sum_dz, a.sum_dzx = scratch[0].data_ptr(), scratch[1].data_ptr()
+    L.check(L.lib().zs3_bn_bwd_reduce(C.byref(a), L.stream_ptr()), "zs3_bn_bwd_reduce")
+    return scratch[0]
+
+
+def sgd_step(p, g, buf, lr, momentum, weight_decay, nesterov, first_step, grad_scale=1.0):
+    L.check(L.lib().zs3_sgd_step(L.ptr(p), L.ptr(g), L.ptr(buf), p.numel(), float(lr), float(momentum),
+                                 float(weight_decay), int(nesterov), int(first_step), float(grad_scale),
+                                 L.stream_ptr()), "zs3_sgd_step")
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    L.check(L.lib().zs3_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1),
+                                  float(beta2), float(eps), int(step), float(grad_scale), L.stream_ptr()),
+            "zs3_adam_step")

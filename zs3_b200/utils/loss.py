@@ -1,0 +1,51 @@
+"""SegmentationLosses / GMMNLoss with the reference's interface (zs3/utils/loss.py), on fused CUDA kernels."""
+import torch
+
+from .. import functional as ZF
+
+
+class SegmentationLosses:
+    """zs3/utils/loss.py:5-81"""
+
+    def __init__(self, weight=None, size_average=True, batch_average=True, ignore_index=255, cuda=False):
+        self.ignore_index = ignore_index
+        self.weight = weight
+        self.size_average = size_average
+        self.batch_average = batch_average
+        self.cuda = cuda
+
+    def build_loss(self, mode="ce"):
+        if mode == "ce":
+            return self.CrossEntropyLoss
+        elif mode == "focal":
+            return self.FocalLoss
+        elif mode == "ce_finetune":
+            return self.CrossEntropyLossFinetune
+        else:
+            raise NotImplementedError
+
+    def _ce(self, logit, target, weight, div=1.0):
+        if not self.size_average:
+            raise NotImplementedError("size_average=False is not used by any reference trainer")
+        if not logit.is_cuda:
+            raise RuntimeError("zs3_b200 losses run on CUDA tensors only")
+        w = weight
+        if w is not None and w.device != logit.device:
+            w = w.to(logit.device)
+        return ZF.CrossEntropy.apply(logit, target, w, self.ignore_index, float(div))
+
+    def CrossEntropyLoss(self, logit, target):
+        # the division by the batch size (loss.py:43-44) is folded into the kernel
+        return self._ce(logit, target, self.weight, logit.shape[0] if self.batch_average else 1.0)
+
+    def CrossEntropyLossFinetune(self, logit, target):
+        return self._ce(logit, target, None, logit.shape[0] if self.batch_average else 1.0)
+
+    def FocalLoss(self, logit, target, gamma=2, alpha=0.5):
+        n = logit.shape[0]
+        logpt = -self._ce(logit, target, self.weight)
+        pt = torch.exp(logpt)
+        if alpha is not None:
+            logpt = logpt * alpha
+        loss = -((1 - pt) ** gamma) * logpt
+        return loss / n if self.batch_average else loss
