@@ -238,6 +238,47 @@ int zs3_sgd_step(float* p, const float* g, float* momentum_buf, long long n, flo
 int zs3_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, int step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GMMN generator (zs3/modeling/gmmn.py) and GMMNLoss.moment_loss (zs3/utils/loss.py:84-115), fp32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* A; long long lda; int transA; /* op(A)(i,k) = transA ? A[k*lda+i] : A[i*lda+k] */
+  const int* idxA;                           /* optional gather of A's stored rows */
+  const float* B; long long ldb; int transB; /* op(B)(k,j) = transB ? B[j*ldb+k] : B[k*ldb+j] */
+  const int* idxB;
+  float* C; long long ldc;                   /* C[M][N] (+)= op(A) op(B) + bias[j] */
+  int M, N, K;
+  const float* bias;
+  int accumulate;
+  const int* dyn_count;                      /* device int: dynamic extent ... */
+  int dyn_dim;                               /* ... of M (1) or K (2); 0 = static */
+} zs3_sgemm_args;
+
+/* nn.Linear forward/backward (cuBLAS sgemm in the reference: gmmn.py:18,31,34) and pygcn's dense adj@(x@W) */
+int zs3_sgemm(const zs3_sgemm_args* a, void* stream);
+/* rows[0..*count) = indices of the rows of g[n][f] holding any non-zero (only the batch_size_generator=128
+ * sampled rows of train_pascal_GMMN.py:229-237 carry gradient) */
+int zs3_find_active_rows(const float* g, int n, int f, int* rows, int* count, void* stream);
+/* out[j] (+)= sum_r A[idx[r]][j] (bias gradients) */
+int zs3_col_sum(const float* A, long long lda, const int* idx, const int* count, int n, int ncols, float* out,
+                int accumulate, void* stream);
+/* nn.LeakyReLU(0.2) + nn.Dropout(p) (gmmn.py:19-20); drop_mode as in zs3_bn_apply_args */
+int zs3_leaky_dropout_fwd(const float* x, float* y, long long n, float slope, int drop_mode, float p,
+                          unsigned long long seed, unsigned long long offset, const unsigned char* keep_mask,
+                          void* stream);
+/* dx[r][c] = dy[r][c] * f'(.) reconstructed from the forward output h (rows gathered through idx) */
+int zs3_leaky_dropout_bwd(const float* dy, const float* h, float* dx, int rows, int cols, const int* idx,
+                          const int* count, float slope, float p, void* stream);
+/* moment_loss forward: loss = sqrt(sum_ij s_i s_j sum_sigma exp(e_ij/sigma)); P [(M+N)^2] and loss2 are kept
+ * for the backward.  `sigma` is a HOST array of nsigma <= 8 bandwidths. */
+int zs3_mmd_fwd(const float* gen, const float* real, int M, int N, int D, const float* sigma, int nsigma, float* P,
+                double* loss2, float* loss, void* stream);
+/* analytic gradient wrt gen [M][D] and/or real [N][D] (either may be NULL) */
+int zs3_mmd_bwd(const float* gen, const float* real, int M, int N, int D, const float* P, const float* loss,
+                const float* grad_out, float* dgen, float* dreal, void* stream);
+/* torch.cat((embd, noise), 1) (gmmn.py:44) */
+int zs3_concat2(const float* a, int c1, const float* b, int c2, float* y, long long rows, void* stream);
+
 /* debug: one im2col TMA load dumped raw (tests/test_tma_probe.py) */
 int zs3_debug_im2col_probe(const void* x, int N, int H, int W, int C, int pad, int upper, int stride, int cpp, int ppc,
                            int c, int w, int h, int n, int off_w, int off_h, void* out, void* stream);

@@ -114,6 +114,17 @@ class BnBwdArgs(C.Structure):
     ]
 
 
+class SgemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_longlong), ("transA", C.c_int), ("idxA", C.c_void_p),
+        ("B", C.c_void_p), ("ldb", C.c_longlong), ("transB", C.c_int), ("idxB", C.c_void_p),
+        ("C", C.c_void_p), ("ldc", C.c_longlong),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("bias", C.c_void_p), ("accumulate", C.c_int),
+        ("dyn_count", C.c_void_p), ("dyn_dim", C.c_int),
+    ]
+
+
 def _EXTRA_SIGS(vp, i, ll, f, d):
     return {
         "zs3_debug_im2col_probe": [vp, i, i, i, i, i, i, i, i, i, i, i, i, i, i, i, vp, vp],
@@ -137,6 +148,14 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_ce_bwd": [vp, vp, vp, i, i, ll, i, f, vp, vp, vp, vp],
         "zs3_sgd_step": [vp, vp, vp, ll, f, f, f, i, i, f, vp],
         "zs3_adam_step": [vp, vp, vp, vp, ll, f, f, f, f, i, f, vp],
+        "zs3_sgemm": [C.POINTER(SgemmArgs), vp],
+        "zs3_find_active_rows": [vp, i, i, vp, vp, vp],
+        "zs3_col_sum": [vp, ll, vp, vp, i, i, vp, i, vp],
+        "zs3_leaky_dropout_fwd": [vp, vp, ll, f, i, f, C.c_ulonglong, C.c_ulonglong, vp, vp],
+        "zs3_leaky_dropout_bwd": [vp, vp, vp, i, i, vp, vp, f, f, vp],
+        "zs3_mmd_fwd": [vp, vp, i, i, i, C.POINTER(C.c_float), i, vp, vp, vp, vp],
+        "zs3_mmd_bwd": [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp],
+        "zs3_concat2": [vp, i, vp, i, vp, ll, vp],
     }
 
 

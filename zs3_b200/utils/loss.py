@@ -49,3 +49,28 @@ class SegmentationLosses:
             logpt = logpt * alpha
         loss = -((1 - pt) ** gamma) * logpt
         return loss / n if self.batch_average else loss
+
+
+class GMMNLoss:
+    """zs3/utils/loss.py:84-115.  build_loss() returns a callable (gen_samples, x) -> differentiable scalar."""
+
+    def __init__(self, sigma=[2, 5, 10, 20, 40, 80], cuda=False):
+        self.sigma = sigma
+        self.cuda = cuda
+
+    def build_loss(self):
+        return self.moment_loss
+
+    def get_scale_matrix(self, M, N):
+        """kept for API compatibility (loss.py:92-97); the kernel applies the same [+1/N]*N ++ [-1/M]*M weights"""
+        s1 = torch.ones((N, 1)) * 1.0 / N
+        s2 = torch.ones((M, 1)) * -1.0 / M
+        if self.cuda:
+            s1, s2 = s1.cuda(), s2.cuda()
+        return torch.cat((s1, s2), 0)
+
+    def moment_loss(self, gen_samples, x):
+        if not gen_samples.is_cuda:
+            raise RuntimeError("zs3_b200 losses run on CUDA tensors only")
+        from ..gmmn_ops import MomentLoss
+        return MomentLoss.apply(gen_samples, x, tuple(self.sigma))
