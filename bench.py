@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the ZS3Net DeepLabv3+ training step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this implementation
+    python bench.py --impl reference --gpus 1 --steps 1 --warmup 1 # reference arm: the CPU implementation
+    torchrun ... bench.py --gpus N ...                             # one rank per GPU, NCCL all-reduce per step
+
+A "step" = zero_grad -> DeepLab forward -> cross-entropy -> backward -> SGD update on one batch of 16 synthetic
+513x513 images per GPU (BASELINE.json configs[1]; weak scaling).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "images/sec at 513x513 bs=16/GPU, DeepLabv3+/GMMN fwd+bwd, 1/2/4/8 B200"
+FWD_GFLOP_PER_IMG = 185.64      # nominal conv FLOPs, forward
+FWDBWD_GFLOP_PER_IMG = 555.68   # forward + dgrad + wgrad (no stem dgrad)
+NUM_CLASSES = 21
+
+
+def synth_batch(n, hw, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(n, 3, hw, hw, generator=g)
+    lab = torch.randint(0, NUM_CLASSES, (n, (hw + 31) // 32, (hw + 31) // 32), generator=g).float()
+    lab = torch.nn.functional.interpolate(lab[:, None], size=(hw, hw), mode="nearest")[:, 0]
+    lab[torch.rand(n, hw, hw, generator=g) < 0.02] = 255
+    if pin and torch.cuda.is_available():
+        img, lab = img.pin_memory(), lab.pin_memory()
+    if device != "cpu":
+        img, lab = img.to(device), lab.to(device)
+    return img, lab.contiguous()
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json, bf16 sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step_rate(batch, hw, steps, warmup, threads):
+    """The reference's CPU implementation of the path = the oracle restatement (oracle/zs3_oracle.py, pinned to
+    the real reference by tests/golden): forward + CE + backward + SGD on `batch` images; returns (img/s, s/step)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zs3_oracle as O
+    torch.set_num_threads(threads)
+    st = O.init_deeplab_state(seed=1)
+    params = [v.requires_grad_(True) for k, v in st.items() if v.is_floating_point() and "running" not in k]
+    bufs = [None] * len(params)
+    img, lab = synth_batch(batch, hw, 1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in params:
+            p.grad = None
+        out = O.deeplab_forward(st, img, training=True, drop_p=(0.0, 0.0, 0.0))
+        loss = O.cross_entropy(out, lab)
+        loss.backward()
+        with torch.no_grad():
+            O.sgd_step(params, [p.grad for p in params], bufs, 0.007)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    s = sum(times) / len(times)
+    return batch / s, s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    batch = 2  # bounded sample of the bs=16 workload: ~3-6 s of CPU work per step
+    rate, s_per_step = cpu_reference_step_rate(batch, 513, max(1, args.steps), max(0, min(args.warmup, 1)), cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DeepLabv3+ ResNet-101 fwd+bwd+SGD, 513x513 synthetic (BASELINE configs[1])",
+                   "num_classes": NUM_CLASSES, "per_gpu_batch": 16, "input": "513x513"},
+        "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+                         "sample": f"bs={batch} 513x513 fwd+CE+bwd+SGD steps of the oracle port on {cores} host threads"},
+        "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    from zs3_b200 import _lib as L
+    from zs3_b200 import kernels as K
+    from zs3_b200.modeling.deeplab import DeepLab
+    from zs3_b200.parallel import DataParallelTrainer, init_distributed
+    from zs3_b200.utils.loss import SegmentationLosses
+    import torch.distributed as dist
+
+    rank, local_rank, world = init_distributed()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if not L.lib().zs3_device_supported():
+        raise SystemExit("zs3_b200 kernels need an sm_100 (B200) device")
+    B, HW = args.batch, args.size
+    torch.manual_seed(1)
+    model = DeepLab(num_classes=NUM_CLASSES, output_stride=16, sync_bn=True, pretrained=False).to(dev).train()
+    crit = SegmentationLosses(weight=None, cuda=True).build_loss("ce")
+    trainer = DataParallelTrainer(model, crit, lr=0.007, world_size=world)
+
+    # per-rank data (different seed per rank), several distinct batches so consecutive steps never reuse L2 contents
+    nbuf = 2
+    host = [synth_batch(B, HW, 100 + rank * 10 + i, pin=True) for i in range(nbuf)]
+    devb = [(h[0].to(dev), h[1].to(dev)) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- device-resident throughput ("value")
+    for i in range(args.warmup):
+        trainer.train_step(*devb[i % nbuf])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.lib().zs3_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = trainer.train_step(*devb[i % nbuf])
+    e1.record()
+    barrier()
+    launches = L.lib().zs3_launch_count() - launches0
+    sampler.stop_flag = True
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---- end to end through the public API with HOST buffers (H2D of inputs + D2H of the loss every step)
+    for i in range(2):
+        trainer.train_step(host[i % nbuf][0].to(dev, non_blocking=True), host[i % nbuf][1].to(dev, non_blocking=True))
+    barrier()
+    t_e2e = []
+    e0.record()
+    for i in range(args.steps):
+        img = host[i % nbuf][0].to(dev, non_blocking=True)
+        lab = host[i % nbuf][1].to(dev, non_blocking=True)
+        l = trainer.train_step(img, lab)
+        t_e2e.append(l.item())  # D2H read of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = world * B / (ms_e2e * 1e-3)
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
+
+    # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), timed per launch with CUDA events
+    roofline = None
+    if rank == 0:
+        K.PROFILE = {}
+        for i in range(2):
+            trainer.train_step(*devb[i % nbuf])
+        torch.cuda.synchronize()
+        prof, K.PROFILE = K.PROFILE, None
+        per_kind = {}
+        for kind, evs in prof.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+            fl = sum(f for _, _, f in evs)
+            per_kind[kind] = {"launches_per_step": len(evs) // 2, "ms_per_step": ms / 2, "tflops": fl / (ms * 1e-3) / 1e12}
+        ms_all = sum(v["ms_per_step"] for v in per_kind.values())
+        fl_all = sum(sum(f for _, _, f in evs) for evs in prof.values()) / 2
+        peak, how = measured_peaks()
+        ach = fl_all / (ms_all * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "kernel": "conv_fprop_kernel/conv_wgrad_kernel (tcgen05 implicit GEMM; fprop+dgrad+wgrad)",
+                    "peak_source": how, "conv_ms_per_step": ms_all, "conv_share_of_step": ms_all / ms_step,
+                    "nominal_tflop_per_step": fl_all / 1e12, "by_kind": per_kind}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, s = cpu_reference_step_rate(2, HW, 2, 1, cores)
+        cpu_baseline = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+                        "sample": f"2 steps of bs=2 {HW}x{HW} fwd+CE+bwd+SGD with the oracle port ({s:.2f} s/step)"}
+
+    if rank == 0:
+        sampler.join(timeout=2)
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "DeepLabv3+ ResNet-101 fwd+bwd+SGD, bs=16/GPU 513x513 synthetic (BASELINE configs[1])",
+                       "num_classes": NUM_CLASSES, "per_gpu_batch": B, "global_batch": B * world, "input": f"{HW}x{HW}",
+                       "parallelism": f"dp{world}", "bn": "rank-local batch statistics",
+                       "l2_policy": "inputs+activations per step (>6 GB) exceed the 126 MB L2; 2 alternating input batches",
+                       "optimizer": "fused SGD momentum 0.9 wd 5e-4, lr 0.007/0.07"},
+            "achieved_tflops_nominal": value * FWDBWD_GFLOP_PER_IMG / 1e3,
+            "final_loss": final_loss,
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "images/sec", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE: 16)")
+    ap.add_argument("--size", type=int, default=513, help="input height=width (BASELINE: 513)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,8 @@ extern "C" {
 const char* zs3_last_error(void);
 /* ABI version, bumped on any signature change */
 int zs3_abi_version(void);
+/* number of kernel-launching calls this library has made in this process (bench.py's gpu_launches) */
+unsigned long long zs3_launch_count(void);
 /* 1 if the current device is compute capability 10.x, else 0 (kernels are sm_100a only) */
 int zs3_device_supported(void);
 

@@ -70,6 +70,8 @@ def _declare(lib):
     lib.zs3_last_error.argtypes = []
     lib.zs3_abi_version.restype = i
     lib.zs3_device_supported.restype = i
+    lib.zs3_launch_count.restype = C.c_ulonglong
+    lib.zs3_launch_count.argtypes = []
     sigs = {
         "zs3_conv_fprop": [C.POINTER(ConvArgs), vp],
         "zs3_conv_wgrad": [C.POINTER(WgradArgs), vp],
@@ -169,7 +171,8 @@ def lib():
                 "(there is no CPU or PyTorch fallback for the zs3_b200 kernels)")
         l = C.CDLL(LIB_PATH)
         declared = _declare(l)
-        l._zs3_declared = sorted(declared) + ["zs3_last_error", "zs3_abi_version", "zs3_device_supported"]
+        l._zs3_declared = sorted(declared) + ["zs3_last_error", "zs3_abi_version", "zs3_device_supported",
+                                                "zs3_launch_count"]
         _lib = l
     return _lib
 

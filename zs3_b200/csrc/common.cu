@@ -8,6 +8,7 @@
 namespace zs3 {
 
 static thread_local char g_err[512] = {0};
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -121,6 +122,8 @@ extern "C" {
 const char* zs3_last_error(void) { return zs3::g_err; }
 
 int zs3_abi_version(void) { return 1; }
+
+unsigned long long zs3_launch_count(void) { return zs3::g_launch_count; }
 
 int zs3_device_supported(void) {
   int dev = 0;

@@ -21,8 +21,11 @@ void set_error(const char* fmt, ...);
     }                                      \
   } while (0)
 
+extern unsigned long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
+
 #define ZS3_CHECK_LAUNCH(name)                                                  \
   do {                                                                          \
+    ++zs3::g_launch_count;                                                      \
     cudaError_t e__ = cudaGetLastError();                                       \
     if (e__ != cudaSuccess) {                                                   \
       zs3::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \

@@ -60,13 +60,22 @@ class _RngState:
         return seed, off
 
 
+_WEIGHT_EPOCH = [0]
+
+
+def invalidate_weight_caches():
+    """Call after parameters were modified behind autograd's back (raw-pointer optimizer kernels, NCCL
+    broadcasts into the flat buffer): torch's version counters do not see those writes."""
+    _WEIGHT_EPOCH[0] += 1
+
+
 def _packed_weight(conv, mode, ci_begin, ci_count, cin_pad, cout_pad):
     """bf16 kernel-layout copy of conv.weight, cached until the parameter changes (version counter)."""
     w = conv.weight
     cache = conv.__dict__.setdefault("_zs3_pack_cache", {})
     key = (mode, ci_begin, ci_count, cin_pad, cout_pad)
     ent = cache.get(key)
-    ver = (w._version, w.data_ptr())
+    ver = (w._version, w.data_ptr(), _WEIGHT_EPOCH[0])
     if ent is None or ent[0] != ver:
         ent = (ver, K.pack_weight(w.detach(), cout_pad, cin_pad, ci_begin, ci_count, mode))
         cache[key] = ent
@@ -114,7 +123,10 @@ class ConvBnAct(torch.autograd.Function):
         if training:
             sc = _scratch64(dev)
             stats = (sc[:cout_p], sc[2048:2048 + cout_p])
-        y = K.conv_fprop(segs, R, S, stride, pad, dil, cout_p, stats=stats)
+        n_, h_, w_, _ = xs[0].shape
+        ho_, wo_ = K.conv_out_size(h_, R, stride, pad, dil), K.conv_out_size(w_, S, stride, pad, dil)
+        macs_per_cin = 2.0 * n_ * ho_ * wo_ * cout * R * S  # nominal FLOPs per input channel
+        y = K.conv_fprop(segs, R, S, stride, pad, dil, cout_p, stats=stats, flops=macs_per_cin * conv.in_channels)
         n, ho, wo, _ = y.shape
         scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
         seed = off = 0
@@ -127,6 +139,7 @@ class ConvBnAct(torch.autograd.Function):
         ctx.ranges = ranges
         ctx.has_res = residual is not None
         ctx.geom = (R, S, stride, pad, dil, cout, cout_p)
+        ctx.flops_per_cin = macs_per_cin
         ctx.save_for_backward(y, out, mean, invstd, scale, *xs)
         return out
 
@@ -166,21 +179,23 @@ class ConvBnAct(torch.autograd.Function):
             ci0, c_real, cin_p = ctx.ranges[i]
             if ctx.needs_input_grad[9 + i]:
                 wt = _packed_weight(conv, 1, ci0, c_real, cin_p, cout_p)  # [cin_p][taps][cout_p]
+                fl = ctx.flops_per_cin * c_real
                 if stride == 1:
-                    dx = K.conv_fprop([(dy, wt)], R, S, 1, dil * (R - 1) - pad, dil, cin_p)
+                    dx = K.conv_fprop([(dy, wt)], R, S, 1, dil * (R - 1) - pad, dil, cin_p, flops=fl, kind="conv_dgrad")
                 elif R == 1:
                     dx = torch.zeros_like(x)
-                    K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, out=dx, scatter=(stride, h_in, w_in))
+                    K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, out=dx, scatter=(stride, h_in, w_in), flops=fl,
+                                 kind="conv_dgrad")
                 else:
                     # zero-inserted dy has (ho-1)*s+1 rows; pad so that the output covers the full input extent
                     dxf = K.conv_fprop([(_pad_to(dy_z, h_in + 2 * pad - dil * (R - 1), w_in + 2 * pad - dil * (S - 1)), wt)],
-                                       R, S, 1, dil * (R - 1) - pad, dil, cin_p)
+                                       R, S, 1, dil * (R - 1) - pad, dil, cin_p, flops=fl, kind="conv_dgrad")
                     dx = dxf
                 dxs.append(dx)
             else:
                 dxs.append(None)
             if need_w:
-                dw = K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p)
+                dw = K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, flops=ctx.flops_per_cin * c_real)
                 K.unpack_wgrad(dw, dweight, ci0, c_real, accumulate=False)
         return (None, None, None, None, None, dweight, dgamma, dbeta, dres, *dxs)
 
@@ -226,8 +241,9 @@ class ConvBias(torch.autograd.Function):
         bias_p = torch.zeros(cout_p, dtype=torch.float32, device=x.device)
         if bias is not None:
             bias_p[:cout] = bias.detach()
-        y = K.conv_fprop([(x, wp)], 1, 1, 1, 0, 1, cout_p, bias=bias_p)
-        ctx.conv = conv
+        fl = 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * cout * cin
+        y = K.conv_fprop([(x, wp)], 1, 1, 1, 0, 1, cout_p, bias=bias_p, flops=fl)
+        ctx.conv, ctx.flops = conv, fl
         ctx.save_for_backward(x)
         return y
 
@@ -241,9 +257,9 @@ class ConvBias(torch.autograd.Function):
         dx = dw_oihw = dbias = None
         if ctx.needs_input_grad[3]:
             wt = _packed_weight(conv, 1, 0, cin, cin_p, cout_p)
-            dx = K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p)
+            dx = K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, flops=ctx.flops, kind="conv_dgrad")
         if ctx.needs_input_grad[1]:
-            dw = K.conv_wgrad(x, dy, 1, 1, 1, 0, 1, cin_p, cout_p)
+            dw = K.conv_wgrad(x, dy, 1, 1, 1, 0, 1, cin_p, cout_p, flops=ctx.flops)
             dw_oihw = torch.empty_like(conv.weight)
             K.unpack_wgrad(dw, dw_oihw)
         if conv.bias is not None and ctx.needs_input_grad[2]:
@@ -271,7 +287,8 @@ class Stem(torch.autograd.Function):
         if training:
             sc = _scratch64(x.device)
             stats = (sc[:cout_p], sc[2048:2048 + cout_p])
-        y = K.conv_fprop([(cols, wp)], 1, 1, 1, 0, 1, cout_p, stats=stats)
+        fl = 2.0 * n * ho * wo * cout * kreal
+        y = K.conv_fprop([(cols, wp)], 1, 1, 1, 0, 1, cout_p, stats=stats, flops=fl)
         scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
         a = K.bn_apply(y, scale, shift, True)
         k, ps, pp = pool.kernel_size, pool.stride, pool.padding
@@ -279,6 +296,7 @@ class Stem(torch.autograd.Function):
         ctx.conv, ctx.bn, ctx.training = conv, bn, training
         ctx.pool = (k, ps, pp)
         ctx.dims = (kreal, kpad, cout, cout_p)
+        ctx.flops = fl
         ctx.save_for_backward(cols, y, a, arg, mean, invstd, scale)
         return out
 
@@ -295,7 +313,7 @@ class Stem(torch.autograd.Function):
         sc = _scratch64(dev, "bwd")
         dy = K.bn_backward(da, a, y, mean, invstd, scale, True, training=ctx.training, dgamma=dgamma, dbeta=dbeta,
                            scratch=sc[:2 * cout_p].view(2, cout_p))
-        dw = K.conv_wgrad(cols, dy, 1, 1, 1, 0, 1, kpad, cout_p)
+        dw = K.conv_wgrad(cols, dy, 1, 1, 1, 0, 1, kpad, cout_p, flops=ctx.flops)
         dweight = torch.empty_like(conv.weight)
         K.unpack_wgrad(dw, dweight.view(cout, kreal, 1, 1))
         return None, None, None, dweight, dgamma, dbeta, None  # the image needs no gradient (stem dgrad is never used)
@@ -306,7 +324,7 @@ def _packed_weight_2d(conv, kreal, kpad, cout_p):
     cache = conv.__dict__.setdefault("_zs3_pack_cache", {})
     key = ("stem", kpad, cout_p)
     ent = cache.get(key)
-    ver = (w._version, w.data_ptr())
+    ver = (w._version, w.data_ptr(), _WEIGHT_EPOCH[0])
     if ent is None or ent[0] != ver:
         ent = (ver, K.pack_weight(w.detach().reshape(w.shape[0], kreal, 1, 1), cout_p, kpad))
         cache[key] = ent

@@ -11,6 +11,27 @@ import torch
 from . import _lib as L
 
 
+# Optional per-launch device timing (bench.py's roofline leg).  When PROFILE is a dict, every conv launch is
+# bracketed by CUDA events on the launching stream: PROFILE[kind] = [(start_event, end_event, nominal_flops)].
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.setdefault(self.kind, []).append((self.e0, e1, self.flops))
+
+
 def cpad(c, to=64):
     return (c + to - 1) // to * to
 
@@ -48,7 +69,7 @@ def unpack_wgrad(dw, grad_oihw, ci_begin=0, ci_count=None, accumulate=False):
 
 
 def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=False, accumulate=False, bias=None,
-               stats=None, scatter=None):
+               stats=None, scatter=None, flops=0.0, kind="conv_fprop"):
     """segments: list of (x [N,H,W,Cs] bf16, w_packed [cout_pad, R*S, cin_pad] bf16).
     stats: optional (sum, sqsum) fp64 [cout_pad] accumulators.  scatter: optional (sp_stride, y_H, y_W).
     Returns y [N,Ho,Wo,cout_pad] (or the provided `out`)."""
@@ -86,11 +107,12 @@ def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=Fal
     if stats is not None:
         a.stat_sum = stats[0].data_ptr()
         a.stat_sqsum = stats[1].data_ptr()
-    L.check(L.lib().zs3_conv_fprop(C.byref(a), L.stream_ptr()), "zs3_conv_fprop")
+    with _Timed(kind, flops):
+        L.check(L.lib().zs3_conv_fprop(C.byref(a), L.stream_ptr()), "zs3_conv_fprop")
     return out
 
 
-def conv_wgrad(x, dy, R, S, stride, pad, dil, cin_pad, cout_pad, dw=None, k_splits=0):
+def conv_wgrad(x, dy, R, S, stride, pad, dil, cin_pad, cout_pad, dw=None, k_splits=0, flops=0.0):
     """dw[cout_pad][R*S][cin_pad] fp32 (+)= sum_p dy[p] (x) x[p@tap].  Returns dw."""
     _chk_act(x, "conv_wgrad x")
     _chk_act(dy, "conv_wgrad dy")
@@ -109,7 +131,8 @@ def conv_wgrad(x, dy, R, S, stride, pad, dil, cin_pad, cout_pad, dw=None, k_spli
     a.cout_pad = cout_pad
     a.dw = dw.data_ptr()
     a.k_splits = k_splits
-    L.check(L.lib().zs3_conv_wgrad(C.byref(a), L.stream_ptr()), "zs3_conv_wgrad")
+    with _Timed("conv_wgrad", flops):
+        L.check(L.lib().zs3_conv_wgrad(C.byref(a), L.stream_ptr()), "zs3_conv_wgrad")
     return dw
 
 

@@ -1,0 +1,116 @@
+"""Data-parallel training runtime: one process per GPU, replicated weights, ONE NCCL all-reduce per step.
+
+Replaces the reference's multi-GPU machinery: torch.nn.DataParallel's per-iteration
+parameter broadcast / logits gather / gradient reduce-add onto GPU 0 (zs3/train_pascal.py:90-93) and the
+per-layer SyncBN reduce+broadcast pairs (zs3/modeling/sync_batchnorm/batchnorm.py:101-122).  Here:
+
+  * all parameters are views into one flat fp32 buffer, all gradients views into a second one;
+  * after backward a single ncclAllReduce(sum) over the flat gradient buffer runs over NVLink/NVSwitch;
+  * a fused SGD kernel (csrc/misc.cu) updates the flat parameter buffer, folding in the 1/world_size.
+
+BatchNorm statistics stay rank-local (16 images per GPU), a documented deviation from the reference's
+SyncBN-on-multi-GPU choice (DESIGN.md "Multi-GPU").
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import functional as ZF
+from . import kernels as K
+
+
+def init_distributed():
+    """Initialise torch.distributed from torchrun's environment; returns (rank, local_rank, world_size)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend)
+    return rank, local_rank, world
+
+
+def shard_batch(n_total, rank, world):
+    """contiguous [begin, end) slice of a global batch owned by `rank` (images shard, weights replicate)"""
+    per = n_total // world
+    rem = n_total % world
+    begin = rank * per + min(rank, rem)
+    return begin, begin + per + (1 if rank < rem else 0)
+
+
+class FlatParams:
+    """Re-homes the parameters of `param_groups` (list of lists) into one flat buffer (+ a flat grad buffer)."""
+
+    def __init__(self, param_groups):
+        params = [p for g in param_groups for p in g]
+        if not params:
+            raise ValueError("no parameters")
+        dev, dt = params[0].device, params[0].dtype
+        total = sum(p.numel() for p in params)
+        self.flat = torch.empty(total, dtype=dt, device=dev)
+        self.grad = torch.zeros(total, dtype=dt, device=dev)
+        self.group_ranges = []
+        off = 0
+        for g in param_groups:
+            start = off
+            for p in g:
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + n].view_as(p)
+                p.grad = self.grad[off:off + n].view_as(p)
+                off += n
+            self.group_ranges.append((start, off))
+        self.params = params
+
+    def zero_grad(self):
+        self.grad.zero_()
+        # autograd accumulates in place into the existing .grad views
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr():
+                raise RuntimeError("parameter gradient was detached from the flat buffer (use zero_grad of this runtime)")
+
+
+class FusedSGD:
+    """torch.optim.SGD semantics (momentum, weight decay, nesterov, per-group lr) over FlatParams ranges."""
+
+    def __init__(self, flat, lrs, momentum=0.9, weight_decay=5e-4, nesterov=False):
+        self.flat, self.lrs = flat, list(lrs)
+        self.momentum, self.weight_decay, self.nesterov = momentum, weight_decay, nesterov
+        self.buf = torch.zeros_like(flat.flat)
+        self.steps = 0
+
+    def step(self, grad_scale=1.0):
+        for (a, b), lr in zip(self.flat.group_ranges, self.lrs):
+            K.sgd_step(self.flat.flat[a:b], self.flat.grad[a:b], self.buf[a:b], lr, self.momentum, self.weight_decay,
+                       self.nesterov, self.steps == 0, grad_scale)
+        self.steps += 1
+        ZF.invalidate_weight_caches()
+
+
+class DataParallelTrainer:
+    """step-1 training step of zs3/base_trainer.py:16-20 (zero_grad, forward, CE, backward, SGD) for one rank."""
+
+    def __init__(self, model, criterion, lr=0.007, momentum=0.9, weight_decay=5e-4, nesterov=False, world_size=1):
+        self.model, self.criterion, self.world = model, criterion, world_size
+        groups = [list(model.get_1x_lr_params()), list(model.get_10x_lr_params())]
+        self.flat = FlatParams(groups)
+        self.opt = FusedSGD(self.flat, [lr, lr * 10], momentum, weight_decay, nesterov)
+        ZF.invalidate_weight_caches()
+        if world_size > 1:
+            # identical replicas: broadcast rank 0's weights and BN buffers once
+            dist.broadcast(self.flat.flat, 0)
+            for b in model.buffers():
+                dist.broadcast(b, 0)
+
+    def train_step(self, image, target):
+        self.flat.zero_grad()
+        output = self.model(image)
+        loss = self.criterion(output, target)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad)  # the one collective of the step
+        self.opt.step(grad_scale=1.0 / self.world)
+        return loss
