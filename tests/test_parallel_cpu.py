@@ -1,0 +1,96 @@
+"""CPU (gloo, world_size 2): host logic of the data-parallel runtime -- batch sharding, flat parameter/gradient
+buffers, one all-reduce per step, averaging equivalent to the single-process full batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_shard_batch_partitions_exactly():
+    from zs3_b200.parallel import shard_batch
+    for n in (16, 17, 3, 128):
+        for world in (1, 2, 3, 8):
+            spans = [shard_batch(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_flat_params_views_and_grad_accumulation():
+    from zs3_b200.parallel import FlatParams
+    torch.manual_seed(0)
+    m1, m2 = torch.nn.Linear(5, 3), torch.nn.Linear(3, 2)
+    ref = [p.detach().clone() for p in list(m1.parameters()) + list(m2.parameters())]
+    fp = FlatParams([list(m1.parameters()), list(m2.parameters())])
+    assert fp.group_ranges == [(0, 18), (18, 26)]
+    for p, r in zip(fp.params, ref):
+        assert torch.equal(p.detach(), r)
+        assert p.data_ptr() >= fp.flat.data_ptr()
+    fp.zero_grad()
+    out = m2(torch.relu(m1(torch.randn(4, 5)))).sum()
+    out.backward()
+    assert fp.grad.abs().sum() > 0
+    assert all(p.grad.data_ptr() >= fp.grad.data_ptr() for p in fp.params)  # autograd accumulated in place
+    g1 = fp.grad.clone()
+    out2 = m2(torch.relu(m1(torch.randn(4, 5)))).sum()
+    out2.backward()
+    assert not torch.equal(fp.grad, g1)
+    fp.zero_grad()
+    assert fp.grad.abs().sum() == 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from zs3_b200.parallel import FlatParams, init_distributed, shard_batch
+    r, _, w = init_distributed()
+    assert (r, w) == (rank, world) and dist.get_backend() == "gloo"
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.ReLU(), torch.nn.Linear(4, 2))
+    x, y = torch.randn(8, 6), torch.randn(8, 2)
+    fp = FlatParams([list(model.parameters())])
+    dist.broadcast(fp.flat, 0)
+    a, b = shard_batch(8, rank, world)
+    fp.zero_grad()
+    # per-rank mean loss over its shard, as the CE kernel divides by the local batch
+    loss = ((model(x[a:b]) - y[a:b]) ** 2).mean()
+    loss.backward()
+    dist.all_reduce(fp.grad)          # the one collective of the step
+    fp.grad.mul_(1.0 / world)         # folded into the fused SGD kernel on the GPU path (grad_scale)
+    q.put((rank, fp.grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gloo_allreduce_matches_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=90) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.ReLU(), torch.nn.Linear(4, 2))
+    x, y = torch.randn(8, 6), torch.randn(8, 2)
+    loss = ((model(x) - y) ** 2).mean()
+    loss.backward()
+    full = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.allclose(got[0], got[1])
+    assert torch.allclose(got[0], full, atol=1e-6)
