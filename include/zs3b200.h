@@ -143,6 +143,8 @@ typedef struct {
   float drop_p;
   unsigned long long seed, offset;
   const unsigned char* keep_mask; /* drop_mode 2: [M][C] bytes, 1 = keep */
+  const unsigned long long* offset_dev; /* optional device counter added to `offset` at run time (lets a captured
+                                           CUDA graph draw fresh masks on every replay) */
 } zs3_bn_apply_args;
 
 /* out = dropout(relu?(scale*y + shift (+ residual))) */

@@ -97,6 +97,7 @@ class BnApplyArgs(C.Structure):
         ("relu", C.c_int), ("drop_mode", C.c_int), ("drop_p", C.c_float),
         ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
         ("keep_mask", C.c_void_p),
+        ("offset_dev", C.c_void_p),
     ]
 
 

@@ -107,11 +107,12 @@ struct ApplyP {
   __nv_bfloat16* out; long long out_cs;
   const float* scale; const float* shift;
   long long M; int C; int relu; int drop_mode; uint32_t thresh16; float keep_scale;
-  uint64_t seed, offset; const unsigned char* mask;
+  uint64_t seed, offset; const unsigned char* mask; const unsigned long long* offset_dev;
 };
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyP p) {
   const int vpc = p.C >> 3;  // 16-byte vectors per pixel
+  const uint64_t rng_offset = p.offset + (p.offset_dev ? *p.offset_dev : 0ull);
   const long long total = p.M * vpc;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
        v += (long long)gridDim.x * blockDim.x) {
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyP p) {
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
     }
     if (p.drop_mode == 1) {
-      const uint32_t keep = dropout_keep8(p.seed, p.offset, (uint64_t)(m * p.C + c), p.thresh16);
+      const uint32_t keep = dropout_keep8(p.seed, rng_offset, (uint64_t)(m * p.C + c), p.thresh16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1) ? f[j] * p.keep_scale : 0.f;
     } else if (p.drop_mode == 2) {
@@ -378,7 +379,7 @@ extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
   p.drop_mode = (a->drop_p > 0.f) ? a->drop_mode : 0;
   p.thresh16 = (uint32_t)(a->drop_p * 65536.0f + 0.5f);
   p.keep_scale = 1.f / (1.f - a->drop_p);
-  p.seed = a->seed; p.offset = a->offset; p.mask = a->keep_mask;
+  p.seed = a->seed; p.offset = a->offset; p.mask = a->keep_mask; p.offset_dev = a->offset_dev;
   bn_apply_kernel<<<ew_grid(a->M * (a->C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   ZS3_CHECK_LAUNCH("bn_apply");
   return ZS3_OK;

@@ -49,8 +49,11 @@ def _scratch64(dev, tag="fwd", n=2 * 2048):
 
 
 class _RngState:
-    """Counter-based dropout RNG: (seed, running offset) on the host, in the spirit of torch's Philox state."""
+    """Counter-based dropout RNG: (seed, running offset) on the host, in the spirit of torch's Philox state.
+    `device_counter` (an int64 CUDA tensor, optional) is added on the device so that a captured CUDA graph
+    draws fresh masks on every replay (the trainer bumps it once per step)."""
     offset = 0
+    device_counter = None
 
     @classmethod
     def next(cls, numel):
@@ -134,7 +137,8 @@ class ConvBnAct(torch.autograd.Function):
         if p > 0 and keep_mask is None:
             seed, off = _RngState.next(y.numel())
         out = K.bn_apply(y, scale, shift, relu, residual=residual, drop_p=p, seed=seed, offset=off,
-                         keep_mask=keep_mask if p > 0 else None)
+                         keep_mask=keep_mask if p > 0 else None,
+                         offset_dev=_RngState.device_counter if (p > 0 and keep_mask is None) else None)
         ctx.conv, ctx.bn, ctx.relu, ctx.p, ctx.training = conv, bn, relu, p, training
         ctx.ranges = ranges
         ctx.has_res = residual is not None

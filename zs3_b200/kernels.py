@@ -179,7 +179,8 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, cpad_):
     return coef[0], coef[1], coef[2], coef[3]
 
 
-def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0, offset=0, keep_mask=None):
+def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0, offset=0, keep_mask=None,
+             offset_dev=None):
     _chk_act(y, "bn_apply y")
     n, h, w, cs = y.shape
     if out is None:
@@ -200,6 +201,8 @@ def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0,
     elif drop_p > 0:
         a.drop_mode = 1
     a.seed, a.offset = int(seed), int(offset)
+    if offset_dev is not None:
+        a.offset_dev = offset_dev.data_ptr()
     L.check(L.lib().zs3_bn_apply(C.byref(a), L.stream_ptr()), "zs3_bn_apply")
     return out
 

@@ -93,8 +93,10 @@ class FusedSGD:
 class DataParallelTrainer:
     """step-1 training step of zs3/base_trainer.py:16-20 (zero_grad, forward, CE, backward, SGD) for one rank."""
 
-    def __init__(self, model, criterion, lr=0.007, momentum=0.9, weight_decay=5e-4, nesterov=False, world_size=1):
+    def __init__(self, model, criterion, lr=0.007, momentum=0.9, weight_decay=5e-4, nesterov=False, world_size=1,
+                 use_cuda_graph=False):
         self.model, self.criterion, self.world = model, criterion, world_size
+        self.use_cuda_graph, self.graph = use_cuda_graph, None
         groups = [list(model.get_1x_lr_params()), list(model.get_10x_lr_params())]
         self.flat = FlatParams(groups)
         self.opt = FusedSGD(self.flat, [lr, lr * 10], momentum, weight_decay, nesterov)
@@ -106,6 +108,35 @@ class DataParallelTrainer:
                 dist.broadcast(b, 0)
 
     def train_step(self, image, target):
+        """One optimisation step; returns the (device) loss tensor.  With use_cuda_graph the whole step --
+        ~1.2k kernel launches, the NCCL all-reduce and the optimizer -- is captured once and replayed."""
+        if not self.use_cuda_graph:
+            return self._step(image, target)
+        if self.graph is None:
+            self._capture(image, target)
+        self.static_image.copy_(image, non_blocking=True)
+        self.static_target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
+
+    def _capture(self, image, target):
+        dev = image.device
+        self.static_image, self.static_target = image.clone(), target.clone()
+        ZF._RngState.device_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up outside capture: lazy inits (cudaFuncSetAttribute, scratch buffers, NCCL)
+                self._step(self.static_image, self.static_target)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._step(self.static_image, self.static_target)
+
+    def _step(self, image, target):
+        if ZF._RngState.device_counter is not None:
+            ZF._RngState.device_counter.add_(1 << 32)  # fresh dropout masks per step, also under graph replay
         self.flat.zero_grad()
         output = self.model(image)
         loss = self.criterion(output, target)
