@@ -221,6 +221,18 @@ def run_ours(args):
         if args.mode == "graph":
             launches = launches_per_step * args.steps  # replayed from the captured graph, not re-issued by Python
         prof, K.PROFILE = K.PROFILE, None
+        tags = prof.pop("_tags", [])
+        if args.layer_table:
+            rows = {}
+            for kind, tag, a, b, f in tags:
+                r = rows.setdefault((kind, tag), [0, 0.0, 0.0])
+                r[0] += 1
+                r[1] += a.elapsed_time(b)
+                r[2] += f
+            with open(args.layer_table, "w") as ft:
+                ft.write("| kind | shape | launches/step | ms/step | TFLOP/s |\n|---|---|---:|---:|---:|\n")
+                for (kind, tag), (cnt, ms, f) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+                    ft.write(f"| {kind} | {tag} | {cnt / 2:.0f} | {ms / 2:.4f} | {f / (ms * 1e-3) / 1e12 if ms > 0 else 0:.0f} |\n")
         per_kind = {}
         for kind, evs in prof.items():
             ms = sum(a.elapsed_time(b) for a, b, _ in evs)
@@ -277,6 +289,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE: 16)")
     ap.add_argument("--size", type=int, default=513, help="input height=width (BASELINE: 513)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default="", help="write a per-conv-shape timing table (markdown) to this path")
     ap.add_argument("--mode", default="eager", choices=["eager", "graph"],
                     help="graph: capture the whole training step in one CUDA graph and replay it")
     args = ap.parse_args()

@@ -224,10 +224,29 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdP p) {
   }
 }
 
+// dy = A*dz + B*y + C per channel, with A = scale, B = -scale*m2*invstd, C = -scale*m1 + scale*m2*invstd*mean
+// (m1 = sum_dz/M, m2 = sum_dzx/M): the fp64 sums are folded into three fp32 coefficients per channel ONCE per
+// CTA (shared memory), so the streaming loop is 2 FMAs per element and touches no fp64.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
-  const int vpc = p.C >> 3;
-  const long long total = p.M * vpc;
-  const float inv_m = 1.f / (float)p.M;
+  extern __shared__ float coef[];  // [3][C]
+  float* cA = coef;
+  float* cB = coef + p.C;
+  float* cC = coef + 2 * p.C;
+  const double inv_m = 1.0 / (double)p.M;
+  for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
+    const float sc = p.scale[ch];
+    if (p.training) {
+      const float m1 = (float)(p.sum_dz[ch] * inv_m), m2 = (float)(p.sum_dzx[ch] * inv_m);
+      const float is = p.invstd[ch], mu = p.mean[ch];
+      cA[ch] = sc;
+      cB[ch] = -sc * m2 * is;
+      cC[ch] = -sc * m1 + sc * m2 * is * mu;
+    } else {
+      cA[ch] = sc;
+      cB[ch] = 0.f;
+      cC[ch] = 0.f;
+    }
+  }
   if (blockIdx.x == 0 && p.dgamma != nullptr) {
     for (int ch = threadIdx.x; ch < p.C_real; ch += blockDim.x) {
       const float dg = (float)p.sum_dzx[ch], db = (float)p.sum_dz[ch];
@@ -235,6 +254,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
       p.dbeta[ch] = p.param_acc ? p.dbeta[ch] + db : db;
     }
   }
+  __syncthreads();
+  const int vpc = p.C >> 3;
+  const long long total = p.M * vpc;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
        v += (long long)gridDim.x * blockDim.x) {
     const long long m = v / vpc;
@@ -242,9 +264,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
     float dz[8];
     load_dz(p, m, c, dz);
     if (p.dres) {
-      float r[8];
       uint4* dst = reinterpret_cast<uint4*>(p.dres + m * p.dres_cs + c);
       if (p.dres_acc) {
+        float r[8];
         unpack8(*dst, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] += dz[j];
@@ -253,24 +275,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
         *dst = pack8(dz);
       }
     }
-    float sc[8], g[8];
-    load8f(p.scale + c, sc);
-    if (p.training) {
-      float mu[8], is[8], yv[8];
-      load8f(p.mean + c, mu);
-      load8f(p.invstd + c, is);
-      unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
+    float g[8], yv[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (yv[j] - mu[j]) * is[j];
-        const float m1 = (float)p.sum_dz[c + j] * inv_m;
-        const float m2 = (float)p.sum_dzx[c + j] * inv_m;
-        g[j] = sc[j] * (dz[j] - m1 - xh * m2);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = sc[j] * dz[j];
-    }
+    for (int j = 0; j < 8; ++j) g[j] = fmaf(cA[c + j], dz[j], fmaf(cB[c + j], yv[j], cC[c + j]));
     long long pix = m;
     if (p.sp_stride > 1) {
       const long long img = m / p.sp_HoWo;
@@ -434,7 +442,8 @@ extern "C" int zs3_bn_bwd_apply(const zs3_bn_bwd_args* a, void* stream) {
   ZS3_CHECK_ARG((a->dgamma == nullptr) == (a->dbeta == nullptr) && (a->dgamma == nullptr || a->C_real <= a->C),
                 "bn_bwd_apply: bad parameter gradient buffers");
   if (a->M <= 0) return ZS3_OK;
-  bn_bwd_apply_kernel<<<ew_grid(a->M * (a->C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  bn_bwd_apply_kernel<<<ew_grid(a->M * (a->C / 8), 256), 256, 3 * a->C * sizeof(float),
+                        static_cast<cudaStream_t>(stream)>>>(p);
   ZS3_CHECK_LAUNCH("bn_bwd_apply");
   return ZS3_OK;
 }

@@ -10,9 +10,10 @@
 // shared-memory descriptors.  Accumulators live in TMEM (double buffered), epilogue warps read them back
 // with tcgen05.ld, fuse bias / BatchNorm batch statistics / accumulate, and store NHWC.
 //
-// Warp roles (256 threads, 1 persistent CTA per SM):
+// Warp roles (384 threads, 1 persistent CTA per SM):
 //   warp 0: TMA producer (one elected lane)      warp 1: MMA issuer (one elected lane)
-//   warp 2: TMEM allocator                       warps 4-7: epilogue (one TMEM lane quarter each)
+//   warp 2: TMEM allocator                       warps 4-11: epilogue (TMEM lane quarter = warp%4, two warps
+//                                                per quarter split the 32-column chunks between them)
 //
 // Reference call sites replaced: every nn.Conv2d on the DeepLab path (see include/zs3b200.h).
 #include "common.cuh"
@@ -23,8 +24,11 @@ namespace zs3 {
 constexpr int BLOCK_M = 128;      // output pixels per tile (= TMEM lanes)
 constexpr int BLOCK_K = 64;       // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // fprop: 4 control warps + 8 epilogue warps
+constexpr int WG_THREADS = 256;    // wgrad: 4 control warps + 4 epilogue warps
 constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int MAX_STAT_CH = 2048;  // per-CTA shared-memory BatchNorm statistic accumulators
 
 struct alignas(64) FpropSegment {
   CUtensorMap a;  // im2col map over the segment's activation tensor
@@ -57,7 +61,8 @@ struct FpropSmem {
   static constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
+  static constexpr int STAT_OFFSET = BAR_OFFSET + 256;  // barriers + tmem slot
+  static constexpr int TOTAL = STAT_OFFSET + 2 * MAX_STAT_CH * 4 + 1024 /*alignment slack*/;
 };
 
 // Column sums over the 32 lanes of a warp: lane j ends up with sum over lanes of v[j].
@@ -86,10 +91,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   uint64_t* acc_full = empty_bar + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_sum = reinterpret_cast<float*>(smem + L::STAT_OFFSET);  // [MAX_STAT_CH] per-CTA partial sums
+  float* s_sq = s_sum + MAX_STAT_CH;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  if (p.stat_sum != nullptr) {
+    for (int i = threadIdx.x; i < p.cout_pad; i += NUM_THREADS) {
+      s_sum[i] = 0.f;
+      s_sq[i] = 0.f;
+    }
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -192,6 +205,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   } else if (warp >= EPI_WARP0) {
     // ========================================================================= epilogue
     const int quarter = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;  // which 32-column chunks this warp owns (even / odd)
     const int row = quarter * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
       mbar_wait(&acc_full[as], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
         const int n = n_tile * BN + chunk * 32;
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + chunk * 32, raw);
@@ -278,8 +292,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
           }
           const float s1 = warp_column_sums(f, lane);
           const float s2 = warp_column_sums(sq, lane);
-          atomicAdd(p.stat_sum + n + lane, (double)s1);
-          atomicAdd(p.stat_sqsum + n + lane, (double)s2);
+          atomicAdd(&s_sum[n + lane], s1);  // shared-memory partials, flushed once per CTA at the end
+          atomicAdd(&s_sq[n + lane], s2);
         }
       }
       // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
@@ -293,6 +307,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+  if (p.stat_sum != nullptr) {
+    for (int i = threadIdx.x; i < p.cout_pad; i += NUM_THREADS) {
+      atomicAdd(p.stat_sum + i, (double)s_sum[i]);
+      atomicAdd(p.stat_sqsum + i, (double)s_sq[i]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------ wgrad
@@ -323,7 +343,7 @@ struct WgradSmem {
 };
 
 template <int CN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   using L = WgradSmem<CN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -433,9 +453,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_wgrad_kernel(const __grid
         tmem_ld_wait();
         const int ci = ci_tile * CN + chunk * 32;
         if (co < p.cout_pad && ci < p.cin_pad) {
-          float* dst = p.dw + ((long long)co * taps + tap) * p.cin_pad + ci;
+          float4* dst = reinterpret_cast<float4*>(p.dw + ((long long)co * taps + tap) * p.cin_pad + ci);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(raw[j]));
+          for (int j = 0; j < 8; ++j)  // 16-byte vector reductions (sm_90+): 8 instead of 32 atomics per row chunk
+            atomicAdd(dst + j, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                           __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
         }
       }
     }
@@ -447,45 +469,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_wgrad_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------- weight packing
-__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, int ci_begin,
-                                   int ci_count, __nv_bfloat16* __restrict__ dst, int cout_pad, int cin_pad,
-                                   int mode) {
+// Tiled through shared memory so that both the fp32 OIHW reads and the bf16 packed writes are contiguous runs:
+// one CTA repacks a 32 (co) x 32 (ci) x taps block.
+constexpr int PK_T = 32;
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S,
+                                                          int ci_begin, int ci_count, __nv_bfloat16* __restrict__ dst,
+                                                          int cout_pad, int cin_pad, int mode) {
+  extern __shared__ float tile[];  // [PK_T co][PK_T ci][taps] (+1 padding per co row)
   const int taps = R * S;
-  const long long total = (long long)cout_pad * taps * cin_pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int co, ci, tap;
-    if (mode == 0) {  // [cout_pad][taps][cin_pad]
-      ci = (int)(i % cin_pad);
-      tap = (int)((i / cin_pad) % taps);
-      co = (int)(i / ((long long)cin_pad * taps));
-    } else {  // [cin_pad][taps][cout_pad], spatially flipped taps
-      co = (int)(i % cout_pad);
-      int tflip = (int)((i / cout_pad) % taps);
-      ci = (int)(i / ((long long)cout_pad * taps));
-      tap = taps - 1 - tflip;
-    }
+  const int ld = PK_T * taps + 1;
+  const int co0 = blockIdx.y * PK_T, ci0 = blockIdx.x * PK_T;
+  // read: for each co a contiguous run of (PK_T ci x taps) floats
+  for (int i = threadIdx.x; i < PK_T * PK_T * taps; i += blockDim.x) {
+    const int co = i / (PK_T * taps), rem = i - co * (PK_T * taps);
+    const int ci = rem / taps;
     float v = 0.f;
-    if (co < Cout && ci < ci_count) {
-      const int r = tap / S, s = tap - r * S;
-      v = w[(((long long)co * Cin + (ci_begin + ci)) * R + r) * S + s];
+    if (co0 + co < Cout && ci0 + ci < ci_count)
+      v = w[((long long)(co0 + co) * Cin + ci_begin + ci0) * taps + rem];
+    tile[co * ld + rem] = v;
+  }
+  __syncthreads();
+  if (mode == 0) {  // dst[co][tap][ci]
+    for (int i = threadIdx.x; i < PK_T * taps * PK_T; i += blockDim.x) {
+      const int ci = i % PK_T, tap = (i / PK_T) % taps, co = i / (PK_T * taps);
+      if (co0 + co < cout_pad && ci0 + ci < cin_pad)
+        dst[((long long)(co0 + co) * taps + tap) * cin_pad + ci0 + ci] = __float2bfloat16(tile[co * ld + ci * taps + tap]);
     }
-    dst[i] = __float2bfloat16(v);
+  } else {  // dst[ci][taps-1-tap][co]
+    for (int i = threadIdx.x; i < PK_T * taps * PK_T; i += blockDim.x) {
+      const int co = i % PK_T, tap = (i / PK_T) % taps, ci = i / (PK_T * taps);
+      if (co0 + co < cout_pad && ci0 + ci < cin_pad)
+        dst[((long long)(ci0 + ci) * taps + (taps - 1 - tap)) * cout_pad + co0 + co] =
+            __float2bfloat16(tile[co * ld + ci * taps + tap]);
+    }
   }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int cout_pad, int cin_pad, float* __restrict__ g,
-                                    int Cout, int Cin, int R, int S, int ci_begin, int ci_count, int accumulate) {
+// grad_oihw[co][ci_begin+ci][tap] (+)= dw[co][tap][ci]: same tiling, reversed direction
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, int cout_pad, int cin_pad,
+                                                           float* __restrict__ g, int Cout, int Cin, int R, int S,
+                                                           int ci_begin, int ci_count, int accumulate) {
+  extern __shared__ float tile[];
   const int taps = R * S;
-  const long long total = (long long)Cout * ci_count * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % taps);
-    const int ci = (int)((i / taps) % ci_count);
-    const int co = (int)(i / ((long long)taps * ci_count));
-    const float v = dw[((long long)co * taps + tap) * cin_pad + ci];
-    float* d = g + ((long long)co * Cin + ci_begin + ci) * taps + tap;
-    *d = accumulate ? (*d + v) : v;
+  const int ld = PK_T * taps + 1;
+  const int co0 = blockIdx.y * PK_T, ci0 = blockIdx.x * PK_T;
+  for (int i = threadIdx.x; i < PK_T * taps * PK_T; i += blockDim.x) {
+    const int ci = i % PK_T, tap = (i / PK_T) % taps, co = i / (PK_T * taps);
+    float v = 0.f;
+    if (co0 + co < Cout && ci0 + ci < ci_count) v = dw[((long long)(co0 + co) * taps + tap) * cin_pad + ci0 + ci];
+    tile[co * ld + ci * taps + tap] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PK_T * PK_T * taps; i += blockDim.x) {
+    const int co = i / (PK_T * taps), rem = i - co * (PK_T * taps);
+    const int ci = rem / taps;
+    if (co0 + co < Cout && ci0 + ci < ci_count) {
+      float* d = g + ((long long)(co0 + co) * Cin + ci_begin + ci0) * taps + rem;
+      *d = accumulate ? (*d + tile[co * ld + rem]) : tile[co * ld + rem];
+    }
   }
 }
 
@@ -534,7 +575,7 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(p.num_ci_tiles * p.num_co_tiles * p.R * p.S, p.k_splits);
-  conv_wgrad_kernel<CN, STAGES><<<grid, NUM_THREADS, L::TOTAL, st>>>(p);
+  conv_wgrad_kernel<CN, STAGES><<<grid, WG_THREADS, L::TOTAL, st>>>(p);
   ZS3_CHECK_LAUNCH("conv_wgrad");
   return ZS3_OK;
 }
@@ -556,6 +597,8 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
                 "conv_fprop: pad/dilation outside the TMA im2col range");
   ZS3_CHECK_ARG(a->y != nullptr && a->y_cstride >= a->cout_pad, "conv_fprop: bad output");
   ZS3_CHECK_ARG((a->stat_sum == nullptr) == (a->stat_sqsum == nullptr), "conv_fprop: stat_sum/stat_sqsum mismatch");
+  ZS3_CHECK_ARG(a->stat_sum == nullptr || a->cout_pad <= MAX_STAT_CH, "conv_fprop: statistics need cout_pad <= %d",
+                MAX_STAT_CH);
   const long long M = (long long)a->N * a->Ho * a->Wo;
   ZS3_CHECK_ARG(M < (1ll << 31), "conv_fprop: too many output pixels");
 
@@ -674,10 +717,10 @@ extern "C" int zs3_pack_weight(const float* w_oihw, int Cout, int Cin, int R, in
   ZS3_CHECK_ARG(Cout <= cout_pad && ci_count <= cin_pad && ci_begin >= 0 && ci_begin + ci_count <= Cin,
                 "pack_weight: bad channel ranges");
   ZS3_CHECK_ARG(mode == 0 || mode == 1, "pack_weight: mode=%d", mode);
-  const long long total = (long long)cout_pad * cin_pad * R * S;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ZS3_CHECK_ARG(R * S <= 9, "pack_weight: at most 9 taps (the 7x7 stem goes through its [Cout][147][1][1] view)");
+  const size_t smem = (size_t)PK_T * (PK_T * R * S + 1) * sizeof(float);
+  dim3 grid(ceil_div(cin_pad, PK_T), ceil_div(cout_pad, PK_T));
+  pack_weight_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       w_oihw, Cout, Cin, R, S, ci_begin, ci_count, static_cast<__nv_bfloat16*>(dst_bf16), cout_pad, cin_pad, mode);
   ZS3_CHECK_LAUNCH("pack_weight");
   return ZS3_OK;
@@ -688,11 +731,11 @@ extern "C" int zs3_unpack_wgrad(const float* dw, int cout_pad, int cin_pad, floa
   ZS3_CHECK_ARG(dw && grad_oihw, "unpack_wgrad: null pointer");
   ZS3_CHECK_ARG(Cout <= cout_pad && ci_count <= cin_pad && ci_begin >= 0 && ci_begin + ci_count <= Cin,
                 "unpack_wgrad: bad channel ranges");
-  const long long total = (long long)Cout * ci_count * R * S;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dw, cout_pad, cin_pad, grad_oihw, Cout,
-                                                                             Cin, R, S, ci_begin, ci_count, accumulate);
+  ZS3_CHECK_ARG(R * S <= 9, "unpack_wgrad: at most 9 taps");
+  const size_t smem = (size_t)PK_T * (PK_T * R * S + 1) * sizeof(float);
+  dim3 grid(ceil_div(ci_count, PK_T), ceil_div(Cout, PK_T));
+  unpack_wgrad_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(dw, cout_pad, cin_pad, grad_oihw, Cout,
+                                                                              Cin, R, S, ci_begin, ci_count, accumulate);
   ZS3_CHECK_LAUNCH("unpack_wgrad");
   return ZS3_OK;
 }

@@ -17,8 +17,8 @@ PROFILE = None
 
 
 class _Timed:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, tag=""):
+        self.kind, self.flops, self.tag = kind, flops, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -30,6 +30,7 @@ class _Timed:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             PROFILE.setdefault(self.kind, []).append((self.e0, e1, self.flops))
+            PROFILE.setdefault("_tags", []).append((self.kind, self.tag, self.e0, e1, self.flops))
 
 
 def cpad(c, to=64):
@@ -107,7 +108,11 @@ def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=Fal
     if stats is not None:
         a.stat_sum = stats[0].data_ptr()
         a.stat_sqsum = stats[1].data_ptr()
-    with _Timed(kind, flops):
+    tag = ""
+    if PROFILE is not None:
+        tag = (f"N{n} {h}x{w_}->{ho}x{wo} k{R} s{stride} d{dil} cin{sum(wp.shape[2] for _, wp in segments)} "
+               f"cout{cout_pad} segs{len(segments)}{' stats' if stats is not None else ''}")
+    with _Timed(kind, flops, tag):
         L.check(L.lib().zs3_conv_fprop(C.byref(a), L.stream_ptr()), "zs3_conv_fprop")
     return out
 
@@ -131,7 +136,8 @@ def conv_wgrad(x, dy, R, S, stride, pad, dil, cin_pad, cout_pad, dw=None, k_spli
     a.cout_pad = cout_pad
     a.dw = dw.data_ptr()
     a.k_splits = k_splits
-    with _Timed("conv_wgrad", flops):
+    tag = f"N{n} {h}x{w_}->{ho}x{wo} k{R} s{stride} d{dil} cin{cin_pad} cout{cout_pad}" if PROFILE is not None else ""
+    with _Timed("conv_wgrad", flops, tag):
         L.check(L.lib().zs3_conv_wgrad(C.byref(a), L.stream_ptr()), "zs3_conv_wgrad")
     return dw
 
