@@ -122,6 +122,10 @@ int zs3_unpack_wgrad(const float* dw, int cout_pad, int cin_pad, float* grad_oih
 int zs3_bn_finalize(double* stat_sum, double* stat_sqsum, long long count, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                     float* mean, float* invstd, int C, int Cpad, int reset_stats, void* stream);
+/* standalone batch statistics of a bf16 tensor y[M][y_cstride]: stat_sum[c] += sum y, stat_sqsum[c] += sum y^2.
+ * Used for short-K (1x1) convolutions, where fusing the reduction into the conv epilogue would make the epilogue
+ * the bottleneck; long-K convolutions keep the fused statistics of zs3_conv_fprop. */
+int zs3_bn_stats(const void* y, int y_cstride, long long M, int C, double* stat_sum, double* stat_sqsum, void* stream);
 /* eval-mode / frozen BN: coefficients from the running statistics (deeplab.py:68-73 freeze_bn) */
 int zs3_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                        float eps, float* scale, float* shift, float* mean, float* invstd, int C, int Cpad,

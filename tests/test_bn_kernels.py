@@ -87,3 +87,14 @@ def test_bn_eval_and_dropout():
         rate = kept.sum().item() / pos.sum().item()
         assert abs(rate - (1 - p)) < 0.01, rate
         assert rel_l2(o1.float()[kept], out.float()[kept] / (1 - p)) < 4e-3
+
+
+def test_bn_stats_kernel():
+    from zs3_b200 import kernels as K
+    g = torch.Generator().manual_seed(3)
+    for C, hw in ((64, 33), (1024, 9), (2048, 5)):
+        y = (torch.randn(3, C, hw, hw, generator=g) * 2 + 1).to(torch.bfloat16).float().cuda()
+        stats = torch.zeros(2, C, dtype=torch.float64, device="cuda")
+        K.bn_stats(K.nchw_to_nhwc(y, C), (stats[0], stats[1]))
+        assert rel_l2(stats[0], y.double().sum(dim=(0, 2, 3))) < 1e-5
+        assert rel_l2(stats[1], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-5

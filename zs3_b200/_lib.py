@@ -135,6 +135,7 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_nhwc_bf16_to_nchw_f32": [vp, vp, i, i, ll, i, vp],
         "zs3_bn_finalize": [vp, vp, ll, vp, vp, f, f, vp, vp, vp, vp, vp, vp, i, i, i, vp],
         "zs3_bn_eval_coeffs": [vp, vp, vp, vp, f, vp, vp, vp, vp, i, i, vp],
+        "zs3_bn_stats": [vp, i, ll, i, vp, vp, vp],
         "zs3_bn_apply": [C.POINTER(BnApplyArgs), vp],
         "zs3_bn_bwd_reduce": [C.POINTER(BnBwdArgs), vp],
         "zs3_bn_bwd_apply": [C.POINTER(BnBwdArgs), vp],

@@ -291,6 +291,50 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
   }
 }
 
+// ----------------------------------------------------------------------- standalone statistics
+// sum[c] += sum_m y[m][c], sqsum[c] += sum_m y[m][c]^2 (used instead of the conv epilogue's fused statistics for
+// short-K convolutions whose epilogue would otherwise be the bottleneck; costs one extra read of y)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long y_cs, long long M,
+                                                       int C, int rows_per_block, double* __restrict__ sum,
+                                                       double* __restrict__ sqsum) {
+  extern __shared__ float red[];  // [rows_per_block][C] x 2
+  const int vpc = C >> 3;
+  const int vc = threadIdx.x % vpc;
+  const int rl = threadIdx.x / vpc;
+  const int c = vc << 3;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  if (rl < rows_per_block) {
+    for (long long m = (long long)blockIdx.x * rows_per_block + rl; m < M; m += (long long)gridDim.x * rows_per_block) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(y + m * y_cs + c), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += v[j];
+        a2[j] = fmaf(v[j], v[j], a2[j]);
+      }
+    }
+    float* r1 = red + (size_t)rl * C + c;
+    float* r2 = red + (size_t)rows_per_block * C + (size_t)rl * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r1[j] = a1[j];
+      r2[j] = a2[j];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < rows_per_block; ++r) {
+      s1 += red[(size_t)r * C + ch];
+      s2 += red[(size_t)rows_per_block * C + (size_t)r * C + ch];
+    }
+    atomicAdd(sum + ch, (double)s1);
+    atomicAdd(sqsum + ch, (double)s2);
+  }
+}
+
 // ------------------------------------------------------------------------- layout changes
 // NCHW fp32 -> NHWC bf16 through a 32x32 shared-memory transpose (coalesced on both sides).
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, long long HW,
@@ -354,6 +398,24 @@ extern "C" int zs3_bn_finalize(double* stat_sum, double* stat_sqsum, long long c
       stat_sum, stat_sqsum, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd,
       C, Cpad, reset_stats);
   ZS3_CHECK_LAUNCH("bn_finalize");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_bn_stats(const void* y, int y_cstride, long long M, int C, double* stat_sum, double* stat_sqsum,
+                            void* stream) {
+  ZS3_CHECK_ARG(y && stat_sum && stat_sqsum, "bn_stats: null pointer");
+  ZS3_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 2048 && y_cstride % 8 == 0 && y_cstride >= C,
+                "bn_stats: C=%d must be a multiple of 8 and <= 2048", C);
+  if (M <= 0) return ZS3_OK;
+  const int vpc = C / 8;
+  int rpb = 256 / vpc;
+  if (rpb < 1) rpb = 1;
+  const size_t smem = (size_t)2 * rpb * C * sizeof(float);
+  long long blocks = (M + rpb - 1) / rpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_stats_kernel<<<(int)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), y_cstride, M, C, rpb, stat_sum, stat_sqsum);
+  ZS3_CHECK_LAUNCH("bn_stats");
   return ZS3_OK;
 }
 

@@ -16,6 +16,8 @@
 //                                                per quarter split the 32-column chunks between them)
 //
 // Reference call sites replaced: every nn.Conv2d on the DeepLab path (see include/zs3b200.h).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -44,7 +46,8 @@ struct FpropParams {
   int stride, pad, dil, R, S;
   int cout_pad;
   int num_m_tiles, num_n_tiles;
-  int kb_per_tile;  // total k-blocks per output tile
+  int num_m_groups;  // ceil(num_m_tiles / cluster size): the CTAs of a cluster take consecutive m-tiles of one n-tile
+  int kb_per_tile;   // total k-blocks per output tile
   void* y;
   long long y_cstride;
   // output pixel (n,p,q) is stored at pixel index n*y_img + p*y_row + q*y_pix of y
@@ -96,7 +99,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // Thread-block cluster (1, 2 or 4 CTAs): the CTAs of a cluster work on consecutive m-tiles of the SAME n-tile in
+  // lock step; each loads 1/csize of the weight tile and multicasts it to all, cutting L2->SM weight traffic.
+  const int csize = (int)cluster_nctarank();
+  const int crank = (int)cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const int num_groups = p.num_m_groups * p.num_n_tiles;
+  const int cluster_id = blockIdx.x / csize;
+  const int num_clusters = gridDim.x / csize;
   if (p.stat_sum != nullptr) {
     for (int i = threadIdx.x; i < p.cout_pad; i += NUM_THREADS) {
       s_sum[i] = 0.f;
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], csize);  // one tcgen05.commit per CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -127,6 +137,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -135,9 +146,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = tile / p.num_n_tiles;
+      const int b_rows = BN / csize;  // rows of the weight tile this CTA fetches (and multicasts)
+      for (int g = cluster_id; g < num_groups; g += num_clusters) {
+        const int n_tile = g % p.num_n_tiles;
+        const int m_tile = (g / p.num_n_tiles) * csize + crank;  // may be >= num_m_tiles: TMA zero-fills, epilogue masks
         const int m0 = m_tile * BLOCK_M;
         const int img = m0 / p.HoWo;
         const int rem = m0 - img * p.HoWo;
@@ -157,7 +169,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
                 mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                 tma_load_im2col_4d(sa, &sg.a, &full_bar[stage], cb * BLOCK_K, base_w, base_h, img,
                                    (uint16_t)(q * p.dil), (uint16_t)(r * p.dil));
-                tma_load_3d(sb, &sg.b, &full_bar[stage], cb * BLOCK_K, tap, n_tile * BN);
+                if (csize == 1)
+                  tma_load_3d(sb, &sg.b, &full_bar[stage], cb * BLOCK_K, tap, n_tile * BN);
+                else
+                  tma_load_3d_mc(sb + crank * b_rows * 128, &sg.b, &full_bar[stage], cb * BLOCK_K, tap,
+                                 n_tile * BN + crank * b_rows, cmask);
                 if (++stage == STAGES) {
                   stage = 0;
                   phase ^= 1;
@@ -175,7 +191,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int g = cluster_id; g < num_groups; g += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&acc_empty[as], acc_phase ^ 1);
@@ -193,7 +209,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if (csize == 1)
+            umma_commit(&empty_bar[stage]);
+          else
+            umma_commit_mc(&empty_bar[stage], cmask);  // the stage is free once EVERY CTA of the cluster has read it
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -208,9 +227,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
     const int half = (warp - EPI_WARP0) >> 2;  // which 32-column chunks this warp owns (even / odd)
     const int row = quarter * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = tile / p.num_n_tiles;
+    for (int g = cluster_id; g < num_groups; g += num_clusters, ++it) {
+      const int n_tile = g % p.num_n_tiles;
+      const int m_tile = (g / p.num_n_tiles) * csize + crank;
       const int as = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m = m_tile * BLOCK_M + row;
@@ -305,6 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
   if (p.stat_sum != nullptr) {
@@ -333,18 +353,21 @@ struct WgradParams {
   float* dw;
 };
 
-template <int CN, int STAGES>
+// MB = number of 128-row output-channel blocks per CTA (1 or 2): MB = 2 reuses every X tile for 256 output
+// channels, raising the arithmetic intensity of the L2->SM stream from 85 to 128 FLOP/B.
+template <int CN, int STAGES, int MB>
 struct WgradSmem {
-  static constexpr int A_BYTES = 2 * WG_CHUNK_BYTES;          // 128 output channels
+  static constexpr int A_BYTES = MB * 2 * WG_CHUNK_BYTES;     // MB * 128 output channels
   static constexpr int B_BYTES = (CN / 64) * WG_CHUNK_BYTES;  // CN input channels
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <int CN, int STAGES>
+template <int CN, int STAGES, int MB>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using L = WgradSmem<CN, STAGES>;
+  using L = WgradSmem<CN, STAGES, MB>;
+  constexpr int TMEM_COLS = (MB * CN) < 32 ? 32 : (MB * CN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -377,7 +400,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, CN < 32 ? 32 : CN);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -401,8 +424,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
           uint8_t* sb = sa + L::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-            tma_load_2d(sa + c * WG_CHUNK_BYTES, &p.dy, &full_bar[stage], co_tile * 128 + c * 64, p0);
+          for (int c = 0; c < 2 * MB; ++c)
+            tma_load_2d(sa + c * WG_CHUNK_BYTES, &p.dy, &full_bar[stage], co_tile * (128 * MB) + c * 64, p0);
 #pragma unroll
           for (int c = 0; c < CN / 64; ++c)
             tma_load_im2col_4d(sb + c * WG_CHUNK_BYTES, &p.x, &full_bar[stage], ci_tile * CN + c * 64,
@@ -428,9 +451,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
           for (int k = 0; k < WG_BLOCK_P / 16; ++k) {
             // MN-major SW128: LBO = byte distance between 64-channel sub-tiles, SBO = 8 pixel rows = 1024 B;
             // one UMMA_K step = 16 pixel rows = 2048 B.
-            const uint64_t adesc = make_smem_desc_sw128(sa + k * 2048, WG_CHUNK_BYTES, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * 2048, WG_CHUNK_BYTES, 1024);
-            umma_f16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint64_t adesc = make_smem_desc_sw128(sa + mb * 2 * WG_CHUNK_BYTES + k * 2048, WG_CHUNK_BYTES, 1024);
+              umma_f16(tmem_base + mb * CN, adesc, bdesc, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
@@ -442,16 +468,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
       }
     } else if (warp >= EPI_WARP0) {
       const int quarter = warp & 3;
-      const int co = co_tile * 128 + quarter * 32 + lane;
       mbar_wait(acc_full, 0);
       tc_fence_after();
       const int taps = p.R * p.S;
 #pragma unroll 1
-      for (int chunk = 0; chunk < CN / 32; ++chunk) {
+      for (int chunk = 0; chunk < MB * CN / 32; ++chunk) {
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + chunk * 32, raw);
         tmem_ld_wait();
-        const int ci = ci_tile * CN + chunk * 32;
+        const int mb = chunk / (CN / 32);
+        const int co = co_tile * (128 * MB) + mb * 128 + quarter * 32 + lane;
+        const int ci = ci_tile * CN + (chunk - mb * (CN / 32)) * 32;
         if (co < p.cout_pad && ci < p.cin_pad) {
           float4* dst = reinterpret_cast<float4*>(p.dw + ((long long)co * taps + tap) * p.cin_pad + ci);
 #pragma unroll
@@ -465,7 +492,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, CN < 32 ? 32 : CN);
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------- weight packing
@@ -542,7 +569,7 @@ static int num_sms() {
 }
 
 template <int BN, int STAGES>
-static int launch_fprop(const FpropParams& p, cudaStream_t st) {
+static int launch_fprop(const FpropParams& p, int csize, cudaStream_t st) {
   using L = FpropSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -554,19 +581,37 @@ static int launch_fprop(const FpropParams& p, cudaStream_t st) {
     }
     configured = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fprop_kernel<BN, STAGES><<<grid, NUM_THREADS, L::TOTAL, st>>>(p);
+  const int groups = p.num_m_groups * p.num_n_tiles;
+  const int max_clusters = num_sms() / csize;
+  const int clusters = groups < max_clusters ? groups : max_clusters;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * csize);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BN, STAGES>, p);
+  if (e != cudaSuccess) {
+    set_error("conv_fprop: cudaLaunchKernelEx(cluster=%d) failed: %s", csize, cudaGetErrorString(e));
+    return ZS3_ERR_LAUNCH;
+  }
   ZS3_CHECK_LAUNCH("conv_fprop");
   return ZS3_OK;
 }
 
-template <int CN, int STAGES>
+template <int CN, int STAGES, int MB>
 static int launch_wgrad(const WgradParams& p, cudaStream_t st) {
-  using L = WgradSmem<CN, STAGES>;
+  using L = WgradSmem<CN, STAGES, MB>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<CN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<CN, STAGES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL);
     if (e != cudaSuccess) {
       set_error("conv_wgrad: cudaFuncSetAttribute(%d bytes) failed: %s", L::TOTAL, cudaGetErrorString(e));
@@ -575,7 +620,7 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(p.num_ci_tiles * p.num_co_tiles * p.R * p.S, p.k_splits);
-  conv_wgrad_kernel<CN, STAGES><<<grid, WG_THREADS, L::TOTAL, st>>>(p);
+  conv_wgrad_kernel<CN, STAGES, MB><<<grid, WG_THREADS, L::TOTAL, st>>>(p);
   ZS3_CHECK_LAUNCH("conv_wgrad");
   return ZS3_OK;
 }
@@ -605,6 +650,16 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   FpropParams p;
   memset(&p, 0, sizeof(p));
   const int BN = a->cout_pad >= 256 ? 256 : (a->cout_pad >= 128 ? 128 : 64);
+  // cluster size: CTAs of a cluster share (multicast) the weight tile.  ZS3_CLUSTER overrides (1, 2 or 4).
+  static int cluster_pref = -1;
+  if (cluster_pref < 0) {
+    const char* env = getenv("ZS3_CLUSTER");
+    cluster_pref = env ? atoi(env) : 2;
+    if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 2;
+  }
+  const int m_tiles_total = (int)ceil_div_ll(M, BLOCK_M);
+  int csize = cluster_pref;
+  while (csize > 1 && m_tiles_total < 2 * csize) csize >>= 1;
   int kb = 0;
   for (int s = 0; s < a->num_segments; ++s) {
     const zs3_conv_segment& sg = a->seg[s];
@@ -618,7 +673,7 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
     int rc = encode_im2col_bf16(&p.seg[s].a, sg.x, a->N, a->H, a->W, sg.x_cstride, a->pad, upper_w, a->stride, BLOCK_K,
                                 BLOCK_M);
     if (rc) return rc;
-    rc = encode_tiled3d_bf16(&p.seg[s].b, sg.w, a->cout_pad, a->R * a->S, sg.cin_pad, BN, 1, BLOCK_K);
+    rc = encode_tiled3d_bf16(&p.seg[s].b, sg.w, a->cout_pad, a->R * a->S, sg.cin_pad, BN / csize, 1, BLOCK_K);
     if (rc) return rc;
     p.seg[s].num_cblk = sg.cin_pad / BLOCK_K;
     kb += a->R * a->S * p.seg[s].num_cblk;
@@ -633,7 +688,8 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   p.R = a->R;
   p.S = a->S;
   p.cout_pad = a->cout_pad;
-  p.num_m_tiles = (int)ceil_div_ll(M, BLOCK_M);
+  p.num_m_tiles = m_tiles_total;
+  p.num_m_groups = ceil_div(m_tiles_total, csize);
   p.num_n_tiles = ceil_div(a->cout_pad, BN);
   p.kb_per_tile = kb;
   p.y = a->y;
@@ -655,9 +711,9 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   p.stat_sum = a->stat_sum;
   p.stat_sqsum = a->stat_sqsum;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (BN == 256) return launch_fprop<256, 4>(p, st);
-  if (BN == 128) return launch_fprop<128, 6>(p, st);
-  return launch_fprop<64, 8>(p, st);
+  if (BN == 256) return launch_fprop<256, 4>(p, csize, st);
+  if (BN == 128) return launch_fprop<128, 6>(p, csize, st);
+  return launch_fprop<64, 8>(p, csize, st);
 }
 
 extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
@@ -690,7 +746,8 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   p.S = a->S;
   p.cout_pad = a->cout_pad;
   p.cin_pad = a->cin_pad;
-  p.num_co_tiles = ceil_div(a->cout_pad, 128);
+  const int MB = a->cout_pad >= 256 ? 2 : 1;  // 256 output channels per CTA when the layer has them
+  p.num_co_tiles = ceil_div(a->cout_pad, 128 * MB);
   p.num_ci_tiles = ceil_div(a->cin_pad, CN);
   p.pblocks_total = (int)ceil_div_ll(M, WG_BLOCK_P);
   const int out_tiles = p.num_co_tiles * p.num_ci_tiles * a->R * a->S;
@@ -706,9 +763,14 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   p.k_splits = ks;
   p.dw = a->dw;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (CN == 256) return launch_wgrad<256, 4>(p, st);
-  if (CN == 128) return launch_wgrad<128, 6>(p, st);
-  return launch_wgrad<64, 8>(p, st);
+  if (MB == 2) {
+    if (CN == 256) return launch_wgrad<256, 3, 2>(p, st);
+    if (CN == 128) return launch_wgrad<128, 4, 2>(p, st);
+    return launch_wgrad<64, 5, 2>(p, st);
+  }
+  if (CN == 256) return launch_wgrad<256, 4, 1>(p, st);
+  if (CN == 128) return launch_wgrad<128, 6, 1>(p, st);
+  return launch_wgrad<64, 8, 1>(p, st);
 }
 
 extern "C" int zs3_pack_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int ci_begin, int ci_count,

@@ -63,6 +63,8 @@ class _RngState:
         return seed, off
 
 
+FUSE_STATS_MIN_KB = 18  # 3x3 convs with >= 128 input channels, 1x1 convs with >= 1152
+
 _WEIGHT_EPOCH = [0]
 
 
@@ -129,7 +131,14 @@ class ConvBnAct(torch.autograd.Function):
         n_, h_, w_, _ = xs[0].shape
         ho_, wo_ = K.conv_out_size(h_, R, stride, pad, dil), K.conv_out_size(w_, S, stride, pad, dil)
         macs_per_cin = 2.0 * n_ * ho_ * wo_ * cout * R * S  # nominal FLOPs per input channel
-        y = K.conv_fprop(segs, R, S, stride, pad, dil, cout_p, stats=stats, flops=macs_per_cin * conv.in_channels)
+        # BatchNorm statistics: fused into the conv epilogue when the main loop is long enough to hide it
+        # (>= FUSE_STATS_MIN_KB k-blocks of 64 per tile), otherwise one extra streaming pass over y
+        kblocks = R * S * sum(x.shape[3] for x in xs) // 64
+        fuse_stats = stats is not None and kblocks >= FUSE_STATS_MIN_KB
+        y = K.conv_fprop(segs, R, S, stride, pad, dil, cout_p, stats=stats if fuse_stats else None,
+                         flops=macs_per_cin * conv.in_channels)
+        if stats is not None and not fuse_stats:
+            K.bn_stats(y, stats)
         n, ho, wo, _ = y.shape
         scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
         seed = off = 0

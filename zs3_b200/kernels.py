@@ -175,6 +175,14 @@ def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_
     return coef[0], coef[1], coef[2], coef[3]
 
 
+def bn_stats(y, stats):
+    """stats[0] += per-channel sum of y, stats[1] += per-channel sum of squares (y: NHWC bf16)"""
+    _chk_act(y, "bn_stats")
+    n, h, w, cs = y.shape
+    L.check(L.lib().zs3_bn_stats(L.ptr(y), cs, n * h * w, cs, L.ptr(stats[0]), L.ptr(stats[1]), L.stream_ptr()),
+            "zs3_bn_stats")
+
+
 def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, cpad_):
     dev = running_mean.device
     c = running_mean.numel()
