@@ -90,8 +90,13 @@ typedef struct {
   const void* dy;  /* bf16 [N*Ho*Wo][dy_cstride] */
   int dy_cstride;
   int cout_pad;    /* multiple of 64 */
-  float* dw;       /* fp32 [cout_pad][R*S][cin_pad] */
+  float* dw;       /* fp32 [cout][R*S][dw_ld]: row (co, tap) starts at dw + (co*R*S + tap)*dw_ld */
   int k_splits;    /* number of pixel-range splits (>=1); 0 = choose automatically */
+  long long dw_ld; /* 0 = cin_pad (dense packed buffer); else the total input-channel count of a KRSC
+                      (torch channels_last) gradient tensor that is accumulated into directly */
+  int dw_ci_offset;/* first input channel of this K-segment inside a dw row */
+  int cout_valid;  /* 0 = cout_pad; rows >= cout_valid are not written */
+  int cin_valid;   /* 0 = cin_pad; columns >= cin_valid are not written */
 } zs3_wgrad_args;
 
 int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream);
@@ -100,7 +105,9 @@ int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream);
  *   mode 0 (fprop):  dst[co][r*S+s][ci - ci_begin]            = src[co][ci][r][s]
  *   mode 1 (dgrad):  dst[ci - ci_begin][(R-1-r)*S+(S-1-s)][co] = src[co][ci][r][s]
  * ci in [ci_begin, ci_begin+ci_count); rows/cols beyond the real sizes are zero filled.
- * dst dims: mode 0 [cout_pad][R*S][cin_pad], mode 1 [cin_pad][R*S][cout_pad]. */
+ * dst dims: mode 0 [cout_pad][R*S][cin_pad], mode 1 [cin_pad][R*S][cout_pad].
+ * modes 2 / 3 = modes 0 / 1 reading a KRSC source (torch channels_last memory format: src[co][r][s][ci]),
+ * the layout this package keeps its conv parameters in. */
 int zs3_pack_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int ci_begin, int ci_count, void* dst_bf16,
                     int cout_pad, int cin_pad, int mode, void* stream);
 /* grad_oihw[co][ci_begin+ci][r][s] (+)= dw[co][r*S+s][ci]  (fp32) */
@@ -203,7 +210,8 @@ int zs3_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, long lo
  * cols[N*Ho*Wo][kpad] bf16 with k = c*R*R + r*R + s (the OIHW flattening), so that the stem runs as a
  * 1x1 zs3_conv_fprop / zs3_conv_wgrad over `cols` with the weight viewed as [Cout][C*R*R][1][1]. */
 int zs3_stem_im2col(const float* x_nchw, void* cols, int N, int C, int H, int W, int R, int stride, int pad, int Ho,
-                    int Wo, int kpad, void* stream);
+                    int Wo, int kpad, int krsc /* 1: k = (r*R + s)*C + c, the channels_last flattening */,
+                    void* stream);
 
 /* nn.MaxPool2d(3, 2, 1) (resnet.py:82); argmax keeps the winning window slot (first max wins) per element */
 int zs3_maxpool_fwd(const void* x, void* y, unsigned char* argmax, int N, int H, int W, int C, int Ho, int Wo, int k,

@@ -58,6 +58,10 @@ class WgradArgs(C.Structure):
         ("cout_pad", C.c_int),
         ("dw", C.c_void_p),
         ("k_splits", C.c_int),
+        ("dw_ld", C.c_longlong),
+        ("dw_ci_offset", C.c_int),
+        ("cout_valid", C.c_int),
+        ("cin_valid", C.c_int),
     ]
 
 
@@ -139,7 +143,7 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_bn_apply": [C.POINTER(BnApplyArgs), vp],
         "zs3_bn_bwd_reduce": [C.POINTER(BnBwdArgs), vp],
         "zs3_bn_bwd_apply": [C.POINTER(BnBwdArgs), vp],
-        "zs3_stem_im2col": [vp, vp, i, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_stem_im2col": [vp, vp, i, i, i, i, i, i, i, i, i, i, i, vp],
         "zs3_maxpool_fwd": [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
         "zs3_maxpool_bwd": [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
         "zs3_bilinear_fwd": [vp, vp, i, i, i, i, i, i, i, i, vp],

@@ -351,6 +351,9 @@ struct WgradParams {
   int k_splits;
   int pblocks_total;  // ceil(M / 64)
   float* dw;
+  long long dw_ld;       // elements between consecutive (co, tap) rows of dw
+  int dw_ci_offset;      // first input channel of this segment inside a dw row
+  int cout_valid, cin_valid;  // logical extents (rows / columns beyond them are not written)
 };
 
 // MB = number of 128-row output-channel blocks per CTA (1 or 2): MB = 2 reuses every X tile for 256 output
@@ -471,6 +474,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
       mbar_wait(acc_full, 0);
       tc_fence_after();
       const int taps = p.R * p.S;
+      const bool vec_ok = (p.dw_ld % 4 == 0) && (p.dw_ci_offset % 4 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0);
 #pragma unroll 1
       for (int chunk = 0; chunk < MB * CN / 32; ++chunk) {
         uint32_t raw[32];
@@ -479,12 +484,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
         const int mb = chunk / (CN / 32);
         const int co = co_tile * (128 * MB) + mb * 128 + quarter * 32 + lane;
         const int ci = ci_tile * CN + (chunk - mb * (CN / 32)) * 32;
-        if (co < p.cout_pad && ci < p.cin_pad) {
-          float4* dst = reinterpret_cast<float4*>(p.dw + ((long long)co * taps + tap) * p.cin_pad + ci);
+        if (co < p.cout_valid && ci < p.cin_valid) {
+          float* row = p.dw + ((long long)co * taps + tap) * p.dw_ld + p.dw_ci_offset + ci;
+          if (vec_ok && ci + 32 <= p.cin_valid) {
+            float4* dst = reinterpret_cast<float4*>(row);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)  // 16-byte vector reductions (sm_90+): 8 instead of 32 atomics per row chunk
-            atomicAdd(dst + j, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                                           __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
+            for (int j = 0; j < 8; ++j)  // 16-byte vector reductions (sm_90+): 8 instead of 32 atomics per row chunk
+              atomicAdd(dst + j, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                             __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ci + j < p.cin_valid) atomicAdd(row + j, __uint_as_float(raw[j]));
+          }
         }
       }
     }
@@ -501,19 +513,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
 constexpr int PK_T = 32;
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S,
                                                           int ci_begin, int ci_count, __nv_bfloat16* __restrict__ dst,
-                                                          int cout_pad, int cin_pad, int mode) {
+                                                          int cout_pad, int cin_pad, int mode, int src_krsc) {
   extern __shared__ float tile[];  // [PK_T co][PK_T ci][taps] (+1 padding per co row)
   const int taps = R * S;
   const int ld = PK_T * taps + 1;
   const int co0 = blockIdx.y * PK_T, ci0 = blockIdx.x * PK_T;
-  // read: for each co a contiguous run of (PK_T ci x taps) floats
-  for (int i = threadIdx.x; i < PK_T * PK_T * taps; i += blockDim.x) {
-    const int co = i / (PK_T * taps), rem = i - co * (PK_T * taps);
-    const int ci = rem / taps;
-    float v = 0.f;
-    if (co0 + co < Cout && ci0 + ci < ci_count)
-      v = w[((long long)(co0 + co) * Cin + ci_begin + ci0) * taps + rem];
-    tile[co * ld + rem] = v;
+  if (!src_krsc) {
+    // OIHW source: for each co a contiguous run of (PK_T ci x taps) floats
+    for (int i = threadIdx.x; i < PK_T * PK_T * taps; i += blockDim.x) {
+      const int co = i / (PK_T * taps), rem = i - co * (PK_T * taps);
+      const int ci = rem / taps;
+      float v = 0.f;
+      if (co0 + co < Cout && ci0 + ci < ci_count)
+        v = w[((long long)(co0 + co) * Cin + ci_begin + ci0) * taps + rem];
+      tile[co * ld + rem] = v;
+    }
+  } else {
+    // KRSC (torch channels_last) source: for each (co, tap) a contiguous run of PK_T input channels
+    for (int i = threadIdx.x; i < PK_T * taps * PK_T; i += blockDim.x) {
+      const int ci = i % PK_T, tap = (i / PK_T) % taps, co = i / (PK_T * taps);
+      float v = 0.f;
+      if (co0 + co < Cout && ci0 + ci < ci_count)
+        v = w[((long long)(co0 + co) * taps + tap) * Cin + ci_begin + ci0 + ci];
+      tile[co * ld + ci * taps + tap] = v;
+    }
   }
   __syncthreads();
   if (mode == 0) {  // dst[co][tap][ci]
@@ -762,6 +785,14 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   if (ks > p.pblocks_total) ks = p.pblocks_total;
   p.k_splits = ks;
   p.dw = a->dw;
+  p.dw_ld = a->dw_ld > 0 ? a->dw_ld : a->cin_pad;
+  p.dw_ci_offset = a->dw_ci_offset;
+  p.cout_valid = a->cout_valid > 0 ? a->cout_valid : a->cout_pad;
+  p.cin_valid = a->cin_valid > 0 ? a->cin_valid : a->cin_pad;
+  ZS3_CHECK_ARG(p.cout_valid <= a->cout_pad && p.cin_valid <= a->cin_pad && p.dw_ci_offset >= 0 &&
+                    p.dw_ld >= p.dw_ci_offset + p.cin_valid,
+                "conv_wgrad: bad dw view (ld=%lld offset=%d cin_valid=%d cout_valid=%d)", p.dw_ld, p.dw_ci_offset,
+                p.cin_valid, p.cout_valid);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (MB == 2) {
     if (CN == 256) return launch_wgrad<256, 3, 2>(p, st);
@@ -778,12 +809,15 @@ extern "C" int zs3_pack_weight(const float* w_oihw, int Cout, int Cin, int R, in
   ZS3_CHECK_ARG(w_oihw && dst_bf16, "pack_weight: null pointer");
   ZS3_CHECK_ARG(Cout <= cout_pad && ci_count <= cin_pad && ci_begin >= 0 && ci_begin + ci_count <= Cin,
                 "pack_weight: bad channel ranges");
-  ZS3_CHECK_ARG(mode == 0 || mode == 1, "pack_weight: mode=%d", mode);
+  ZS3_CHECK_ARG(mode >= 0 && mode <= 3, "pack_weight: mode=%d", mode);
+  const int src_krsc = mode >> 1;
+  mode &= 1;
   ZS3_CHECK_ARG(R * S <= 9, "pack_weight: at most 9 taps (the 7x7 stem goes through its [Cout][147][1][1] view)");
   const size_t smem = (size_t)PK_T * (PK_T * R * S + 1) * sizeof(float);
   dim3 grid(ceil_div(cin_pad, PK_T), ceil_div(cout_pad, PK_T));
   pack_weight_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, Cout, Cin, R, S, ci_begin, ci_count, static_cast<__nv_bfloat16*>(dst_bf16), cout_pad, cin_pad, mode);
+      w_oihw, Cout, Cin, R, S, ci_begin, ci_count, static_cast<__nv_bfloat16*>(dst_bf16), cout_pad, cin_pad, mode,
+      src_krsc);
   ZS3_CHECK_LAUNCH("pack_weight");
   return ZS3_OK;
 }

@@ -25,27 +25,43 @@ static int ew_blocks(long long items, int threads, int cap = 148 * 16) {
 }
 
 // ------------------------------------------------------------------------------ stem im2col
-// cols[m][k], k = c*R*S + r*S + s (the OIHW flattening of the weight), zero padded to kpad columns.
-__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, int N, int C, int H,
-                                   int W, int R, int stride, int pad, int Ho, int Wo, int kpad) {
+// cols[m][k], k = c*R*R + r*R + s (the OIHW flattening of the weight), zero padded to kpad columns.
+// One CTA per (image, output row): the R input rows it needs are staged in shared memory (zero-padded borders),
+// then every thread owns one PAIR of k columns and walks along the output row: coalesced 4-byte stores.
+__global__ void __launch_bounds__(192) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols,
+                                                          int C, int H, int W, int R, int stride, int pad, int Ho,
+                                                          int Wo, int kpad, int krsc) {
+  extern __shared__ float rows[];  // [C][R][W + 2*pad]
+  const int Wp = W + 2 * pad;
+  const int p = blockIdx.x % Ho, n = blockIdx.x / Ho;
   const int K = C * R * R;
-  const long long total = (long long)N * Ho * Wo * kpad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % kpad);
-    const long long m = i / kpad;
-    float v = 0.f;
-    if (k < K) {
-      const int c = k / (R * R);
-      const int rs = k - c * R * R;
-      const int r = rs / R, s = rs - r * R;
-      const int q = (int)(m % Wo);
-      const int p = (int)((m / Wo) % Ho);
-      const int n = (int)(m / ((long long)Wo * Ho));
-      const int ih = p * stride - pad + r, iw = q * stride - pad + s;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((long long)n * C + c) * H + ih) * W + iw);
-    }
-    cols[i] = __float2bfloat16(v);
+  for (int i = threadIdx.x; i < C * R * Wp; i += blockDim.x) {
+    const int wv = i % Wp, r = (i / Wp) % R, c = i / (Wp * R);
+    const int ih = p * stride - pad + r, iw = wv - pad;
+    rows[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + (((long long)n * C + c) * H + ih) * W + iw) : 0.f;
+  }
+  __syncthreads();
+  const int pairs = kpad >> 1;                  // k pairs per pixel
+  const int ppi = blockDim.x / pairs;           // pixels per iteration
+  const int kp = threadIdx.x % pairs, ql = threadIdx.x / pairs;
+  int off[2];
+  bool live[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = 2 * kp + e;
+    live[e] = k < K;
+    // k = c*R*R + r*R + s (OIHW flattening) or (r*R + s)*C + c (KRSC / channels_last flattening)
+    const int c = krsc ? k % C : k / (R * R);
+    const int rs = krsc ? k / C : k - c * R * R;
+    const int r = rs / R, sft = rs - r * R;
+    off[e] = live[e] ? (c * R + r) * Wp + sft : 0;
+  }
+  if (ql >= ppi) return;
+  __nv_bfloat16* out = cols + ((long long)n * Ho + p) * Wo * kpad;
+  for (int q = ql; q < Wo; q += ppi) {
+    const float v0 = live[0] ? rows[off[0] + q * stride] : 0.f;
+    const float v1 = live[1] ? rows[off[1] + q * stride] : 0.f;
+    *reinterpret_cast<uint32_t*>(out + (long long)q * kpad + 2 * kp) = pack_bf16x2(v0, v1);
   }
 }
 
@@ -419,11 +435,13 @@ using namespace zs3;
 #define CBF(p) static_cast<const __nv_bfloat16*>(p)
 
 extern "C" int zs3_stem_im2col(const float* x, void* cols, int N, int C, int H, int W, int R, int stride, int pad,
-                               int Ho, int Wo, int kpad, void* stream) {
+                               int Ho, int Wo, int kpad, int krsc, void* stream) {
   ZS3_CHECK_ARG(x && cols && kpad >= C * R * R && kpad % 8 == 0, "stem_im2col: bad args");
-  const long long total = (long long)N * Ho * Wo * kpad;
-  stem_im2col_kernel<<<ew_blocks(total, 256, 148 * 32), 256, 0, ST(stream)>>>(x, BF(cols), N, C, H, W, R, stride, pad,
-                                                                              Ho, Wo, kpad);
+  ZS3_CHECK_ARG(kpad / 2 <= 192, "stem_im2col: kpad=%d too large", kpad);
+  const size_t smem = (size_t)C * R * (W + 2 * pad) * sizeof(float);
+  ZS3_CHECK_ARG(smem <= 200 * 1024, "stem_im2col: input rows do not fit in shared memory");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  stem_im2col_kernel<<<N * Ho, 192, smem, ST(stream)>>>(x, BF(cols), C, H, W, R, stride, pad, Ho, Wo, kpad, krsc);
   ZS3_CHECK_LAUNCH("stem_im2col");
   return ZS3_OK;
 }

@@ -46,13 +46,22 @@ def conv_out_size(h, k, stride, pad, dil):
     return (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
 
+def is_krsc(w):
+    """True if the 4-D weight is stored KRSC (torch channels_last), the layout the kernels pack from cheaply."""
+    return w.dim() == 4 and w.is_contiguous(memory_format=torch.channels_last)
+
+
 def pack_weight(w, cout_pad, cin_pad, ci_begin=0, ci_count=None, mode=0):
-    """OIHW fp32 -> packed bf16.  mode 0: [cout_pad][R*S][cin_pad]; mode 1 (dgrad): [cin_pad][R*S][cout_pad]
-    with spatially flipped taps."""
+    """fp32 conv weight [O,I,R,S] (OIHW-contiguous or channels_last) -> packed bf16.
+    mode 0: [cout_pad][R*S][cin_pad]; mode 1 (dgrad): [cin_pad][R*S][cout_pad] with spatially flipped taps."""
     cout, cin, r, s = w.shape
     if ci_count is None:
         ci_count = cin - ci_begin
-    w = w.detach().contiguous().float()
+    w = w.detach().float()
+    if is_krsc(w) and not (w.is_contiguous() and r * s > 1):
+        mode += 2  # KRSC source
+    else:
+        w = w.contiguous()
     shape = (cout_pad, r * s, cin_pad) if mode == 0 else (cin_pad, r * s, cout_pad)
     dst = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
     L.check(L.lib().zs3_pack_weight(L.ptr(w), cout, cin, r, s, ci_begin, ci_count, L.ptr(dst), cout_pad, cin_pad, mode,
@@ -117,8 +126,9 @@ def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=Fal
     return out
 
 
-def conv_wgrad(x, dy, R, S, stride, pad, dil, cin_pad, cout_pad, dw=None, k_splits=0, flops=0.0):
-    """dw[cout_pad][R*S][cin_pad] fp32 (+)= sum_p dy[p] (x) x[p@tap].  Returns dw."""
+def conv_wgrad(x, dy, R, S, stride, pad, dil, cin_pad, cout_pad, dw=None, k_splits=0, flops=0.0, dw_view=None):
+    """dw[cout_pad][R*S][cin_pad] fp32 (+)= sum_p dy[p] (x) x[p@tap].  Returns dw.
+    dw_view = (ld, ci_offset, cout_valid, cin_valid): accumulate straight into a KRSC gradient tensor `dw`."""
     _chk_act(x, "conv_wgrad x")
     _chk_act(dy, "conv_wgrad dy")
     n, h, w_, _ = x.shape
@@ -136,6 +146,8 @@ def conv_wgrad(x, dy, R, S, stride, pad, dil, cin_pad, cout_pad, dw=None, k_spli
     a.cout_pad = cout_pad
     a.dw = dw.data_ptr()
     a.k_splits = k_splits
+    if dw_view is not None:
+        a.dw_ld, a.dw_ci_offset, a.cout_valid, a.cin_valid = dw_view
     tag = f"N{n} {h}x{w_}->{ho}x{wo} k{R} s{stride} d{dil} cin{cin_pad} cout{cout_pad}" if PROFILE is not None else ""
     with _Timed("conv_wgrad", flops, tag):
         L.check(L.lib().zs3_conv_wgrad(C.byref(a), L.stream_ptr()), "zs3_conv_wgrad")
@@ -269,13 +281,14 @@ def im2col_probe(x, pad, upper, stride, cpp, ppc, c, w, h, n, off_w, off_h):
     return out
 
 
-def stem_im2col(x, R, stride, pad, ho, wo, kpad):
-    """fp32 NCHW image -> bf16 im2col matrix viewed as NHWC [N, ho, wo, kpad] (k = c*R*R + r*R + s)."""
+def stem_im2col(x, R, stride, pad, ho, wo, kpad, krsc=False):
+    """fp32 NCHW image -> bf16 im2col matrix viewed as NHWC [N, ho, wo, kpad]
+    (k = c*R*R + r*R + s, or (r*R + s)*C + c with krsc=True)."""
     n, c, h, w = x.shape
     x = x.contiguous().float()
     cols = torch.empty((n, ho, wo, kpad), dtype=torch.bfloat16, device=x.device)
-    L.check(L.lib().zs3_stem_im2col(L.ptr(x), L.ptr(cols), n, c, h, w, R, stride, pad, ho, wo, kpad, L.stream_ptr()),
-            "zs3_stem_im2col")
+    L.check(L.lib().zs3_stem_im2col(L.ptr(x), L.ptr(cols), n, c, h, w, R, stride, pad, ho, wo, kpad, int(krsc),
+                                    L.stream_ptr()), "zs3_stem_im2col")
     return cols
 
 
