@@ -159,3 +159,32 @@ def test_pack_roundtrip_and_layout():
     xh = K.nchw_to_nhwc(x, 64)
     assert torch.equal(xh[..., :5].float(), x.to(torch.bfloat16).float().permute(0, 2, 3, 1))
     assert torch.equal(K.nhwc_to_nchw(xh, 5), x.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("case", [(2, 33, 33, 64, 128, 3, 1, 1, 1), (3, 20, 20, 48, 21, 3, 1, 1, 1),
+                                  (2, 17, 17, 256, 256, 1, 1, 0, 1)])
+def test_wgrad_direct_into_krsc_grad_and_krsc_pack(case):
+    """parameters stored KRSC (torch channels_last): packing reads them as is, wgrad accumulates into .grad in place"""
+    from zs3_b200 import kernels as K
+    N, H, W, Cin, Cout, R, stride, pad, dil = case
+    x, w = _mk(N, H, W, Cin, Cout, R)
+    w_cl = w.contiguous(memory_format=torch.channels_last)
+    cin_p, cout_p = K.cpad(Cin), K.cpad(Cout)
+    assert torch.equal(K.pack_weight(w_cl, cout_p, cin_p), K.pack_weight(w, cout_p, cin_p))
+    assert torch.equal(K.pack_weight(w_cl, cout_p, cin_p, mode=1), K.pack_weight(w, cout_p, cin_p, mode=1))
+    w.requires_grad_(True)
+    y = F.conv2d(x, w, stride=stride, padding=pad, dilation=dil)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16).float().cuda()
+    (dw_ref,) = torch.autograd.grad(y, w, dy)
+    # two K-segments accumulate into the same KRSC gradient tensor, twice (gradient accumulation semantics)
+    g = torch.zeros_like(w_cl)
+    half = (Cin // 2) // 8 * 8
+    xh = K.nchw_to_nhwc(x, cin_p)
+    xa, xb = K.nchw_to_nhwc(x[:, :half], K.cpad(half)), K.nchw_to_nhwc(x[:, half:], K.cpad(Cin - half))
+    dyh = K.nchw_to_nhwc(dy, cout_p)
+    for _ in range(2):
+        K.conv_wgrad(xa, dyh, R, R, stride, pad, dil, K.cpad(half), cout_p, dw=g, dw_view=(Cin, 0, Cout, half))
+        K.conv_wgrad(xb, dyh, R, R, stride, pad, dil, K.cpad(Cin - half), cout_p, dw=g,
+                     dw_view=(Cin, half, Cout, Cin - half))
+    assert g.is_contiguous(memory_format=torch.channels_last)
+    assert rel_l2(g, 2 * dw_ref) < 5e-5

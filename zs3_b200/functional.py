@@ -87,6 +87,30 @@ def _packed_weight(conv, mode, ci_begin, ci_count, cin_pad, cout_pad):
     return ent[1]
 
 
+def to_krsc_(module):
+    """Store every conv weight of `module` in KRSC order (torch channels_last): shapes, names and values are
+    unchanged (state_dict compatible), but the kernels' packed bf16 copy becomes a plain cast and the weight
+    gradient kernel can accumulate straight into `.grad`."""
+    for m in module.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+            if m.weight.grad is not None:
+                m.weight.grad = m.weight.grad.contiguous(memory_format=torch.channels_last)
+    return module
+
+
+def _direct_grad_buffer(w):
+    """fp32 KRSC gradient tensor of parameter `w` to accumulate into in place, or None if the layout does not allow it"""
+    if not (K.is_krsc(w) and w.dtype == torch.float32):
+        return None
+    if w.grad is None:
+        w.grad = torch.zeros_like(w)  # preserve_format keeps the KRSC strides
+    g = w.grad
+    if K.is_krsc(g) and g.dtype == torch.float32 and g.stride() == w.stride():
+        return g
+    return None
+
+
 def _bn_forward_coeffs(bn, stats, count, cs):
     """(scale, shift, mean, invstd) for this BN: batch statistics in training mode (updates the running
     buffers like F.batch_norm), running statistics otherwise."""
@@ -187,7 +211,10 @@ class ConvBnAct(torch.autograd.Function):
             dy_z = torch.zeros((n, scatter[1], scatter[2], cout_p), dtype=torch.bfloat16, device=dev)
             dy_z[:, ::stride, ::stride] = dy
         dxs = []
-        dweight = torch.empty_like(conv.weight) if need_w else None
+        # weight gradient: accumulated in place into conv.weight.grad when the parameter is stored KRSC (then
+        # nothing is returned to autograd for it), else produced as a fresh OIHW tensor
+        gbuf = _direct_grad_buffer(conv.weight) if need_w else None
+        dweight = torch.empty_like(conv.weight) if (need_w and gbuf is None) else None
         for i, x in enumerate(xs):
             ci0, c_real, cin_p = ctx.ranges[i]
             if ctx.needs_input_grad[9 + i]:
@@ -207,7 +234,10 @@ class ConvBnAct(torch.autograd.Function):
                 dxs.append(dx)
             else:
                 dxs.append(None)
-            if need_w:
+            if need_w and gbuf is not None:
+                K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, dw=gbuf, flops=ctx.flops_per_cin * c_real,
+                             dw_view=(conv.in_channels, ci0, cout, c_real))
+            elif need_w:
                 dw = K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, flops=ctx.flops_per_cin * c_real)
                 K.unpack_wgrad(dw, dweight, ci0, c_real, accumulate=False)
         return (None, None, None, None, None, dweight, dgamma, dbeta, dres, *dxs)
@@ -272,9 +302,14 @@ class ConvBias(torch.autograd.Function):
             wt = _packed_weight(conv, 1, 0, cin, cin_p, cout_p)
             dx = K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, flops=ctx.flops, kind="conv_dgrad")
         if ctx.needs_input_grad[1]:
-            dw = K.conv_wgrad(x, dy, 1, 1, 1, 0, 1, cin_p, cout_p, flops=ctx.flops)
-            dw_oihw = torch.empty_like(conv.weight)
-            K.unpack_wgrad(dw, dw_oihw)
+            gbuf = _direct_grad_buffer(conv.weight)
+            if gbuf is not None:
+                K.conv_wgrad(x, dy, 1, 1, 1, 0, 1, cin_p, cout_p, dw=gbuf, flops=ctx.flops,
+                             dw_view=(cin, 0, cout, cin))
+            else:
+                dw = K.conv_wgrad(x, dy, 1, 1, 1, 0, 1, cin_p, cout_p, flops=ctx.flops)
+                dw_oihw = torch.empty_like(conv.weight)
+                K.unpack_wgrad(dw, dw_oihw)
         if conv.bias is not None and ctx.needs_input_grad[2]:
             dbias = K.channel_sums(dy)[:cout].float()
         return None, dw_oihw, dbias, dx
@@ -293,8 +328,9 @@ class Stem(torch.autograd.Function):
         ho, wo = K.conv_out_size(h, R, stride, pad, 1), K.conv_out_size(w, R, stride, pad, 1)
         kreal = c * R * R
         kpad = K.cpad(kreal)
-        cols = K.stem_im2col(x, R, stride, pad, ho, wo, kpad)          # [n, ho, wo, kpad]
-        wp = _packed_weight_2d(conv, kreal, kpad, cout_p)
+        krsc = K.is_krsc(conv.weight) and not conv.weight.is_contiguous()
+        cols = K.stem_im2col(x, R, stride, pad, ho, wo, kpad, krsc=krsc)          # [n, ho, wo, kpad]
+        wp = _packed_weight_2d(conv, kreal, kpad, cout_p, krsc)
         training = bn.training
         stats = None
         if training:
@@ -306,7 +342,7 @@ class Stem(torch.autograd.Function):
         a = K.bn_apply(y, scale, shift, True)
         k, ps, pp = pool.kernel_size, pool.stride, pool.padding
         out, arg = K.maxpool_fwd(a, k, ps, pp)
-        ctx.conv, ctx.bn, ctx.training = conv, bn, training
+        ctx.conv, ctx.bn, ctx.training, ctx.krsc = conv, bn, training, krsc
         ctx.pool = (k, ps, pp)
         ctx.dims = (kreal, kpad, cout, cout_p)
         ctx.flops = fl
@@ -326,20 +362,32 @@ class Stem(torch.autograd.Function):
         sc = _scratch64(dev, "bwd")
         dy = K.bn_backward(da, a, y, mean, invstd, scale, True, training=ctx.training, dgamma=dgamma, dbeta=dbeta,
                            scratch=sc[:2 * cout_p].view(2, cout_p))
-        dw = K.conv_wgrad(cols, dy, 1, 1, 1, 0, 1, kpad, cout_p, flops=ctx.flops)
-        dweight = torch.empty_like(conv.weight)
-        K.unpack_wgrad(dw, dweight.view(cout, kreal, 1, 1))
+        gbuf = _direct_grad_buffer(conv.weight) if ctx.krsc else None
+        if gbuf is not None:
+            # KRSC memory of the [cout,3,7,7] gradient is exactly the [cout][147] GEMM weight gradient
+            K.conv_wgrad(cols, dy, 1, 1, 1, 0, 1, kpad, cout_p, dw=gbuf, flops=ctx.flops, dw_view=(kreal, 0, cout, kreal))
+            dweight = None
+        else:
+            dw = K.conv_wgrad(cols, dy, 1, 1, 1, 0, 1, kpad, cout_p, flops=ctx.flops)
+            flat = torch.empty((cout, kreal, 1, 1), dtype=torch.float32, device=dev)
+            K.unpack_wgrad(dw, flat)
+            if ctx.krsc:  # k ran over (r, s, c)
+                dweight = flat.view(cout, conv.kernel_size[0], conv.kernel_size[1], -1).permute(0, 3, 1, 2)
+            else:
+                dweight = flat.view_as(conv.weight) if conv.weight.is_contiguous() else flat.reshape(conv.weight.shape)
         return None, None, None, dweight, dgamma, dbeta, None  # the image needs no gradient (stem dgrad is never used)
 
 
-def _packed_weight_2d(conv, kreal, kpad, cout_p):
+def _packed_weight_2d(conv, kreal, kpad, cout_p, krsc=False):
     w = conv.weight
     cache = conv.__dict__.setdefault("_zs3_pack_cache", {})
-    key = ("stem", kpad, cout_p)
+    key = ("stem", kpad, cout_p, krsc)
     ent = cache.get(key)
     ver = (w._version, w.data_ptr(), _WEIGHT_EPOCH[0])
     if ent is None or ent[0] != ver:
-        ent = (ver, K.pack_weight(w.detach().reshape(w.shape[0], kreal, 1, 1), cout_p, kpad))
+        w2 = w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], kreal, 1, 1) if krsc else \
+            w.detach().reshape(w.shape[0], kreal, 1, 1)
+        ent = (ver, K.pack_weight(w2, cout_p, kpad))
         cache[key] = ent
     return ent[1]
 

@@ -23,6 +23,9 @@ class DeepLab(nn.Module):
         self.aspp = build_aspp(output_stride, BatchNorm, global_avg_pool_bn)
         self.decoder = build_decoder(num_classes, BatchNorm)
         self.num_classes = num_classes
+        # conv parameters live in HBM in KRSC order (torch channels_last): same names/shapes/values as the
+        # reference's OIHW tensors, but directly consumable by the packing and weight-gradient kernels
+        ZF.to_krsc_(self)
         if freeze_bn:
             self.freeze_bn()
 

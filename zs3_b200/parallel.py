@@ -58,9 +58,11 @@ class FlatParams:
             start = off
             for p in g:
                 n = p.numel()
-                self.flat[off:off + n].copy_(p.detach().reshape(-1))
-                p.data = self.flat[off:off + n].view_as(p)
-                p.grad = self.grad[off:off + n].view_as(p)
+                # keep each parameter's memory layout (conv weights are KRSC / channels_last): dense strided views
+                view = torch.as_strided(self.flat, p.shape, p.stride(), off)
+                view.copy_(p.detach())
+                p.data = view
+                p.grad = torch.as_strided(self.grad, p.shape, p.stride(), off)
                 off += n
             self.group_ranges.append((start, off))
         self.params = params
