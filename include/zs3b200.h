@@ -295,6 +295,30 @@ int zs3_mmd_bwd(const float* gen, const float* real, int M, int N, int D, const 
 /* torch.cat((embd, noise), 1) (gmmn.py:44) */
 int zs3_concat2(const float* a, int c1, const float* b, int c2, float* y, long long rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp32-grade parity mode (forward only; csrc/parity.cu).  An fp32 convolution is emulated on the bf16 tensor
+ * cores by splitting both operands into three bf16 pieces and reducing the six significant cross products as
+ * six K-segments of one fp32 TMEM accumulator (zs3_conv_fprop).  Activations stay fp32 NHWC between layers;
+ * these are the fp32-I/O versions of the glue kernels plus the splitters.  Same reference call sites as their
+ * bf16 counterparts above.
+ * ---------------------------------------------------------------------------------------------- */
+int zs3_split3_f32(const float* x, void* hi, void* mid, void* lo, long long n, void* stream);
+/* component 0/1/2 (hi/mid/lo) of an fp32 weight in the packed fprop layout [cout_pad][R*S][cin_pad] */
+int zs3_pack_weight_component(const float* w, int Cout, int Cin, int R, int S, int ci_begin, int ci_count, void* dst,
+                              int cout_pad, int cin_pad, int src_krsc, int component, void* stream);
+int zs3_bn_apply_f32(const float* y, int y_cs, const float* residual, int res_cs, float* out, int out_cs,
+                     const float* scale, const float* shift, long long M, int C, int relu, void* stream);
+int zs3_maxpool_f32(const float* x, float* y, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
+                    void* stream);
+/* bilinear align_corners; to_nchw = 1 writes NCHW [N][C_out][Ho][Wo] (the final logits), else NHWC stride Cs */
+int zs3_bilinear_f32(const float* x, float* y, int N, int Hi, int Wi, int Ho, int Wo, int Cs, int C_out, int to_nchw,
+                     void* stream);
+int zs3_spatial_sum_f32(const float* x, float* y, int N, int HW, int C, float scale, void* stream);
+int zs3_spatial_broadcast_f32(const float* x, float* y, int N, int HW, int C, void* stream);
+int zs3_nchw_to_nhwc_f32(const float* src, float* dst, int N, int C, long long HW, int cs, void* stream);
+int zs3_stem_im2col_f32(const float* x, float* cols, int N, int C, int H, int W, int R, int stride, int pad, int Ho,
+                        int Wo, int kpad, int krsc, void* stream);
+
 /* debug: one im2col TMA load dumped raw (tests/test_tma_probe.py) */
 int zs3_debug_im2col_probe(const void* x, int N, int H, int W, int C, int pad, int upper, int stride, int cpp, int ppc,
                            int c, int w, int h, int n, int off_w, int off_h, void* out, void* stream);

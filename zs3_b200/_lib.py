@@ -164,6 +164,15 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_mmd_fwd": [vp, vp, i, i, i, C.POINTER(C.c_float), i, vp, vp, vp, vp],
         "zs3_mmd_bwd": [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp],
         "zs3_concat2": [vp, i, vp, i, vp, ll, vp],
+        "zs3_split3_f32": [vp, vp, vp, vp, ll, vp],
+        "zs3_pack_weight_component": [vp, i, i, i, i, i, i, vp, i, i, i, i, vp],
+        "zs3_bn_apply_f32": [vp, i, vp, i, vp, i, vp, vp, ll, i, i, vp],
+        "zs3_maxpool_f32": [vp, vp, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_bilinear_f32": [vp, vp, i, i, i, i, i, i, i, i, vp],
+        "zs3_spatial_sum_f32": [vp, vp, i, i, i, f, vp],
+        "zs3_spatial_broadcast_f32": [vp, vp, i, i, i, vp],
+        "zs3_nchw_to_nhwc_f32": [vp, vp, i, i, ll, i, vp],
+        "zs3_stem_im2col_f32": [vp, vp, i, i, i, i, i, i, i, i, i, i, i, vp],
     }
 
 
