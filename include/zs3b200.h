@@ -171,9 +171,10 @@ typedef struct {
   const float* mean;    /* [C] batch (training) or running (frozen) mean */
   const float* invstd;  /* [C] */
   const float* scale;   /* [C] gamma * invstd */
+  const float* shift;   /* [C] beta - mean*scale; only read when relu == 2 */
   long long M;
   int C;                /* multiple of 8 */
-  int relu;
+  int relu;             /* 0: none; 1: mask = out > 0 (residual / dropout layers); 2: mask = scale*y + shift > 0 */
   float grad_scale;     /* 1/(1-p) when the forward applied dropout after the ReLU, else 1 */
   int training;         /* 1: batch-statistics backward; 0: frozen statistics (dy = scale * dz) */
   double* sum_dz;       /* [C] accumulators: reduce phase adds, apply phase reads */

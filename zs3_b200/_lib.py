@@ -110,7 +110,7 @@ class BnBwdArgs(C.Structure):
         ("dout", C.c_void_p), ("dout_cstride", C.c_int),
         ("out", C.c_void_p), ("out_cstride", C.c_int),
         ("y", C.c_void_p), ("y_cstride", C.c_int),
-        ("mean", C.c_void_p), ("invstd", C.c_void_p), ("scale", C.c_void_p),
+        ("mean", C.c_void_p), ("invstd", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("M", C.c_longlong), ("C", C.c_int),
         ("relu", C.c_int), ("grad_scale", C.c_float), ("training", C.c_int),
         ("sum_dz", C.c_void_p), ("sum_dzx", C.c_void_p),

@@ -155,7 +155,7 @@ struct BwdP {
   const __nv_bfloat16* dout; long long dout_cs;
   const __nv_bfloat16* out; long long out_cs;
   const __nv_bfloat16* y; long long y_cs;
-  const float* mean; const float* invstd; const float* scale;
+  const float* mean; const float* invstd; const float* scale; const float* shift;
   long long M; int C; int relu; float grad_scale; int training;
   double* sum_dz; double* sum_dzx;
   __nv_bfloat16* dy; long long dy_cs;
@@ -165,10 +165,18 @@ struct BwdP {
   int rows_per_block;  // reduce kernel: pixel rows handled concurrently by one CTA
 };
 
-// dz for 8 channels of pixel m
-__device__ __forceinline__ void load_dz(const BwdP& p, long long m, int c, float (&dz)[8]) {
+// dz for 8 channels of pixel m.  relu == 1: mask from the saved forward output (needed when a residual or a dropout
+// mask went into it); relu == 2: mask recomputed as scale*y + shift > 0 from the y values the caller already holds,
+// which saves reading `out` (2 of ~10 bytes per element in each backward pass).
+__device__ __forceinline__ void load_dz(const BwdP& p, long long m, int c, const float (&yv)[8], float (&dz)[8]) {
   unpack8(*reinterpret_cast<const uint4*>(p.dout + m * p.dout_cs + c), dz);
-  if (p.relu) {
+  if (p.relu == 2) {
+    float sc[8], sh[8];
+    load8f(p.scale + c, sc);
+    load8f(p.shift + c, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = fmaf(yv[j], sc[j], sh[j]) > 0.f ? dz[j] * p.grad_scale : 0.f;
+  } else if (p.relu) {
     float o[8];
     unpack8(*reinterpret_cast<const uint4*>(p.out + m * p.out_cs + c), o);
 #pragma unroll
@@ -196,8 +204,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdP p) {
     for (long long m = (long long)blockIdx.x * p.rows_per_block + rl; m < p.M;
          m += (long long)gridDim.x * p.rows_per_block) {
       float dz[8], yv[8];
-      load_dz(p, m, c, dz);
       unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
+      load_dz(p, m, c, yv, dz);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a1[j] += dz[j];
@@ -261,8 +269,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
        v += (long long)gridDim.x * blockDim.x) {
     const long long m = v / vpc;
     const int c = (int)(v - m * vpc) << 3;
-    float dz[8];
-    load_dz(p, m, c, dz);
+    float dz[8], yv[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
+    load_dz(p, m, c, yv, dz);
     if (p.dres) {
       uint4* dst = reinterpret_cast<uint4*>(p.dres + m * p.dres_cs + c);
       if (p.dres_acc) {
@@ -275,8 +284,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
         *dst = pack8(dz);
       }
     }
-    float g[8], yv[8];
-    unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
+    float g[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = fmaf(cA[c + j], dz[j], fmaf(cB[c + j], yv[j], cC[c + j]));
     long long pix = m;
@@ -460,11 +468,12 @@ static int fill_bwd(const zs3_bn_bwd_args* a, BwdP& p, const char* who) {
                 "%s: null pointer", who);
   ZS3_CHECK_ARG(a->C > 0 && a->C % 8 == 0 && a->C <= 2048 && a->dout_cstride % 8 == 0 && a->y_cstride % 8 == 0,
                 "%s: C=%d must be a multiple of 8 and <= 2048", who, a->C);
-  ZS3_CHECK_ARG(!a->relu || (a->out && a->out_cstride % 8 == 0), "%s: relu needs the forward output", who);
+  ZS3_CHECK_ARG(a->relu != 1 || (a->out && a->out_cstride % 8 == 0), "%s: relu=1 needs the forward output", who);
+  ZS3_CHECK_ARG(a->relu != 2 || a->shift != nullptr, "%s: relu=2 (mask recomputed from y) needs shift", who);
   p.dout = static_cast<const __nv_bfloat16*>(a->dout); p.dout_cs = a->dout_cstride;
   p.out = static_cast<const __nv_bfloat16*>(a->out); p.out_cs = a->out_cstride;
   p.y = static_cast<const __nv_bfloat16*>(a->y); p.y_cs = a->y_cstride;
-  p.mean = a->mean; p.invstd = a->invstd; p.scale = a->scale;
+  p.mean = a->mean; p.invstd = a->invstd; p.scale = a->scale; p.shift = a->shift;
   p.M = a->M; p.C = a->C; p.relu = a->relu; p.grad_scale = a->grad_scale; p.training = a->training;
   p.sum_dz = a->sum_dz; p.sum_dzx = a->sum_dzx;
   p.dy = static_cast<__nv_bfloat16*>(a->dy); p.dy_cs = a->dy_cstride;

@@ -673,12 +673,14 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   FpropParams p;
   memset(&p, 0, sizeof(p));
   const int BN = a->cout_pad >= 256 ? 256 : (a->cout_pad >= 128 ? 128 : 64);
-  // cluster size: CTAs of a cluster share (multicast) the weight tile.  ZS3_CLUSTER overrides (1, 2 or 4).
+  // cluster size: CTAs of a cluster share (multicast) the weight tile.  Measured on B200 (profiles/r01_cluster_*):
+  // multicast at cluster sizes <= 4 does not reduce L2->SM traffic and the lock step costs 8-60 %, so the default is
+  // 1; ZS3_CLUSTER=2|4 keeps the path testable.
   static int cluster_pref = -1;
   if (cluster_pref < 0) {
     const char* env = getenv("ZS3_CLUSTER");
-    cluster_pref = env ? atoi(env) : 2;
-    if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 2;
+    cluster_pref = env ? atoi(env) : 1;
+    if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 1;
   }
   const int m_tiles_total = (int)ceil_div_ll(M, BLOCK_M);
   int csize = cluster_pref;

@@ -177,12 +177,14 @@ class ConvBnAct(torch.autograd.Function):
         ctx.has_res = residual is not None
         ctx.geom = (R, S, stride, pad, dil, cout, cout_p)
         ctx.flops_per_cin = macs_per_cin
-        ctx.save_for_backward(y, out, mean, invstd, scale, *xs)
+        # plain conv->BN->ReLU: the backward recomputes the ReLU mask from y, `out` need not be re-read
+        ctx.mask_from_y = bool(relu) and residual is None and p == 0.0
+        ctx.save_for_backward(y, out, mean, invstd, scale, shift, *xs)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        y, out, mean, invstd, scale, *xs = ctx.saved_tensors
+        y, out, mean, invstd, scale, shift, *xs = ctx.saved_tensors
         conv, bn = ctx.conv, ctx.bn
         R, S, stride, pad, dil, cout, cout_p = ctx.geom
         dout = dout.contiguous()
@@ -204,7 +206,7 @@ class ConvBnAct(torch.autograd.Function):
         dy_dense_needed = need_w and zero_insert
         dy = K.bn_backward(dout, out, y, mean, invstd, scale, ctx.relu, grad_scale=1.0 / (1.0 - ctx.p),
                            training=ctx.training, dres=dres, dgamma=dgamma, dbeta=dbeta, scratch=scratch,
-                           scatter=None if dy_dense_needed else scatter)
+                           scatter=None if dy_dense_needed else scatter, shift=shift if ctx.mask_from_y else None)
         dy_z = dy
         if dy_dense_needed:
             # both layouts are needed: dense for wgrad, zero-inserted for dgrad

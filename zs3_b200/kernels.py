@@ -62,7 +62,7 @@ def pack_weight(w, cout_pad, cin_pad, ci_begin=0, ci_count=None, mode=0):
         mode += 2  # KRSC source
     else:
         w = w.contiguous()
-    shape = (cout_pad, r * s, cin_pad) if mode == 0 else (cin_pad, r * s, cout_pad)
+    shape = (cout_pad, r * s, cin_pad) if (mode & 1) == 0 else (cin_pad, r * s, cout_pad)
     dst = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
     L.check(L.lib().zs3_pack_weight(L.ptr(w), cout, cin, r, s, ci_begin, ci_count, L.ptr(dst), cout_pad, cin_pad, mode,
                                     L.stream_ptr()), "zs3_pack_weight")
@@ -235,8 +235,9 @@ def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0,
 
 def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, training=True, dres=None,
                 dres_accumulate=False, dgamma=None, dbeta=None, param_accumulate=False, scatter=None, dy=None,
-                scratch=None):
-    """Two-phase BatchNorm(+ReLU/+Dropout) backward.  Returns dy (bf16, same layout as y unless scatter)."""
+                scratch=None, shift=None):
+    """Two-phase BatchNorm(+ReLU/+Dropout) backward.  Returns dy (bf16, same layout as y unless scatter).
+    With `shift` given (plain conv->BN->ReLU layers) the ReLU mask is recomputed from y instead of read from `out`."""
     _chk_act(dout, "bn_backward dout")
     n, h, w, cs = y.shape
     if scratch is None:
@@ -245,12 +246,17 @@ def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, trainin
         scratch.zero_()
     a = L.BnBwdArgs()
     a.dout, a.dout_cstride = dout.data_ptr(), dout.shape[3]
-    if relu:
+    relu_mode = 0
+    if relu and shift is not None:
+        relu_mode = 2
+        a.shift = shift.data_ptr()
+    elif relu:
+        relu_mode = 1
         a.out, a.out_cstride = out.data_ptr(), out.shape[3]
     a.y, a.y_cstride = y.data_ptr(), cs
     a.mean, a.invstd, a.scale = mean.data_ptr(), invstd.data_ptr(), scale.data_ptr()
     a.M, a.C = n * h * w, cs
-    a.relu, a.grad_scale, a.training = int(relu), float(grad_scale), int(training)
+    a.relu, a.grad_scale, a.training = relu_mode, float(grad_scale), int(training)
     a.sum_dz, a.sum_dzx = scratch[0].data_ptr(), scratch[1].data_ptr()
     if scatter is not None:
         sp, hy, wy = scatter
