@@ -1,0 +1,63 @@
+"""CPU oracle of one ZS3Net step-2 iteration -- TEST INFRASTRUCTURE (see oracle/zs3_oracle.py's header).
+
+Restates zs3/train_pascal_GMMN.py:152-268 with the functional oracle: given the decoder features (real features),
+labels, per-pixel embeddings and injected randomness, runs the sequential per-(image, class) generator updates
+(Adam), assembles the classifier input and performs the pred_conv SGD update.  Returns the losses and the updated
+parameter dictionaries.
+"""
+import torch
+import torch.nn.functional as F
+
+import zs3_oracle as O
+
+
+def step2(st_deeplab, st_gen, real_features, target, embedding, input_size, seen, unseen, noise_fn, index_fn, mask_fn,
+          class_weight, lr=0.07, lr_generator=2e-4, momentum=0.9, weight_decay=5e-4, real_seen_features=True,
+          feature_dim=256, embed_dim=300):
+    gen = {k: v.clone().requires_grad_(True) for k, v in st_gen.items()}
+    adam = {k: [torch.zeros_like(v), torch.zeros_like(v)] for k, v in gen.items()}
+    adam_step = 0
+    fh, fw = real_features.shape[2], real_features.shape[3]
+    fake_features = torch.zeros_like(real_features)
+    g_losses, generator_loss_batch = [], 0.0
+    for i in range(real_features.shape[0]):
+        rf = real_features[i].permute(1, 2, 0).reshape(-1, feature_dim)                  # :170-174
+        tg = F.interpolate(target[i][None, None], size=(fh, fw), mode="nearest").view(-1)  # :175-179
+        emb = F.interpolate(embedding[i][None], size=(fh, fw), mode="nearest")[0].permute(1, 2, 0).reshape(-1, embed_dim)
+        fake_i = torch.zeros_like(rf)
+        uniq = torch.unique(tg)
+        has_unseen = any(int(u) in unseen for u in uniq)
+        sample_loss = 0.0
+        for c in uniq:
+            if c == 255:
+                continue
+            sel = tg == c
+            real_c, emb_c = rf[sel], emb[sel]
+            z = noise_fn(emb_c.shape[0])
+            mask = mask_fn(emb_c.shape[0])
+            fake_c = O.gmmn_forward(gen, emb_c, z.float(), training=True, keep_mask=mask)
+            if int(c) in seen and not has_unseen:
+                ridx = index_fn(fake_c.shape[0])
+                loss = O.moment_loss(fake_c[ridx], real_c[ridx])
+                g_losses.append(loss.item())
+                sample_loss += loss.item()
+                grads = torch.autograd.grad(loss, list(gen.values()))
+                adam_step += 1
+                with torch.no_grad():
+                    for (k, p), g in zip(gen.items(), grads):
+                        O.adam_step(p, g, adam[k][0], adam[k][1], adam_step, lr=lr_generator)
+            fake_i[sel] = fake_c.detach()
+        generator_loss_batch += sample_loss / len(uniq)
+        src = rf if (real_seen_features and not has_unseen) else fake_i
+        fake_features[i] = src.view(fh, fw, feature_dim).permute(2, 0, 1)
+    w = st_deeplab["decoder.pred_conv.weight"].clone().requires_grad_(True)
+    b = st_deeplab["decoder.pred_conv.bias"].clone().requires_grad_(True)
+    out = O.class_prediction({"decoder.pred_conv.weight": w, "decoder.pred_conv.bias": b}, fake_features, input_size)
+    loss = O.cross_entropy(out, target, weight=class_weight)
+    gw, gb = torch.autograd.grad(loss, [w, b])
+    with torch.no_grad():
+        bufs = [None, None]
+        O.sgd_step([w, b], [gw, gb], bufs, lr, momentum, weight_decay)
+    return {"loss": loss.item(), "g_losses": g_losses, "generator_loss_batch": generator_loss_batch,
+            "pred_conv.weight": w.detach(), "pred_conv.bias": b.detach(),
+            "generator": {k: v.detach() for k, v in gen.items()}, "fake_features": fake_features}
