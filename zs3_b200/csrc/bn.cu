@@ -101,6 +101,12 @@ __global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, con
 }
 
 // ---------------------------------------------------------------------------------- apply
+// Streaming pattern shared by the kernels below: a thread owns ONE 8-channel slice (16 bytes of every pixel row) for
+// the whole kernel, so the per-channel coefficients live in registers and there is no index arithmetic in the loop;
+// rows are visited with a grid stride and UNROLL rows are in flight per thread (all loads issued before any use) to
+// keep enough bytes outstanding for HBM.  A 256-thread CTA covers rows_per_block = 256 / (C/8) rows at a time.
+constexpr int UNROLL = 4;
+
 struct ApplyP {
   const __nv_bfloat16* y; long long y_cs;
   const __nv_bfloat16* res; long long res_cs;
@@ -108,45 +114,67 @@ struct ApplyP {
   const float* scale; const float* shift;
   long long M; int C; int relu; int drop_mode; uint32_t thresh16; float keep_scale;
   uint64_t seed, offset; const unsigned char* mask; const unsigned long long* offset_dev;
+  int rows_per_block;
 };
 
+__device__ __forceinline__ void apply_one(const ApplyP& p, long long m, int c, const float (&sc)[8],
+                                          const float (&sh)[8], uint64_t rng_offset, const uint4& yraw,
+                                          const uint4& rraw) {
+  float f[8];
+  unpack8(yraw, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+  if (p.res) {
+    float r[8];
+    unpack8(rraw, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += r[j];
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (p.drop_mode == 1) {
+    const uint32_t keep = dropout_keep8(p.seed, rng_offset, (uint64_t)(m * p.C + c), p.thresh16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1) ? f[j] * p.keep_scale : 0.f;
+  } else if (p.drop_mode == 2) {
+    const uint2 mk = *reinterpret_cast<const uint2*>(p.mask + m * p.C + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t b = ((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xFF;
+      f[j] = b ? f[j] * p.keep_scale : 0.f;
+    }
+  }
+  *reinterpret_cast<uint4*>(p.out + m * p.out_cs + c) = pack8(f);
+}
+
 __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyP p) {
-  const int vpc = p.C >> 3;  // 16-byte vectors per pixel
+  const int vpc = p.C >> 3;
+  const int c = (threadIdx.x % vpc) << 3;
+  const int rl = threadIdx.x / vpc;
+  if (rl >= p.rows_per_block) return;
   const uint64_t rng_offset = p.offset + (p.offset_dev ? *p.offset_dev : 0ull);
-  const long long total = p.M * vpc;
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
-       v += (long long)gridDim.x * blockDim.x) {
-    const long long m = v / vpc;
-    const int c = (int)(v - m * vpc) << 3;
-    float f[8], sc[8], sh[8];
-    unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), f);
-    load8f(p.scale + c, sc);
-    load8f(p.shift + c, sh);
+  float sc[8], sh[8];
+  load8f(p.scale + c, sc);
+  load8f(p.shift + c, sh);
+  const long long stride = (long long)gridDim.x * p.rows_per_block;
+  long long m = (long long)blockIdx.x * p.rows_per_block + rl;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (; m + (UNROLL - 1) * stride < p.M; m += UNROLL * stride) {
+    uint4 yr[UNROLL], rr[UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-    if (p.res) {
-      float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(p.res + m * p.res_cs + c), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    for (int u = 0; u < UNROLL; ++u) {
+      yr[u] = *reinterpret_cast<const uint4*>(p.y + (m + u * stride) * p.y_cs + c);
+      rr[u] = p.res ? *reinterpret_cast<const uint4*>(p.res + (m + u * stride) * p.res_cs + c) : zero;
     }
-    if (p.relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-    }
-    if (p.drop_mode == 1) {
-      const uint32_t keep = dropout_keep8(p.seed, rng_offset, (uint64_t)(m * p.C + c), p.thresh16);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1) ? f[j] * p.keep_scale : 0.f;
-    } else if (p.drop_mode == 2) {
-      const uint2 mk = *reinterpret_cast<const uint2*>(p.mask + m * p.C + c);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t b = ((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xFF;
-        f[j] = b ? f[j] * p.keep_scale : 0.f;
-      }
-    }
-    *reinterpret_cast<uint4*>(p.out + m * p.out_cs + c) = pack8(f);
+    for (int u = 0; u < UNROLL; ++u) apply_one(p, m + u * stride, c, sc, sh, rng_offset, yr[u], rr[u]);
+  }
+  for (; m < p.M; m += stride) {
+    const uint4 yr = *reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c);
+    const uint4 rr = p.res ? *reinterpret_cast<const uint4*>(p.res + m * p.res_cs + c) : zero;
+    apply_one(p, m, c, sc, sh, rng_offset, yr, rr);
   }
 }
 
@@ -162,23 +190,21 @@ struct BwdP {
   int sp_stride, sp_HoWo, sp_Wo; long long dy_img, dy_row;
   __nv_bfloat16* dres; long long dres_cs; int dres_acc;
   float* dgamma; float* dbeta; int C_real; int param_acc;
-  int rows_per_block;  // reduce kernel: pixel rows handled concurrently by one CTA
+  int rows_per_block;  // pixel rows handled concurrently by one CTA
 };
 
-// dz for 8 channels of pixel m.  relu == 1: mask from the saved forward output (needed when a residual or a dropout
-// mask went into it); relu == 2: mask recomputed as scale*y + shift > 0 from the y values the caller already holds,
-// which saves reading `out` (2 of ~10 bytes per element in each backward pass).
-__device__ __forceinline__ void load_dz(const BwdP& p, long long m, int c, const float (&yv)[8], float (&dz)[8]) {
-  unpack8(*reinterpret_cast<const uint4*>(p.dout + m * p.dout_cs + c), dz);
+// dz = dout * [forward activation > 0] * grad_scale for one 8-channel slice.
+// relu == 1: mask from the saved forward output (residual / dropout layers); relu == 2: mask recomputed as
+// scale*y + shift > 0 (plain conv->BN->ReLU layers: saves reading `out` in both backward passes).
+__device__ __forceinline__ void make_dz(const BwdP& p, const uint4& draw, const uint4& oraw, const float (&yv)[8],
+                                        const float (&sc)[8], const float (&sh)[8], float (&dz)[8]) {
+  unpack8(draw, dz);
   if (p.relu == 2) {
-    float sc[8], sh[8];
-    load8f(p.scale + c, sc);
-    load8f(p.shift + c, sh);
 #pragma unroll
     for (int j = 0; j < 8; ++j) dz[j] = fmaf(yv[j], sc[j], sh[j]) > 0.f ? dz[j] * p.grad_scale : 0.f;
-  } else if (p.relu) {
+  } else if (p.relu == 1) {
     float o[8];
-    unpack8(*reinterpret_cast<const uint4*>(p.out + m * p.out_cs + c), o);
+    unpack8(oraw, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) dz[j] = o[j] > 0.f ? dz[j] * p.grad_scale : 0.f;
   } else if (p.grad_scale != 1.f) {
@@ -187,30 +213,49 @@ __device__ __forceinline__ void load_dz(const BwdP& p, long long m, int c, const
   }
 }
 
-// grid-stride over pixel rows; thread (vc, rl) owns 8 channels and every rows_per_block-th row.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdP p) {
   extern __shared__ float red[];  // [rows_per_block][C] x 2
   const int vpc = p.C >> 3;
-  const int vc = threadIdx.x % vpc;
+  const int c = (threadIdx.x % vpc) << 3;
   const int rl = threadIdx.x / vpc;
-  const int c = vc << 3;
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
   if (rl < p.rows_per_block) {
-    float mu[8], is[8];
+    float mu[8], is[8], sc[8], sh[8];
     load8f(p.mean + c, mu);
     load8f(p.invstd + c, is);
-    for (long long m = (long long)blockIdx.x * p.rows_per_block + rl; m < p.M;
-         m += (long long)gridDim.x * p.rows_per_block) {
-      float dz[8], yv[8];
-      unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
-      load_dz(p, m, c, yv, dz);
+    load8f(p.scale + c, sc);
+    if (p.relu == 2) load8f(p.shift + c, sh);
+    const long long stride = (long long)gridDim.x * p.rows_per_block;
+    long long m = (long long)blockIdx.x * p.rows_per_block + rl;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    auto accumulate = [&](const uint4& yr, const uint4& dr, const uint4& orw) {
+      float yv[8], dz[8];
+      unpack8(yr, yv);
+      make_dz(p, dr, orw, yv, sc, sh, dz);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a1[j] += dz[j];
-        a2[j] += dz[j] * ((yv[j] - mu[j]) * is[j]);
+        a2[j] = fmaf(dz[j], (yv[j] - mu[j]) * is[j], a2[j]);
       }
+    };
+    for (; m + (UNROLL - 1) * stride < p.M; m += UNROLL * stride) {
+      uint4 yr[UNROLL], dr[UNROLL], orw[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        yr[u] = *reinterpret_cast<const uint4*>(p.y + (m + u * stride) * p.y_cs + c);
+        dr[u] = *reinterpret_cast<const uint4*>(p.dout + (m + u * stride) * p.dout_cs + c);
+        orw[u] = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + (m + u * stride) * p.out_cs + c) : zero;
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) accumulate(yr[u], dr[u], orw[u]);
+    }
+    for (; m < p.M; m += stride) {
+      const uint4 yr = *reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c);
+      const uint4 dr = *reinterpret_cast<const uint4*>(p.dout + m * p.dout_cs + c);
+      const uint4 orw = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + m * p.out_cs + c) : zero;
+      accumulate(yr, dr, orw);
     }
     float* r1 = red + (size_t)rl * p.C + c;
     float* r2 = red + (size_t)p.rows_per_block * p.C + (size_t)rl * p.C + c;
@@ -233,28 +278,43 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdP p) {
 }
 
 // dy = A*dz + B*y + C per channel, with A = scale, B = -scale*m2*invstd, C = -scale*m1 + scale*m2*invstd*mean
-// (m1 = sum_dz/M, m2 = sum_dzx/M): the fp64 sums are folded into three fp32 coefficients per channel ONCE per
-// CTA (shared memory), so the streaming loop is 2 FMAs per element and touches no fp64.
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
-  extern __shared__ float coef[];  // [3][C]
-  float* cA = coef;
-  float* cB = coef + p.C;
-  float* cC = coef + 2 * p.C;
-  const double inv_m = 1.0 / (double)p.M;
-  for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
-    const float sc = p.scale[ch];
-    if (p.training) {
-      const float m1 = (float)(p.sum_dz[ch] * inv_m), m2 = (float)(p.sum_dzx[ch] * inv_m);
-      const float is = p.invstd[ch], mu = p.mean[ch];
-      cA[ch] = sc;
-      cB[ch] = -sc * m2 * is;
-      cC[ch] = -sc * m1 + sc * m2 * is * mu;
+// (m1 = sum_dz/M, m2 = sum_dzx/M): the fp64 sums are folded into three fp32 coefficients per channel once per
+// thread, so the streaming loop is 2 FMAs per element and touches no fp64.
+__device__ __forceinline__ void bwd_apply_one(const BwdP& p, long long m, int c, const float (&cA)[8],
+                                              const float (&cB)[8], const float (&cC)[8], const float (&sc)[8],
+                                              const float (&sh)[8], const uint4& yr, const uint4& dr, const uint4& orw) {
+  float yv[8], dz[8], g[8];
+  unpack8(yr, yv);
+  make_dz(p, dr, orw, yv, sc, sh, dz);
+  if (p.dres) {
+    uint4* dst = reinterpret_cast<uint4*>(p.dres + m * p.dres_cs + c);
+    if (p.dres_acc) {
+      float r[8];
+      unpack8(*dst, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] += dz[j];
+      *dst = pack8(r);
     } else {
-      cA[ch] = sc;
-      cB[ch] = 0.f;
-      cC[ch] = 0.f;
+      *dst = pack8(dz);
     }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = fmaf(cA[j], dz[j], fmaf(cB[j], yv[j], cC[j]));
+  long long pix = m;
+  if (p.sp_stride > 1) {
+    const long long img = m / p.sp_HoWo;
+    const int rem = (int)(m - img * p.sp_HoWo);
+    const int op = rem / p.sp_Wo;
+    const int oq = rem - op * p.sp_Wo;
+    pix = img * p.dy_img + (long long)op * p.dy_row + (long long)oq * p.sp_stride;
+  }
+  *reinterpret_cast<uint4*>(p.dy + pix * p.dy_cs + c) = pack8(g);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
+  const int vpc = p.C >> 3;
+  const int c = (threadIdx.x % vpc) << 3;
+  const int rl = threadIdx.x / vpc;
   if (blockIdx.x == 0 && p.dgamma != nullptr) {
     for (int ch = threadIdx.x; ch < p.C_real; ch += blockDim.x) {
       const float dg = (float)p.sum_dzx[ch], db = (float)p.sum_dz[ch];
@@ -262,40 +322,48 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
       p.dbeta[ch] = p.param_acc ? p.dbeta[ch] + db : db;
     }
   }
-  __syncthreads();
-  const int vpc = p.C >> 3;
-  const long long total = p.M * vpc;
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
-       v += (long long)gridDim.x * blockDim.x) {
-    const long long m = v / vpc;
-    const int c = (int)(v - m * vpc) << 3;
-    float dz[8], yv[8];
-    unpack8(*reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c), yv);
-    load_dz(p, m, c, yv, dz);
-    if (p.dres) {
-      uint4* dst = reinterpret_cast<uint4*>(p.dres + m * p.dres_cs + c);
-      if (p.dres_acc) {
-        float r[8];
-        unpack8(*dst, r);
+  if (rl >= p.rows_per_block) return;
+  float cA[8], cB[8], cC[8], sc[8], sh[8];
+  load8f(p.scale + c, sc);
+  if (p.relu == 2) load8f(p.shift + c, sh);
+  {
+    float mu[8], is[8];
+    load8f(p.mean + c, mu);
+    load8f(p.invstd + c, is);
+    const double inv_m = 1.0 / (double)p.M;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] += dz[j];
-        *dst = pack8(r);
+    for (int j = 0; j < 8; ++j) {
+      if (p.training) {
+        const float m1 = (float)(p.sum_dz[c + j] * inv_m), m2 = (float)(p.sum_dzx[c + j] * inv_m);
+        cA[j] = sc[j];
+        cB[j] = -sc[j] * m2 * is[j];
+        cC[j] = -sc[j] * m1 + sc[j] * m2 * is[j] * mu[j];
       } else {
-        *dst = pack8(dz);
+        cA[j] = sc[j];
+        cB[j] = 0.f;
+        cC[j] = 0.f;
       }
     }
-    float g[8];
+  }
+  const long long stride = (long long)gridDim.x * p.rows_per_block;
+  long long m = (long long)blockIdx.x * p.rows_per_block + rl;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (; m + (UNROLL - 1) * stride < p.M; m += UNROLL * stride) {
+    uint4 yr[UNROLL], dr[UNROLL], orw[UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = fmaf(cA[c + j], dz[j], fmaf(cB[c + j], yv[j], cC[c + j]));
-    long long pix = m;
-    if (p.sp_stride > 1) {
-      const long long img = m / p.sp_HoWo;
-      const int rem = (int)(m - img * p.sp_HoWo);
-      const int op = rem / p.sp_Wo;
-      const int oq = rem - op * p.sp_Wo;
-      pix = img * p.dy_img + (long long)op * p.dy_row + (long long)oq * p.sp_stride;
+    for (int u = 0; u < UNROLL; ++u) {
+      yr[u] = *reinterpret_cast<const uint4*>(p.y + (m + u * stride) * p.y_cs + c);
+      dr[u] = *reinterpret_cast<const uint4*>(p.dout + (m + u * stride) * p.dout_cs + c);
+      orw[u] = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + (m + u * stride) * p.out_cs + c) : zero;
     }
-    *reinterpret_cast<uint4*>(p.dy + pix * p.dy_cs + c) = pack8(g);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) bwd_apply_one(p, m + u * stride, c, cA, cB, cC, sc, sh, yr[u], dr[u], orw[u]);
+  }
+  for (; m < p.M; m += stride) {
+    const uint4 yr = *reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c);
+    const uint4 dr = *reinterpret_cast<const uint4*>(p.dout + m * p.dout_cs + c);
+    const uint4 orw = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + m * p.out_cs + c) : zero;
+    bwd_apply_one(p, m, c, cA, cB, cC, sc, sh, yr, dr, orw);
   }
 }
 
@@ -307,22 +375,31 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
                                                        double* __restrict__ sqsum) {
   extern __shared__ float red[];  // [rows_per_block][C] x 2
   const int vpc = C >> 3;
-  const int vc = threadIdx.x % vpc;
+  const int c = (threadIdx.x % vpc) << 3;
   const int rl = threadIdx.x / vpc;
-  const int c = vc << 3;
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
   if (rl < rows_per_block) {
-    for (long long m = (long long)blockIdx.x * rows_per_block + rl; m < M; m += (long long)gridDim.x * rows_per_block) {
+    const long long stride = (long long)gridDim.x * rows_per_block;
+    long long m = (long long)blockIdx.x * rows_per_block + rl;
+    auto acc = [&](const uint4& raw) {
       float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + m * y_cs + c), v);
+      unpack8(raw, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a1[j] += v[j];
         a2[j] = fmaf(v[j], v[j], a2[j]);
       }
+    };
+    for (; m + (2 * UNROLL - 1) * stride < M; m += 2 * UNROLL * stride) {
+      uint4 r[2 * UNROLL];
+#pragma unroll
+      for (int u = 0; u < 2 * UNROLL; ++u) r[u] = *reinterpret_cast<const uint4*>(y + (m + u * stride) * y_cs + c);
+#pragma unroll
+      for (int u = 0; u < 2 * UNROLL; ++u) acc(r[u]);
     }
+    for (; m < M; m += stride) acc(*reinterpret_cast<const uint4*>(y + m * y_cs + c));
     float* r1 = red + (size_t)rl * C + c;
     float* r2 = red + (size_t)rows_per_block * C + (size_t)rl * C + c;
 #pragma unroll
@@ -383,6 +460,15 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
   }
 }
 
+// grid for the row-streaming kernels: every thread should see at least UNROLL rows, at most 8 CTAs per SM
+static int stream_grid(long long M, int rows_per_block) {
+  long long b = (M + (long long)rows_per_block * UNROLL - 1) / ((long long)rows_per_block * UNROLL);
+  const long long cap = 148ll * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
 static int ew_grid(long long work_items, int threads) {
   long long b = (work_items + threads - 1) / threads;
   const long long cap = 148ll * 16;
@@ -419,9 +505,7 @@ extern "C" int zs3_bn_stats(const void* y, int y_cstride, long long M, int C, do
   int rpb = 256 / vpc;
   if (rpb < 1) rpb = 1;
   const size_t smem = (size_t)2 * rpb * C * sizeof(float);
-  long long blocks = (M + rpb - 1) / rpb;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_stats_kernel<<<(int)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  bn_stats_kernel<<<stream_grid(M, rpb), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), y_cstride, M, C, rpb, stat_sum, stat_sqsum);
   ZS3_CHECK_LAUNCH("bn_stats");
   return ZS3_OK;
@@ -458,7 +542,9 @@ extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
   p.thresh16 = (uint32_t)(a->drop_p * 65536.0f + 0.5f);
   p.keep_scale = 1.f / (1.f - a->drop_p);
   p.seed = a->seed; p.offset = a->offset; p.mask = a->keep_mask; p.offset_dev = a->offset_dev;
-  bn_apply_kernel<<<ew_grid(a->M * (a->C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ZS3_CHECK_ARG(a->C <= 2048, "bn_apply: C=%d > 2048", a->C);
+  p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
+  bn_apply_kernel<<<stream_grid(a->M, p.rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   ZS3_CHECK_LAUNCH("bn_apply");
   return ZS3_OK;
 }
@@ -494,9 +580,7 @@ extern "C" int zs3_bn_bwd_reduce(const zs3_bn_bwd_args* a, void* stream) {
   p.rows_per_block = 256 / vpc;  // C <= 2048 -> vpc <= 256
   if (p.rows_per_block < 1) p.rows_per_block = 1;
   const size_t smem = (size_t)2 * p.rows_per_block * a->C * sizeof(float);
-  long long blocks = (a->M + p.rows_per_block - 1) / p.rows_per_block;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  bn_bwd_reduce_kernel<<<(int)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  bn_bwd_reduce_kernel<<<stream_grid(a->M, p.rows_per_block), 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
   ZS3_CHECK_LAUNCH("bn_bwd_reduce");
   return ZS3_OK;
 }
@@ -513,8 +597,8 @@ extern "C" int zs3_bn_bwd_apply(const zs3_bn_bwd_args* a, void* stream) {
   ZS3_CHECK_ARG((a->dgamma == nullptr) == (a->dbeta == nullptr) && (a->dgamma == nullptr || a->C_real <= a->C),
                 "bn_bwd_apply: bad parameter gradient buffers");
   if (a->M <= 0) return ZS3_OK;
-  bn_bwd_apply_kernel<<<ew_grid(a->M * (a->C / 8), 256), 256, 3 * a->C * sizeof(float),
-                        static_cast<cudaStream_t>(stream)>>>(p);
+  p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
+  bn_bwd_apply_kernel<<<stream_grid(a->M, p.rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   ZS3_CHECK_LAUNCH("bn_bwd_apply");
   return ZS3_OK;
 }

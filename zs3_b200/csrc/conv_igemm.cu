@@ -555,6 +555,53 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
   }
 }
 
+// KRSC (channels_last) sources are one cast / one 2-D transpose per tap away from the kernel layouts:
+// mode 0: dst[co][tap][ci] = src[co][tap][ci_begin + ci]   (contiguous runs on both sides)
+__global__ void __launch_bounds__(256) pack_krsc_fprop_kernel(const float* __restrict__ w, int Cout, int Cin, int taps,
+                                                              int ci_begin, int ci_count,
+                                                              __nv_bfloat16* __restrict__ dst, int cout_pad,
+                                                              int cin_pad) {
+  const int vpr = cin_pad >> 2;  // 4-element vectors per (co, tap) row
+  const long long total = (long long)cout_pad * taps * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % vpr) << 2;
+    const long long row = i / vpr;  // co * taps + tap
+    const int co = (int)(row / taps);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (co < Cout) {
+      const float* src = w + row * Cin + ci_begin + ci;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (ci + j < ci_count) v[j] = src[j];
+    }
+    uint2 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(dst + row * cin_pad + ci) = o;
+  }
+}
+
+// mode 1: dst[ci][taps-1-tap][co] = src[co][tap][ci_begin + ci]: a 32x32 shared-memory transpose per tap
+__global__ void __launch_bounds__(256) pack_krsc_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int taps,
+                                                              int ci_begin, int ci_count,
+                                                              __nv_bfloat16* __restrict__ dst, int cout_pad,
+                                                              int cin_pad) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + tx;
+    tile[r][tx] = (co < Cout && ci < ci_count) ? w[((long long)co * taps + tap) * Cin + ci_begin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + tx;
+    if (ci < cin_pad && co < cout_pad)
+      dst[((long long)ci * taps + (taps - 1 - tap)) * cout_pad + co] = __float2bfloat16(tile[tx][r]);
+  }
+}
+
 // grad_oihw[co][ci_begin+ci][tap] (+)= dw[co][tap][ci]: same tiling, reversed direction
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, int cout_pad, int cin_pad,
                                                            float* __restrict__ g, int Cout, int Cin, int R, int S,
@@ -814,6 +861,20 @@ extern "C" int zs3_pack_weight(const float* w_oihw, int Cout, int Cin, int R, in
   ZS3_CHECK_ARG(mode >= 0 && mode <= 3, "pack_weight: mode=%d", mode);
   const int src_krsc = mode >> 1;
   mode &= 1;
+  if (src_krsc) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst_bf16);
+    if (mode == 0) {
+      const long long total = (long long)cout_pad * R * S * (cin_pad / 4);
+      int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+      pack_krsc_fprop_kernel<<<blocks, 256, 0, st>>>(w_oihw, Cout, Cin, R * S, ci_begin, ci_count, d, cout_pad, cin_pad);
+    } else {
+      dim3 grid(ceil_div(cin_pad, 32), ceil_div(cout_pad, 32), R * S);
+      pack_krsc_dgrad_kernel<<<grid, 256, 0, st>>>(w_oihw, Cout, Cin, R * S, ci_begin, ci_count, d, cout_pad, cin_pad);
+    }
+    ZS3_CHECK_LAUNCH("pack_weight(krsc)");
+    return ZS3_OK;
+  }
   ZS3_CHECK_ARG(R * S <= 9, "pack_weight: at most 9 taps (the 7x7 stem goes through its [Cout][147][1][1] view)");
   const size_t smem = (size_t)PK_T * (PK_T * R * S + 1) * sizeof(float);
   dim3 grid(ceil_div(cin_pad, PK_T), ceil_div(cout_pad, PK_T));

@@ -111,6 +111,16 @@ def _direct_grad_buffer(w):
     return None
 
 
+def _direct_small_grad(p):
+    """1-D fp32 parameter gradient buffer to accumulate into in place (created on first use)"""
+    if p is None:
+        return None
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    g = p.grad
+    return g if (g.dtype == torch.float32 and g.is_contiguous()) else None
+
+
 def _bn_forward_coeffs(bn, stats, count, cs):
     """(scale, shift, mean, invstd) for this BN: batch statistics in training mode (updates the running
     buffers like F.batch_norm), running statistics otherwise."""
@@ -190,8 +200,15 @@ class ConvBnAct(torch.autograd.Function):
         dout = dout.contiguous()
         dev = dout.device
         need_w = ctx.needs_input_grad[5]
-        dgamma = torch.empty(cout, dtype=torch.float32, device=dev) if bn.weight is not None else None
-        dbeta = torch.empty(cout, dtype=torch.float32, device=dev) if bn.weight is not None else None
+        # BatchNorm affine gradients: accumulated in place into .grad (no autograd add kernels), like the conv weights
+        dgamma = dbeta = None
+        direct_affine = False
+        if bn.weight is not None and ctx.needs_input_grad[6]:
+            dgamma, dbeta = _direct_small_grad(bn.weight), _direct_small_grad(bn.bias)
+            direct_affine = dgamma is not None and dbeta is not None
+            if not direct_affine:
+                dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
+                dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
         dres = torch.empty_like(dout) if ctx.has_res else None
         sc = _scratch64(dev, "bwd")
         scratch = sc[:2 * cout_p].view(2, cout_p)
@@ -206,7 +223,10 @@ class ConvBnAct(torch.autograd.Function):
         dy_dense_needed = need_w and zero_insert
         dy = K.bn_backward(dout, out, y, mean, invstd, scale, ctx.relu, grad_scale=1.0 / (1.0 - ctx.p),
                            training=ctx.training, dres=dres, dgamma=dgamma, dbeta=dbeta, scratch=scratch,
+                           param_accumulate=direct_affine,
                            scatter=None if dy_dense_needed else scatter, shift=shift if ctx.mask_from_y else None)
+        if direct_affine:
+            dgamma = dbeta = None  # already added to bn.weight.grad / bn.bias.grad
         dy_z = dy
         if dy_dense_needed:
             # both layouts are needed: dense for wgrad, zero-inserted for dgrad
