@@ -89,6 +89,10 @@ def test_step2_iteration_matches_oracle():
                    mask_fn=rp.mask)
     with torch.no_grad():
         real = model.module.forward_before_class_prediction(image.cuda())
+        # frozen random-init BN leaves the features at magnitude ~1e3, where the reference's fp32 formula
+        # XX^T - |x|^2/2 - |x|^2/2^T overflows to +inf (our kernel evaluates -|xi-xj|^2/2 and stays finite);
+        # rescale to the O(1) range of trained post-ReLU features so that the oracle is well defined
+        real = real / real.std()
     loss, glb, g_losses = step.training_step(image.cuda(), target.cuda(), embedding.cuda(), real_features=real)
     torch.cuda.synchronize()
 

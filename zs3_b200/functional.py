@@ -134,6 +134,140 @@ def _bn_forward_coeffs(bn, stats, count, cs):
     return K.bn_eval_coeffs(w, b, bn.running_mean, bn.running_var, bn.eps, cs)
 
 
+class _Saved:
+    """what a conv->BN->act forward keeps for its backward"""
+    __slots__ = ("conv", "bn", "relu", "p", "training", "ranges", "has_res", "geom", "flops_per_cin", "mask_from_y",
+                 "y", "out", "mean", "invstd", "scale", "shift", "xs")
+
+
+def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, channels):
+    """[concat ->] conv -> BatchNorm -> (+residual) -> (ReLU) -> (Dropout).  Returns (out, saved)."""
+    R, S = conv.kernel_size
+    stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
+    cout = conv.out_channels
+    cout_p = K.cpad(cout)
+    training = bn.training
+    if len(channels) != len(xs):
+        raise ValueError("conv_bn_act: segment count mismatch")
+    # input channel ranges of the (virtually concatenated) segments
+    segs, ranges, ci = [], [], 0
+    for x, c_real in zip(xs, channels):
+        cin_p = x.shape[3]
+        segs.append((x, _packed_weight(conv, 0, ci, c_real, cin_p, cout_p)))
+        ranges.append((ci, c_real, cin_p))
+        ci += c_real
+    if ci != conv.in_channels:
+        raise ValueError(f"segments provide {ci} channels, conv expects {conv.in_channels}")
+    dev = xs[0].device
+    stats = None
+    if training:
+        sc = _scratch64(dev)
+        stats = (sc[:cout_p], sc[2048:2048 + cout_p])
+    n_, h_, w_, _ = xs[0].shape
+    ho_, wo_ = K.conv_out_size(h_, R, stride, pad, dil), K.conv_out_size(w_, S, stride, pad, dil)
+    macs_per_cin = 2.0 * n_ * ho_ * wo_ * cout * R * S  # nominal FLOPs per input channel
+    # BatchNorm statistics: fused into the conv epilogue when the main loop is long enough to hide it
+    # (>= FUSE_STATS_MIN_KB k-blocks of 64 per tile), otherwise one extra streaming pass over y
+    kblocks = R * S * sum(x.shape[3] for x in xs) // 64
+    fuse_stats = stats is not None and kblocks >= FUSE_STATS_MIN_KB
+    y = K.conv_fprop(segs, R, S, stride, pad, dil, cout_p, stats=stats if fuse_stats else None,
+                     flops=macs_per_cin * conv.in_channels)
+    if stats is not None and not fuse_stats:
+        K.bn_stats(y, stats)
+    n, ho, wo, _ = y.shape
+    scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
+    seed = off = 0
+    p = float(drop_p) if (drop_p and drop_training) else 0.0
+    if p > 0 and keep_mask is None:
+        seed, off = _RngState.next(y.numel())
+    out = K.bn_apply(y, scale, shift, relu, residual=residual, drop_p=p, seed=seed, offset=off,
+                     keep_mask=keep_mask if p > 0 else None,
+                     offset_dev=_RngState.device_counter if (p > 0 and keep_mask is None) else None)
+    sv = _Saved()
+    sv.conv, sv.bn, sv.relu, sv.p, sv.training = conv, bn, relu, p, training
+    sv.ranges, sv.has_res = ranges, residual is not None
+    sv.geom = (R, S, stride, pad, dil, cout, cout_p)
+    sv.flops_per_cin = macs_per_cin
+    # plain conv->BN->ReLU: the backward recomputes the ReLU mask from y, `out` need not be re-read
+    sv.mask_from_y = bool(relu) and residual is None and p == 0.0
+    sv.y, sv.out, sv.mean, sv.invstd, sv.scale, sv.shift, sv.xs = y, out, mean, invstd, scale, shift, list(xs)
+    return out, sv
+
+
+def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None):
+    """Backward of cba_forward.  need_dx: per-segment flags.  dx_into: optional per-segment (tensor, accumulate)
+    targets the data gradient is written (or added) into -- how a residual join is summed without an extra kernel.
+    Returns (dxs, dweight, dgamma, dbeta, dres); parameter gradients that were accumulated in place come back None."""
+    conv, bn = sv.conv, sv.bn
+    R, S, stride, pad, dil, cout, cout_p = sv.geom
+    y, xs = sv.y, sv.xs
+    dout = dout.contiguous()
+    dev = dout.device
+    dgamma = dbeta = None
+    direct_affine = False
+    if bn.weight is not None and need_affine:
+        dgamma, dbeta = _direct_small_grad(bn.weight), _direct_small_grad(bn.bias)
+        direct_affine = dgamma is not None and dbeta is not None
+        if not direct_affine:
+            dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+    dres = torch.empty_like(dout) if sv.has_res else None
+    sc = _scratch64(dev, "bwd")
+    scratch = sc[:2 * cout_p].view(2, cout_p)
+    # strided 3x3: write dy zero-inserted so that the data gradient is a stride-1 conv (see conv_igemm.cu)
+    zero_insert = stride > 1 and R > 1
+    n, ho, wo, _ = y.shape
+    h_in, w_in = xs[0].shape[1], xs[0].shape[2]
+    scatter = None
+    if zero_insert:
+        scatter = (stride, (ho - 1) * stride + 1, (wo - 1) * stride + 1)
+    dy_dense_needed = need_w and zero_insert
+    dy = K.bn_backward(dout, sv.out, y, sv.mean, sv.invstd, sv.scale, sv.relu, grad_scale=1.0 / (1.0 - sv.p),
+                       training=sv.training, dres=dres, dgamma=dgamma, dbeta=dbeta, scratch=scratch,
+                       param_accumulate=direct_affine, scatter=None if dy_dense_needed else scatter,
+                       shift=sv.shift if sv.mask_from_y else None)
+    if direct_affine:
+        dgamma = dbeta = None  # already added to bn.weight.grad / bn.bias.grad
+    dy_z = dy
+    if dy_dense_needed:
+        # both layouts are needed: dense for wgrad, zero-inserted for dgrad
+        dy_z = torch.zeros((n, scatter[1], scatter[2], cout_p), dtype=torch.bfloat16, device=dev)
+        dy_z[:, ::stride, ::stride] = dy
+    dxs = []
+    # weight gradient: accumulated in place into conv.weight.grad when the parameter is stored KRSC (then
+    # nothing is returned to autograd for it), else produced as a fresh OIHW tensor
+    gbuf = _direct_grad_buffer(conv.weight) if need_w else None
+    dweight = torch.empty_like(conv.weight) if (need_w and gbuf is None) else None
+    for i, x in enumerate(xs):
+        ci0, c_real, cin_p = sv.ranges[i]
+        if need_dx[i]:
+            wt = _packed_weight(conv, 1, ci0, c_real, cin_p, cout_p)  # [cin_p][taps][cout_p]
+            fl = sv.flops_per_cin * c_real
+            tgt, acc = (dx_into[i] if dx_into is not None and dx_into[i] is not None else (None, False))
+            if stride == 1:
+                dx = K.conv_fprop([(dy, wt)], R, S, 1, dil * (R - 1) - pad, dil, cin_p, out=tgt, accumulate=acc, flops=fl,
+                                  kind="conv_dgrad")
+            elif R == 1:
+                dx = tgt if tgt is not None else torch.zeros_like(x)
+                K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, out=dx, scatter=(stride, h_in, w_in), accumulate=acc,
+                             flops=fl, kind="conv_dgrad")
+            else:
+                # zero-inserted dy has (ho-1)*s+1 rows; pad so that the output covers the full input extent
+                dx = K.conv_fprop([(_pad_to(dy_z, h_in + 2 * pad - dil * (R - 1), w_in + 2 * pad - dil * (S - 1)), wt)],
+                                  R, S, 1, dil * (R - 1) - pad, dil, cin_p, out=tgt, accumulate=acc, flops=fl,
+                                  kind="conv_dgrad")
+            dxs.append(dx)
+        else:
+            dxs.append(None)
+        if need_w and gbuf is not None:
+            K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, dw=gbuf, flops=sv.flops_per_cin * c_real,
+                         dw_view=(conv.in_channels, ci0, cout, c_real))
+        elif need_w:
+            dw = K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, flops=sv.flops_per_cin * c_real)
+            K.unpack_wgrad(dw, dweight, ci0, c_real, accumulate=False)
+    return dxs, dweight, dgamma, dbeta, dres
+
+
 class ConvBnAct(torch.autograd.Function):
     """[concat ->] conv -> BatchNorm -> (+residual) -> (ReLU) -> (Dropout), one fused forward/backward.
 
@@ -141,128 +275,69 @@ class ConvBnAct(torch.autograd.Function):
     zs3/modeling/aspp.py:25-29,111-116 and zs3/modeling/decoder.py:30-38."""
 
     @staticmethod
-    def forward(ctx, conv, bn, relu, drop_p, keep_mask, weight, gamma, beta, residual, *xs):
-        R, S = conv.kernel_size
-        stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
-        cout = conv.out_channels
-        cout_p = K.cpad(cout)
-        training = bn.training
-        # input channel ranges of the (virtually concatenated) segments
-        segs, ranges, ci = [], [], 0
-        for x, c_real in xs_with_channels(xs, ctx_channels=conv.__dict__.get("_zs3_seg_channels")):
-            cin_p = x.shape[3]
-            wp = _packed_weight(conv, 0, ci, c_real, cin_p, cout_p)
-            segs.append((x, wp))
-            ranges.append((ci, c_real, cin_p))
-            ci += c_real
-        if ci != conv.in_channels:
-            raise ValueError(f"segments provide {ci} channels, conv expects {conv.in_channels}")
-        dev = xs[0].device
-        stats = None
-        if training:
-            sc = _scratch64(dev)
-            stats = (sc[:cout_p], sc[2048:2048 + cout_p])
-        n_, h_, w_, _ = xs[0].shape
-        ho_, wo_ = K.conv_out_size(h_, R, stride, pad, dil), K.conv_out_size(w_, S, stride, pad, dil)
-        macs_per_cin = 2.0 * n_ * ho_ * wo_ * cout * R * S  # nominal FLOPs per input channel
-        # BatchNorm statistics: fused into the conv epilogue when the main loop is long enough to hide it
-        # (>= FUSE_STATS_MIN_KB k-blocks of 64 per tile), otherwise one extra streaming pass over y
-        kblocks = R * S * sum(x.shape[3] for x in xs) // 64
-        fuse_stats = stats is not None and kblocks >= FUSE_STATS_MIN_KB
-        y = K.conv_fprop(segs, R, S, stride, pad, dil, cout_p, stats=stats if fuse_stats else None,
-                         flops=macs_per_cin * conv.in_channels)
-        if stats is not None and not fuse_stats:
-            K.bn_stats(y, stats)
-        n, ho, wo, _ = y.shape
-        scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
-        seed = off = 0
-        p = float(drop_p) if (drop_p and training_dropout(conv, bn)) else 0.0
-        if p > 0 and keep_mask is None:
-            seed, off = _RngState.next(y.numel())
-        out = K.bn_apply(y, scale, shift, relu, residual=residual, drop_p=p, seed=seed, offset=off,
-                         keep_mask=keep_mask if p > 0 else None,
-                         offset_dev=_RngState.device_counter if (p > 0 and keep_mask is None) else None)
-        ctx.conv, ctx.bn, ctx.relu, ctx.p, ctx.training = conv, bn, relu, p, training
-        ctx.ranges = ranges
-        ctx.has_res = residual is not None
-        ctx.geom = (R, S, stride, pad, dil, cout, cout_p)
-        ctx.flops_per_cin = macs_per_cin
-        # plain conv->BN->ReLU: the backward recomputes the ReLU mask from y, `out` need not be re-read
-        ctx.mask_from_y = bool(relu) and residual is None and p == 0.0
-        ctx.save_for_backward(y, out, mean, invstd, scale, shift, *xs)
+    def forward(ctx, conv, bn, relu, drop_p, drop_training, keep_mask, channels, weight, gamma, beta, residual, *xs):
+        out, sv = cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, channels)
+        ctx.sv = sv
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        y, out, mean, invstd, scale, shift, *xs = ctx.saved_tensors
-        conv, bn = ctx.conv, ctx.bn
-        R, S, stride, pad, dil, cout, cout_p = ctx.geom
-        dout = dout.contiguous()
-        dev = dout.device
-        need_w = ctx.needs_input_grad[5]
-        # BatchNorm affine gradients: accumulated in place into .grad (no autograd add kernels), like the conv weights
-        dgamma = dbeta = None
-        direct_affine = False
-        if bn.weight is not None and ctx.needs_input_grad[6]:
-            dgamma, dbeta = _direct_small_grad(bn.weight), _direct_small_grad(bn.bias)
-            direct_affine = dgamma is not None and dbeta is not None
-            if not direct_affine:
-                dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
-                dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
-        dres = torch.empty_like(dout) if ctx.has_res else None
-        sc = _scratch64(dev, "bwd")
-        scratch = sc[:2 * cout_p].view(2, cout_p)
-        # strided 3x3: write dy zero-inserted so that the data gradient is a stride-1 conv (see conv_igemm.cu)
-        zero_insert = stride > 1 and R > 1
-        n, ho, wo, _ = y.shape
-        h_in, w_in = xs[0].shape[1], xs[0].shape[2]
-        scatter = None
-        if zero_insert:
-            hz, wz = (ho - 1) * stride + 1, (wo - 1) * stride + 1
-            scatter = (stride, hz, wz)
-        dy_dense_needed = need_w and zero_insert
-        dy = K.bn_backward(dout, out, y, mean, invstd, scale, ctx.relu, grad_scale=1.0 / (1.0 - ctx.p),
-                           training=ctx.training, dres=dres, dgamma=dgamma, dbeta=dbeta, scratch=scratch,
-                           param_accumulate=direct_affine,
-                           scatter=None if dy_dense_needed else scatter, shift=shift if ctx.mask_from_y else None)
-        if direct_affine:
-            dgamma = dbeta = None  # already added to bn.weight.grad / bn.bias.grad
-        dy_z = dy
-        if dy_dense_needed:
-            # both layouts are needed: dense for wgrad, zero-inserted for dgrad
-            dy_z = torch.zeros((n, scatter[1], scatter[2], cout_p), dtype=torch.bfloat16, device=dev)
-            dy_z[:, ::stride, ::stride] = dy
-        dxs = []
-        # weight gradient: accumulated in place into conv.weight.grad when the parameter is stored KRSC (then
-        # nothing is returned to autograd for it), else produced as a fresh OIHW tensor
-        gbuf = _direct_grad_buffer(conv.weight) if need_w else None
-        dweight = torch.empty_like(conv.weight) if (need_w and gbuf is None) else None
-        for i, x in enumerate(xs):
-            ci0, c_real, cin_p = ctx.ranges[i]
-            if ctx.needs_input_grad[9 + i]:
-                wt = _packed_weight(conv, 1, ci0, c_real, cin_p, cout_p)  # [cin_p][taps][cout_p]
-                fl = ctx.flops_per_cin * c_real
-                if stride == 1:
-                    dx = K.conv_fprop([(dy, wt)], R, S, 1, dil * (R - 1) - pad, dil, cin_p, flops=fl, kind="conv_dgrad")
-                elif R == 1:
-                    dx = torch.zeros_like(x)
-                    K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, out=dx, scatter=(stride, h_in, w_in), flops=fl,
-                                 kind="conv_dgrad")
-                else:
-                    # zero-inserted dy has (ho-1)*s+1 rows; pad so that the output covers the full input extent
-                    dxf = K.conv_fprop([(_pad_to(dy_z, h_in + 2 * pad - dil * (R - 1), w_in + 2 * pad - dil * (S - 1)), wt)],
-                                       R, S, 1, dil * (R - 1) - pad, dil, cin_p, flops=fl, kind="conv_dgrad")
-                    dx = dxf
-                dxs.append(dx)
-            else:
-                dxs.append(None)
-            if need_w and gbuf is not None:
-                K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, dw=gbuf, flops=ctx.flops_per_cin * c_real,
-                             dw_view=(conv.in_channels, ci0, cout, c_real))
-            elif need_w:
-                dw = K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, flops=ctx.flops_per_cin * c_real)
-                K.unpack_wgrad(dw, dweight, ci0, c_real, accumulate=False)
-        return (None, None, None, None, None, dweight, dgamma, dbeta, dres, *dxs)
+        need = ctx.needs_input_grad
+        dxs, dweight, dgamma, dbeta, dres = cba_backward(ctx.sv, dout, list(need[11:]), need_w=need[7],
+                                                         need_affine=need[8])
+        ctx.sv = None
+        return (None, None, None, None, None, None, None, dweight, dgamma, dbeta, dres, *dxs)
+
+
+class BottleneckFn(torch.autograd.Function):
+    """A whole residual bottleneck (zs3/modeling/backbone/resnet.py:33-53) as ONE autograd node: conv1-bn1-relu,
+    conv2-bn2-relu, conv3-bn3 (+ downsample conv-bn), residual add, relu.  Fusing the block lets the backward sum
+    the two gradients that meet at the block input inside the data-gradient conv's epilogue (accumulate) instead of
+    a separate elementwise add."""
+
+    @staticmethod
+    def forward(ctx, blk, x, *params):
+        out1, s1 = cba_forward(blk.conv1, blk.bn1, True, 0.0, False, None, None, [x], [blk.inplanes])
+        out2, s2 = cba_forward(blk.conv2, blk.bn2, True, 0.0, False, None, None, [out1], [blk.planes])
+        sd = None
+        res = x
+        if blk.downsample is not None:
+            res, sd = cba_forward(blk.downsample[0], blk.downsample[1], False, 0.0, False, None, None, [x],
+                                  [blk.inplanes])
+        out3, s3 = cba_forward(blk.conv3, blk.bn3, True, 0.0, False, None, res, [out2], [blk.planes])
+        ctx.saved = (s1, s2, s3, sd)
+        ctx.nparams = len(params)
+        return out3
+
+    @staticmethod
+    def backward(ctx, dout):
+        s1, s2, s3, sd = ctx.saved
+        ctx.saved = None
+        need_x = ctx.needs_input_grad[1]
+        need_p = any(ctx.needs_input_grad[2:])
+        grads = {}
+        (d2,), grads["w3"], grads["g3"], grads["b3"], dres = cba_backward(s3, dout, [True], need_p, need_p)
+        (d1,), grads["w2"], grads["g2"], grads["b2"], _ = cba_backward(s2, d2, [True], need_p, need_p)
+        dx = None
+        if sd is not None:
+            (dx,), grads["wd"], grads["gd"], grads["bd"], _ = cba_backward(sd, dres, [need_x], need_p, need_p)
+        elif need_x:
+            dx = dres
+        # the gradient through conv1 is ADDED onto the residual-path gradient in the dgrad epilogue
+        into = [(dx, True)] if (need_x and dx is not None) else None
+        (dx1,), grads["w1"], grads["g1"], grads["b1"], _ = cba_backward(s1, d1, [need_x], need_p, need_p, dx_into=into)
+        if need_x and dx is None:
+            dx = dx1
+        order = ["w1", "g1", "b1", "w2", "g2", "b2", "w3", "g3", "b3"] + (["wd", "gd", "bd"] if sd is not None else [])
+        return (None, dx, *[grads[k] for k in order])
+
+
+def bottleneck(blk, x):
+    params = [blk.conv1.weight, blk.bn1.weight, blk.bn1.bias, blk.conv2.weight, blk.bn2.weight, blk.bn2.bias,
+              blk.conv3.weight, blk.bn3.weight, blk.bn3.bias]
+    if blk.downsample is not None:
+        params += [blk.downsample[0].weight, blk.downsample[1].weight, blk.downsample[1].bias]
+    return BottleneckFn.apply(blk, x, *params)
 
 
 def _pad_to(t, h, w):
@@ -275,24 +350,10 @@ def _pad_to(t, h, w):
     return out
 
 
-def xs_with_channels(xs, ctx_channels):
-    """pair every segment tensor with its logical channel count"""
-    if ctx_channels is None:
-        raise ValueError("conv_bn_act: segment channel counts missing")
-    if len(ctx_channels) != len(xs):
-        raise ValueError("conv_bn_act: segment count mismatch")
-    return list(zip(xs, ctx_channels))
-
-
-def training_dropout(conv, bn):
-    return conv.__dict__.get("_zs3_drop_training", False)
-
-
 def conv_bn_act(xs, channels, conv, bn, relu=True, residual=None, drop_p=0.0, drop_training=False, keep_mask=None):
     """xs: list of NHWC bf16 tensors (a virtual channel concat), channels: their logical channel counts."""
-    conv.__dict__["_zs3_seg_channels"] = list(channels)
-    conv.__dict__["_zs3_drop_training"] = bool(drop_training)
-    return ConvBnAct.apply(conv, bn, relu, drop_p, keep_mask, conv.weight, bn.weight, bn.bias, residual, *xs)
+    return ConvBnAct.apply(conv, bn, relu, drop_p, bool(drop_training), keep_mask, list(channels), conv.weight,
+                           bn.weight, bn.bias, residual, *xs)
 
 
 class ConvBias(torch.autograd.Function):

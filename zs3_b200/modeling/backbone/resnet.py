@@ -32,12 +32,7 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         """x: NHWC bf16 [N,H,W,cpad(inplanes)]"""
-        out = ZF.conv_bn_act([x], [self.inplanes], self.conv1, self.bn1, relu=True)
-        out = ZF.conv_bn_act([out], [self.planes], self.conv2, self.bn2, relu=True)
-        residual = x
-        if self.downsample is not None:
-            residual = ZF.conv_bn_act([x], [self.inplanes], self.downsample[0], self.downsample[1], relu=False)
-        return ZF.conv_bn_act([out], [self.planes], self.conv3, self.bn3, relu=True, residual=residual)
+        return ZF.bottleneck(self, x)  # one fused autograd node per block (see functional.BottleneckFn)
 
 
 class ResNet(nn.Module):
