@@ -98,6 +98,25 @@ int encode_tiled2d_bf16(CUtensorMap* out, const void* base, long long rows, int 
   return ZS3_OK;
 }
 
+int encode_tiled2d_bf16_sw64(CUtensorMap* out, const void* base, long long rows, int cols, long long ld, int box_rows,
+                             int box_cols) {
+  int rc = ensure_driver();
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d, sw64) failed (%d): rows=%lld cols=%d ld=%lld box=%dx%d", (int)r, rows, cols,
+              ld, box_rows, box_cols);
+    return ZS3_ERR_DRIVER;
+  }
+  return ZS3_OK;
+}
+
 int encode_tiled3d_bf16(CUtensorMap* out, const void* base, int d2, int d1, int d0, int b2, int b1, int b0) {
   int rc = ensure_driver();
   if (rc) return rc;

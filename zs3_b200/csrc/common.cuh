@@ -43,6 +43,9 @@ int encode_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int W, 
 // tiled 2-D map over a row-major [rows][cols] bf16 matrix with row stride ld (elements); box = [box_rows][box_cols].
 int encode_tiled2d_bf16(CUtensorMap* out, const void* base, long long rows, int cols, long long ld, int box_rows,
                         int box_cols);
+// same with SWIZZLE_64B and a 32-column (64-byte) box: the epilogue's TMA store tiles
+int encode_tiled2d_bf16_sw64(CUtensorMap* out, const void* base, long long rows, int cols, long long ld, int box_rows,
+                             int box_cols);
 // tiled 3-D map over [d2][d1][d0] bf16 (d0 contiguous); box = [b2][b1][b0].
 int encode_tiled3d_bf16(CUtensorMap* out, const void* base, int d2, int d1, int d0, int b2, int b1, int b0);
 

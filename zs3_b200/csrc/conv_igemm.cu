@@ -40,6 +40,8 @@ struct alignas(64) FpropSegment {
 
 struct FpropParams {
   FpropSegment seg[ZS3_MAX_SEGMENTS];
+  CUtensorMap ymap;    // tiled 2-D map over y [M][cout_pad] (box 32 rows x 32 channels, SWIZZLE_64B) for the TMA-store epilogue
+  int use_tma_store;   // dense bf16 output without accumulate: stage through shared memory and store with TMA
   int num_segments;
   int M;          // N*Ho*Wo
   int HoWo, Wo;
@@ -63,8 +65,10 @@ template <int BN, int STAGES>
 struct FpropSmem {
   static constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAT_OFFSET = BAR_OFFSET + 256;  // barriers + tmem slot
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;      // 1024-byte aligned: the 64B swizzle is address based
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 64;    // one [32 rows][32 ch] bf16 box (2 KiB) per warp
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
+  static constexpr int STAT_OFFSET = BAR_OFFSET + 256;             // barriers + tmem slot
   static constexpr int TOTAL = STAT_OFFSET + 2 * MAX_STAT_CH * 4 + 1024 /*alignment slack*/;
 };
 
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
       tma_prefetch_desc(&p.seg[s].a);
       tma_prefetch_desc(&p.seg[s].b);
     }
+    if (p.use_tma_store) tma_prefetch_desc(&p.ymap);
   }
   tc_fence_before();
   __syncthreads();
@@ -258,7 +263,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n + j);
         }
-        if (valid) {
+        if (p.use_tma_store) {
+          // coalesced path: the warp's [32 rows][32 channels] bf16 block goes through a 64B-swizzled staging box
+          // and leaves as one TMA store (full 64-byte row segments; rows >= M are clipped by the tensor map)
+          uint8_t* stg = smem + L::STAGING_OFFSET + (warp - EPI_WARP0) * (32 * 64);
+          tma_store_wait_read();  // previous store from this buffer has been read out (only lane 0 has groups)
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            // SWIZZLE_64B: 16-byte chunk index ^= (byte address bits [7,9)) = (row >> 1) & 3
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.ymap, stg, n, m_tile * BLOCK_M + quarter * 32);
+            tma_store_commit();
+          }
+        } else if (valid) {
           if (p.y_is_f32) {
             float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.y) + pix * p.y_cstride + n);
             if (p.accumulate) {
@@ -320,6 +347,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
+    if (p.use_tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -779,6 +807,18 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   }
   p.y_is_f32 = a->y_is_f32;
   p.accumulate = a->accumulate;
+  p.use_tma_store = 0;
+  static int tma_store_pref = -1;
+  if (tma_store_pref < 0) {
+    const char* env = getenv("ZS3_TMA_STORE");
+    tma_store_pref = env ? atoi(env) : 1;
+  }
+  if (tma_store_pref && !a->y_is_f32 && !a->accumulate && a->y_sp_stride <= 1 && a->y_cstride % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(a->y) & 15) == 0) {
+    int rc2 = encode_tiled2d_bf16_sw64(&p.ymap, a->y, M, a->cout_pad, a->y_cstride, 32, 32);
+    if (rc2) return rc2;
+    p.use_tma_store = 1;
+  }
   p.bias = a->bias;
   p.stat_sum = a->stat_sum;
   p.stat_sqsum = a->stat_sqsum;
