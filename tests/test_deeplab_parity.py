@@ -65,3 +65,27 @@ def test_deeplab_logits_within_north_star_tolerance(mode):
     # the fp64 oracle is the ground truth both fp32 computations approximate
     assert e64 < TOL
     assert e < TOL or e64 <= 2 * self_noise
+
+
+def test_config0_full_resolution_eval_forward():
+    """BASELINE.json configs[0]: DeepLabv3+ ResNet-101 forward on 1x3x513x513 (the reference's CPU-runnable case):
+    bf16 throughput path within its storage bound, fp32x3 parity mode within the north-star 1e-3."""
+    import zs3_oracle as O
+    from zs3_b200 import parity as P
+    from zs3_b200.modeling.deeplab import DeepLab
+    x = torch.randn(1, 3, 513, 513, generator=torch.Generator().manual_seed(1))
+    st = O.init_deeplab_state(seed=1, randomize_bn=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = O.deeplab_forward(st, x, training=False)
+    model = DeepLab(num_classes=21, sync_bn=False, pretrained=False)
+    model.load_state_dict(st)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        fast = model(x.cuda())
+    exact = P.deeplab_forward_fp32x3(model, x.cuda())
+    e_fast, e_exact = rel_l2(fast.cpu(), ref), rel_l2(exact.cpu(), ref)
+    print(f"config0 513x513: bf16 path rel_l2={e_fast:.2e}, fp32x3 rel_l2={e_exact:.2e}")
+    assert tuple(fast.shape) == (1, 21, 513, 513)
+    assert e_fast < 3e-2
+    assert e_exact < TOL
