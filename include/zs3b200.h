@@ -75,6 +75,9 @@ typedef struct {
   const float* bias; /* optional [cout_pad] fp32 added before store (decoder.pred_conv bias), or NULL */
   double* stat_sum;  /* optional [cout_pad]: += per-channel sum of the (fp32) conv output, or NULL */
   double* stat_sqsum;/* optional [cout_pad]: += per-channel sum of squares */
+  int w_forward_layout; /* 1 (data-gradient mode): seg[i].w is the FORWARD-packed weight of the layer being
+                           differentiated, [seg.cin_pad = forward cout][R*S][cout_pad = forward cin]; the kernel reads it
+                           as MN-major B tiles and flips the taps itself, so no transposed copy has to be packed */
 } zs3_conv_args;
 
 int zs3_conv_fprop(const zs3_conv_args* a, void* stream);

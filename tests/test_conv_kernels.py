@@ -188,3 +188,28 @@ def test_wgrad_direct_into_krsc_grad_and_krsc_pack(case):
                      dw_view=(Cin, half, Cout, Cin - half))
     assert g.is_contiguous(memory_format=torch.channels_last)
     assert rel_l2(g, 2 * dw_ref) < 5e-5
+
+
+@pytest.mark.parametrize("case", [
+    (2, 33, 33, 64, 64, 3, 1, 1, 1),
+    (2, 33, 33, 128, 256, 3, 1, 4, 4),
+    (2, 33, 33, 256, 64, 1, 1, 0, 1),
+    (3, 20, 20, 48, 21, 3, 1, 1, 1),
+    (2, 17, 17, 1024, 256, 1, 1, 0, 1),
+])
+def test_dgrad_from_forward_packed_weights(case):
+    """data gradient straight from the forward-packed weights (MN-major B tiles, taps flipped in the kernel)"""
+    from zs3_b200 import kernels as K
+    N, H, W, Cin, Cout, R, stride, pad, dil = case
+    x, w = _mk(N, H, W, Cin, Cout, R)
+    x.requires_grad_(True)
+    y = F.conv2d(x, w, stride=stride, padding=pad, dilation=dil)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).float().cuda()
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    cin_p, cout_p = K.cpad(Cin), K.cpad(Cout)
+    wp = K.pack_weight(w, cout_p, cin_p)  # forward layout [cout_p][taps][cin_p]
+    dx = K.conv_fprop([(K.nchw_to_nhwc(dy, cout_p), wp)], R, R, 1, dil * (R - 1) - pad, dil, cin_p, out_f32=True,
+                      w_forward_layout=True)
+    assert rel_l2(dx[..., :Cin].permute(0, 3, 1, 2), dx_ref) < TOL_F32_OUT
+    if cin_p > Cin:
+        assert dx[..., Cin:].abs().max() == 0

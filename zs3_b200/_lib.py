@@ -43,6 +43,7 @@ class ConvArgs(C.Structure):
         ("bias", C.c_void_p),
         ("stat_sum", C.c_void_p),
         ("stat_sqsum", C.c_void_p),
+        ("w_forward_layout", C.c_int),
     ]
 
 

@@ -40,6 +40,7 @@ struct alignas(64) FpropSegment {
 
 struct FpropParams {
   FpropSegment seg[ZS3_MAX_SEGMENTS];
+  int b_mn;            // 1: data-gradient mode on forward-packed weights W[k][tap][n] (MN-major B tiles, flipped taps)
   CUtensorMap ymap;    // tiled 2-D map over y [M][cout_pad] (box 32 rows x 32 channels, SWIZZLE_64B) for the TMA-store epilogue
   int use_tma_store;   // dense bf16 output without accumulate: stage through shared memory and store with TMA
   int num_segments;
@@ -174,7 +175,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
                 mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                 tma_load_im2col_4d(sa, &sg.a, &full_bar[stage], cb * BLOCK_K, base_w, base_h, img,
                                    (uint16_t)(q * p.dil), (uint16_t)(r * p.dil));
-                if (csize == 1)
+                if (p.b_mn) {
+                  // weights stay in their forward layout [k = forward cout][tap][n = forward cin]: BN/64 boxes of
+                  // [64 k rows][64 n] form MN-major B tiles; the data gradient uses the spatially flipped tap
+                  const int ftap = (p.R - 1 - r) * p.S + (p.S - 1 - q);
+#pragma unroll
+                  for (int j = 0; j < BN / 64; ++j)
+                    tma_load_3d(sb + j * 8192, &sg.b, &full_bar[stage], n_tile * BN + j * 64, ftap, cb * BLOCK_K);
+                } else if (csize == 1)
                   tma_load_3d(sb, &sg.b, &full_bar[stage], cb * BLOCK_K, tap, n_tile * BN);
                 else
                   tma_load_3d_mc(sb + crank * b_rows * 128, &sg.b, &full_bar[stage], cb * BLOCK_K, tap,
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, p.b_mn);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -208,11 +216,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + A_TILE_BYTES;
           const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+          if (p.b_mn) {
+            // MN-major B: LBO = 8192 B between 64-column sub-tiles, SBO = 1024 B per 8 k rows, 2048 B per UMMA_K
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_f16(tmem_d, adesc + 2 * k, make_smem_desc_sw128(sb + k * 2048, 8192, 1024), idesc, (kb | k) != 0);
+          } else {
+            const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           if (csize == 1)
             umma_commit(&empty_bar[stage]);
@@ -758,7 +773,7 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
     if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 1;
   }
   const int m_tiles_total = (int)ceil_div_ll(M, BLOCK_M);
-  int csize = cluster_pref;
+  int csize = a->w_forward_layout ? 1 : cluster_pref;
   while (csize > 1 && m_tiles_total < 2 * csize) csize >>= 1;
   int kb = 0;
   for (int s = 0; s < a->num_segments; ++s) {
@@ -773,7 +788,10 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
     int rc = encode_im2col_bf16(&p.seg[s].a, sg.x, a->N, a->H, a->W, sg.x_cstride, a->pad, upper_w, a->stride, BLOCK_K,
                                 BLOCK_M);
     if (rc) return rc;
-    rc = encode_tiled3d_bf16(&p.seg[s].b, sg.w, a->cout_pad, a->R * a->S, sg.cin_pad, BN / csize, 1, BLOCK_K);
+    if (a->w_forward_layout)  // w[k = sg.cin_pad][taps][n = cout_pad]
+      rc = encode_tiled3d_bf16(&p.seg[s].b, sg.w, sg.cin_pad, a->R * a->S, a->cout_pad, 64, 1, 64);
+    else
+      rc = encode_tiled3d_bf16(&p.seg[s].b, sg.w, a->cout_pad, a->R * a->S, sg.cin_pad, BN / csize, 1, BLOCK_K);
     if (rc) return rc;
     p.seg[s].num_cblk = sg.cin_pad / BLOCK_K;
     kb += a->R * a->S * p.seg[s].num_cblk;
@@ -807,6 +825,7 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   }
   p.y_is_f32 = a->y_is_f32;
   p.accumulate = a->accumulate;
+  p.b_mn = a->w_forward_layout ? 1 : 0;
   p.use_tma_store = 0;
   static int tma_store_pref = -1;
   if (tma_store_pref < 0) {
@@ -865,11 +884,13 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   const int out_tiles = p.num_co_tiles * p.num_ci_tiles * a->R * a->S;
   int ks = a->k_splits;
   if (ks <= 0) {
-    // fill the machine about twice over, but keep at least 8 k-blocks per CTA
-    ks = ceil_div(2 * num_sms(), out_tiles);
-    const int max_ks = p.pblocks_total / 8 > 0 ? p.pblocks_total / 8 : 1;
-    if (ks > max_ks) ks = max_ks;
+    // Split the pixel reduction so that the grid is (at most) ONE full wave of CTAs: every extra split costs a
+    // whole fp32 atomic pass over the dW tile, and a grid of waves*SMs + 1 CTAs costs a whole extra wave
+    // (ncu, profiles/r01: 297 CTAs on 148 SMs ran as three waves).
+    ks = num_sms() / out_tiles;
     if (ks < 1) ks = 1;
+    const int max_ks = p.pblocks_total / 4 > 0 ? p.pblocks_total / 4 : 1;  // >= 4 k-blocks of 64 pixels per CTA
+    if (ks > max_ks) ks = max_ks;
   }
   if (ks > p.pblocks_total) ks = p.pblocks_total;
   p.k_splits = ks;

@@ -241,21 +241,23 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
     for i, x in enumerate(xs):
         ci0, c_real, cin_p = sv.ranges[i]
         if need_dx[i]:
-            wt = _packed_weight(conv, 1, ci0, c_real, cin_p, cout_p)  # [cin_p][taps][cout_p]
+            # the data gradient reads the FORWARD-packed weights (MN-major B tiles, taps flipped in the kernel):
+            # no transposed weight copy is ever materialised
+            wt = _packed_weight(conv, 0, ci0, c_real, cin_p, cout_p)  # [cout_p][taps][cin_p]
             fl = sv.flops_per_cin * c_real
             tgt, acc = (dx_into[i] if dx_into is not None and dx_into[i] is not None else (None, False))
             if stride == 1:
                 dx = K.conv_fprop([(dy, wt)], R, S, 1, dil * (R - 1) - pad, dil, cin_p, out=tgt, accumulate=acc, flops=fl,
-                                  kind="conv_dgrad")
+                                  kind="conv_dgrad", w_forward_layout=True)
             elif R == 1:
                 dx = tgt if tgt is not None else torch.zeros_like(x)
                 K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, out=dx, scatter=(stride, h_in, w_in), accumulate=acc,
-                             flops=fl, kind="conv_dgrad")
+                             flops=fl, kind="conv_dgrad", w_forward_layout=True)
             else:
                 # zero-inserted dy has (ho-1)*s+1 rows; pad so that the output covers the full input extent
                 dx = K.conv_fprop([(_pad_to(dy_z, h_in + 2 * pad - dil * (R - 1), w_in + 2 * pad - dil * (S - 1)), wt)],
                                   R, S, 1, dil * (R - 1) - pad, dil, cin_p, out=tgt, accumulate=acc, flops=fl,
-                                  kind="conv_dgrad")
+                                  kind="conv_dgrad", w_forward_layout=True)
             dxs.append(dx)
         else:
             dxs.append(None)
@@ -382,8 +384,9 @@ class ConvBias(torch.autograd.Function):
         dy = dy.contiguous()
         dx = dw_oihw = dbias = None
         if ctx.needs_input_grad[3]:
-            wt = _packed_weight(conv, 1, 0, cin, cin_p, cout_p)
-            dx = K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, flops=ctx.flops, kind="conv_dgrad")
+            wt = _packed_weight(conv, 0, 0, cin, cin_p, cout_p)
+            dx = K.conv_fprop([(dy, wt)], 1, 1, 1, 0, 1, cin_p, flops=ctx.flops, kind="conv_dgrad",
+                              w_forward_layout=True)
         if ctx.needs_input_grad[1]:
             gbuf = _direct_grad_buffer(conv.weight)
             if gbuf is not None:

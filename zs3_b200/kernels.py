@@ -79,7 +79,7 @@ def unpack_wgrad(dw, grad_oihw, ci_begin=0, ci_count=None, accumulate=False):
 
 
 def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=False, accumulate=False, bias=None,
-               stats=None, scatter=None, flops=0.0, kind="conv_fprop"):
+               stats=None, scatter=None, flops=0.0, kind="conv_fprop", w_forward_layout=False):
     """segments: list of (x [N,H,W,Cs] bf16, w_packed [cout_pad, R*S, cin_pad] bf16).
     stats: optional (sum, sqsum) fp64 [cout_pad] accumulators.  scatter: optional (sp_stride, y_H, y_W).
     Returns y [N,Ho,Wo,cout_pad] (or the provided `out`)."""
@@ -97,12 +97,13 @@ def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=Fal
         _chk_act(x, f"conv_fprop seg{i}")
         if tuple(x.shape[:3]) != (n, h, w_):
             raise ValueError("conv_fprop: segments disagree on N/H/W")
-        if wp.dtype != torch.bfloat16 or wp.shape[0] != cout_pad or wp.shape[1] != R * S:
+        kdim, ndim = (0, 2) if w_forward_layout else (2, 0)  # forward layout: [k][taps][n]
+        if wp.dtype != torch.bfloat16 or wp.shape[ndim] != cout_pad or wp.shape[1] != R * S:
             raise ValueError(f"conv_fprop: packed weight shape {tuple(wp.shape)} does not match")
         a.seg[i].x = x.data_ptr()
         a.seg[i].x_cstride = x.shape[3]
         a.seg[i].w = wp.data_ptr()
-        a.seg[i].cin_pad = wp.shape[2]
+        a.seg[i].cin_pad = wp.shape[kdim]
     if out is None:
         if scatter is not None:
             raise ValueError("scatter needs an explicit output tensor")
@@ -113,13 +114,14 @@ def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=Fal
     if scatter is not None:
         a.y_sp_stride, a.y_H, a.y_W = scatter
     a.accumulate = int(accumulate)
+    a.w_forward_layout = int(w_forward_layout)
     a.bias = None if bias is None else bias.data_ptr()
     if stats is not None:
         a.stat_sum = stats[0].data_ptr()
         a.stat_sqsum = stats[1].data_ptr()
     tag = ""
     if PROFILE is not None:
-        tag = (f"N{n} {h}x{w_}->{ho}x{wo} k{R} s{stride} d{dil} cin{sum(wp.shape[2] for _, wp in segments)} "
+        tag = (f"N{n} {h}x{w_}->{ho}x{wo} k{R} s{stride} d{dil} cin{sum(s_.cin_pad for s_ in a.seg[:len(segments)])} "
                f"cout{cout_pad} segs{len(segments)}{' stats' if stats is not None else ''}")
     with _Timed(kind, flops, tag):
         L.check(L.lib().zs3_conv_fprop(C.byref(a), L.stream_ptr()), "zs3_conv_fprop")
