@@ -253,6 +253,9 @@ int zs3_ce_bwd(const float* logit, const float* target, const float* weight, int
 
 /* torch.optim.SGD (zs3/train_pascal.py:55-60) and torch.optim.Adam (zs3/train_pascal_GMMN.py:65-67) over one
  * flat fp32 buffer; grad_scale multiplies the gradient first (1/world_size after the NCCL all-reduce). */
+/* bf16 shadow of a (flat) fp32 parameter buffer: conv weights are stored KRSC, so for every layer without channel
+ * padding its slice of the shadow IS the packed forward weight [cout][R*S][cin] */
+int zs3_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 int zs3_sgd_step(float* p, const float* g, float* momentum_buf, long long n, float lr, float momentum,
                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 int zs3_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

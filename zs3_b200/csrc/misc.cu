@@ -400,6 +400,21 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logit, const float* __re
   }
 }
 
+// bf16 shadow of the flat fp32 parameter buffer (one launch per step instead of one pack kernel per layer)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
 // -------------------------------------------------------------------------------- optimizers
 // torch.optim.SGD: d = g*gscale + wd*p; buf = first ? d : mom*buf + d; p -= lr * (nesterov ? d + mom*buf : buf)
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
@@ -545,6 +560,16 @@ extern "C" int zs3_ce_bwd(const float* logit, const float* target, const float* 
   ce_bwd_kernel<<<ew_blocks(total, 256, 148 * 8), 256, 0, ST(stream)>>>(logit, target, weight, C, HW, total,
                                                                         ignore_index, accum2, div, grad_out, dlogit);
   ZS3_CHECK_LAUNCH("ce_bwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  ZS3_CHECK_ARG(src && dst && n >= 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+                "cast_f32_to_bf16: bad args");
+  if (n == 0) return ZS3_OK;
+  cast_f32_bf16_kernel<<<ew_blocks(n / 4 + 1, 256), 256, 0, ST(stream)>>>(src, BF(dst), n);
+  ZS3_CHECK_LAUNCH("cast_f32_to_bf16");
   return ZS3_OK;
 }
 

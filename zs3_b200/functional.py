@@ -77,6 +77,11 @@ def invalidate_weight_caches():
 def _packed_weight(conv, mode, ci_begin, ci_count, cin_pad, cout_pad):
     """bf16 kernel-layout copy of conv.weight, cached until the parameter changes (version counter)."""
     w = conv.weight
+    shadow = conv.__dict__.get("_zs3_bf16_shadow")
+    if (shadow is not None and mode == 0 and ci_begin == 0 and ci_count == w.shape[1] == cin_pad
+            and cout_pad == w.shape[0] and shadow[1] == w.data_ptr()):
+        # parameter lives in a trainer's flat KRSC buffer whose bf16 shadow is refreshed once per step
+        return shadow[0]
     cache = conv.__dict__.setdefault("_zs3_pack_cache", {})
     key = (mode, ci_begin, ci_count, cin_pad, cout_pad)
     ent = cache.get(key)

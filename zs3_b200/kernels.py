@@ -391,6 +391,10 @@ def channel_sums(t):
     return scratch[0]
 
 
+def cast_f32_to_bf16(src, dst):
+    L.check(L.lib().zs3_cast_f32_to_bf16(L.ptr(src), L.ptr(dst), src.numel(), L.stream_ptr()), "zs3_cast_f32_to_bf16")
+
+
 def sgd_step(p, g, buf, lr, momentum, weight_decay, nesterov, first_step, grad_scale=1.0):
     L.check(L.lib().zs3_sgd_step(L.ptr(p), L.ptr(g), L.ptr(buf), p.numel(), float(lr), float(momentum),
                                  float(weight_decay), int(nesterov), int(first_step), float(grad_scale),

@@ -103,6 +103,17 @@ class DataParallelTrainer:
         self.flat = FlatParams(groups)
         self.opt = FusedSGD(self.flat, [lr, lr * 10], momentum, weight_decay, nesterov)
         ZF.invalidate_weight_caches()
+        # bf16 shadow of the flat parameter buffer: conv weights are KRSC, so a layer's slice of the shadow is its
+        # packed forward weight [cout][R*S][cin] (layers with channel padding keep their own packed copies)
+        self.shadow = torch.empty(self.flat.flat.numel(), dtype=torch.bfloat16, device=self.flat.flat.device)
+        base = self.flat.flat.data_ptr()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Conv2d) and K.is_krsc(m.weight):
+                off = (m.weight.data_ptr() - base) // 4
+                if 0 <= off < self.flat.flat.numel() and off % 8 == 0:
+                    co, ci, r, s = m.weight.shape
+                    m.__dict__["_zs3_bf16_shadow"] = (self.shadow[off:off + m.weight.numel()].view(co, r * s, ci),
+                                                      m.weight.data_ptr())
         if world_size > 1:
             # identical replicas: broadcast rank 0's weights and BN buffers once
             dist.broadcast(self.flat.flat, 0)
@@ -140,6 +151,7 @@ class DataParallelTrainer:
         if ZF._RngState.device_counter is not None:
             ZF._RngState.device_counter.add_(1 << 32)  # fresh dropout masks per step, also under graph replay
         self.flat.zero_grad()
+        K.cast_f32_to_bf16(self.flat.flat, self.shadow)  # one launch refreshes every layer's bf16 forward weight
         output = self.model(image)
         loss = self.criterion(output, target)
         loss.backward()
