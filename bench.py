@@ -293,7 +293,7 @@ def main():
     ap.add_argument("--size", type=int, default=513, help="input height=width (BASELINE: 513)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default="", help="write a per-conv-shape timing table (markdown) to this path")
-    ap.add_argument("--mode", default="eager", choices=["eager", "graph"],
+    ap.add_argument("--mode", default="graph", choices=["eager", "graph"],
                     help="graph: capture the whole training step in one CUDA graph and replay it")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -159,6 +159,22 @@ typedef struct {
   const unsigned char* keep_mask; /* drop_mode 2: [M][C] bytes, 1 = keep */
   const unsigned long long* offset_dev; /* optional device counter added to `offset` at run time (lets a captured
                                            CUDA graph draw fresh masks on every replay) */
+  /* Fused finalize (optional, training mode): if stat_sum != NULL, scale/shift above are ignored and every thread
+   * derives the affine of its channels from the raw batch statistics exactly like zs3_bn_finalize; CTA 0 publishes
+   * mean/invstd/scale/shift (fp32 [C], read by the backward), updates the running statistics and zeroes
+   * reset_sum/reset_sqsum (the statistics buffer the NEXT layer will accumulate into: two buffers alternate). */
+  const double* stat_sum;
+  const double* stat_sqsum;
+  long long count;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  int C_real;           /* channels with real statistics; [C_real, C) get scale = shift = 0 */
+  float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
+  double* reset_sum; double* reset_sqsum;
+  int reset_count;      /* number of leading entries of reset_sum/reset_sqsum to zero */
 } zs3_bn_apply_args;
 
 /* out = dropout(relu?(scale*y + shift (+ residual))) */
@@ -194,6 +210,9 @@ typedef struct {
   float* dbeta;
   int C_real;
   int param_accumulate; /* 1: dgamma/dbeta += */
+  double* reset_sum_dz; /* optional: the apply phase zeroes the first reset_count entries of these two arrays (the */
+  double* reset_sum_dzx;/* sums buffer the NEXT layer's reduce phase will accumulate into; two buffers alternate) */
+  int reset_count;
 } zs3_bn_bwd_args;
 
 /* phase 1: sum_dz += sum(dz), sum_dzx += sum(dz * xhat) with dz = dout * [out > 0] * grad_scale */

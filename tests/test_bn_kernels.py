@@ -98,3 +98,35 @@ def test_bn_stats_kernel():
         K.bn_stats(K.nchw_to_nhwc(y, C), (stats[0], stats[1]))
         assert rel_l2(stats[0], y.double().sum(dim=(0, 2, 3))) < 1e-5
         assert rel_l2(stats[1], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-5
+
+
+def test_bn_apply_fused_finalize_matches_separate_finalize():
+    from zs3_b200 import kernels as K
+    g = torch.Generator().manual_seed(11)
+    N, C, hw = 3, 48, 14
+    Cp = K.cpad(C)
+    y = (torch.randn(N, C, hw, hw, generator=g) * 1.5 - 0.3).to(torch.bfloat16).float().cuda()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    yh = K.nchw_to_nhwc(y, Cp)
+    def fresh_stats():
+        st = torch.zeros(2, 2048, dtype=torch.float64, device="cuda")
+        K.bn_stats(yh, (st[0, :Cp], st[1, :Cp]))
+        return st
+    rm1, rv1 = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    st1 = fresh_stats()
+    sc, sh, mu, istd = K.bn_finalize((st1[0, :Cp], st1[1, :Cp]), N * hw * hw, gamma, beta, 1e-5, 0.1, rm1, rv1, Cp)
+    ref = K.bn_apply(yh, sc, sh, True)
+    rm2, rv2 = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    st2 = fresh_stats()
+    other = torch.full((2, 2048), 7.0, dtype=torch.float64, device="cuda")
+    coef = torch.empty(4, Cp, device="cuda")
+    out = K.bn_apply(yh, None, None, True, finalize=dict(stats=(st2[0, :Cp], st2[1, :Cp]), count=N * hw * hw, gamma=gamma,
+                                                          beta=beta, eps=1e-5, momentum=0.1, running_mean=rm2,
+                                                          running_var=rv2, coef=coef, c_real=C,
+                                                          reset=(other[0], other[1], 300)))
+    assert torch.equal(out, ref)
+    assert torch.allclose(coef[0], sc) and torch.allclose(coef[1], sh) and torch.allclose(coef[2], mu) and torch.allclose(coef[3], istd)
+    assert torch.allclose(rm1, rm2) and torch.allclose(rv1, rv2)
+    assert other[:, :300].abs().max() == 0 and (other[:, 300:] == 7.0).all()
+    ref_bn = F.batch_norm(y, torch.zeros(C).cuda(), torch.ones(C).cuda(), gamma, beta, True, 0.1, 1e-5)
+    assert rel_l2(K.nhwc_to_nchw(out, C), F.relu(ref_bn)) < 4e-3

@@ -103,6 +103,11 @@ class BnApplyArgs(C.Structure):
         ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
         ("keep_mask", C.c_void_p),
         ("offset_dev", C.c_void_p),
+        ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("count", C.c_longlong),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("C_real", C.c_int),
+        ("mean_out", C.c_void_p), ("invstd_out", C.c_void_p), ("scale_out", C.c_void_p), ("shift_out", C.c_void_p),
+        ("reset_sum", C.c_void_p), ("reset_sqsum", C.c_void_p), ("reset_count", C.c_int),
     ]
 
 
@@ -119,6 +124,7 @@ class BnBwdArgs(C.Structure):
         ("sp_Ho", C.c_int), ("sp_Wo", C.c_int), ("dy_H", C.c_int), ("dy_W", C.c_int),
         ("dres", C.c_void_p), ("dres_cstride", C.c_int), ("dres_accumulate", C.c_int),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("C_real", C.c_int), ("param_accumulate", C.c_int),
+        ("reset_sum_dz", C.c_void_p), ("reset_sum_dzx", C.c_void_p), ("reset_count", C.c_int),
     ]
 
 

@@ -115,6 +115,12 @@ struct ApplyP {
   long long M; int C; int relu; int drop_mode; uint32_t thresh16; float keep_scale;
   uint64_t seed, offset; const unsigned char* mask; const unsigned long long* offset_dev;
   int rows_per_block;
+  // fused finalize (training mode): coefficients are derived from the raw batch statistics inside this kernel
+  const double* stat_sum; const double* stat_sqsum; long long count; const float* gamma; const float* beta;
+  float eps, momentum; float* rmean; float* rvar; int C_real;
+  float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
+  double* reset_a; double* reset_b;  // the OTHER statistics buffer, zeroed for the next layer
+  int reset_count;
 };
 
 __device__ __forceinline__ void apply_one(const ApplyP& p, long long m, int c, const float (&sc)[8],
@@ -153,11 +159,51 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyP p) {
   const int vpc = p.C >> 3;
   const int c = (threadIdx.x % vpc) << 3;
   const int rl = threadIdx.x / vpc;
+  if (blockIdx.x == 0 && p.reset_a != nullptr) {
+    for (int i = threadIdx.x; i < p.reset_count; i += blockDim.x) {
+      p.reset_a[i] = 0.0;
+      p.reset_b[i] = 0.0;
+    }
+  }
   if (rl >= p.rows_per_block) return;
   const uint64_t rng_offset = p.offset + (p.offset_dev ? *p.offset_dev : 0ull);
   float sc[8], sh[8];
-  load8f(p.scale + c, sc);
-  load8f(p.shift + c, sh);
+  if (p.stat_sum != nullptr) {
+    // fused bn_finalize: every thread derives the affine of its 8 channels from the fp64 sums; the first row lane
+    // of CTA 0 also publishes mean/invstd/scale/shift for the backward pass and updates the running statistics
+    const bool publish = blockIdx.x == 0 && rl == 0;
+    const double n = (double)p.count;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = c + j;
+      float s = 0.f, b = 0.f, mu = 0.f, is = 0.f;
+      if (ch < p.C_real) {
+        const double mean = p.stat_sum[ch] / n;
+        double var = p.stat_sqsum[ch] / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        is = (float)(1.0 / sqrt(var + (double)p.eps));
+        mu = (float)mean;
+        s = (p.gamma ? p.gamma[ch] : 1.f) * is;
+        b = (p.beta ? p.beta[ch] : 0.f) - mu * s;
+        if (publish && p.rmean) {
+          const double unbiased = p.count > 1 ? var * n / (n - 1.0) : var;
+          p.rmean[ch] = (1.f - p.momentum) * p.rmean[ch] + p.momentum * mu;
+          p.rvar[ch] = (1.f - p.momentum) * p.rvar[ch] + p.momentum * (float)unbiased;
+        }
+      }
+      sc[j] = s;
+      sh[j] = b;
+      if (publish) {
+        p.scale_out[ch] = s;
+        p.shift_out[ch] = b;
+        p.mean_out[ch] = mu;
+        p.invstd_out[ch] = is;
+      }
+    }
+  } else {
+    load8f(p.scale + c, sc);
+    load8f(p.shift + c, sh);
+  }
   const long long stride = (long long)gridDim.x * p.rows_per_block;
   long long m = (long long)blockIdx.x * p.rows_per_block + rl;
   const uint4 zero = make_uint4(0, 0, 0, 0);
@@ -191,6 +237,7 @@ struct BwdP {
   __nv_bfloat16* dres; long long dres_cs; int dres_acc;
   float* dgamma; float* dbeta; int C_real; int param_acc;
   int rows_per_block;  // pixel rows handled concurrently by one CTA
+  double* reset_a; double* reset_b; int reset_count;  // the other sums buffer, zeroed by the apply phase
 };
 
 // dz = dout * [forward activation > 0] * grad_scale for one 8-channel slice.
@@ -315,6 +362,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
   const int vpc = p.C >> 3;
   const int c = (threadIdx.x % vpc) << 3;
   const int rl = threadIdx.x / vpc;
+  if (blockIdx.x == 0 && p.reset_a != nullptr) {
+    for (int i = threadIdx.x; i < p.reset_count; i += blockDim.x) {
+      p.reset_a[i] = 0.0;
+      p.reset_b[i] = 0.0;
+    }
+  }
   if (blockIdx.x == 0 && p.dgamma != nullptr) {
     for (int ch = threadIdx.x; ch < p.C_real; ch += blockDim.x) {
       const float dg = (float)p.sum_dzx[ch], db = (float)p.sum_dz[ch];
@@ -523,7 +576,12 @@ extern "C" int zs3_bn_eval_coeffs(const float* gamma, const float* beta, const f
 }
 
 extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
-  ZS3_CHECK_ARG(a && a->y && a->out && a->scale && a->shift, "bn_apply: null pointer");
+  ZS3_CHECK_ARG(a && a->y && a->out && ((a->scale && a->shift) || a->stat_sum), "bn_apply: null pointer");
+  ZS3_CHECK_ARG(a->stat_sum == nullptr ||
+                    (a->stat_sqsum && a->count > 0 && a->mean_out && a->invstd_out && a->scale_out && a->shift_out &&
+                     a->C_real > 0 && a->C_real <= a->C && (a->running_mean == nullptr) == (a->running_var == nullptr) &&
+                     (a->reset_sum == nullptr) == (a->reset_sqsum == nullptr)),
+                "bn_apply: incomplete fused-finalize arguments");
   ZS3_CHECK_ARG(a->C > 0 && a->C % 8 == 0 && a->y_cstride % 8 == 0 && a->out_cstride % 8 == 0 &&
                     a->y_cstride >= a->C && a->out_cstride >= a->C,
                 "bn_apply: C=%d strides %d/%d must be multiples of 8", a->C, a->y_cstride, a->out_cstride);
@@ -542,6 +600,10 @@ extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
   p.thresh16 = (uint32_t)(a->drop_p * 65536.0f + 0.5f);
   p.keep_scale = 1.f / (1.f - a->drop_p);
   p.seed = a->seed; p.offset = a->offset; p.mask = a->keep_mask; p.offset_dev = a->offset_dev;
+  p.stat_sum = a->stat_sum; p.stat_sqsum = a->stat_sqsum; p.count = a->count; p.gamma = a->gamma; p.beta = a->beta;
+  p.eps = a->eps; p.momentum = a->momentum; p.rmean = a->running_mean; p.rvar = a->running_var; p.C_real = a->C_real;
+  p.mean_out = a->mean_out; p.invstd_out = a->invstd_out; p.scale_out = a->scale_out; p.shift_out = a->shift_out;
+  p.reset_a = a->reset_sum; p.reset_b = a->reset_sqsum; p.reset_count = a->reset_count;
   ZS3_CHECK_ARG(a->C <= 2048, "bn_apply: C=%d > 2048", a->C);
   p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
   bn_apply_kernel<<<stream_grid(a->M, p.rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -567,6 +629,7 @@ static int fill_bwd(const zs3_bn_bwd_args* a, BwdP& p, const char* who) {
   p.dy_img = (long long)a->dy_H * a->dy_W; p.dy_row = (long long)a->dy_W * a->dy_sp_stride;
   p.dres = static_cast<__nv_bfloat16*>(a->dres); p.dres_cs = a->dres_cstride; p.dres_acc = a->dres_accumulate;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.C_real = a->C_real; p.param_acc = a->param_accumulate;
+  p.reset_a = a->reset_sum_dz; p.reset_b = a->reset_sum_dzx; p.reset_count = a->reset_count;
   p.rows_per_block = 1;
   return ZS3_OK;
 }

@@ -37,6 +37,56 @@ class IdentityBN:
 
 
 
+class _StatBuffers:
+    """Two alternating fp64 (sum, sqsum) accumulators per device for the training-mode BatchNorm statistics.
+    Layer L accumulates into buffer `cur` (conv epilogue or bn_stats), its bn_apply derives the affine from it
+    (fused finalize) and zeroes the OTHER buffer, which layer L+1 then uses: no separate finalize/reset launches."""
+    per_device = {}
+
+    def __init__(self, dev):
+        self.buf = [torch.zeros(2, 2048, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.cur = 0
+        self.dirty = [0, 0]
+
+    @classmethod
+    def get(cls, dev):
+        key = str(dev)
+        if key not in cls.per_device:
+            cls.per_device[key] = cls(dev)
+        return cls.per_device[key]
+
+    def current(self, c):
+        self.dirty[self.cur] = max(self.dirty[self.cur], c)
+        b = self.buf[self.cur]
+        return b[0, :c], b[1, :c]
+
+    def flip(self):
+        """returns (sum, sqsum, count) of the other buffer to be zeroed by this layer's bn_apply, then switches"""
+        o = 1 - self.cur
+        res = (self.buf[o][0], self.buf[o][1], self.dirty[o])
+        self.dirty[o] = 0
+        self.cur = o
+        return res
+
+    def reset(self):
+        """both buffers zero and a fixed starting side: called once per model forward so that a captured CUDA graph
+        replays a self-consistent sequence"""
+        if self.dirty[0] or self.dirty[1] or self.cur != 0:
+            for b in self.buf:
+                b.zero_()
+        self.cur, self.dirty = 0, [0, 0]
+
+
+class _BwdSumBuffers(_StatBuffers):
+    """same alternation for the BatchNorm-backward sums (sum dz, sum dz*xhat)"""
+    per_device = {}
+
+
+def reset_stat_buffers(dev):
+    _StatBuffers.get(dev).reset()
+    _BwdSumBuffers.get(dev).reset()
+
+
 def _scratch64(dev, tag="fwd", n=2 * 2048):
     """fp64 scratch: "fwd" holds the conv-epilogue BN statistics (kept zero between uses by bn_finalize's
     reset), "bwd" the BN-backward sums (zeroed before each use)."""
@@ -166,8 +216,8 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
     dev = xs[0].device
     stats = None
     if training:
-        sc = _scratch64(dev)
-        stats = (sc[:cout_p], sc[2048:2048 + cout_p])
+        sb = _StatBuffers.get(dev)
+        stats = sb.current(cout_p)
     n_, h_, w_, _ = xs[0].shape
     ho_, wo_ = K.conv_out_size(h_, R, stride, pad, dil), K.conv_out_size(w_, S, stride, pad, dil)
     macs_per_cin = 2.0 * n_ * ho_ * wo_ * cout * R * S  # nominal FLOPs per input channel
@@ -180,14 +230,27 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
     if stats is not None and not fuse_stats:
         K.bn_stats(y, stats)
     n, ho, wo, _ = y.shape
-    scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
     seed = off = 0
     p = float(drop_p) if (drop_p and drop_training) else 0.0
     if p > 0 and keep_mask is None:
         seed, off = _RngState.next(y.numel())
+    fin = None
+    if training:
+        # fused finalize: bn_apply derives scale/shift from the raw sums, publishes the coefficients for the
+        # backward, updates the running statistics and zeroes the other statistics buffer
+        coef = torch.empty((4, cout_p), dtype=torch.float32, device=dev)
+        scale, shift, mean, invstd = coef[0], coef[1], coef[2], coef[3]
+        if bn.num_batches_tracked is not None:
+            PENDING_BATCH_COUNTERS.append(bn.num_batches_tracked)
+        fin = dict(stats=stats, count=n * ho * wo, gamma=bn.weight.detach() if bn.weight is not None else None,
+                   beta=bn.bias.detach() if bn.bias is not None else None, eps=bn.eps,
+                   momentum=bn.momentum if bn.momentum is not None else 0.1, running_mean=bn.running_mean,
+                   running_var=bn.running_var, coef=coef, c_real=cout, reset=sb.flip())
+    else:
+        scale, shift, mean, invstd = _bn_forward_coeffs(bn, None, n * ho * wo, cout_p)
     out = K.bn_apply(y, scale, shift, relu, residual=residual, drop_p=p, seed=seed, offset=off,
                      keep_mask=keep_mask if p > 0 else None,
-                     offset_dev=_RngState.device_counter if (p > 0 and keep_mask is None) else None)
+                     offset_dev=_RngState.device_counter if (p > 0 and keep_mask is None) else None, finalize=fin)
     sv = _Saved()
     sv.conv, sv.bn, sv.relu, sv.p, sv.training = conv, bn, relu, p, training
     sv.ranges, sv.has_res = ranges, residual is not None
@@ -217,8 +280,8 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
             dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
             dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
     dres = torch.empty_like(dout) if sv.has_res else None
-    sc = _scratch64(dev, "bwd")
-    scratch = sc[:2 * cout_p].view(2, cout_p)
+    bb = _BwdSumBuffers.get(dev)
+    sums = bb.current(cout_p)
     # strided 3x3: write dy zero-inserted so that the data gradient is a stride-1 conv (see conv_igemm.cu)
     zero_insert = stride > 1 and R > 1
     n, ho, wo, _ = y.shape
@@ -228,7 +291,7 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
         scatter = (stride, (ho - 1) * stride + 1, (wo - 1) * stride + 1)
     dy_dense_needed = need_w and zero_insert
     dy = K.bn_backward(dout, sv.out, y, sv.mean, sv.invstd, sv.scale, sv.relu, grad_scale=1.0 / (1.0 - sv.p),
-                       training=sv.training, dres=dres, dgamma=dgamma, dbeta=dbeta, scratch=scratch,
+                       training=sv.training, dres=dres, dgamma=dgamma, dbeta=dbeta, sums=sums, reset=bb.flip(),
                        param_accumulate=direct_affine, scatter=None if dy_dense_needed else scatter,
                        shift=sv.shift if sv.mask_from_y else None)
     if direct_affine:
@@ -423,14 +486,24 @@ class Stem(torch.autograd.Function):
         cols = K.stem_im2col(x, R, stride, pad, ho, wo, kpad, krsc=krsc)          # [n, ho, wo, kpad]
         wp = _packed_weight_2d(conv, kreal, kpad, cout_p, krsc)
         training = bn.training
-        stats = None
-        if training:
-            sc = _scratch64(x.device)
-            stats = (sc[:cout_p], sc[2048:2048 + cout_p])
         fl = 2.0 * n * ho * wo * cout * kreal
-        y = K.conv_fprop([(cols, wp)], 1, 1, 1, 0, 1, cout_p, stats=stats, flops=fl)
-        scale, shift, mean, invstd = _bn_forward_coeffs(bn, stats, n * ho * wo, cout_p)
-        a = K.bn_apply(y, scale, shift, True)
+        if training:
+            sb = _StatBuffers.get(x.device)
+            stats = sb.current(cout_p)
+            y = K.conv_fprop([(cols, wp)], 1, 1, 1, 0, 1, cout_p, flops=fl)
+            K.bn_stats(y, stats)  # K = 192: far too short to hide the statistics in the conv epilogue
+            coef = torch.empty((4, cout_p), dtype=torch.float32, device=x.device)
+            scale, shift, mean, invstd = coef[0], coef[1], coef[2], coef[3]
+            if bn.num_batches_tracked is not None:
+                PENDING_BATCH_COUNTERS.append(bn.num_batches_tracked)
+            fin = dict(stats=stats, count=n * ho * wo, gamma=bn.weight.detach(), beta=bn.bias.detach(), eps=bn.eps,
+                       momentum=bn.momentum if bn.momentum is not None else 0.1, running_mean=bn.running_mean,
+                       running_var=bn.running_var, coef=coef, c_real=cout, reset=sb.flip())
+            a = K.bn_apply(y, scale, shift, True, finalize=fin)
+        else:
+            y = K.conv_fprop([(cols, wp)], 1, 1, 1, 0, 1, cout_p, flops=fl)
+            scale, shift, mean, invstd = _bn_forward_coeffs(bn, None, n * ho * wo, cout_p)
+            a = K.bn_apply(y, scale, shift, True)
         k, ps, pp = pool.kernel_size, pool.stride, pool.padding
         out, arg = K.maxpool_fwd(a, k, ps, pp)
         ctx.conv, ctx.bn, ctx.training, ctx.krsc = conv, bn, training, krsc

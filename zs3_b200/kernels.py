@@ -208,7 +208,9 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, cpad_):
 
 
 def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0, offset=0, keep_mask=None,
-             offset_dev=None):
+             offset_dev=None, finalize=None):
+    """finalize = dict(stats=(sum, sqsum), count, gamma, beta, eps, momentum, running_mean, running_var, coef [4][C],
+    reset=(sum, sqsum) or None): derive the affine from raw batch statistics inside the kernel (fused bn_finalize)."""
     _chk_act(y, "bn_apply y")
     n, h, w, cs = y.shape
     if out is None:
@@ -219,7 +221,23 @@ def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0,
         _chk_act(residual, "bn_apply residual")
         a.residual, a.res_cstride = residual.data_ptr(), residual.shape[3]
     a.out, a.out_cstride = out.data_ptr(), out.shape[3]
-    a.scale, a.shift = scale.data_ptr(), shift.data_ptr()
+    if finalize is not None:
+        f = finalize
+        a.stat_sum, a.stat_sqsum, a.count = f["stats"][0].data_ptr(), f["stats"][1].data_ptr(), int(f["count"])
+        a.gamma = None if f["gamma"] is None else f["gamma"].data_ptr()
+        a.beta = None if f["beta"] is None else f["beta"].data_ptr()
+        a.eps, a.momentum = float(f["eps"]), float(f["momentum"])
+        if f["running_mean"] is not None:
+            a.running_mean, a.running_var = f["running_mean"].data_ptr(), f["running_var"].data_ptr()
+        a.C_real = int(f["c_real"])
+        coef = f["coef"]
+        a.scale_out, a.shift_out = coef[0].data_ptr(), coef[1].data_ptr()
+        a.mean_out, a.invstd_out = coef[2].data_ptr(), coef[3].data_ptr()
+        if f.get("reset") is not None:
+            a.reset_sum, a.reset_sqsum = f["reset"][0].data_ptr(), f["reset"][1].data_ptr()
+            a.reset_count = int(f["reset"][2])
+    else:
+        a.scale, a.shift = scale.data_ptr(), shift.data_ptr()
     a.M, a.C = n * h * w, cs
     a.relu = int(relu)
     a.drop_p = float(drop_p)
@@ -237,12 +255,14 @@ def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0,
 
 def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, training=True, dres=None,
                 dres_accumulate=False, dgamma=None, dbeta=None, param_accumulate=False, scatter=None, dy=None,
-                scratch=None, shift=None):
+                scratch=None, shift=None, sums=None, reset=None):
     """Two-phase BatchNorm(+ReLU/+Dropout) backward.  Returns dy (bf16, same layout as y unless scatter).
     With `shift` given (plain conv->BN->ReLU layers) the ReLU mask is recomputed from y instead of read from `out`."""
     _chk_act(dout, "bn_backward dout")
     n, h, w, cs = y.shape
-    if scratch is None:
+    if sums is not None:
+        scratch = sums  # (sum_dz, sum_dzx): pre-zeroed; the caller alternates two buffers and passes `reset`
+    elif scratch is None:
         scratch = torch.zeros((2, cs), dtype=torch.float64, device=y.device)
     else:
         scratch.zero_()
@@ -273,6 +293,8 @@ def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, trainin
     if dgamma is not None:
         a.dgamma, a.dbeta, a.C_real = dgamma.data_ptr(), dbeta.data_ptr(), dgamma.numel()
         a.param_accumulate = int(param_accumulate)
+    if reset is not None:
+        a.reset_sum_dz, a.reset_sum_dzx, a.reset_count = reset[0].data_ptr(), reset[1].data_ptr(), int(reset[2])
     st = L.stream_ptr()
     L.check(L.lib().zs3_bn_bwd_reduce(C.byref(a), st), "zs3_bn_bwd_reduce")
     L.check(L.lib().zs3_bn_bwd_apply(C.byref(a), st), "zs3_bn_bwd_apply")

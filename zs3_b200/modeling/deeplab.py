@@ -32,6 +32,8 @@ class DeepLab(nn.Module):
     # ---------------------------------------------------------------------------------------- forward
     def _features(self, input, keep_masks=None):
         km = keep_masks or {}
+        if input.is_cuda:
+            ZF.reset_stat_buffers(input.device)
         x, low_level_feat = self.backbone(input)
         x = self.aspp(x, km.get("aspp.dropout"))
         x = self.decoder.forward_before_class_prediction(
@@ -56,6 +58,8 @@ class DeepLab(nn.Module):
         return ZF.UpsampleLogits.apply(x, self.num_classes, int(input_size[0]), int(input_size[1]))
 
     def forward_before_last_conv_finetune(self, input):
+        if input.is_cuda:
+            ZF.reset_stat_buffers(input.device)
         x, low_level_feat = self.backbone(input)
         x = self.aspp(x)
         x = self.decoder.forward_before_last_conv_finetune(x, low_level_feat)
