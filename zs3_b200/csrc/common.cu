@@ -117,6 +117,25 @@ int encode_tiled2d_bf16_sw64(CUtensorMap* out, const void* base, long long rows,
   return ZS3_OK;
 }
 
+int encode_tiled3d_f32(CUtensorMap* out, const void* base, int d2, int d1, int d0, long long stride2, long long stride1,
+                       int b2, int b1, int b0) {
+  int rc = ensure_driver();
+  if (rc) return rc;
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)stride1 * 4, (cuuint64_t)stride2 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d f32) failed (%d): dims=%d,%d,%d strides=%lld,%lld box=%d,%d,%d", (int)r, d2, d1,
+              d0, stride2, stride1, b2, b1, b0);
+    return ZS3_ERR_DRIVER;
+  }
+  return ZS3_OK;
+}
+
 int encode_tiled3d_bf16(CUtensorMap* out, const void* base, int d2, int d1, int d0, int b2, int b1, int b0) {
   int rc = ensure_driver();
   if (rc) return rc;

@@ -46,6 +46,10 @@ int encode_tiled2d_bf16(CUtensorMap* out, const void* base, long long rows, int 
 // same with SWIZZLE_64B and a 32-column (64-byte) box: the epilogue's TMA store tiles
 int encode_tiled2d_bf16_sw64(CUtensorMap* out, const void* base, long long rows, int cols, long long ld, int box_rows,
                              int box_cols);
+// fp32 3-D map (SWIZZLE_128B) over a strided [d2][d1][d0] view (strides in ELEMENTS, d0 contiguous): the weight-gradient
+// tensor the wgrad epilogue reduces into with cp.reduce.async.bulk (.add)
+int encode_tiled3d_f32(CUtensorMap* out, const void* base, int d2, int d1, int d0, long long stride2, long long stride1,
+                       int b2, int b1, int b0);
 // tiled 3-D map over [d2][d1][d0] bf16 (d0 contiguous); box = [b2][b1][b0].
 int encode_tiled3d_bf16(CUtensorMap* out, const void* base, int d2, int d1, int d0, int b2, int b1, int b0);
 

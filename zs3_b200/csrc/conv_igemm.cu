@@ -68,9 +68,12 @@ struct FpropSmem {
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;      // 1024-byte aligned: the 64B swizzle is address based
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 64;    // one [32 rows][32 ch] bf16 box (2 KiB) per warp
-  static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
-  static constexpr int STAT_OFFSET = BAR_OFFSET + 256;             // barriers + tmem slot
-  static constexpr int TOTAL = STAT_OFFSET + 2 * MAX_STAT_CH * 4 + 1024 /*alignment slack*/;
+  // the statistics partials (2 x 2048 floats) double as a SECOND set of staging boxes when no statistics are fused
+  // (short-K layers, where the epilogue is the bottleneck and store latency must be overlapped)
+  static constexpr int STAT_OFFSET = STAGING_OFFSET + STAGING_BYTES;
+  static constexpr int BAR_OFFSET = STAT_OFFSET + 2 * MAX_STAT_CH * 4;
+  static constexpr int TOTAL = BAR_OFFSET + 256 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
+  static_assert(2 * MAX_STAT_CH * 4 >= STAGING_BYTES, "statistics region must hold the second staging set");
 };
 
 // Column sums over the 32 lanes of a warp: lane j ends up with sum over lanes of v[j].
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
     const int quarter = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;  // which 32-column chunks this warp owns (even / odd)
     const int row = quarter * 32 + lane;
+    uint32_t store_seq = 0;
     int it = 0;
     for (int g = cluster_id; g < num_groups; g += num_clusters, ++it) {
       const int n_tile = g % p.num_n_tiles;
@@ -281,8 +285,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
         if (p.use_tma_store) {
           // coalesced path: the warp's [32 rows][32 channels] bf16 block goes through a 64B-swizzled staging box
           // and leaves as one TMA store (full 64-byte row segments; rows >= M are clipped by the tensor map)
-          uint8_t* stg = smem + L::STAGING_OFFSET + (warp - EPI_WARP0) * (32 * 64);
-          tma_store_wait_read();  // previous store from this buffer has been read out (only lane 0 has groups)
+          // two boxes per warp (the second one lives in the unused statistics region): the store of chunk i
+          // overlaps the TMEM read / packing of chunk i+1
+          const bool dbl = p.stat_sum == nullptr;
+          uint8_t* stg = smem + ((dbl && (store_seq & 1)) ? L::STAT_OFFSET : L::STAGING_OFFSET) +
+                         (warp - EPI_WARP0) * (32 * 64);
+          if (dbl)
+            tma_store_wait_read1();  // the store issued two chunks ago (same box) has been read out
+          else
+            tma_store_wait_read();
+          ++store_seq;
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -397,6 +409,8 @@ struct WgradParams {
   long long dw_ld;       // elements between consecutive (co, tap) rows of dw
   int dw_ci_offset;      // first input channel of this segment inside a dw row
   int cout_valid, cin_valid;  // logical extents (rows / columns beyond them are not written)
+  CUtensorMap dwmap;          // fp32 3-D map (ci, tap, co) over the valid region of dw; box 32 ci x 1 x 32 co
+  int use_tma_reduce;
 };
 
 // MB = number of 128-row output-channel blocks per CTA (1 or 2): MB = 2 reuses every X tile for 256 output
@@ -519,6 +533,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
       const int taps = p.R * p.S;
       const bool vec_ok = (p.dw_ld % 4 == 0) && (p.dw_ci_offset % 4 == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0);
+      // TMA-reduce path: the main loop is over, so the pipeline stages are free: two 4 KiB fp32 boxes per warp
+      uint8_t* stg_base = smem + (warp - EPI_WARP0) * 8192;
+      uint32_t seq = 0;
 #pragma unroll 1
       for (int chunk = 0; chunk < MB * CN / 32; ++chunk) {
         uint32_t raw[32];
@@ -527,7 +544,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
         const int mb = chunk / (CN / 32);
         const int co = co_tile * (128 * MB) + mb * 128 + quarter * 32 + lane;
         const int ci = ci_tile * CN + (chunk - mb * (CN / 32)) * 32;
-        if (co < p.cout_valid && ci < p.cin_valid) {
+        if (p.use_tma_reduce) {
+          // [32 co rows][32 ci] fp32 box, 128-byte rows with the 128B swizzle (16-byte chunk ^= row & 7), then ONE
+          // cp.reduce.async.bulk (.add): rows/columns outside the valid extents are clipped by the tensor map
+          uint8_t* stg = stg_base + (seq & 1) * 4096;
+          tma_store_wait_read1();
+          ++seq;
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_3d(&p.dwmap, stg, ci, tap, co_tile * (128 * MB) + mb * 128 + quarter * 32);
+            tma_store_commit();
+          }
+        } else if (co < p.cout_valid && ci < p.cin_valid) {
           float* row = p.dw + ((long long)co * taps + tap) * p.dw_ld + p.dw_ci_offset + ci;
           if (vec_ok && ci + 32 <= p.cin_valid) {
             float4* dst = reinterpret_cast<float4*>(row);
@@ -542,6 +576,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
           }
         }
       }
+      if (p.use_tma_reduce && lane == 0) tma_store_wait_all();
     }
   }
   tc_fence_before();
@@ -899,6 +934,20 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   p.dw_ci_offset = a->dw_ci_offset;
   p.cout_valid = a->cout_valid > 0 ? a->cout_valid : a->cout_pad;
   p.cin_valid = a->cin_valid > 0 ? a->cin_valid : a->cin_pad;
+  p.use_tma_reduce = 0;
+  {
+    static int pref = -1;
+    if (pref < 0) {
+      const char* env = getenv("ZS3_TMA_REDUCE");
+      pref = env ? atoi(env) : 1;
+    }
+    if (pref && p.dw_ld % 4 == 0 && p.dw_ci_offset % 4 == 0 && (reinterpret_cast<uintptr_t>(a->dw) & 15) == 0) {
+      int rc3 = encode_tiled3d_f32(&p.dwmap, a->dw + p.dw_ci_offset, p.cout_valid, a->R * a->S, p.cin_valid,
+                                   (long long)a->R * a->S * p.dw_ld, p.dw_ld, 32, 1, 32);
+      if (rc3) return rc3;
+      p.use_tma_reduce = 1;
+    }
+  }
   ZS3_CHECK_ARG(p.cout_valid <= a->cout_pad && p.cin_valid <= a->cin_pad && p.dw_ci_offset >= 0 &&
                     p.dw_ld >= p.dw_ci_offset + p.cin_valid,
                 "conv_wgrad: bad dw view (ld=%lld offset=%d cin_valid=%d cout_valid=%d)", p.dw_ld, p.dw_ci_offset,
