@@ -92,6 +92,42 @@ class FusedSGD:
         ZF.invalidate_weight_caches()
 
 
+class HostPrefetcher:
+    """Double-buffered host->device staging of (image, target) batches on a side stream, so that the PCIe copy of
+    batch i+1 overlaps the training step of batch i (the reference gets this from DataLoader(pin_memory=True) +
+    .cuda(); zs3/base_trainer.py:12-14).  Usage: stage(0, batch0); for i: a, b = take(i); stage(i+1, next); step(a, b)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [None, None]
+
+    def stage(self, i, host_batch):
+        k = i & 1
+        with torch.cuda.stream(self.stream):
+            if self.consumed[k] is not None:
+                self.stream.wait_event(self.consumed[k])  # the step that read this slot has finished reading it
+            if self.slots[k] is None:
+                self.slots[k] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_batch)
+            for dst, src in zip(self.slots[k], host_batch):
+                dst.copy_(src, non_blocking=True)
+            self.ready[k].record(self.stream)
+
+    def take(self, i):
+        k = i & 1
+        torch.cuda.current_stream(self.device).wait_event(self.ready[k])
+        return self.slots[k]
+
+    def release(self, i):
+        """call after the consumer has enqueued its reads of slot i (e.g. after train_step)"""
+        k = i & 1
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.consumed[k] = ev
+
+
 class DataParallelTrainer:
     """step-1 training step of zs3/base_trainer.py:16-20 (zero_grad, forward, CE, backward, SGD) for one rank."""
 
