@@ -266,6 +266,26 @@ def run_ours(args):
                     "peak_source": how, "conv_ms_per_step": ms_all, "conv_share_of_step": ms_all / ms_step,
                     "nominal_tflop_per_step": fl_all / 1e12, "by_kind": per_kind}
 
+    # ---- forward-only pass (north star: tensor-pipe utilisation of the ResNet-101+ASPP forward), GPU-bound timing
+    forward_only = None
+    if rank == 0:
+        with torch.no_grad():
+            model(devb[0][0])
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(1.2e8))  # head start for the host: the forward launches then run back to back
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            nf = 3
+            for i in range(nf):
+                model(devb[i % nbuf][0])
+            f1.record()
+            torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / nf
+        peak, _ = measured_peaks()
+        ftf = B * FWD_GFLOP_PER_IMG / 1e3 / (fms * 1e-3)
+        forward_only = {"ms": fms, "images_per_sec": B / (fms * 1e-3), "nominal_tflops": ftf,
+                        "frac_of_measured_bf16_peak": ftf / peak, "mode": "train-mode BN, no_grad, eager launches"}
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -293,6 +313,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "forward_only": forward_only,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))

@@ -75,7 +75,7 @@ def test_config0_full_resolution_eval_forward():
     from zs3_b200.modeling.deeplab import DeepLab
     x = torch.randn(1, 3, 513, 513, generator=torch.Generator().manual_seed(1))
     st = O.init_deeplab_state(seed=1, randomize_bn=True)
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(max(1, min(os.cpu_count() or 1, 32)))
     with torch.no_grad():
         ref = O.deeplab_forward(st, x, training=False)
     model = DeepLab(num_classes=21, sync_bn=False, pretrained=False)
