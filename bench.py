@@ -227,18 +227,19 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), timed per launch with CUDA events
     roofline = None
+    # EVERY rank runs the two profiled steps (they contain the all-reduce); only rank 0 records and reports
+    K.PROFILE = {} if rank == 0 else None
+    lc0 = L.lib().zs3_launch_count()
+    for i in range(2):
+        # a spin kernel gives the host a head start, so the bracketed launches run back to back on the GPU
+        # (otherwise the event pairs would also time the host's launch latency of the eager step)
+        torch.cuda._sleep(int(1.2e8))
+        trainer._step(*devb[i % nbuf])  # eager even in graph mode: events bracket individual launches
+    torch.cuda.synchronize()
+    launches_per_step = (L.lib().zs3_launch_count() - lc0) // 2
+    if args.mode == "graph":
+        launches = launches_per_step * args.steps  # replayed from the captured graph, not re-issued by Python
     if rank == 0:
-        K.PROFILE = {}
-        lc0 = L.lib().zs3_launch_count()
-        for i in range(2):
-            # a spin kernel gives the host a head start, so the bracketed launches run back to back on the GPU
-            # (otherwise the event pairs would also time the host's launch latency of the eager step)
-            torch.cuda._sleep(int(1.2e8))
-            trainer._step(*devb[i % nbuf])  # eager even in graph mode: events bracket individual launches
-        torch.cuda.synchronize()
-        launches_per_step = (L.lib().zs3_launch_count() - lc0) // 2
-        if args.mode == "graph":
-            launches = launches_per_step * args.steps  # replayed from the captured graph, not re-issued by Python
         prof, K.PROFILE = K.PROFILE, None
         tags = prof.pop("_tags", [])
         if args.layer_table:
