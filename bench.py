@@ -270,22 +270,28 @@ def run_ours(args):
     # ---- forward-only pass (north star: tensor-pipe utilisation of the ResNet-101+ASPP forward), GPU-bound timing
     forward_only = None
     if rank == 0:
-        with torch.no_grad():
-            model(devb[0][0])
-            torch.cuda.synchronize()
-            torch.cuda._sleep(int(1.2e8))  # head start for the host: the forward launches then run back to back
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            nf = 3
-            for i in range(nf):
-                model(devb[i % nbuf][0])
-            f1.record()
-            torch.cuda.synchronize()
-        fms = f0.elapsed_time(f1) / nf
         peak, _ = measured_peaks()
-        ftf = B * FWD_GFLOP_PER_IMG / 1e3 / (fms * 1e-3)
-        forward_only = {"ms": fms, "images_per_sec": B / (fms * 1e-3), "nominal_tflops": ftf,
-                        "frac_of_measured_bf16_peak": ftf / peak, "mode": "train-mode BN, no_grad, eager launches"}
+
+        def time_forward(nf=3):
+            with torch.no_grad():
+                model(devb[0][0])
+                torch.cuda.synchronize()
+                torch.cuda._sleep(int(1.2e8))  # head start for the host: the forward launches then run back to back
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for i in range(nf):
+                    model(devb[i % nbuf][0])
+                f1.record()
+                torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / nf
+            ftf = B * FWD_GFLOP_PER_IMG / 1e3 / (fms * 1e-3)
+            return {"ms": fms, "images_per_sec": B / (fms * 1e-3), "nominal_tflops": ftf,
+                    "frac_of_measured_bf16_peak": ftf / peak}
+
+        forward_only = {"train_mode_bn": time_forward()}  # batch statistics: conv + statistics + normalisation passes
+        model.eval()                                      # running statistics: BN/ReLU/residual folded into the convs
+        forward_only["eval_mode_bn_fused_epilogue"] = time_forward()
+        model.train()
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu_baseline = None

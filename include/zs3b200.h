@@ -75,6 +75,13 @@ typedef struct {
   const float* bias; /* optional [cout_pad] fp32 added before store (decoder.pred_conv bias), or NULL */
   double* stat_sum;  /* optional [cout_pad]: += per-channel sum of the (fp32) conv output, or NULL */
   double* stat_sqsum;/* optional [cout_pad]: += per-channel sum of squares */
+  /* inference epilogue: eval-mode / frozen BatchNorm (+ residual add, + ReLU) folded into the conv, i.e.
+   * y = relu?(conv * ep_scale[n] + ep_shift[n] (+ ep_residual)); all NULL/0 = plain conv output */
+  const float* ep_scale;    /* [cout_pad] gamma / sqrt(running_var + eps) (zs3_bn_eval_coeffs) */
+  const float* ep_shift;    /* [cout_pad] */
+  const void* ep_residual;  /* optional bf16 [N*Ho*Wo][ep_res_cstride] */
+  int ep_res_cstride;
+  int ep_relu;
   int w_forward_layout; /* 1 (data-gradient mode): seg[i].w is the FORWARD-packed weight of the layer being
                            differentiated, [seg.cin_pad = forward cout][R*S][cout_pad = forward cin]; the kernel reads it
                            as MN-major B tiles and flips the taps itself, so no transposed copy has to be packed */

@@ -213,3 +213,20 @@ def test_dgrad_from_forward_packed_weights(case):
     assert rel_l2(dx[..., :Cin].permute(0, 3, 1, 2), dx_ref) < TOL_F32_OUT
     if cin_p > Cin:
         assert dx[..., Cin:].abs().max() == 0
+
+
+def test_inference_epilogue_folds_bn_residual_relu():
+    from zs3_b200 import kernels as K
+    N, H, W, Cin, Cout = 2, 33, 33, 128, 256
+    x, w = _mk(N, H, W, Cin, Cout, 3)
+    g = torch.Generator().manual_seed(4)
+    scale, shift = (torch.rand(Cout, generator=g) + 0.5).cuda(), torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, Cout, H, W, generator=g).to(torch.bfloat16).float().cuda()
+    ref = F.relu(F.conv2d(x, w, padding=2, dilation=2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+    y = K.conv_fprop([(K.nchw_to_nhwc(x, Cin), K.pack_weight(w, Cout, Cin))], 3, 3, 1, 2, 2, Cout,
+                     epilogue=(scale, shift, K.nchw_to_nhwc(res, Cout), True))
+    assert rel_l2(y.permute(0, 3, 1, 2).float(), ref) < TOL_BF16_OUT
+    y2 = K.conv_fprop([(K.nchw_to_nhwc(x, Cin), K.pack_weight(w, Cout, Cin))], 3, 3, 1, 2, 2, Cout, out_f32=True,
+                      epilogue=(scale, shift, None, False))
+    ref2 = F.conv2d(x, w, padding=2, dilation=2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    assert rel_l2(y2.permute(0, 3, 1, 2), ref2) < TOL_F32_OUT

@@ -43,6 +43,8 @@ class ConvArgs(C.Structure):
         ("bias", C.c_void_p),
         ("stat_sum", C.c_void_p),
         ("stat_sqsum", C.c_void_p),
+        ("ep_scale", C.c_void_p), ("ep_shift", C.c_void_p), ("ep_residual", C.c_void_p),
+        ("ep_res_cstride", C.c_int), ("ep_relu", C.c_int),
         ("w_forward_layout", C.c_int),
     ]
 

@@ -60,6 +60,12 @@ struct FpropParams {
   const float* bias;
   double* stat_sum;
   double* stat_sqsum;
+  // inference epilogue (frozen / eval-mode BatchNorm folded in): out = relu?(acc*scale[n] + shift[n] (+ residual))
+  const float* ep_scale;
+  const float* ep_shift;
+  const __nv_bfloat16* ep_res;
+  long long ep_res_cs;
+  int ep_relu;
 };
 
 template <int BN, int STAGES>
@@ -281,6 +287,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n + j);
+        }
+        if (p.ep_scale != nullptr) {
+          // eval-mode BatchNorm (+residual, +ReLU) folded into the epilogue: no separate normalisation pass
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], __ldg(p.ep_scale + n + j), __ldg(p.ep_shift + n + j));
+          if (p.ep_res != nullptr && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.ep_res + pix * p.ep_res_cs + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 o = __ldg(rp + j);
+              f[8 * j + 0] += bf16_lo(o.x);
+              f[8 * j + 1] += bf16_hi(o.x);
+              f[8 * j + 2] += bf16_lo(o.y);
+              f[8 * j + 3] += bf16_hi(o.y);
+              f[8 * j + 4] += bf16_lo(o.z);
+              f[8 * j + 5] += bf16_hi(o.z);
+              f[8 * j + 6] += bf16_lo(o.w);
+              f[8 * j + 7] += bf16_hi(o.w);
+            }
+          }
+          if (p.ep_relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
         }
         if (p.use_tma_store) {
           // coalesced path: the warp's [32 rows][32 channels] bf16 block goes through a 64B-swizzled staging box
@@ -876,6 +906,15 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   p.bias = a->bias;
   p.stat_sum = a->stat_sum;
   p.stat_sqsum = a->stat_sqsum;
+  ZS3_CHECK_ARG((a->ep_scale == nullptr) == (a->ep_shift == nullptr), "conv_fprop: ep_scale/ep_shift mismatch");
+  ZS3_CHECK_ARG(a->ep_residual == nullptr || (a->ep_scale != nullptr && a->ep_res_cstride >= a->cout_pad &&
+                                              a->ep_res_cstride % 8 == 0 && a->y_sp_stride <= 1),
+                "conv_fprop: bad epilogue residual");
+  p.ep_scale = a->ep_scale;
+  p.ep_shift = a->ep_shift;
+  p.ep_res = static_cast<const __nv_bfloat16*>(a->ep_residual);
+  p.ep_res_cs = a->ep_res_cstride;
+  p.ep_relu = a->ep_relu;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (BN == 256) return launch_fprop<256, 4>(p, csize, st);
   if (BN == 128) return launch_fprop<128, 6>(p, csize, st);

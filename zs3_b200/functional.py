@@ -214,11 +214,19 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
     if ci != conv.in_channels:
         raise ValueError(f"segments provide {ci} channels, conv expects {conv.in_channels}")
     dev = xs[0].device
+    n_, h_, w_, _ = xs[0].shape
+    if not training and not torch.is_grad_enabled() and not (drop_p and drop_training):
+        # inference: eval-mode BatchNorm, residual add and ReLU are folded into the conv epilogue -- the layer is
+        # ONE kernel and neither the pre-BN tensor nor any statistic is ever written
+        ho_, wo_ = K.conv_out_size(h_, R, stride, pad, dil), K.conv_out_size(w_, S, stride, pad, dil)
+        scale, shift, _, _ = _bn_forward_coeffs(bn, None, 0, cout_p)
+        out = K.conv_fprop(segs, R, S, stride, pad, dil, cout_p, epilogue=(scale, shift, residual, relu),
+                           flops=2.0 * n_ * ho_ * wo_ * cout * R * S * conv.in_channels)
+        return out, None
     stats = None
     if training:
         sb = _StatBuffers.get(dev)
         stats = sb.current(cout_p)
-    n_, h_, w_, _ = xs[0].shape
     ho_, wo_ = K.conv_out_size(h_, R, stride, pad, dil), K.conv_out_size(w_, S, stride, pad, dil)
     macs_per_cin = 2.0 * n_ * ho_ * wo_ * cout * R * S  # nominal FLOPs per input channel
     # BatchNorm statistics: fused into the conv epilogue when the main loop is long enough to hide it

@@ -79,7 +79,8 @@ def unpack_wgrad(dw, grad_oihw, ci_begin=0, ci_count=None, accumulate=False):
 
 
 def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=False, accumulate=False, bias=None,
-               stats=None, scatter=None, flops=0.0, kind="conv_fprop", w_forward_layout=False):
+               stats=None, scatter=None, flops=0.0, kind="conv_fprop", w_forward_layout=False, epilogue=None):
+    # epilogue = (scale, shift, residual or None, relu): eval-mode BatchNorm folded into the conv (inference)
     """segments: list of (x [N,H,W,Cs] bf16, w_packed [cout_pad, R*S, cin_pad] bf16).
     stats: optional (sum, sqsum) fp64 [cout_pad] accumulators.  scatter: optional (sp_stride, y_H, y_W).
     Returns y [N,Ho,Wo,cout_pad] (or the provided `out`)."""
@@ -115,6 +116,12 @@ def conv_fprop(segments, R, S, stride, pad, dil, cout_pad, out=None, out_f32=Fal
         a.y_sp_stride, a.y_H, a.y_W = scatter
     a.accumulate = int(accumulate)
     a.w_forward_layout = int(w_forward_layout)
+    if epilogue is not None:
+        sc, sh, res, relu = epilogue
+        a.ep_scale, a.ep_shift, a.ep_relu = sc.data_ptr(), sh.data_ptr(), int(relu)
+        if res is not None:
+            _chk_act(res, "conv_fprop epilogue residual")
+            a.ep_residual, a.ep_res_cstride = res.data_ptr(), res.shape[3]
     a.bias = None if bias is None else bias.data_ptr()
     if stats is not None:
         a.stat_sum = stats[0].data_ptr()
