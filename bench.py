@@ -149,6 +149,11 @@ def run_ours(args):
     import torch.distributed as dist
 
     rank, local_rank, world = init_distributed()
+
+    def phase(msg):  # progress marker on stderr (rank-tagged): pinpoints a stuck collective in multi-GPU runs
+        sys.stderr.write(f"[bench rank {rank}] {msg}\n")
+        sys.stderr.flush()
+
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     dev = torch.device("cuda", local_rank)
@@ -179,6 +184,7 @@ def run_ours(args):
         return t.item()
 
     # ---- device-resident throughput ("value")
+    phase("model built, warm-up")
     for i in range(args.warmup):
         trainer.train_step(*devb[i % nbuf])
     barrier()
@@ -188,6 +194,7 @@ def run_ours(args):
     launches0 = L.lib().zs3_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    phase("timed region")
     e0.record()
     for i in range(args.steps):
         loss = trainer.train_step(*devb[i % nbuf])
@@ -201,6 +208,7 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers: every step uploads its inputs from pinned host memory
     # (double-buffered on a copy stream so the PCIe transfer overlaps the previous step) and reads the loss back
+    phase("end-to-end region")
     pre = HostPrefetcher(dev)
     pre.stage(0, host[0])
     for i in range(2):
@@ -228,6 +236,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), timed per launch with CUDA events
     roofline = None
     # EVERY rank runs the two profiled steps (they contain the all-reduce); only rank 0 records and reports
+    phase("per-launch profile")
     K.PROFILE = {} if rank == 0 else None
     lc0 = L.lib().zs3_launch_count()
     for i in range(2):
@@ -324,6 +333,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
+    phase("done")
     if world > 1:
         dist.destroy_process_group()
 

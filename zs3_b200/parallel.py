@@ -166,6 +166,8 @@ class DataParallelTrainer:
         self.static_image.copy_(image, non_blocking=True)
         self.static_target.copy_(target, non_blocking=True)
         self.graph.replay()
+        if self.world > 1:
+            self._reduce_and_update()  # the collective and the optimizer stay outside the captured graph
         return self.static_loss
 
     def _capture(self, image, target):
@@ -179,11 +181,19 @@ class DataParallelTrainer:
                 self._step(self.static_image, self.static_target)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # single GPU: the whole step (forward, backward, optimizer) is one graph.  Multi-GPU: the graph holds
+        # forward+backward; the NCCL all-reduce and the two fused-SGD launches are issued eagerly after each replay
+        # (3 launches; keeps NCCL out of stream capture)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.static_loss = self._step(self.static_image, self.static_target)
+            self.static_loss = self._step(self.static_image, self.static_target, update=self.world == 1)
 
-    def _step(self, image, target):
+    def _reduce_and_update(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad)  # the one collective of the step
+        self.opt.step(grad_scale=1.0 / self.world)
+
+    def _step(self, image, target, update=True):
         if ZF._RngState.device_counter is not None:
             ZF._RngState.device_counter.add_(1 << 32)  # fresh dropout masks per step, also under graph replay
         self.flat.zero_grad()
@@ -191,7 +201,6 @@ class DataParallelTrainer:
         output = self.model(image)
         loss = self.criterion(output, target)
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.flat.grad)  # the one collective of the step
-        self.opt.step(grad_scale=1.0 / self.world)
+        if update:
+            self._reduce_and_update()
         return loss
