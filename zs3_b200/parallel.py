@@ -25,8 +25,12 @@ def init_distributed():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # test knobs: ZS3_DIST_BACKEND=gloo and ZS3_DEVICE_INDEX=0 let several ranks share one GPU (NCCL refuses that),
+    # which exercises the multi-rank control flow on a single-GPU box
+    if "ZS3_DEVICE_INDEX" in os.environ:
+        local_rank = int(os.environ["ZS3_DEVICE_INDEX"])
     if world > 1 and not dist.is_initialized():
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        backend = os.environ.get("ZS3_DIST_BACKEND", "nccl" if torch.cuda.is_available() else "gloo")
         if torch.cuda.is_available():
             torch.cuda.set_device(local_rank)
         dist.init_process_group(backend=backend)
