@@ -136,7 +136,7 @@ def run_reference(args):
                                    f"(host has {os.cpu_count()} cores)"},
         "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -332,13 +332,35 @@ def run_ours(args):
             "forward_only": forward_only,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
+        emit(line)
     phase("done")
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout; libraries (NCCL's version banner, torch warnings) also write to
+    fd 1.  Park the real stdout on a private descriptor and point fd 1 at stderr for everything else."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -1,88 +1,61 @@
-"""ASPP (atrous spatial pyramid pooling) on the fused kernels; mirrors zs3/modeling/aspp.py."""
-import torch
+"""ASPP (atrous spatial pyramid pooling) on the fused kernels; parameter tree as in zs3/modeling/aspp.py."""
 import torch.nn as nn
 
 from .. import functional as ZF
-from .sync_batchnorm.batchnorm import SynchronizedBatchNorm2d
+from . import _build as B
 
-
-def _init(module):
-    for m in module.modules():
-        if isinstance(m, nn.Conv2d):
-            torch.nn.init.kaiming_normal_(m.weight)
-        elif isinstance(m, (SynchronizedBatchNorm2d, nn.BatchNorm2d)):
-            m.weight.data.fill_(1)
-            m.bias.data.zero_()
+ASPP_WIDTH = 256
+BACKBONE_WIDTH = 2048
 
 
 class _ASPPModule(nn.Module):
-    """zs3/modeling/aspp.py:8-40"""
+    """one pyramid branch: (atrous) conv -> BN -> ReLU, reference aspp.py:8-40"""
 
     def __init__(self, inplanes, planes, kernel_size, padding, dilation, BatchNorm):
         super().__init__()
+        self.inplanes = inplanes
         self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, stride=1, padding=padding,
                                      dilation=dilation, bias=False)
         self.bn = BatchNorm(planes)
         self.relu = nn.ReLU()
-        self.inplanes = inplanes
-        _init(self)
+        B.init_kaiming_(self)
 
     def forward(self, x):
         return ZF.conv_bn_act([x], [self.inplanes], self.atrous_conv, self.bn, relu=True)
 
 
 class ASPP(nn.Module):
-    """zs3/modeling/aspp.py:43-116"""
+    """four atrous branches + image-level pooling branch -> 1x1 projection -> Dropout, reference aspp.py:43-116"""
 
     def __init__(self, output_stride, BatchNorm, global_avg_pool_bn=True):
         super().__init__()
-        inplanes = 2048
-        if output_stride == 16:
-            dilations = [1, 6, 12, 18]
-        elif output_stride == 8:
-            dilations = [1, 12, 24, 36]
-        else:
-            raise NotImplementedError
-        self.aspp1 = _ASPPModule(inplanes, 256, 1, padding=0, dilation=dilations[0], BatchNorm=BatchNorm)
-        self.aspp2 = _ASPPModule(inplanes, 256, 3, padding=dilations[1], dilation=dilations[1], BatchNorm=BatchNorm)
-        self.aspp3 = _ASPPModule(inplanes, 256, 3, padding=dilations[2], dilation=dilations[2], BatchNorm=BatchNorm)
-        self.aspp4 = _ASPPModule(inplanes, 256, 3, padding=dilations[3], dilation=dilations[3], BatchNorm=BatchNorm)
+        rates = B.geometry(B.ASPP_RATES, output_stride)
+        self.inplanes = BACKBONE_WIDTH
+        for i, rate in enumerate(rates, start=1):
+            k = 1 if i == 1 else 3
+            setattr(self, f"aspp{i}", _ASPPModule(BACKBONE_WIDTH, ASPP_WIDTH, k, 0 if k == 1 else rate, rate, BatchNorm))
+        pool = [nn.AdaptiveAvgPool2d((1, 1)), nn.Conv2d(BACKBONE_WIDTH, ASPP_WIDTH, 1, stride=1, bias=False)]
         if global_avg_pool_bn:
-            self.global_avg_pool = nn.Sequential(
-                nn.AdaptiveAvgPool2d((1, 1)),
-                nn.Conv2d(inplanes, 256, 1, stride=1, bias=False),
-                BatchNorm(256),
-                nn.ReLU(),
-            )
-        else:
-            self.global_avg_pool = nn.Sequential(
-                nn.AdaptiveAvgPool2d((1, 1)),
-                nn.Conv2d(inplanes, 256, 1, stride=1, bias=False),
-                nn.ReLU(),
-            )
+            pool.append(BatchNorm(ASPP_WIDTH))
+        self.global_avg_pool = nn.Sequential(*pool, nn.ReLU())
         self.global_avg_pool_bn = global_avg_pool_bn
-        self.conv1 = nn.Conv2d(1280, 256, 1, bias=False)
-        self.bn1 = BatchNorm(256)
+        self.conv1 = nn.Conv2d(5 * ASPP_WIDTH, ASPP_WIDTH, 1, bias=False)
+        self.bn1 = BatchNorm(ASPP_WIDTH)
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(0.5)
-        self.inplanes = inplanes
-        _init(self)
+        B.init_kaiming_(self)
 
     def forward(self, x, keep_mask=None):
         n, h, w, _ = x.shape
-        x1 = self.aspp1(x)
-        x2 = self.aspp2(x)
-        x3 = self.aspp3(x)
-        x4 = self.aspp4(x)
-        g = ZF.SpatialMean.apply(x)
-        gconv = self.global_avg_pool[1]
-        gbn = self.global_avg_pool[2] if self.global_avg_pool_bn else ZF.IdentityBN(256, x.device)
-        g = ZF.conv_bn_act([g], [self.inplanes], gconv, gbn, relu=True)
-        # F.interpolate of a 1x1 map with align_corners=True is a pure broadcast (aspp.py:109)
-        x5 = ZF.SpatialBroadcast.apply(g, h, w)
-        # torch.cat + conv1 (aspp.py:110-112): the concat is never materialised, conv1 reduces over 5 K-segments
-        return ZF.conv_bn_act([x1, x2, x3, x4, x5], [256] * 5, self.conv1, self.bn1, relu=True,
-                              drop_p=self.dropout.p, drop_training=self.dropout.training, keep_mask=keep_mask)
+        pyramid = [getattr(self, f"aspp{i}")(x) for i in range(1, 5)]
+        # image-level branch: global mean -> 1x1 conv (-> BN) -> ReLU; its bilinear "upsampling" from 1x1 is a broadcast
+        pooled = ZF.SpatialMean.apply(x)
+        norm = self.global_avg_pool[2] if self.global_avg_pool_bn else ZF.IdentityBN(ASPP_WIDTH, x.device)
+        pooled = ZF.conv_bn_act([pooled], [self.inplanes], self.global_avg_pool[1], norm, relu=True)
+        pyramid.append(ZF.SpatialBroadcast.apply(pooled, h, w))
+        # concat + 1x1 projection: five K-segments of one implicit GEMM, the concat is never materialised
+        return ZF.conv_bn_act(pyramid, [ASPP_WIDTH] * 5, self.conv1, self.bn1, relu=True, drop_p=self.dropout.p,
+                              drop_training=self.dropout.training, keep_mask=keep_mask)
 
 
 def build_aspp(output_stride, BatchNorm, global_avg_pool_bn=True):

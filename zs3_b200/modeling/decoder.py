@@ -3,31 +3,28 @@ import torch
 import torch.nn as nn
 
 from .. import functional as ZF
-from .sync_batchnorm.batchnorm import SynchronizedBatchNorm2d
+from . import _build as B
 
 
 class Decoder(nn.Module):
     """zs3/modeling/decoder.py:8-87.  Internal tensors are NHWC bf16; see DeepLab for the NCHW boundary."""
 
+    LOW_LEVEL_WIDTH, REDUCED_WIDTH, WIDTH = 256, 48, 256
+    REFINE_DROPOUT = (0.5, 0.1)     # dropout after the two 3x3 refinement convs
+
     def __init__(self, num_classes, BatchNorm):
         super().__init__()
-        low_level_inplanes = 256
-        self.conv1 = nn.Conv2d(low_level_inplanes, 48, 1, bias=False)
-        self.bn1 = BatchNorm(48)
+        self.conv1 = B.conv(self.LOW_LEVEL_WIDTH, self.REDUCED_WIDTH, 1)
+        self.bn1 = BatchNorm(self.REDUCED_WIDTH)
         self.relu = nn.ReLU()
-        self.last_conv = nn.Sequential(
-            nn.Conv2d(304, 256, kernel_size=3, stride=1, padding=1, bias=False),
-            BatchNorm(256),
-            nn.ReLU(),
-            nn.Dropout(0.5),
-            nn.Conv2d(256, 256, kernel_size=3, stride=1, padding=1, bias=False),
-            BatchNorm(256),
-            nn.ReLU(),
-            nn.Dropout(0.1),
-        )
-        self.pred_conv = nn.Conv2d(256, num_classes, kernel_size=1, stride=1)
+        refine, cin = [], self.WIDTH + self.REDUCED_WIDTH
+        for p in self.REFINE_DROPOUT:   # indices 0-3 and 4-7 of last_conv: conv, BN, ReLU, Dropout
+            refine += [B.conv(cin, self.WIDTH, 3), BatchNorm(self.WIDTH), nn.ReLU(), nn.Dropout(p)]
+            cin = self.WIDTH
+        self.last_conv = nn.Sequential(*refine)
+        self.pred_conv = nn.Conv2d(self.WIDTH, num_classes, kernel_size=1, stride=1)
         self.num_classes = num_classes
-        self._init_weight()
+        B.init_kaiming_(self)
 
     # -- pieces -------------------------------------------------------------------------------------
     def _fuse_low_level(self, x, low_level_feat, keep_mask=None):
@@ -66,12 +63,7 @@ class Decoder(nn.Module):
         return self._second_conv(x)
 
     def _init_weight(self):
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                torch.nn.init.kaiming_normal_(m.weight)
-            elif isinstance(m, (SynchronizedBatchNorm2d, nn.BatchNorm2d)):
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()
+        B.init_kaiming_(self)
 
 
 def build_decoder(num_classes, BatchNorm):

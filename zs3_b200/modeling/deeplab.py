@@ -7,6 +7,7 @@ include/zs3b200.h.
 import torch.nn as nn
 
 from .. import functional as ZF
+from . import _build as B
 from .aspp import build_aspp
 from .backbone import build_backbone
 from .decoder import build_decoder
@@ -73,20 +74,19 @@ class DeepLab(nn.Module):
 
     # ------------------------------------------------------------------------------- reference helpers
     def freeze_bn(self):
-        for m in self.modules():
-            if isinstance(m, (SynchronizedBatchNorm2d, nn.BatchNorm2d)):
-                m.eval()
+        for m in filter(B.is_norm, self.modules()):
+            m.eval()
 
-    def _lr_params(self, modules):
-        for mod in modules:
-            for _, m in mod.named_modules():
-                if isinstance(m, (nn.Conv2d, SynchronizedBatchNorm2d, nn.BatchNorm2d)):
-                    for p in m.parameters():
-                        if p.requires_grad:
-                            yield p
+    @staticmethod
+    def _trainable(*roots):
+        """parameters of the conv / norm layers under `roots` that still require grad (deeplab.py:71-99)"""
+        for root in roots:
+            for m in root.modules():
+                if isinstance(m, nn.Conv2d) or B.is_norm(m):
+                    yield from (p for p in m.parameters(recurse=False) if p.requires_grad)
 
     def get_1x_lr_params(self):
-        return self._lr_params([self.backbone])
+        return self._trainable(self.backbone)
 
     def get_10x_lr_params(self):
-        return self._lr_params([self.aspp, self.decoder])
+        return self._trainable(self.aspp, self.decoder)

@@ -31,25 +31,28 @@ def _run_sequential(model, x, keep_mask=None):
     return x
 
 
+def _xavier_(root, kind=nn.Linear):
+    """xavier-uniform weights, bias 0.01 (gmmn.py:24-27, 62-65); the reconstruction layer keeps torch's default"""
+    for m in root.modules():
+        if type(m) is kind:
+            nn.init.xavier_uniform_(m.weight)
+            nn.init.constant_(m.bias, 0.01)
+
+
 class GMMNnetwork(nn.Module):
     """zs3/modeling/gmmn.py:6-49; parameters live under model.0 / model.3 like the reference's nn.Sequential."""
 
     def __init__(self, noise_dim, embed_dim, hidden_size, feature_dim, semantic_reconstruction=False):
         super().__init__()
 
-        def block(in_feat, out_feat):
-            return [nn.Linear(in_feat, out_feat), nn.LeakyReLU(0.2, inplace=True), nn.Dropout(p=0.5)]
-
-        def init_weights(m):
-            if type(m) == nn.Linear:
-                torch.nn.init.xavier_uniform_(m.weight)
-                m.bias.data.fill_(0.01)
-
-        if hidden_size:
-            self.model = nn.Sequential(*block(noise_dim + embed_dim, hidden_size), nn.Linear(hidden_size, feature_dim))
-        else:
-            self.model = nn.Linear(noise_dim + embed_dim, feature_dim)
-        self.model.apply(init_weights)
+        width_in = noise_dim + embed_dim
+        if hidden_size:   # one hidden layer: Linear -> LeakyReLU(0.2) -> Dropout(0.5) -> Linear  (model.0 / model.3)
+            layers = [nn.Linear(width_in, hidden_size), nn.LeakyReLU(0.2, inplace=True), nn.Dropout(p=0.5),
+                      nn.Linear(hidden_size, feature_dim)]
+            self.model = nn.Sequential(*layers)
+        else:             # linear generator
+            self.model = nn.Linear(width_in, feature_dim)
+        _xavier_(self.model)
         self.semantic_reconstruction = semantic_reconstruction
         if self.semantic_reconstruction:
             self.semantic_reconstruction_layer = nn.Linear(feature_dim, noise_dim + embed_dim)
@@ -95,10 +98,7 @@ class GMMNnetwork_GCN(nn.Module):
         self.relu = nn.LeakyReLU(0.2)
         self.dropout = nn.Dropout(p=0.5)
         self.gcn2 = GraphConvolution(hidden_size, feature_dim)
-        for m in self.modules():
-            if isinstance(m, GraphConvolution):
-                torch.nn.init.xavier_uniform_(m.weight)
-                m.bias.data.fill_(0.01)
+        _xavier_(self, GraphConvolution)
 
     def forward(self, embd, noise, adj_mat, keep_mask=None):
         _require_cuda(embd)

@@ -15,14 +15,10 @@ class SegmentationLosses:
         self.cuda = cuda
 
     def build_loss(self, mode="ce"):
-        if mode == "ce":
-            return self.CrossEntropyLoss
-        elif mode == "focal":
-            return self.FocalLoss
-        elif mode == "ce_finetune":
-            return self.CrossEntropyLossFinetune
-        else:
-            raise NotImplementedError
+        modes = {"ce": self.CrossEntropyLoss, "focal": self.FocalLoss, "ce_finetune": self.CrossEntropyLossFinetune}
+        if mode not in modes:
+            raise NotImplementedError(mode)
+        return modes[mode]
 
     def _ce(self, logit, target, weight, div=1.0):
         if not self.size_average:
