@@ -129,6 +129,37 @@ def test_deeplab_train_step_vs_oracle(small_input):
     assert int(model.backbone.layer3[5].bn2.num_batches_tracked) == 1
 
 
+def test_trainer_fused_loss_matches_unfused(small_input):
+    """The training runtime fuses the final x4 upsample into the loss (DeepLab.forward_scores +
+    SegmentationLosses.UpsampledCrossEntropyLoss); same loss (1e-5 rel) and same parameter gradients (bf16-rounding
+    level, 2e-2 rel-L2 over the whole flat gradient) as criterion(model(image), target)."""
+    from zs3_b200.modeling.deeplab import DeepLab
+    from zs3_b200.parallel import DataParallelTrainer
+    from zs3_b200.utils.loss import SegmentationLosses
+    torch.manual_seed(3)
+    model = DeepLab(num_classes=21, sync_bn=True, pretrained=False).cuda().train()
+    model.aspp.dropout.p = 0.0
+    model.decoder.last_conv[3].p = 0.0
+    model.decoder.last_conv[7].p = 0.0
+    crit = SegmentationLosses(weight=None, cuda=True).build_loss("ce")
+    trainer = DataParallelTrainer(model, crit)
+    image = small_input.cuda()
+    target = torch.randint(0, 21, (2, 65, 65), generator=torch.Generator().manual_seed(12)).float().cuda()
+    target[:, :3] = 255
+    results = []
+    for fuse in (True, False):
+        trainer.fuse_loss = fuse
+        trainer.flat.zero_grad()
+        loss = trainer._forward_loss(image, target)
+        loss.backward()
+        torch.cuda.synchronize()
+        results.append((loss.item(), trainer.flat.grad.clone()))
+    (l_f, g_f), (l_u, g_u) = results
+    print(f"fused loss {l_f:.6f} unfused {l_u:.6f} grad rel_l2 {rel_l2(g_f, g_u):.3e}")
+    assert abs(l_f - l_u) < 1e-5 * abs(l_u)
+    assert rel_l2(g_f, g_u) < 2e-2
+
+
 def test_reference_api_surface():
     from zs3.modeling.deeplab import DeepLab
     from zs3.modeling.sync_batchnorm.replicate import patch_replication_callback

@@ -110,6 +110,43 @@ def test_cross_entropy(C, weighted):
     assert abs(l2.item() - r2.item()) < 1e-5 * abs(r2.item())
 
 
+@pytest.mark.parametrize("C,hi,ho,weighted", [(21, 33, 129, False), (21, 17, 65, True), (5, 9, 33, True), (21, 129, 513, False)])
+def test_fused_upsample_cross_entropy(C, hi, ho, weighted):
+    """loss = CE(interpolate(scores)) straight from the low-resolution NHWC bf16 scores (training-loss fusion) against
+    torch's interpolate + cross_entropy in fp32 on the same bf16-representable scores; tolerances: loss 1e-5 rel,
+    d loss / d scores 4e-3 rel-L2 (the gradient is stored in bf16, 2^-9 per element)."""
+    from zs3_b200 import kernels as K
+    from zs3_b200.utils.loss import SegmentationLosses
+    g = torch.Generator().manual_seed(11)
+    N = 2
+    x = _bf(torch.randn(N, C, hi, hi, generator=g) * 2).cuda().requires_grad_(True)
+    target = torch.randint(0, C, (N, ho, ho), generator=g).float()
+    target[torch.rand(N, ho, ho, generator=g) < 0.05] = 255
+    target = target.cuda()
+    w = None
+    if weighted:
+        w = torch.ones(C)
+        w[[1, 3]] = 7.0
+        w = w.cuda()
+    up = F.interpolate(x, size=(ho, ho), mode="bilinear", align_corners=True)
+    ref = F.cross_entropy(up, target.long(), weight=w, ignore_index=255) / N
+    (g_ref,) = torch.autograd.grad(ref, x)
+    losses = SegmentationLosses(weight=w, cuda=True)
+    xh = K.nchw_to_nhwc(x.detach(), 64).requires_grad_(True)
+    loss = losses.UpsampledCrossEntropyLoss(xh, C, target)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel_l2(K.nhwc_to_nchw(xh.grad, C), g_ref) < 4e-3
+    assert xh.grad[..., C:].abs().max() == 0
+    # and against the unfused path of this package (upsample kernel + CE kernel)
+    xh2 = xh.detach().clone().requires_grad_(True)
+    from zs3_b200 import functional as ZF
+    l2 = losses.build_loss("ce")(ZF.UpsampleLogits.apply(xh2, C, ho, ho), target)
+    l2.backward()
+    assert abs(loss.item() - l2.item()) < 1e-6 * abs(l2.item())
+    assert rel_l2(xh.grad.float(), xh2.grad.float()) < 4e-3
+
+
 def test_optimizers():
     from zs3_b200 import kernels as K
     torch.manual_seed(0)

@@ -163,6 +163,8 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_spatial_broadcast": [vp, vp, i, i, i, i, i, f, i, vp],
         "zs3_ce_fwd": [vp, vp, vp, i, i, ll, i, f, vp, vp, vp],
         "zs3_ce_bwd": [vp, vp, vp, i, i, ll, i, f, vp, vp, vp, vp],
+        "zs3_upsample_ce_fwd": [vp, vp, vp, i, i, i, i, i, i, i, i, f, vp, vp, vp],
+        "zs3_upsample_ce_bwd": [vp, vp, vp, i, i, i, i, i, i, i, i, f, vp, vp, vp, vp],
         "zs3_cast_f32_to_bf16": [vp, vp, ll, vp],
         "zs3_sgd_step": [vp, vp, vp, ll, f, f, f, i, i, f, vp],
         "zs3_adam_step": [vp, vp, vp, vp, ll, f, f, f, f, i, f, vp],

@@ -5,6 +5,8 @@
 // Reference semantics: F.batch_norm as called from zs3/modeling/sync_batchnorm/batchnorm.py:48-58
 // (biased variance for normalisation, unbiased for running_var, momentum 0.1, eps 1e-5),
 // nn.ReLU, `out += residual` (zs3/modeling/backbone/resnet.py:50), nn.Dropout (aspp.py:101, decoder.py:19,23).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -43,6 +45,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+__device__ __forceinline__ void lds8f(const float* p, float (&f)[8]) {  // shared-memory flavour (no __ldg)
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
@@ -116,7 +124,7 @@ struct ApplyP {
   uint64_t seed, offset; const unsigned char* mask; const unsigned long long* offset_dev;
   int rows_per_block;
   // fused finalize (training mode): coefficients are derived from the raw batch statistics inside this kernel
-  const double* stat_sum; const double* stat_sqsum; long long count; const float* gamma; const float* beta;
+  const double* stat_sum; const double* stat_sqsum; long long count; double inv_count; const float* gamma; const float* beta;
   float eps, momentum; float* rmean; float* rvar; int C_real;
   float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
   double* reset_a; double* reset_b;  // the OTHER statistics buffer, zeroed for the next layer
@@ -156,43 +164,59 @@ __device__ __forceinline__ void apply_one(const ApplyP& p, long long m, int c, c
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyP p) {
+  griddep_sync();
+  extern __shared__ float s_coef[];  // [2][C] scale, shift (fused-finalize launches only)
   const int vpc = p.C >> 3;
   const int c = (threadIdx.x % vpc) << 3;
   const int rl = threadIdx.x / vpc;
+  const bool active = rl < p.rows_per_block;
   if (blockIdx.x == 0 && p.reset_a != nullptr) {
     for (int i = threadIdx.x; i < p.reset_count; i += blockDim.x) {
       p.reset_a[i] = 0.0;
       p.reset_b[i] = 0.0;
     }
   }
-  if (rl >= p.rows_per_block) return;
   const uint64_t rng_offset = p.offset + (p.offset_dev ? *p.offset_dev : 0ull);
+  const long long stride = (long long)gridDim.x * p.rows_per_block;
+  long long m = (long long)blockIdx.x * p.rows_per_block + rl;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  // the first batch of rows is requested BEFORE the coefficients are derived, so that the statistics loads + math
+  // and the first activation loads share one memory round trip (most launches of this kernel are 5-20 us long)
+  const bool first = active && m + (UNROLL - 1) * stride < p.M;
+  uint4 yr0[UNROLL], rr0[UNROLL];
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      yr0[u] = *reinterpret_cast<const uint4*>(p.y + (m + u * stride) * p.y_cs + c);
+      rr0[u] = p.res ? *reinterpret_cast<const uint4*>(p.res + (m + u * stride) * p.res_cs + c) : zero;
+    }
+  }
   float sc[8], sh[8];
   if (p.stat_sum != nullptr) {
-    // fused bn_finalize: every thread derives the affine of its 8 channels from the fp64 sums; the first row lane
-    // of CTA 0 also publishes mean/invstd/scale/shift for the backward pass and updates the running statistics
-    const bool publish = blockIdx.x == 0 && rl == 0;
-    const double n = (double)p.count;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = c + j;
+    // fused bn_finalize, once per CTA: thread t derives the affine of channel t (t, t+256, ...) from the fp64 sums
+    // into shared memory -- NOT every thread for its own 8 channels, which had all 300k threads of the grid hammer
+    // the same 2*C doubles in L2 and cost 8-15 us per launch.  The cancellation E[x^2] - mean^2 stays in fp64, the
+    // rest is fp32.  CTA 0 also publishes mean/invstd/scale/shift for the backward pass and updates the running
+    // statistics.
+    const bool publish = blockIdx.x == 0;
+    for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
       float s = 0.f, b = 0.f, mu = 0.f, is = 0.f;
       if (ch < p.C_real) {
-        const double mean = p.stat_sum[ch] / n;
-        double var = p.stat_sqsum[ch] / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        is = (float)(1.0 / sqrt(var + (double)p.eps));
+        const double mean = p.stat_sum[ch] * p.inv_count;
+        const double dvar = fma(-mean, mean, p.stat_sqsum[ch] * p.inv_count);
+        const float var = fmaxf((float)dvar, 0.f);
+        is = rsqrtf(var + p.eps);
         mu = (float)mean;
         s = (p.gamma ? p.gamma[ch] : 1.f) * is;
         b = (p.beta ? p.beta[ch] : 0.f) - mu * s;
         if (publish && p.rmean) {
-          const double unbiased = p.count > 1 ? var * n / (n - 1.0) : var;
+          const float unbiased = p.count > 1 ? var * ((float)p.count / (float)(p.count - 1)) : var;
           p.rmean[ch] = (1.f - p.momentum) * p.rmean[ch] + p.momentum * mu;
-          p.rvar[ch] = (1.f - p.momentum) * p.rvar[ch] + p.momentum * (float)unbiased;
+          p.rvar[ch] = (1.f - p.momentum) * p.rvar[ch] + p.momentum * unbiased;
         }
       }
-      sc[j] = s;
-      sh[j] = b;
+      s_coef[ch] = s;
+      s_coef[p.C + ch] = b;
       if (publish) {
         p.scale_out[ch] = s;
         p.shift_out[ch] = b;
@@ -200,13 +224,19 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyP p) {
         p.invstd_out[ch] = is;
       }
     }
+    __syncthreads();
+    lds8f(s_coef + c, sc);
+    lds8f(s_coef + p.C + c, sh);
   } else {
     load8f(p.scale + c, sc);
     load8f(p.shift + c, sh);
   }
-  const long long stride = (long long)gridDim.x * p.rows_per_block;
-  long long m = (long long)blockIdx.x * p.rows_per_block + rl;
-  const uint4 zero = make_uint4(0, 0, 0, 0);
+  if (!active) return;
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) apply_one(p, m + u * stride, c, sc, sh, rng_offset, yr0[u], rr0[u]);
+    m += UNROLL * stride;
+  }
   for (; m + (UNROLL - 1) * stride < p.M; m += UNROLL * stride) {
     uint4 yr[UNROLL], rr[UNROLL];
 #pragma unroll
@@ -261,6 +291,7 @@ __device__ __forceinline__ void make_dz(const BwdP& p, const uint4& draw, const 
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdP p) {
+  griddep_sync();
   extern __shared__ float red[];  // [rows_per_block][C] x 2
   const int vpc = p.C >> 3;
   const int c = (threadIdx.x % vpc) << 3;
@@ -359,48 +390,71 @@ __device__ __forceinline__ void bwd_apply_one(const BwdP& p, long long m, int c,
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
+  griddep_sync();
+  extern __shared__ float s_coef[];  // [3][C]: A, B, C of dy = A*dz + B*y + C
   const int vpc = p.C >> 3;
   const int c = (threadIdx.x % vpc) << 3;
   const int rl = threadIdx.x / vpc;
+  const bool active = rl < p.rows_per_block;
   if (blockIdx.x == 0 && p.reset_a != nullptr) {
     for (int i = threadIdx.x; i < p.reset_count; i += blockDim.x) {
       p.reset_a[i] = 0.0;
       p.reset_b[i] = 0.0;
     }
   }
-  if (blockIdx.x == 0 && p.dgamma != nullptr) {
-    for (int ch = threadIdx.x; ch < p.C_real; ch += blockDim.x) {
-      const float dg = (float)p.sum_dzx[ch], db = (float)p.sum_dz[ch];
-      p.dgamma[ch] = p.param_acc ? p.dgamma[ch] + dg : dg;
-      p.dbeta[ch] = p.param_acc ? p.dbeta[ch] + db : db;
-    }
-  }
-  if (rl >= p.rows_per_block) return;
-  float cA[8], cB[8], cC[8], sc[8], sh[8];
-  load8f(p.scale + c, sc);
-  if (p.relu == 2) load8f(p.shift + c, sh);
-  {
-    float mu[8], is[8];
-    load8f(p.mean + c, mu);
-    load8f(p.invstd + c, is);
-    const double inv_m = 1.0 / (double)p.M;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (p.training) {
-        const float m1 = (float)(p.sum_dz[c + j] * inv_m), m2 = (float)(p.sum_dzx[c + j] * inv_m);
-        cA[j] = sc[j];
-        cB[j] = -sc[j] * m2 * is[j];
-        cC[j] = -sc[j] * m1 + sc[j] * m2 * is[j] * mu[j];
-      } else {
-        cA[j] = sc[j];
-        cB[j] = 0.f;
-        cC[j] = 0.f;
-      }
-    }
-  }
   const long long stride = (long long)gridDim.x * p.rows_per_block;
   long long m = (long long)blockIdx.x * p.rows_per_block + rl;
   const uint4 zero = make_uint4(0, 0, 0, 0);
+  // first batch requested before the coefficient loads/math (see bn_apply_kernel)
+  const bool first = active && m + (UNROLL - 1) * stride < p.M;
+  uint4 yr0[UNROLL], dr0[UNROLL], or0[UNROLL];
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      yr0[u] = *reinterpret_cast<const uint4*>(p.y + (m + u * stride) * p.y_cs + c);
+      dr0[u] = *reinterpret_cast<const uint4*>(p.dout + (m + u * stride) * p.dout_cs + c);
+      or0[u] = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + (m + u * stride) * p.out_cs + c) : zero;
+    }
+  }
+  // per-channel coefficients once per CTA (thread t -> channel t, t+256, ...), through shared memory; CTA 0 also
+  // writes the affine-parameter gradients
+  {
+    const float inv_m = 1.f / (float)p.M;
+    for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
+      const float scl = p.scale[ch];
+      float B = 0.f, Cc = 0.f;
+      const bool params = blockIdx.x == 0 && p.dgamma != nullptr && ch < p.C_real;
+      if (p.training || params) {
+        const float sdz = (float)p.sum_dz[ch], sdzx = (float)p.sum_dzx[ch];
+        if (p.training) {
+          const float m1 = sdz * inv_m, m2 = sdzx * inv_m, is = p.invstd[ch];
+          B = -scl * m2 * is;
+          Cc = -scl * m1 + scl * m2 * is * p.mean[ch];
+        }
+        if (params) {
+          p.dgamma[ch] = p.param_acc ? p.dgamma[ch] + sdzx : sdzx;
+          p.dbeta[ch] = p.param_acc ? p.dbeta[ch] + sdz : sdz;
+        }
+      }
+      s_coef[ch] = scl;
+      s_coef[p.C + ch] = B;
+      s_coef[2 * p.C + ch] = Cc;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float cA[8], cB[8], cC[8], sc[8], sh[8];
+  lds8f(s_coef + c, cA);
+  lds8f(s_coef + p.C + c, cB);
+  lds8f(s_coef + 2 * p.C + c, cC);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sc[j] = cA[j];
+  if (p.relu == 2) load8f(p.shift + c, sh);
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) bwd_apply_one(p, m + u * stride, c, cA, cB, cC, sc, sh, yr0[u], dr0[u], or0[u]);
+    m += UNROLL * stride;
+  }
   for (; m + (UNROLL - 1) * stride < p.M; m += UNROLL * stride) {
     uint4 yr[UNROLL], dr[UNROLL], orw[UNROLL];
 #pragma unroll
@@ -426,6 +480,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long y_cs, long long M,
                                                        int C, int rows_per_block, double* __restrict__ sum,
                                                        double* __restrict__ sqsum) {
+  griddep_sync();
   extern __shared__ float red[];  // [rows_per_block][C] x 2
   const int vpc = C >> 3;
   const int c = (threadIdx.x % vpc) << 3;
@@ -513,13 +568,37 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
   }
 }
 
-// grid for the row-streaming kernels: every thread should see at least UNROLL rows, at most 8 CTAs per SM
-static int stream_grid(long long M, int rows_per_block) {
-  long long b = (M + (long long)rows_per_block * UNROLL - 1) / ((long long)rows_per_block * UNROLL);
-  const long long cap = 148ll * 8;
+// grids for the row-streaming kernels: every thread should see at least UNROLL rows.  The map kernels (apply,
+// bwd_apply) run up to 8 CTAs per SM.  The reducing kernels (stats, bwd_reduce) end with one fp64 atomic per channel
+// and CTA onto the SAME 2*C addresses -- measured ~19 ns per same-address atomic, i.e. 20 us of tail at 1184 CTAs --
+// so they use fewer, longer-running CTAs.  ZS3_BN_MAP_CTAS / ZS3_BN_REDUCE_CTAS (per SM) override for experiments.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return v > 0 ? v : dflt;  // non-positive / unset -> default
+}
+
+static int stream_grid_cap(long long M, int rows_per_block, int ctas_per_sm, int rows_per_thread) {
+  long long b = (M + (long long)rows_per_block * rows_per_thread - 1) / ((long long)rows_per_block * rows_per_thread);
+  const long long cap = 148ll * ctas_per_sm;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
+}
+
+static int stream_grid(long long M, int rows_per_block) {
+  static const int per_sm = env_int("ZS3_BN_MAP_CTAS", 8);
+  return stream_grid_cap(M, rows_per_block, per_sm, UNROLL);
+}
+
+// measured (tools/bn_bench.py, profiles/r01_bn_bench.md): 2 CTAs/SM is best for the backward reduction at every
+// size; the lighter statistics kernel prefers 4 CTAs/SM on tensors that do not fit L2 and 1 on the smallest ones
+static int reduce_grid(long long M, int rows_per_block, long long bytes = 0, bool stats = false) {
+  static const int forced = env_int("ZS3_BN_REDUCE_CTAS", -1);
+  int per_sm = 2;
+  if (stats) per_sm = bytes >= (48ll << 20) ? 4 : (bytes <= (12ll << 20) ? 1 : 2);
+  if (forced > 0) per_sm = forced;
+  return stream_grid_cap(M, rows_per_block, per_sm, 2 * UNROLL);
 }
 
 static int ew_grid(long long work_items, int threads) {
@@ -558,8 +637,8 @@ extern "C" int zs3_bn_stats(const void* y, int y_cstride, long long M, int C, do
   int rpb = 256 / vpc;
   if (rpb < 1) rpb = 1;
   const size_t smem = (size_t)2 * rpb * C * sizeof(float);
-  bn_stats_kernel<<<stream_grid(M, rpb), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), y_cstride, M, C, rpb, stat_sum, stat_sqsum);
+  launch_pdl(PDL_BN, bn_stats_kernel, dim3(reduce_grid(M, rpb, M * C * 2, true)), dim3(256), smem, static_cast<cudaStream_t>(stream),
+             static_cast<const __nv_bfloat16*>(y), (long long)y_cstride, M, C, rpb, stat_sum, stat_sqsum);
   ZS3_CHECK_LAUNCH("bn_stats");
   return ZS3_OK;
 }
@@ -600,13 +679,16 @@ extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
   p.thresh16 = (uint32_t)(a->drop_p * 65536.0f + 0.5f);
   p.keep_scale = 1.f / (1.f - a->drop_p);
   p.seed = a->seed; p.offset = a->offset; p.mask = a->keep_mask; p.offset_dev = a->offset_dev;
-  p.stat_sum = a->stat_sum; p.stat_sqsum = a->stat_sqsum; p.count = a->count; p.gamma = a->gamma; p.beta = a->beta;
+  p.stat_sum = a->stat_sum; p.stat_sqsum = a->stat_sqsum; p.count = a->count;
+  p.inv_count = a->count > 0 ? 1.0 / (double)a->count : 0.0; p.gamma = a->gamma; p.beta = a->beta;
   p.eps = a->eps; p.momentum = a->momentum; p.rmean = a->running_mean; p.rvar = a->running_var; p.C_real = a->C_real;
   p.mean_out = a->mean_out; p.invstd_out = a->invstd_out; p.scale_out = a->scale_out; p.shift_out = a->shift_out;
   p.reset_a = a->reset_sum; p.reset_b = a->reset_sqsum; p.reset_count = a->reset_count;
   ZS3_CHECK_ARG(a->C <= 2048, "bn_apply: C=%d > 2048", a->C);
   p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
-  bn_apply_kernel<<<stream_grid(a->M, p.rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const size_t smem = a->stat_sum ? (size_t)2 * a->C * sizeof(float) : 0;
+  launch_pdl(PDL_BN, bn_apply_kernel, dim3(stream_grid(a->M, p.rows_per_block)), dim3(256), smem, static_cast<cudaStream_t>(stream),
+             p);
   ZS3_CHECK_LAUNCH("bn_apply");
   return ZS3_OK;
 }
@@ -643,7 +725,8 @@ extern "C" int zs3_bn_bwd_reduce(const zs3_bn_bwd_args* a, void* stream) {
   p.rows_per_block = 256 / vpc;  // C <= 2048 -> vpc <= 256
   if (p.rows_per_block < 1) p.rows_per_block = 1;
   const size_t smem = (size_t)2 * p.rows_per_block * a->C * sizeof(float);
-  bn_bwd_reduce_kernel<<<stream_grid(a->M, p.rows_per_block), 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(PDL_BN, bn_bwd_reduce_kernel, dim3(reduce_grid(a->M, p.rows_per_block)), dim3(256), smem,
+             static_cast<cudaStream_t>(stream), p);
   ZS3_CHECK_LAUNCH("bn_bwd_reduce");
   return ZS3_OK;
 }
@@ -661,7 +744,8 @@ extern "C" int zs3_bn_bwd_apply(const zs3_bn_bwd_args* a, void* stream) {
                 "bn_bwd_apply: bad parameter gradient buffers");
   if (a->M <= 0) return ZS3_OK;
   p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
-  bn_bwd_apply_kernel<<<stream_grid(a->M, p.rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(PDL_BN, bn_bwd_apply_kernel, dim3(stream_grid(a->M, p.rows_per_block)), dim3(256), (size_t)3 * a->C * sizeof(float),
+             static_cast<cudaStream_t>(stream), p);
   ZS3_CHECK_LAUNCH("bn_bwd_apply");
   return ZS3_OK;
 }

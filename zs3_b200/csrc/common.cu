@@ -3,12 +3,23 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace zs3 {
 
 static thread_local char g_err[512] = {0};
 unsigned long long g_launch_count = 0;
+
+bool pdl_enabled(int kind) {
+  static int pref = -1;
+  if (pref < 0) {
+    const char* e = getenv("ZS3_PDL");
+    pref = e ? atoi(e) : PDL_CONV;
+    if (pref < 0 || pref > 3) pref = PDL_CONV;
+  }
+  return (pref & kind) != 0;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

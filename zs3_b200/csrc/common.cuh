@@ -33,6 +33,33 @@ extern unsigned long long g_launch_count;  // kernels launched by this library (
     }                                                                           \
   } while (0)
 
+// Programmatic dependent launch: a kernel launched through launch_pdl() may be scheduled while its predecessor in
+// the stream is still draining (the predecessor executes griddepcontrol.launch_dependents, or finishes); the kernel
+// itself must execute griddepcontrol.wait (ptx.cuh: griddep_sync()) before its first global-memory access.  This
+// hides launch latency and kernel prologues (barrier init, TMEM allocation, descriptor prefetch) behind the previous
+// kernel's tail; the edges survive CUDA-graph capture.  Measured on B200 inside the captured training step
+// (profiles/r01_pdl_experiment.md): +1.9 % with the attribute on the conv kernels (long prologues), -1.1 % on the
+// BatchNorm streaming kernels (no prologue to hide), so the default is ZS3_PDL=1: 1 = conv kernels, 2 = BatchNorm
+// kernels, 3 = both, 0 = off.
+constexpr int PDL_CONV = 1, PDL_BN = 2;
+bool pdl_enabled(int kind);
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(kind) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   if (csize > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_sync();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -312,6 +313,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
         }
+        if (p.stat_sum != nullptr && !valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows past M must not reach the batch statistics
+        }
+        bool stats_done = false;
         if (p.use_tma_store) {
           // coalesced path: the warp's [32 rows][32 channels] bf16 block goes through a 64B-swizzled staging box
           // and leaves as one TMA store (full 64-byte row segments; rows >= M are clipped by the tensor map)
@@ -341,6 +347,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
           if (lane == 0) {
             tma_store_2d(&p.ymap, stg, n, m_tile * BLOCK_M + quarter * 32);
             tma_store_commit();
+          }
+          if (p.stat_sum != nullptr) {
+            // BatchNorm batch statistics straight from the staged tile (i.e. of the bf16 values the normalisation
+            // pass will read): the box is [32 rows][16 bf16x2 words]; lane (w = lane/2, h = lane%2) walks the 16
+            // rows of parity h of word column w -- 16 conflict-free LDS.32 instead of a 5-level shuffle tree.
+            const int h = lane & 1, w = lane >> 1;
+            float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t word = *reinterpret_cast<const uint32_t*>(stg + (2 * i + h) * 64 +
+                                                                       (((w >> 2) ^ (i & 3)) << 4) + ((w & 3) << 2));
+              const float lo = bf16_lo(word), hi = bf16_hi(word);
+              s_lo += lo;
+              q_lo = fmaf(lo, lo, q_lo);
+              s_hi += hi;
+              q_hi = fmaf(hi, hi, q_hi);
+            }
+            s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
+            q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 1);
+            s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+            q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 1);
+            // shared-memory partials, flushed once per CTA at the end; parity 0 owns the sums, parity 1 the squares
+            atomicAdd(h == 0 ? &s_sum[n + 2 * w] : &s_sq[n + 2 * w], h == 0 ? s_lo : q_lo);
+            atomicAdd(h == 0 ? &s_sum[n + 2 * w + 1] : &s_sq[n + 2 * w + 1], h == 0 ? s_hi : q_hi);
+            stats_done = true;
           }
         } else if (valid) {
           if (p.y_is_f32) {
@@ -384,15 +415,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
             }
           }
         }
-        if (p.stat_sum != nullptr) {
-          // BatchNorm batch statistics of the fp32 conv output (F.batch_norm training path,
-          // zs3/modeling/sync_batchnorm/batchnorm.py:48-58): per-channel sum and sum of squares.
+        if (p.stat_sum != nullptr && !stats_done) {
+          // direct-store path (fp32 / accumulating outputs): batch statistics of the fp32 conv output (F.batch_norm
+          // training path, zs3/modeling/sync_batchnorm/batchnorm.py:48-58): per-channel sum and sum of squares.
           float sq[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (!valid) f[j] = 0.f;
-            sq[j] = f[j] * f[j];
-          }
+          for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
           const float s1 = warp_column_sums(f, lane);
           const float s2 = warp_column_sums(sq, lane);
           atomicAdd(&s_sum[n + lane], s1);  // shared-memory partials, flushed once per CTA at the end
@@ -414,8 +442,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
   if (p.stat_sum != nullptr) {
     for (int i = threadIdx.x; i < p.cout_pad; i += NUM_THREADS) {
-      atomicAdd(p.stat_sum + i, (double)s_sum[i]);
-      atomicAdd(p.stat_sqsum + i, (double)s_sq[i]);
+      const float a = s_sum[i], b = s_sq[i];
+      if (b != 0.f) {  // channels of n-tiles this CTA never visited (and all-zero channels) add nothing
+        atomicAdd(p.stat_sum + i, (double)a);
+        atomicAdd(p.stat_sqsum + i, (double)b);
+      }
     }
   }
 }
@@ -497,6 +528,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_sync();
 
   if (num_kb > 0) {
     if (warp == 0) {
@@ -768,13 +800,15 @@ static int launch_fprop(const FpropParams& p, int csize, cudaStream_t st) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (csize == 1 && pdl_enabled(PDL_CONV)) ? 2 : 1;  // PDL only for the (default) non-cluster launch
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BN, STAGES>, p);
   if (e != cudaSuccess) {
     set_error("conv_fprop: cudaLaunchKernelEx(cluster=%d) failed: %s", csize, cudaGetErrorString(e));
@@ -798,7 +832,11 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(p.num_ci_tiles * p.num_co_tiles * p.R * p.S, p.k_splits);
-  conv_wgrad_kernel<CN, STAGES, MB><<<grid, WG_THREADS, L::TOTAL, st>>>(p);
+  cudaError_t le = launch_pdl(PDL_CONV, conv_wgrad_kernel<CN, STAGES, MB>, grid, dim3(WG_THREADS), L::TOTAL, st, p);
+  if (le != cudaSuccess) {
+    set_error("conv_wgrad: launch failed: %s", cudaGetErrorString(le));
+    return ZS3_ERR_LAUNCH;
+  }
   ZS3_CHECK_LAUNCH("conv_wgrad");
   return ZS3_OK;
 }

@@ -400,6 +400,158 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logit, const float* __re
   }
 }
 
+// ------------------------------------------------- fused x4 upsample + cross-entropy (training loss)
+// The training step never needs the full-resolution class scores themselves: loss = CE(upsample(x), target).  These
+// two kernels evaluate the bilinear upsample on the fly (same blend order as upsample_logits_fwd_kernel: vertical
+// into fp32, then horizontal), so the [N][C][Ho][Wo] fp32 logits and their gradient (2 x 354 MB at bs=16, 513x513)
+// are never written to or read from HBM.  C <= 32 classes live in registers.
+constexpr int CE_MAX_C = 32;
+
+__global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const float* __restrict__ target,
+                                                              const float* __restrict__ weight, int C, int Hi, int Wi,
+                                                              int cs, int Ho, int Wo, float sh, float sw, int ignore,
+                                                              double* __restrict__ accum) {
+  extern __shared__ float rb[];  // [C][Wi+1] vertically blended input row
+  const int oh = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  int y0, y1; float ly;
+  bl_coord(oh, sh, Hi, y0, y1, ly);
+  const int ld = Wi + 1;
+  const __nv_bfloat16* r0 = x + ((long long)n * Hi + y0) * Wi * cs;
+  const __nv_bfloat16* r1 = x + ((long long)n * Hi + y1) * Wi * cs;
+  for (int i = threadIdx.x; i < Wi * C; i += blockDim.x) {
+    const int c = i % C, w = i / C;
+    rb[c * ld + w] = (1.f - ly) * __bfloat162float(r0[(long long)w * cs + c]) + ly * __bfloat162float(r1[(long long)w * cs + c]);
+  }
+  __syncthreads();
+  const float* trow = target + ((long long)n * Ho + oh) * Wo;
+  float num = 0.f, den = 0.f;
+  for (int ow = threadIdx.x; ow < Wo; ow += blockDim.x) {
+    const int t = (int)trow[ow];
+    if (t == ignore || t < 0 || t >= C) continue;
+    int x0, x1; float lx;
+    bl_coord(ow, sw, Wi, x0, x1, lx);
+    float mx = -INFINITY, s = 0.f, lt = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = (1.f - lx) * rb[c * ld + x0] + lx * rb[c * ld + x1];
+      if (c == t) lt = v;
+      if (v > mx) { s = s * __expf(mx - v); mx = v; }
+      s += __expf(v - mx);
+    }
+    const float w = weight ? weight[t] : 1.f;
+    num += w * (mx + __logf(s) - lt);
+    den += w;
+  }
+  __shared__ float sn[8], sd[8];
+  for (int off = 16; off; off >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, off);
+    den += __shfl_xor_sync(0xffffffffu, den, off);
+  }
+  if ((threadIdx.x & 31) == 0) { sn[threadIdx.x >> 5] = num; sd[threadIdx.x >> 5] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sn[i]; b += sd[i]; }
+    if (b != 0.0) {
+      atomicAdd(accum, a);
+      atomicAdd(accum + 1, b);
+    }
+  }
+}
+
+// backward: dx[n][h][w][c] = sum over the output pixels (oh, ow) whose bilinear footprint contains (h, w) of
+// wy * wx * g * weight[t] * (softmax(logits(oh, ow))[c] - [c == t]).  One CTA per input row h: the three input rows
+// h-1, h, h+1 are staged in shared memory (every contributing output row blends two of them); stage 1 recomputes the
+// softmax per (oh, ow) and accumulates vertically into v[c][ow], stage 2 reduces horizontally (as in
+// upsample_logits_bwd_kernel).
+__global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const float* __restrict__ target,
+                                                              const float* __restrict__ weight, int C, int Hi, int Wi,
+                                                              int cs, int Ho, int Wo, float sh, float sw, int ignore,
+                                                              const double* __restrict__ accum, float div,
+                                                              const float* __restrict__ gout,
+                                                              __nv_bfloat16* __restrict__ dx) {
+  extern __shared__ float smem_f[];
+  const int ldi = Wi + 1, ldo = Wo + 1;
+  float* xs = smem_f;                 // [3][C][Wi+1]: input rows h-1, h, h+1
+  float* v = smem_f + 3 * C * ldi;    // [C][Wo+1]
+  const int h = blockIdx.x % Hi, n = blockIdx.x / Hi;
+  for (int i = threadIdx.x; i < 3 * Wi * C; i += blockDim.x) {
+    const int c = i % C, w = (i / C) % Wi, slot = i / (C * Wi);
+    const int row = h - 1 + slot;
+    xs[(slot * C + c) * ldi + w] =
+        (row >= 0 && row < Hi) ? __bfloat162float(x[(((long long)n * Hi + row) * Wi + w) * cs + c]) : 0.f;
+  }
+  __syncthreads();
+  const float g = gout[0] / ((float)accum[1] * div);
+  const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
+  int oh_lo = sh > 0.f ? (int)floorf((h - 1) * ish) - 1 : 0, oh_hi = sh > 0.f ? (int)ceilf((h + 1) * ish) + 1 : Ho - 1;
+  oh_lo = max(oh_lo, 0); oh_hi = min(oh_hi, Ho - 1);
+  for (int ow = threadIdx.x; ow < Wo; ow += blockDim.x) {
+    int x0, x1; float lx;
+    bl_coord(ow, sw, Wi, x0, x1, lx);
+    float acc[CE_MAX_C];
+#pragma unroll
+    for (int c = 0; c < CE_MAX_C; ++c) acc[c] = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      int y0, y1; float ly;
+      bl_coord(oh, sh, Hi, y0, y1, ly);
+      const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
+      if (wy == 0.f) continue;
+      const int t = (int)target[((long long)n * Ho + oh) * Wo + ow];
+      if (t == ignore || t < 0 || t >= C) continue;
+      const float* s0 = xs + (y0 - (h - 1)) * C * ldi;
+      const float* s1 = xs + (y1 - (h - 1)) * C * ldi;
+      float lg[CE_MAX_C];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CE_MAX_C; ++c) {
+        if (c < C) {
+          const float a0 = (1.f - ly) * s0[c * ldi + x0] + ly * s1[c * ldi + x0];
+          const float a1 = (1.f - ly) * s0[c * ldi + x1] + ly * s1[c * ldi + x1];
+          lg[c] = (1.f - lx) * a0 + lx * a1;
+          mx = fmaxf(mx, lg[c]);
+        }
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < CE_MAX_C; ++c) {
+        if (c < C) {
+          lg[c] = __expf(lg[c] - mx);
+          s += lg[c];
+        }
+      }
+      const float coef = wy * g * (weight ? weight[t] : 1.f);
+      const float inv = coef / s;
+#pragma unroll
+      for (int c = 0; c < CE_MAX_C; ++c) {
+        if (c < C) acc[c] += lg[c] * inv - (c == t ? coef : 0.f);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CE_MAX_C; ++c) {
+      if (c < C) v[c * ldo + ow] = acc[c];
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* out = dx + ((long long)n * Hi + h) * Wi * cs;
+  for (int i = threadIdx.x; i < Wi * cs; i += blockDim.x) {
+    const int c = i % cs, w = i / cs;
+    float a = 0.f;
+    if (c < C) {
+      int ow_lo = sw > 0.f ? (int)floorf((w - 1) * isw) - 1 : 0, ow_hi = sw > 0.f ? (int)ceilf((w + 1) * isw) + 1 : Wo - 1;
+      ow_lo = max(ow_lo, 0); ow_hi = min(ow_hi, Wo - 1);
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        int x0, x1; float lx;
+        bl_coord(ow, sw, Wi, x0, x1, lx);
+        const float wx = (x0 == w ? 1.f - lx : 0.f) + (x1 == w ? lx : 0.f);
+        if (wx != 0.f) a += wx * v[c * ldo + ow];
+      }
+    }
+    out[(long long)w * cs + c] = __float2bfloat16(a);
+  }
+}
+
 // bf16 shadow of the flat fp32 parameter buffer (one launch per step instead of one pack kernel per layer)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   const long long n4 = n >> 2;
@@ -560,6 +712,36 @@ extern "C" int zs3_ce_bwd(const float* logit, const float* target, const float* 
   ce_bwd_kernel<<<ew_blocks(total, 256, 148 * 8), 256, 0, ST(stream)>>>(logit, target, weight, C, HW, total,
                                                                         ignore_index, accum2, div, grad_out, dlogit);
   ZS3_CHECK_LAUNCH("ce_bwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_upsample_ce_fwd(const void* x, const float* target, const float* weight, int N, int C, int Hi, int Wi,
+                                   int cs, int Ho, int Wo, int ignore_index, float div, double* accum2, float* loss,
+                                   void* stream) {
+  ZS3_CHECK_ARG(x && target && accum2 && loss && C > 0 && C <= cs && C <= CE_MAX_C, "upsample_ce_fwd: bad args (C <= %d)",
+                CE_MAX_C);
+  const size_t smem = (size_t)C * (Wi + 1) * sizeof(float);
+  ZS3_CHECK_ARG(smem <= 200 * 1024, "upsample_ce_fwd: C*Wi too large for shared memory");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaMemsetAsync(accum2, 0, 2 * sizeof(double), ST(stream));
+  upsample_ce_fwd_kernel<<<N * Ho, 256, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, bl_scale(Hi, Ho),
+                                                            bl_scale(Wi, Wo), ignore_index, accum2);
+  ce_finalize_kernel<<<1, 1, 0, ST(stream)>>>(accum2, div, loss);
+  ZS3_CHECK_LAUNCH("upsample_ce_fwd");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_upsample_ce_bwd(const void* x, const float* target, const float* weight, int N, int C, int Hi, int Wi,
+                                   int cs, int Ho, int Wo, int ignore_index, float div, const double* accum2,
+                                   const float* grad_out, void* dx, void* stream) {
+  ZS3_CHECK_ARG(x && target && accum2 && grad_out && dx && C > 0 && C <= cs && C <= CE_MAX_C,
+                "upsample_ce_bwd: bad args (C <= %d)", CE_MAX_C);
+  const size_t smem = ((size_t)3 * C * (Wi + 1) + (size_t)C * (Wo + 1)) * sizeof(float);
+  ZS3_CHECK_ARG(smem <= 200 * 1024, "upsample_ce_bwd: rows do not fit in shared memory");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  upsample_ce_bwd_kernel<<<N * Hi, 256, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, bl_scale(Hi, Ho),
+                                                            bl_scale(Wi, Wo), ignore_index, accum2, div, grad_out, BF(dx));
+  ZS3_CHECK_LAUNCH("upsample_ce_bwd");
   return ZS3_OK;
 }
 

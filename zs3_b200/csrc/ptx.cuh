@@ -33,6 +33,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// Programmatic dependent launch (see common.cuh launch_pdl): let the next kernel of the stream start its prologue,
+// then wait until every prerequisite grid has completed and its memory is visible.  Both are no-ops for a kernel that
+// was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void griddep_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

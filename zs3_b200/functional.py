@@ -7,6 +7,8 @@ that layout.
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -20,6 +22,43 @@ def flush_batch_counters():
     if PENDING_BATCH_COUNTERS:
         torch._foreach_add_(PENDING_BATCH_COUNTERS, 1)
         PENDING_BATCH_COUNTERS.clear()
+
+
+class UpsampleCrossEntropy(torch.autograd.Function):
+    """CrossEntropy(F.interpolate(x, size, bilinear, align_corners=True), target) computed from the LOW-resolution
+    NHWC bf16 class scores x (deeplab.py:44 + loss.py:31-46 in one pass each way): the [N,C,H,W] fp32 logits and
+    their gradient never touch HBM.  Used by the training runtime; the module API still returns real logits."""
+
+    @staticmethod
+    def forward(ctx, x, num_classes, target, weight, ignore_index, div):
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+            raise ValueError("UpsampleCrossEntropy: x must be a CUDA NHWC bf16 tensor")
+        target = target.contiguous().float()
+        n, hi, wi, cs = x.shape
+        ho, wo = int(target.shape[-2]), int(target.shape[-1])
+        if target.numel() != n * ho * wo:
+            raise ValueError("UpsampleCrossEntropy: target must be [N, H, W]")
+        x = x.contiguous()
+        accum = torch.empty(2, dtype=torch.float64, device=x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        wt = None if weight is None else weight.contiguous().float()
+        L.check(L.lib().zs3_upsample_ce_fwd(L.ptr(x), L.ptr(target), L.ptr(wt), n, int(num_classes), hi, wi, cs, ho, wo,
+                                            int(ignore_index), float(div), L.ptr(accum), L.ptr(loss), L.stream_ptr()),
+                "zs3_upsample_ce_fwd")
+        ctx.save_for_backward(x, target, accum)
+        ctx.info = (int(num_classes), wt, int(ignore_index), float(div), ho, wo)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, target, accum = ctx.saved_tensors
+        c, wt, ignore, div, ho, wo = ctx.info
+        n, hi, wi, cs = x.shape
+        dx = torch.empty_like(x)
+        gout = gout.contiguous().float()
+        L.check(L.lib().zs3_upsample_ce_bwd(L.ptr(x), L.ptr(target), L.ptr(wt), n, c, hi, wi, cs, ho, wo, ignore, div,
+                                            L.ptr(accum), L.ptr(gout), L.ptr(dx), L.stream_ptr()), "zs3_upsample_ce_bwd")
+        return dx, None, None, None, None, None
 
 
 class IdentityBN:
@@ -113,7 +152,9 @@ class _RngState:
         return seed, off
 
 
-FUSE_STATS_MIN_KB = 18  # 3x3 convs with >= 128 input channels, 1x1 convs with >= 1152
+# BatchNorm statistics are taken in the conv epilogue (from the staged bf16 tile) for every layer with at least this
+# many 64-wide k-blocks per tile; 0 = always.  (The first version, a shuffle-tree reduction, only paid off >= 18.)
+FUSE_STATS_MIN_KB = int(os.environ.get("ZS3_FUSE_STATS_MIN_KB", "0"))
 
 _WEIGHT_EPOCH = [0]
 

@@ -49,6 +49,11 @@ class DeepLab(nn.Module):
         x = self.decoder.forward_class_prediction(x)
         return ZF.UpsampleLogits.apply(x, self.num_classes, input.shape[2], input.shape[3])
 
+    def forward_scores(self, input, keep_masks=None):
+        """Class scores BEFORE the final x4 upsample: NHWC bf16 [N, H/4, W/4, cpad(num_classes)].  The training
+        runtime feeds them to SegmentationLosses.UpsampledCrossEntropyLoss, which fuses the upsample into the loss."""
+        return self.decoder.forward_class_prediction(self._features(input, keep_masks))
+
     def forward_before_class_prediction(self, input, keep_masks=None):
         """deeplab.py:47-51: returns the [B,256,H/4,W/4] decoder features as an NCHW fp32 tensor"""
         return ZF.ToNCHW.apply(self._features(input, keep_masks), 256)

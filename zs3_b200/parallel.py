@@ -136,8 +136,9 @@ class DataParallelTrainer:
     """step-1 training step of zs3/base_trainer.py:16-20 (zero_grad, forward, CE, backward, SGD) for one rank."""
 
     def __init__(self, model, criterion, lr=0.007, momentum=0.9, weight_decay=5e-4, nesterov=False, world_size=1,
-                 use_cuda_graph=False):
+                 use_cuda_graph=False, fuse_loss=True):
         self.model, self.criterion, self.world = model, criterion, world_size
+        self.fuse_loss = fuse_loss
         self.use_cuda_graph, self.graph = use_cuda_graph, None
         groups = [list(model.get_1x_lr_params()), list(model.get_10x_lr_params())]
         self.flat = FlatParams(groups)
@@ -192,6 +193,18 @@ class DataParallelTrainer:
         with torch.cuda.graph(self.graph):
             self.static_loss = self._step(self.static_image, self.static_target, update=self.world == 1)
 
+    def _forward_loss(self, image, target):
+        """criterion(model(image), target) (base_trainer.py:17-18).  When the criterion is this package's
+        CrossEntropyLoss the x4 upsample of the class scores is fused into the loss kernels (identical value, the
+        354 MB logits tensor and its gradient are never materialised)."""
+        owner = getattr(self.criterion, "__self__", None)
+        fusable = (self.fuse_loss and hasattr(self.model, "forward_scores")
+                   and getattr(self.criterion, "__func__", None) is getattr(type(owner), "CrossEntropyLoss", None)
+                   and hasattr(owner, "UpsampledCrossEntropyLoss") and getattr(self.model, "num_classes", 99) <= 32)
+        if fusable:
+            return owner.UpsampledCrossEntropyLoss(self.model.forward_scores(image), self.model.num_classes, target)
+        return self.criterion(self.model(image), target)
+
     def _reduce_and_update(self):
         if self.world > 1:
             dist.all_reduce(self.flat.grad)  # the one collective of the step
@@ -202,8 +215,7 @@ class DataParallelTrainer:
             ZF._RngState.device_counter.add_(1 << 32)  # fresh dropout masks per step, also under graph replay
         self.flat.zero_grad()
         K.cast_f32_to_bf16(self.flat.flat, self.shadow)  # one launch refreshes every layer's bf16 forward weight
-        output = self.model(image)
-        loss = self.criterion(output, target)
+        loss = self._forward_loss(image, target)
         loss.backward()
         if update:
             self._reduce_and_update()

@@ -34,6 +34,17 @@ class SegmentationLosses:
         # the division by the batch size (loss.py:43-44) is folded into the kernel
         return self._ce(logit, target, self.weight, logit.shape[0] if self.batch_average else 1.0)
 
+    def UpsampledCrossEntropyLoss(self, scores, num_classes, target):
+        """== CrossEntropyLoss(F.interpolate(scores, size=target.shape[-2:], bilinear, align_corners=True), target)
+        for NHWC bf16 low-resolution `scores` (DeepLab.forward_scores): deeplab.py:44 fused into loss.py:31-46."""
+        if not self.size_average:
+            raise NotImplementedError("size_average=False is not used by any reference trainer")
+        w = self.weight
+        if w is not None and w.device != scores.device:
+            w = w.to(scores.device)
+        div = scores.shape[0] if self.batch_average else 1.0
+        return ZF.UpsampleCrossEntropy.apply(scores, num_classes, target, w, self.ignore_index, float(div))
+
     def CrossEntropyLossFinetune(self, logit, target):
         return self._ce(logit, target, None, logit.shape[0] if self.batch_average else 1.0)
 
