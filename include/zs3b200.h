@@ -182,6 +182,8 @@ typedef struct {
   float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
   double* reset_sum; double* reset_sqsum;
   int reset_count;      /* number of leading entries of reset_sum/reset_sqsum to zero */
+  unsigned char* relu_mask_out; /* optional [M][C/8]: bit j of byte (m, c/8) = [out[m][c+j] > 0]; lets the backward of
+                                 * residual layers read 1 bit instead of 16 per element for the ReLU mask */
 } zs3_bn_apply_args;
 
 /* out = dropout(relu?(scale*y + shift (+ residual))) */
@@ -220,6 +222,7 @@ typedef struct {
   double* reset_sum_dz; /* optional: the apply phase zeroes the first reset_count entries of these two arrays (the */
   double* reset_sum_dzx;/* sums buffer the NEXT layer's reduce phase will accumulate into; two buffers alternate) */
   int reset_count;
+  const unsigned char* relu_mask; /* relu == 3: the bit mask written by zs3_bn_apply (relu_mask_out); `out` unused */
 } zs3_bn_bwd_args;
 
 /* phase 1: sum_dz += sum(dz), sum_dzx += sum(dz * xhat) with dz = dout * [out > 0] * grad_scale */

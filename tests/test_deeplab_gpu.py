@@ -129,6 +129,31 @@ def test_deeplab_train_step_vs_oracle(small_input):
     assert int(model.backbone.layer3[5].bn2.num_batches_tracked) == 1
 
 
+def test_frozen_bn_training_has_gradients(small_input):
+    """freeze_bn=True (eval-mode BatchNorm) while the convs still train (train_pascal.py --freeze-bn): the eval-BN
+    layers must take the differentiable path, not the folded inference epilogue, whenever a gradient is required."""
+    from zs3_b200.modeling.deeplab import DeepLab
+    from zs3_b200.utils.loss import SegmentationLosses
+    torch.manual_seed(5)
+    model = DeepLab(num_classes=21, sync_bn=True, freeze_bn=True, pretrained=False).cuda()
+    model.train()
+    model.freeze_bn()
+    assert not model.backbone.layer2[1].bn2.training
+    crit = SegmentationLosses(weight=None, cuda=True).build_loss("ce")
+    target = torch.randint(0, 21, (2, 65, 65), generator=torch.Generator().manual_seed(1)).float().cuda()
+    loss = crit(model(small_input.cuda()), target)
+    loss.backward()
+    torch.cuda.synchronize()
+    for name, prm in model.named_parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
+    assert model.backbone.layer1[0].conv1.weight.grad.abs().max() > 0
+    # and with autograd off the same model folds BN into the conv epilogue and agrees with the training-path forward
+    with torch.no_grad():
+        a = model(small_input.cuda())
+    b = model(small_input.cuda())
+    assert rel_l2(a, b.detach()) < 2e-2
+
+
 def test_trainer_fused_loss_matches_unfused(small_input):
     """The training runtime fuses the final x4 upsample into the loss (DeepLab.forward_scores +
     SegmentationLosses.UpsampledCrossEntropyLoss); same loss (1e-5 rel) and same parameter gradients (bf16-rounding

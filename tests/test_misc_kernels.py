@@ -144,6 +144,7 @@ def test_fused_upsample_cross_entropy(C, hi, ho, weighted):
     l2 = losses.build_loss("ce")(ZF.UpsampleLogits.apply(xh2, C, ho, ho), target)
     l2.backward()
     assert abs(loss.item() - l2.item()) < 1e-6 * abs(l2.item())
+    print(f"fused vs unfused d scores rel_l2 = {rel_l2(xh.grad.float(), xh2.grad.float()):.3e}")
     assert rel_l2(xh.grad.float(), xh2.grad.float()) < 4e-3
 
 

@@ -110,6 +110,7 @@ class BnApplyArgs(C.Structure):
         ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("C_real", C.c_int),
         ("mean_out", C.c_void_p), ("invstd_out", C.c_void_p), ("scale_out", C.c_void_p), ("shift_out", C.c_void_p),
         ("reset_sum", C.c_void_p), ("reset_sqsum", C.c_void_p), ("reset_count", C.c_int),
+        ("relu_mask_out", C.c_void_p),
     ]
 
 
@@ -127,6 +128,7 @@ class BnBwdArgs(C.Structure):
         ("dres", C.c_void_p), ("dres_cstride", C.c_int), ("dres_accumulate", C.c_int),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("C_real", C.c_int), ("param_accumulate", C.c_int),
         ("reset_sum_dz", C.c_void_p), ("reset_sum_dzx", C.c_void_p), ("reset_count", C.c_int),
+        ("relu_mask", C.c_void_p),
     ]
 
 

@@ -129,6 +129,7 @@ struct ApplyP {
   float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
   double* reset_a; double* reset_b;  // the OTHER statistics buffer, zeroed for the next layer
   int reset_count;
+  unsigned char* relu_bits;  // optional [M][C/8] ReLU bit mask for the backward
 };
 
 __device__ __forceinline__ void apply_one(const ApplyP& p, long long m, int c, const float (&sc)[8],
@@ -145,6 +146,12 @@ __device__ __forceinline__ void apply_one(const ApplyP& p, long long m, int c, c
     for (int j = 0; j < 8; ++j) f[j] += r[j];
   }
   if (p.relu) {
+    if (p.relu_bits) {
+      unsigned bits = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bits |= (f[j] > 0.f ? 1u : 0u) << j;
+      p.relu_bits[m * (p.C >> 3) + (c >> 3)] = (unsigned char)bits;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
   }
@@ -268,7 +275,15 @@ struct BwdP {
   float* dgamma; float* dbeta; int C_real; int param_acc;
   int rows_per_block;  // pixel rows handled concurrently by one CTA
   double* reset_a; double* reset_b; int reset_count;  // the other sums buffer, zeroed by the apply phase
+  const unsigned char* relu_bits;  // relu == 3
 };
+
+// the "forward activation" operand of make_dz: the saved output row (relu == 1), the ReLU mask byte (relu == 3) or nothing
+__device__ __forceinline__ uint4 load_mask_or_out(const BwdP& p, long long m, int c, const uint4& zero) {
+  if (p.relu == 1) return *reinterpret_cast<const uint4*>(p.out + m * p.out_cs + c);
+  if (p.relu == 3) return make_uint4(p.relu_bits[m * (p.C >> 3) + (c >> 3)], 0u, 0u, 0u);
+  return zero;
+}
 
 // dz = dout * [forward activation > 0] * grad_scale for one 8-channel slice.
 // relu == 1: mask from the saved forward output (residual / dropout layers); relu == 2: mask recomputed as
@@ -284,6 +299,9 @@ __device__ __forceinline__ void make_dz(const BwdP& p, const uint4& draw, const 
     unpack8(oraw, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) dz[j] = o[j] > 0.f ? dz[j] * p.grad_scale : 0.f;
+  } else if (p.relu == 3) {  // oraw.x carries the mask byte of this 8-channel slice
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = ((oraw.x >> j) & 1u) ? dz[j] * p.grad_scale : 0.f;
   } else if (p.grad_scale != 1.f) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) dz[j] *= p.grad_scale;
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdP p) {
       for (int u = 0; u < UNROLL; ++u) {
         yr[u] = *reinterpret_cast<const uint4*>(p.y + (m + u * stride) * p.y_cs + c);
         dr[u] = *reinterpret_cast<const uint4*>(p.dout + (m + u * stride) * p.dout_cs + c);
-        orw[u] = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + (m + u * stride) * p.out_cs + c) : zero;
+        orw[u] = load_mask_or_out(p, m + u * stride, c, zero);
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) accumulate(yr[u], dr[u], orw[u]);
@@ -332,7 +350,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdP p) {
     for (; m < p.M; m += stride) {
       const uint4 yr = *reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c);
       const uint4 dr = *reinterpret_cast<const uint4*>(p.dout + m * p.dout_cs + c);
-      const uint4 orw = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + m * p.out_cs + c) : zero;
+      const uint4 orw = load_mask_or_out(p, m, c, zero);
       accumulate(yr, dr, orw);
     }
     float* r1 = red + (size_t)rl * p.C + c;
@@ -413,7 +431,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
     for (int u = 0; u < UNROLL; ++u) {
       yr0[u] = *reinterpret_cast<const uint4*>(p.y + (m + u * stride) * p.y_cs + c);
       dr0[u] = *reinterpret_cast<const uint4*>(p.dout + (m + u * stride) * p.dout_cs + c);
-      or0[u] = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + (m + u * stride) * p.out_cs + c) : zero;
+      or0[u] = load_mask_or_out(p, m + u * stride, c, zero);
     }
   }
   // per-channel coefficients once per CTA (thread t -> channel t, t+256, ...), through shared memory; CTA 0 also
@@ -461,7 +479,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
     for (int u = 0; u < UNROLL; ++u) {
       yr[u] = *reinterpret_cast<const uint4*>(p.y + (m + u * stride) * p.y_cs + c);
       dr[u] = *reinterpret_cast<const uint4*>(p.dout + (m + u * stride) * p.dout_cs + c);
-      orw[u] = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + (m + u * stride) * p.out_cs + c) : zero;
+      orw[u] = load_mask_or_out(p, m + u * stride, c, zero);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) bwd_apply_one(p, m + u * stride, c, cA, cB, cC, sc, sh, yr[u], dr[u], orw[u]);
@@ -469,7 +487,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
   for (; m < p.M; m += stride) {
     const uint4 yr = *reinterpret_cast<const uint4*>(p.y + m * p.y_cs + c);
     const uint4 dr = *reinterpret_cast<const uint4*>(p.dout + m * p.dout_cs + c);
-    const uint4 orw = p.relu == 1 ? *reinterpret_cast<const uint4*>(p.out + m * p.out_cs + c) : zero;
+    const uint4 orw = load_mask_or_out(p, m, c, zero);
     bwd_apply_one(p, m, c, cA, cB, cC, sc, sh, yr, dr, orw);
   }
 }
@@ -684,6 +702,7 @@ extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
   p.eps = a->eps; p.momentum = a->momentum; p.rmean = a->running_mean; p.rvar = a->running_var; p.C_real = a->C_real;
   p.mean_out = a->mean_out; p.invstd_out = a->invstd_out; p.scale_out = a->scale_out; p.shift_out = a->shift_out;
   p.reset_a = a->reset_sum; p.reset_b = a->reset_sqsum; p.reset_count = a->reset_count;
+  p.relu_bits = a->relu ? a->relu_mask_out : nullptr;
   ZS3_CHECK_ARG(a->C <= 2048, "bn_apply: C=%d > 2048", a->C);
   p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
   const size_t smem = a->stat_sum ? (size_t)2 * a->C * sizeof(float) : 0;
@@ -700,6 +719,8 @@ static int fill_bwd(const zs3_bn_bwd_args* a, BwdP& p, const char* who) {
                 "%s: C=%d must be a multiple of 8 and <= 2048", who, a->C);
   ZS3_CHECK_ARG(a->relu != 1 || (a->out && a->out_cstride % 8 == 0), "%s: relu=1 needs the forward output", who);
   ZS3_CHECK_ARG(a->relu != 2 || a->shift != nullptr, "%s: relu=2 (mask recomputed from y) needs shift", who);
+  ZS3_CHECK_ARG(a->relu != 3 || a->relu_mask != nullptr, "%s: relu=3 needs the ReLU bit mask", who);
+  ZS3_CHECK_ARG(a->relu >= 0 && a->relu <= 3, "%s: relu mode %d", who, a->relu);
   p.dout = static_cast<const __nv_bfloat16*>(a->dout); p.dout_cs = a->dout_cstride;
   p.out = static_cast<const __nv_bfloat16*>(a->out); p.out_cs = a->out_cstride;
   p.y = static_cast<const __nv_bfloat16*>(a->y); p.y_cs = a->y_cstride;
@@ -712,6 +733,7 @@ static int fill_bwd(const zs3_bn_bwd_args* a, BwdP& p, const char* who) {
   p.dres = static_cast<__nv_bfloat16*>(a->dres); p.dres_cs = a->dres_cstride; p.dres_acc = a->dres_accumulate;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.C_real = a->C_real; p.param_acc = a->param_accumulate;
   p.reset_a = a->reset_sum_dz; p.reset_b = a->reset_sum_dzx; p.reset_count = a->reset_count;
+  p.relu_bits = a->relu_mask;
   p.rows_per_block = 1;
   return ZS3_OK;
 }

@@ -27,7 +27,7 @@ constexpr int BLOCK_M = 128;      // output pixels per tile (= TMEM lanes)
 constexpr int BLOCK_K = 64;       // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int NUM_THREADS = 384;   // fprop: 4 control warps + 8 epilogue warps
-constexpr int WG_THREADS = 256;    // wgrad: 4 control warps + 4 epilogue warps
+constexpr int WG_THREADS = 384;    // wgrad: 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int MAX_STAT_CH = 2048;  // per-CTA shared-memory BatchNorm statistic accumulators
@@ -42,7 +42,7 @@ struct FpropParams {
   FpropSegment seg[ZS3_MAX_SEGMENTS];
   int b_mn;            // 1: data-gradient mode on forward-packed weights W[k][tap][n] (MN-major B tiles, flipped taps)
   CUtensorMap ymap;    // tiled 2-D map over y [M][cout_pad] (box 32 rows x 32 channels, SWIZZLE_64B) for the TMA-store epilogue
-  int use_tma_store;   // dense bf16 output without accumulate: stage through shared memory and store with TMA
+  int use_tma_store;   // dense bf16 output: stage through shared memory and store with TMA (accumulate: reduce-add)
   int num_segments;
   int M;          // N*Ho*Wo
   int HoWo, Wo;
@@ -98,7 +98,13 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BN, int STAGES>
+// MODE selects the epilogue that is compiled in (the hot variants stay small enough for the instruction cache):
+//   0  bf16 output through the staged TMA store (or TMA reduce-add when accumulating), nothing else;
+//   1  same + BatchNorm batch statistics kept in REGISTERS across the CTA's tiles (needs one n-tile per CTA, i.e.
+//      gridDim.x % num_n_tiles == 0) and flushed once at the end;
+//   2  generic: bias, fp32 / strided / read-modify-write outputs, the folded inference epilogue, statistics through
+//      per-CTA shared-memory partials.
+template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   using L = FpropSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
   const int num_groups = p.num_m_groups * p.num_n_tiles;
   const int cluster_id = blockIdx.x / csize;
   const int num_clusters = gridDim.x / csize;
-  if (p.stat_sum != nullptr) {
+  if (MODE == 2 && p.stat_sum != nullptr) {
     for (int i = threadIdx.x; i < p.cout_pad; i += NUM_THREADS) {
       s_sum[i] = 0.f;
       s_sq[i] = 0.f;
@@ -256,144 +262,162 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
     const int quarter = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;  // which 32-column chunks this warp owns (even / odd)
     const int row = quarter * 32 + lane;
+    constexpr int CHUNKS = BN / 64;            // chunks per warp and tile
     uint32_t store_seq = 0;
     int it = 0;
-    for (int g = cluster_id; g < num_groups; g += num_clusters, ++it) {
-      const int n_tile = g % p.num_n_tiles;
-      const int m_tile = (g / p.num_n_tiles) * csize + crank;
-      const int as = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int m = m_tile * BLOCK_M + row;
-      const bool valid = m < p.M;
-      long long pix = 0;
-      if (valid) {
-        const int img = m / p.HoWo;
-        const int rem = m - img * p.HoWo;
-        const int op = rem / p.Wo;
-        const int oq = rem - op * p.Wo;
-        pix = img * p.y_img + op * p.y_row + oq * p.y_pix;
-      }
-      mbar_wait(&acc_full[as], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int chunk = half; chunk < BN / 32; chunk += 2) {
-        const int n = n_tile * BN + chunk * 32;
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + chunk * 32, raw);
-        tmem_ld_wait();
-        if (n >= p.cout_pad) continue;  // warp-uniform
-        float f[32];
+    if constexpr (MODE != 2) {
+      // ---- hot variants: TMEM -> registers -> bf16 -> 64B-swizzled staging box -> TMA store / reduce-add.
+      // Two staging boxes per warp (the second set lives in the statistics region, unused here), the TMEM read of
+      // chunk i+1 is in flight while chunk i is converted and staged (two register buffers, fully unrolled), and the
+      // accumulator goes back to the MMA warp as soon as its last read has landed.
+      float st[MODE == 1 ? CHUNKS : 1][4];     // MODE 1: running sum / sum of squares (lo, hi channel of this lane's word)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(raw[j]);
-        if (p.bias != nullptr) {
+      for (int i = 0; i < (MODE == 1 ? CHUNKS : 1); ++i) st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+      const int sh = lane & 1, sw = lane >> 1;  // statistics: row parity and bf16x2 word column of this lane
+      for (int g = cluster_id; g < num_groups; g += num_clusters, ++it) {
+        const int n_tile = g % p.num_n_tiles;
+        const int m_tile = (g / p.num_n_tiles) * csize + crank;
+        const int as = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const bool valid = m_tile * BLOCK_M + row < p.M;
+        mbar_wait(&acc_full[as], acc_phase);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * 32;
+        uint32_t raw2[2][32];
+        tmem_ld_32x32(tacc, raw2[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n + j);
-        }
-        if (p.ep_scale != nullptr) {
-          // eval-mode BatchNorm (+residual, +ReLU) folded into the epilogue: no separate normalisation pass
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], __ldg(p.ep_scale + n + j), __ldg(p.ep_shift + n + j));
-          if (p.ep_res != nullptr && valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.ep_res + pix * p.ep_res_cs + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 o = __ldg(rp + j);
-              f[8 * j + 0] += bf16_lo(o.x);
-              f[8 * j + 1] += bf16_hi(o.x);
-              f[8 * j + 2] += bf16_lo(o.y);
-              f[8 * j + 3] += bf16_hi(o.y);
-              f[8 * j + 4] += bf16_lo(o.z);
-              f[8 * j + 5] += bf16_hi(o.z);
-              f[8 * j + 6] += bf16_lo(o.w);
-              f[8 * j + 7] += bf16_hi(o.w);
-            }
+        for (int ci = 0; ci < CHUNKS; ++ci) {
+          const int n = n_tile * BN + (half + 2 * ci) * 32;
+          uint32_t(&raw)[32] = raw2[ci & 1];
+          tmem_ld_wait_for(raw);
+          if (ci + 1 < CHUNKS) {
+            tmem_ld_32x32(tacc + (ci + 1) * 64, raw2[(ci + 1) & 1]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
           }
-          if (p.ep_relu) {
+          if (n >= p.cout_pad) continue;  // warp-uniform
+          if (MODE == 1 && !valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int j = 0; j < 32; ++j) raw[j] = 0u;  // rows past M must not reach the batch statistics
           }
-        }
-        if (p.stat_sum != nullptr && !valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows past M must not reach the batch statistics
-        }
-        bool stats_done = false;
-        if (p.use_tma_store) {
-          // coalesced path: the warp's [32 rows][32 channels] bf16 block goes through a 64B-swizzled staging box
-          // and leaves as one TMA store (full 64-byte row segments; rows >= M are clipped by the tensor map)
-          // two boxes per warp (the second one lives in the unused statistics region): the store of chunk i
-          // overlaps the TMEM read / packing of chunk i+1
-          const bool dbl = p.stat_sum == nullptr;
-          uint8_t* stg = smem + ((dbl && (store_seq & 1)) ? L::STAT_OFFSET : L::STAGING_OFFSET) +
-                         (warp - EPI_WARP0) * (32 * 64);
-          if (dbl)
-            tma_store_wait_read1();  // the store issued two chunks ago (same box) has been read out
-          else
-            tma_store_wait_read();
+          uint8_t* stg = smem + ((store_seq & 1) ? L::STAT_OFFSET : L::STAGING_OFFSET) + (warp - EPI_WARP0) * (32 * 64);
+          tma_store_wait_read1();  // the store issued two chunks ago (same box) has been read out
           ++store_seq;
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            o.x = pack_bf16x2(__uint_as_float(raw[8 * j + 0]), __uint_as_float(raw[8 * j + 1]));
+            o.y = pack_bf16x2(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3]));
+            o.z = pack_bf16x2(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5]));
+            o.w = pack_bf16x2(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7]));
             // SWIZZLE_64B: 16-byte chunk index ^= (byte address bits [7,9)) = (row >> 1) & 3
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&p.ymap, stg, n, m_tile * BLOCK_M + quarter * 32);
+            if (p.accumulate)  // residual join of the data gradient: y += tile, added in bf16 by the L2 (no SM read)
+              tma_reduce_add_2d(&p.ymap, stg, n, m_tile * BLOCK_M + quarter * 32);
+            else
+              tma_store_2d(&p.ymap, stg, n, m_tile * BLOCK_M + quarter * 32);
             tma_store_commit();
           }
-          if (p.stat_sum != nullptr) {
+          if constexpr (MODE == 1) {
             // BatchNorm batch statistics straight from the staged tile (i.e. of the bf16 values the normalisation
-            // pass will read): the box is [32 rows][16 bf16x2 words]; lane (w = lane/2, h = lane%2) walks the 16
-            // rows of parity h of word column w -- 16 conflict-free LDS.32 instead of a 5-level shuffle tree.
-            const int h = lane & 1, w = lane >> 1;
-            float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+            // pass will read): the box is [32 rows][16 bf16x2 words]; lane (sw, sh) walks the 16 rows of parity sh of
+            // word column sw -- 16 conflict-free LDS.32 -- and keeps the sums in registers until the CTA is done.
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const uint32_t word = *reinterpret_cast<const uint32_t*>(stg + (2 * i + h) * 64 +
-                                                                       (((w >> 2) ^ (i & 3)) << 4) + ((w & 3) << 2));
+              const uint32_t word = *reinterpret_cast<const uint32_t*>(stg + (2 * i + sh) * 64 +
+                                                                       (((sw >> 2) ^ (i & 3)) << 4) + ((sw & 3) << 2));
               const float lo = bf16_lo(word), hi = bf16_hi(word);
-              s_lo += lo;
-              q_lo = fmaf(lo, lo, q_lo);
-              s_hi += hi;
-              q_hi = fmaf(hi, hi, q_hi);
+              st[ci][0] += lo;
+              st[ci][1] = fmaf(lo, lo, st[ci][1]);
+              st[ci][2] += hi;
+              st[ci][3] = fmaf(hi, hi, st[ci][3]);
             }
-            s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1);
-            q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 1);
-            s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
-            q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 1);
-            // shared-memory partials, flushed once per CTA at the end; parity 0 owns the sums, parity 1 the squares
-            atomicAdd(h == 0 ? &s_sum[n + 2 * w] : &s_sq[n + 2 * w], h == 0 ? s_lo : q_lo);
-            atomicAdd(h == 0 ? &s_sum[n + 2 * w + 1] : &s_sq[n + 2 * w + 1], h == 0 ? s_hi : q_hi);
-            stats_done = true;
           }
-        } else if (valid) {
-          if (p.y_is_f32) {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.y) + pix * p.y_cstride + n);
-            if (p.accumulate) {
+        }
+      }
+      if (lane == 0) tma_store_wait_all();
+      if constexpr (MODE == 1) {
+        // every store of this CTA has completed once all epilogue warps are past this point: the staging region is
+        // free and becomes the [2][BN] cross-warp reduction buffer (zeroed below, after the CTA-wide barrier)
+        __syncwarp();
+        tc_fence_before();
+        __syncthreads();  // (A) matched by the non-epilogue warps below
+        float* red = reinterpret_cast<float*>(smem + L::STAGING_OFFSET);
+        for (int i = threadIdx.x - EPI_WARP0 * 32; i < 2 * BN; i += NUM_EPI_WARPS * 32) red[i] = 0.f;
+        named_barrier_sync(1, NUM_EPI_WARPS * 32);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 o = dst[j];
-                f[4 * j + 0] += o.x;
-                f[4 * j + 1] += o.y;
-                f[4 * j + 2] += o.z;
-                f[4 * j + 3] += o.w;
-              }
+        for (int ci = 0; ci < CHUNKS; ++ci) {
+          float v0 = st[ci][0], v1 = st[ci][1], v2 = st[ci][2], v3 = st[ci][3];
+          v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+          v3 += __shfl_xor_sync(0xffffffffu, v3, 1);
+          const int col = (half + 2 * ci) * 32 + 2 * sw;
+          // parity 0 owns the sums, parity 1 the squares
+          atomicAdd(sh == 0 ? &red[col] : &red[BN + col], sh == 0 ? v0 : v1);
+          atomicAdd(sh == 0 ? &red[col + 1] : &red[BN + col + 1], sh == 0 ? v2 : v3);
+        }
+        named_barrier_sync(1, NUM_EPI_WARPS * 32);
+        if (it > 0) {  // this CTA processed tiles, all of n-tile (cluster_id % num_n_tiles)
+          const int n0 = (cluster_id % p.num_n_tiles) * BN;
+          for (int i = threadIdx.x - EPI_WARP0 * 32; i < BN; i += NUM_EPI_WARPS * 32) {
+            const float b2 = red[BN + i];
+            if (n0 + i < p.cout_pad && b2 != 0.f) {
+              atomicAdd(p.stat_sum + n0 + i, (double)red[i]);
+              atomicAdd(p.stat_sqsum + n0 + i, (double)b2);
             }
+          }
+        }
+      }
+    } else {
+      // ---- generic variant
+      for (int g = cluster_id; g < num_groups; g += num_clusters, ++it) {
+        const int n_tile = g % p.num_n_tiles;
+        const int m_tile = (g / p.num_n_tiles) * csize + crank;
+        const int as = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int m = m_tile * BLOCK_M + row;
+        const bool valid = m < p.M;
+        long long pix = 0;
+        if (valid) {
+          const int img = m / p.HoWo;
+          const int rem = m - img * p.HoWo;
+          const int op = rem / p.Wo;
+          const int oq = rem - op * p.Wo;
+          pix = img * p.y_img + op * p.y_row + oq * p.y_pix;
+        }
+        mbar_wait(&acc_full[as], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = half; chunk < BN / 32; chunk += 2) {
+          const int n = n_tile * BN + chunk * 32;
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + chunk * 32, raw);
+          tmem_ld_wait();
+          if (n >= p.cout_pad) continue;  // warp-uniform
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + pix * p.y_cstride + n);
-            if (p.accumulate) {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(raw[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + n + j);
+          }
+          if (p.ep_scale != nullptr) {
+            // eval-mode BatchNorm (+residual, +ReLU) folded into the epilogue: no separate normalisation pass
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], __ldg(p.ep_scale + n + j), __ldg(p.ep_shift + n + j));
+            if (p.ep_res != nullptr && valid) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.ep_res + pix * p.ep_res_cs + n);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                uint4 o = dst[j];
+                const uint4 o = __ldg(rp + j);
                 f[8 * j + 0] += bf16_lo(o.x);
                 f[8 * j + 1] += bf16_hi(o.x);
                 f[8 * j + 2] += bf16_lo(o.y);
@@ -404,6 +428,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
                 f[8 * j + 7] += bf16_hi(o.w);
               }
             }
+            if (p.ep_relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+          }
+          if (p.stat_sum != nullptr && !valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows past M must not reach the batch statistics
+          }
+          if (p.use_tma_store) {
+            // staged TMA store; a single box per warp here (the second set's region holds the statistics partials)
+            uint8_t* stg = smem + L::STAGING_OFFSET + (warp - EPI_WARP0) * (32 * 64);
+            tma_store_wait_read();
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -411,36 +449,87 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
               o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
               o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              dst[j] = o;
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.accumulate)
+                tma_reduce_add_2d(&p.ymap, stg, n, m_tile * BLOCK_M + quarter * 32);
+              else
+                tma_store_2d(&p.ymap, stg, n, m_tile * BLOCK_M + quarter * 32);
+              tma_store_commit();
+            }
+          } else if (valid) {
+            if (p.y_is_f32) {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.y) + pix * p.y_cstride + n);
+              if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float4 o = dst[j];
+                  f[4 * j + 0] += o.x;
+                  f[4 * j + 1] += o.y;
+                  f[4 * j + 2] += o.z;
+                  f[4 * j + 3] += o.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + pix * p.y_cstride + n);
+              if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 o = dst[j];
+                  f[8 * j + 0] += bf16_lo(o.x);
+                  f[8 * j + 1] += bf16_hi(o.x);
+                  f[8 * j + 2] += bf16_lo(o.y);
+                  f[8 * j + 3] += bf16_hi(o.y);
+                  f[8 * j + 4] += bf16_lo(o.z);
+                  f[8 * j + 5] += bf16_hi(o.z);
+                  f[8 * j + 6] += bf16_lo(o.w);
+                  f[8 * j + 7] += bf16_hi(o.w);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                dst[j] = o;
+              }
             }
           }
-        }
-        if (p.stat_sum != nullptr && !stats_done) {
-          // direct-store path (fp32 / accumulating outputs): batch statistics of the fp32 conv output (F.batch_norm
-          // training path, zs3/modeling/sync_batchnorm/batchnorm.py:48-58): per-channel sum and sum of squares.
-          float sq[32];
+          if (p.stat_sum != nullptr) {
+            // batch statistics of the fp32 conv output (F.batch_norm training path,
+            // zs3/modeling/sync_batchnorm/batchnorm.py:48-58): per-channel sum and sum of squares, shuffle-tree
+            // transpose-reduce per 32 columns -> per-CTA shared-memory partials
+            float sq[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
-          const float s1 = warp_column_sums(f, lane);
-          const float s2 = warp_column_sums(sq, lane);
-          atomicAdd(&s_sum[n + lane], s1);  // shared-memory partials, flushed once per CTA at the end
-          atomicAdd(&s_sq[n + lane], s2);
+            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+            const float s1 = warp_column_sums(f, lane);
+            const float s2 = warp_column_sums(sq, lane);
+            atomicAdd(&s_sum[n + lane], s1);
+            atomicAdd(&s_sq[n + lane], s2);
+          }
         }
+        // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
       }
-      // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (p.use_tma_store && lane == 0) tma_store_wait_all();
     }
-    if (p.use_tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (MODE != 1 || warp < EPI_WARP0) __syncthreads();  // MODE 1: the epilogue warps arrived at (A) above
   if (csize > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
-  if (p.stat_sum != nullptr) {
+  if (MODE == 2 && p.stat_sum != nullptr) {
     for (int i = threadIdx.x; i < p.cout_pad; i += NUM_THREADS) {
       const float a = s_sum[i], b = s_sq[i];
       if (b != 0.f) {  // channels of n-tiles this CTA never visited (and all-zero channels) add nothing
@@ -596,13 +685,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
       const bool vec_ok = (p.dw_ld % 4 == 0) && (p.dw_ci_offset % 4 == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0);
       // TMA-reduce path: the main loop is over, so the pipeline stages are free: two 4 KiB fp32 boxes per warp
+      // two epilogue warps per 32-row quarter take alternate 32-column chunks; the TMEM read of the next chunk is in
+      // flight while the current one is staged and reduced (two register buffers, fully unrolled loop) -- this
+      // epilogue is NOT overlapped with a main loop (one tile per CTA), so its latency is on the critical path
       uint8_t* stg_base = smem + (warp - EPI_WARP0) * 8192;
       uint32_t seq = 0;
-#pragma unroll 1
-      for (int chunk = 0; chunk < MB * CN / 32; ++chunk) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + chunk * 32, raw);
-        tmem_ld_wait();
+      const int half = (warp - EPI_WARP0) >> 2;
+      constexpr int CHUNKS = MB * CN / 64;  // per warp
+      const uint32_t tacc = tmem_base + (uint32_t(quarter * 32) << 16) + half * 32;
+      uint32_t raw2[2][32];
+      tmem_ld_32x32(tacc, raw2[0]);
+#pragma unroll
+      for (int it = 0; it < CHUNKS; ++it) {
+        const int chunk = half + 2 * it;
+        uint32_t(&raw)[32] = raw2[it & 1];
+        tmem_ld_wait_for(raw);
+        if (it + 1 < CHUNKS) tmem_ld_32x32(tacc + (it + 1) * 64, raw2[(it + 1) & 1]);
         const int mb = chunk / (CN / 32);
         const int co = co_tile * (128 * MB) + mb * 128 + quarter * 32 + lane;
         const int ci = ci_tile * CN + (chunk - mb * (CN / 32)) * 32;
@@ -778,12 +876,32 @@ static int num_sms() {
   return g_num_sms;
 }
 
+template <int BN, int STAGES, int MODE>
+static int launch_fprop_mode(const FpropParams& p, int csize, int clusters, cudaStream_t st);
+
+// epilogue variant + grid: see conv_fprop_kernel.  The register-statistics variant needs every CTA to stay on one
+// n-tile, i.e. a grid that is a multiple of num_n_tiles (148 already is for 1, 2 and 4 n-tiles; 8 n-tiles run on 144).
 template <int BN, int STAGES>
 static int launch_fprop(const FpropParams& p, int csize, cudaStream_t st) {
+  const int groups = p.num_m_groups * p.num_n_tiles;
+  const int max_clusters = num_sms() / csize;
+  int clusters = groups < max_clusters ? groups : max_clusters;
+  const bool hot = p.use_tma_store && p.bias == nullptr && p.ep_scale == nullptr;
+  if (!hot) return launch_fprop_mode<BN, STAGES, 2>(p, csize, clusters, st);
+  if (p.stat_sum == nullptr) return launch_fprop_mode<BN, STAGES, 0>(p, csize, clusters, st);
+  if (csize == 1 && clusters >= p.num_n_tiles) {
+    clusters -= clusters % p.num_n_tiles;
+    return launch_fprop_mode<BN, STAGES, 1>(p, csize, clusters, st);
+  }
+  return launch_fprop_mode<BN, STAGES, 2>(p, csize, clusters, st);
+}
+
+template <int BN, int STAGES, int MODE>
+static int launch_fprop_mode(const FpropParams& p, int csize, int clusters, cudaStream_t st) {
   using L = FpropSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL);
     if (e != cudaSuccess) {
       set_error("conv_fprop: cudaFuncSetAttribute(%d bytes) failed: %s", L::TOTAL, cudaGetErrorString(e));
@@ -791,9 +909,6 @@ static int launch_fprop(const FpropParams& p, int csize, cudaStream_t st) {
     }
     configured = true;
   }
-  const int groups = p.num_m_groups * p.num_n_tiles;
-  const int max_clusters = num_sms() / csize;
-  const int clusters = groups < max_clusters ? groups : max_clusters;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(clusters * csize);
@@ -809,7 +924,7 @@ static int launch_fprop(const FpropParams& p, int csize, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (csize == 1 && pdl_enabled(PDL_CONV)) ? 2 : 1;  // PDL only for the (default) non-cluster launch
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BN, STAGES>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BN, STAGES, MODE>, p);
   if (e != cudaSuccess) {
     set_error("conv_fprop: cudaLaunchKernelEx(cluster=%d) failed: %s", csize, cudaGetErrorString(e));
     return ZS3_ERR_LAUNCH;
@@ -935,7 +1050,12 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
     const char* env = getenv("ZS3_TMA_STORE");
     tma_store_pref = env ? atoi(env) : 1;
   }
-  if (tma_store_pref && !a->y_is_f32 && !a->accumulate && a->y_sp_stride <= 1 && a->y_cstride % 8 == 0 &&
+  static int tma_acc_pref = -1;
+  if (tma_acc_pref < 0) {
+    const char* env = getenv("ZS3_TMA_ACCUMULATE");
+    tma_acc_pref = env ? atoi(env) : 1;
+  }
+  if (tma_store_pref && !a->y_is_f32 && (!a->accumulate || tma_acc_pref) && a->y_sp_stride <= 1 && a->y_cstride % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(a->y) & 15) == 0) {
     int rc2 = encode_tiled2d_bf16_sw64(&p.ymap, a->y, M, a->cout_pad, a->y_cstride, 32, 32);
     if (rc2) return rc2;

@@ -464,18 +464,28 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const __nv_bfloat1
 // h-1, h, h+1 are staged in shared memory (every contributing output row blends two of them); stage 1 recomputes the
 // softmax per (oh, ow) and accumulates vertically into v[c][ow], stage 2 reduces horizontally (as in
 // upsample_logits_bwd_kernel).
-__global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(512) upsample_ce_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                               const float* __restrict__ target,
                                                               const float* __restrict__ weight, int C, int Hi, int Wi,
                                                               int cs, int Ho, int Wo, float sh, float sw, int ignore,
                                                               const double* __restrict__ accum, float div,
                                                               const float* __restrict__ gout,
-                                                              __nv_bfloat16* __restrict__ dx) {
+                                                              __nv_bfloat16* __restrict__ dx, int max_rows) {
   extern __shared__ float smem_f[];
   const int ldi = Wi + 1, ldo = Wo + 1;
   float* xs = smem_f;                 // [3][C][Wi+1]: input rows h-1, h, h+1
   float* v = smem_f + 3 * C * ldi;    // [C][Wo+1]
+  unsigned char* tg = reinterpret_cast<unsigned char*>(v + C * ldo);  // [max_rows][Wo] labels (255 = no gradient)
   const int h = blockIdx.x % Hi, n = blockIdx.x / Hi;
+  const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
+  int oh_lo = sh > 0.f ? (int)floorf((h - 1) * ish) - 1 : 0, oh_hi = sh > 0.f ? (int)ceilf((h + 1) * ish) + 1 : Ho - 1;
+  oh_lo = max(oh_lo, 0);
+  oh_hi = min(min(oh_hi, Ho - 1), oh_lo + max_rows - 1);
+  const int rows = oh_hi - oh_lo + 1;
+  for (int i = threadIdx.x; i < rows * Wo; i += blockDim.x) {  // contiguous rows: fully coalesced
+    const int t = (int)__ldg(target + ((long long)n * Ho + oh_lo) * Wo + i);
+    tg[i] = (t == ignore || t < 0 || t >= C) ? 255 : (unsigned char)t;
+  }
   for (int i = threadIdx.x; i < 3 * Wi * C; i += blockDim.x) {
     const int c = i % C, w = (i / C) % Wi, slot = i / (C * Wi);
     const int row = h - 1 + slot;
@@ -484,22 +494,19 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const __nv_bfloat1
   }
   __syncthreads();
   const float g = gout[0] / ((float)accum[1] * div);
-  const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
-  int oh_lo = sh > 0.f ? (int)floorf((h - 1) * ish) - 1 : 0, oh_hi = sh > 0.f ? (int)ceilf((h + 1) * ish) + 1 : Ho - 1;
-  oh_lo = max(oh_lo, 0); oh_hi = min(oh_hi, Ho - 1);
   for (int ow = threadIdx.x; ow < Wo; ow += blockDim.x) {
     int x0, x1; float lx;
     bl_coord(ow, sw, Wi, x0, x1, lx);
     float acc[CE_MAX_C];
 #pragma unroll
     for (int c = 0; c < CE_MAX_C; ++c) acc[c] = 0.f;
-    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+    for (int r = 0; r < rows; ++r) {
+      const int oh = oh_lo + r;
       int y0, y1; float ly;
       bl_coord(oh, sh, Hi, y0, y1, ly);
       const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
-      if (wy == 0.f) continue;
-      const int t = (int)target[((long long)n * Ho + oh) * Wo + ow];
-      if (t == ignore || t < 0 || t >= C) continue;
+      const int t = tg[r * Wo + ow];
+      if (wy == 0.f || t == 255) continue;
       const float* s0 = xs + (y0 - (h - 1)) * C * ldi;
       const float* s1 = xs + (y1 - (h - 1)) * C * ldi;
       float lg[CE_MAX_C];
@@ -736,11 +743,15 @@ extern "C" int zs3_upsample_ce_bwd(const void* x, const float* target, const flo
                                    const float* grad_out, void* dx, void* stream) {
   ZS3_CHECK_ARG(x && target && accum2 && grad_out && dx && C > 0 && C <= cs && C <= CE_MAX_C,
                 "upsample_ce_bwd: bad args (C <= %d)", CE_MAX_C);
-  const size_t smem = ((size_t)3 * C * (Wi + 1) + (size_t)C * (Wo + 1)) * sizeof(float);
+  // output rows whose bilinear footprint can touch one input row: (h-1)/sh - 1 .. (h+1)/sh + 1
+  const float shf = bl_scale(Hi, Ho);
+  const int max_rows = shf > 0.f ? (int)ceilf(2.f / shf) + 6 : Ho;
+  const size_t smem = ((size_t)3 * C * (Wi + 1) + (size_t)C * (Wo + 1)) * sizeof(float) + (size_t)max_rows * Wo;
   ZS3_CHECK_ARG(smem <= 200 * 1024, "upsample_ce_bwd: rows do not fit in shared memory");
   if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  upsample_ce_bwd_kernel<<<N * Hi, 256, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, bl_scale(Hi, Ho),
-                                                            bl_scale(Wi, Wo), ignore_index, accum2, div, grad_out, BF(dx));
+  upsample_ce_bwd_kernel<<<N * Hi, 512, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, shf,
+                                                            bl_scale(Wi, Wo), ignore_index, accum2, div, grad_out, BF(dx),
+                                                            max_rows);
   ZS3_CHECK_LAUNCH("upsample_ce_bwd");
   return ZS3_OK;
 }

@@ -236,8 +236,10 @@ class _Saved:
                  "y", "out", "mean", "invstd", "scale", "shift", "xs")
 
 
-def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, channels):
-    """[concat ->] conv -> BatchNorm -> (+residual) -> (ReLU) -> (Dropout).  Returns (out, saved)."""
+def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, channels, need_backward=True):
+    """[concat ->] conv -> BatchNorm -> (+residual) -> (ReLU) -> (Dropout).  Returns (out, saved).
+    need_backward: whether any input of the enclosing autograd node requires grad (torch.is_grad_enabled() is always
+    False inside Function.forward, so the node passes any(ctx.needs_input_grad))."""
     R, S = conv.kernel_size
     stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
     cout = conv.out_channels
@@ -256,7 +258,7 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
         raise ValueError(f"segments provide {ci} channels, conv expects {conv.in_channels}")
     dev = xs[0].device
     n_, h_, w_, _ = xs[0].shape
-    if not training and not torch.is_grad_enabled() and not (drop_p and drop_training):
+    if not training and not need_backward and not (drop_p and drop_training):
         # inference: eval-mode BatchNorm, residual add and ReLU are folded into the conv epilogue -- the layer is
         # ONE kernel and neither the pre-BN tensor nor any statistic is ever written
         ho_, wo_ = K.conv_out_size(h_, R, stride, pad, dil), K.conv_out_size(w_, S, stride, pad, dil)
@@ -297,10 +299,17 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
                    running_var=bn.running_var, coef=coef, c_real=cout, reset=sb.flip())
     else:
         scale, shift, mean, invstd = _bn_forward_coeffs(bn, None, n * ho * wo, cout_p)
+    # residual joins (out = relu(bn(y) + x)): the backward needs the ReLU mask twice; keep it as one bit per element
+    # instead of re-reading the bf16 output in both backward passes
+    relu_bits = None
+    if relu and residual is not None and p == 0.0 and need_backward:
+        relu_bits = torch.empty(y.numel() // 8, dtype=torch.uint8, device=dev)
     out = K.bn_apply(y, scale, shift, relu, residual=residual, drop_p=p, seed=seed, offset=off,
                      keep_mask=keep_mask if p > 0 else None,
-                     offset_dev=_RngState.device_counter if (p > 0 and keep_mask is None) else None, finalize=fin)
+                     offset_dev=_RngState.device_counter if (p > 0 and keep_mask is None) else None, finalize=fin,
+                     relu_mask=relu_bits)
     sv = _Saved()
+    sv.relu_bits = relu_bits
     sv.conv, sv.bn, sv.relu, sv.p, sv.training = conv, bn, relu, p, training
     sv.ranges, sv.has_res = ranges, residual is not None
     sv.geom = (R, S, stride, pad, dil, cout, cout_p)
@@ -342,7 +351,7 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
     dy = K.bn_backward(dout, sv.out, y, sv.mean, sv.invstd, sv.scale, sv.relu, grad_scale=1.0 / (1.0 - sv.p),
                        training=sv.training, dres=dres, dgamma=dgamma, dbeta=dbeta, sums=sums, reset=bb.flip(),
                        param_accumulate=direct_affine, scatter=None if dy_dense_needed else scatter,
-                       shift=sv.shift if sv.mask_from_y else None)
+                       shift=sv.shift if sv.mask_from_y else None, relu_mask=getattr(sv, "relu_bits", None))
     if direct_affine:
         dgamma = dbeta = None  # already added to bn.weight.grad / bn.bias.grad
     dy_z = dy
@@ -395,7 +404,8 @@ class ConvBnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, conv, bn, relu, drop_p, drop_training, keep_mask, channels, weight, gamma, beta, residual, *xs):
-        out, sv = cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, channels)
+        out, sv = cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, channels,
+                              need_backward=any(ctx.needs_input_grad))
         ctx.sv = sv
         return out
 
@@ -416,14 +426,15 @@ class BottleneckFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, blk, x, *params):
-        out1, s1 = cba_forward(blk.conv1, blk.bn1, True, 0.0, False, None, None, [x], [blk.inplanes])
-        out2, s2 = cba_forward(blk.conv2, blk.bn2, True, 0.0, False, None, None, [out1], [blk.planes])
+        nb = any(ctx.needs_input_grad)
+        out1, s1 = cba_forward(blk.conv1, blk.bn1, True, 0.0, False, None, None, [x], [blk.inplanes], nb)
+        out2, s2 = cba_forward(blk.conv2, blk.bn2, True, 0.0, False, None, None, [out1], [blk.planes], nb)
         sd = None
         res = x
         if blk.downsample is not None:
             res, sd = cba_forward(blk.downsample[0], blk.downsample[1], False, 0.0, False, None, None, [x],
-                                  [blk.inplanes])
-        out3, s3 = cba_forward(blk.conv3, blk.bn3, True, 0.0, False, None, res, [out2], [blk.planes])
+                                  [blk.inplanes], nb)
+        out3, s3 = cba_forward(blk.conv3, blk.bn3, True, 0.0, False, None, res, [out2], [blk.planes], nb)
         ctx.saved = (s1, s2, s3, sd)
         ctx.nparams = len(params)
         return out3

@@ -215,7 +215,7 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, cpad_):
 
 
 def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0, offset=0, keep_mask=None,
-             offset_dev=None, finalize=None):
+             offset_dev=None, finalize=None, relu_mask=None):
     """finalize = dict(stats=(sum, sqsum), count, gamma, beta, eps, momentum, running_mean, running_var, coef [4][C],
     reset=(sum, sqsum) or None): derive the affine from raw batch statistics inside the kernel (fused bn_finalize)."""
     _chk_act(y, "bn_apply y")
@@ -256,13 +256,16 @@ def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0,
     a.seed, a.offset = int(seed), int(offset)
     if offset_dev is not None:
         a.offset_dev = offset_dev.data_ptr()
+    if relu_mask is not None:  # uint8 [M * C/8]: one ReLU bit per element for the backward (relu_mask= of bn_backward)
+        assert relu_mask.dtype == torch.uint8 and relu_mask.numel() * 8 >= n * h * w * cs
+        a.relu_mask_out = relu_mask.data_ptr()
     L.check(L.lib().zs3_bn_apply(C.byref(a), L.stream_ptr()), "zs3_bn_apply")
     return out
 
 
 def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, training=True, dres=None,
                 dres_accumulate=False, dgamma=None, dbeta=None, param_accumulate=False, scatter=None, dy=None,
-                scratch=None, shift=None, sums=None, reset=None):
+                scratch=None, shift=None, sums=None, reset=None, relu_mask=None):
     """Two-phase BatchNorm(+ReLU/+Dropout) backward.  Returns dy (bf16, same layout as y unless scatter).
     With `shift` given (plain conv->BN->ReLU layers) the ReLU mask is recomputed from y instead of read from `out`."""
     _chk_act(dout, "bn_backward dout")
@@ -279,6 +282,9 @@ def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, trainin
     if relu and shift is not None:
         relu_mode = 2
         a.shift = shift.data_ptr()
+    elif relu and relu_mask is not None:
+        relu_mode = 3  # bit mask written by bn_apply(relu_mask=...): 1/16 of the bytes of re-reading `out`
+        a.relu_mask = relu_mask.data_ptr()
     elif relu:
         relu_mode = 1
         a.out, a.out_cstride = out.data_ptr(), out.shape[3]
