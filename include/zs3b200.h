@@ -282,9 +282,10 @@ int zs3_ce_bwd(const float* logit, const float* target, const float* weight, int
 
 /* Training-loss fusion of deeplab.py:44 (F.interpolate(x, size=input, bilinear, align_corners=True)) with
  * SegmentationLosses.CrossEntropyLoss (loss.py:31-46): loss = CE(upsample(x), target) straight from the low-resolution
- * class scores x (NHWC bf16 [N][Hi][Wi][cs], C <= 32 real classes), without materialising the [N][C][Ho][Wo] fp32
+ * class scores x (NHWC bf16 [N][Hi][Wi][cs], C <= 24 real classes), without materialising the [N][C][Ho][Wo] fp32
  * logits or their gradient.  Same arguments/semantics as zs3_ce_fwd/bwd; the backward returns d loss / d x (NHWC bf16,
- * padding channels zeroed).  Models that must RETURN the logits (evaluation) use zs3_upsample_logits_* + zs3_ce_*. */
+ * padding channels zeroed; Wo <= 640).  Models that must RETURN the logits (evaluation) use zs3_upsample_logits_* +
+ * zs3_ce_*. */
 int zs3_upsample_ce_fwd(const void* x, const float* target, const float* weight, int N, int C, int Hi, int Wi, int cs,
                         int Ho, int Wo, int ignore_index, float div, double* accum2, float* loss, void* stream);
 int zs3_upsample_ce_bwd(const void* x, const float* target, const float* weight, int N, int C, int Hi, int Wi, int cs,

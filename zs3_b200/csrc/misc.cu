@@ -65,6 +65,46 @@ __global__ void __launch_bounds__(192) stem_im2col_kernel(const float* __restric
   }
 }
 
+// KRSC flavour (k = (r*R + s)*C + c, the order of channels_last weights -- what the model uses): with the staged input
+// rows laid out [r][w][c], the R*C... S*C values of one tap row r of an output pixel are CONTIGUOUS in shared memory
+// (start (q*stride)*C), so a thread produces 8 consecutive k (one 16-byte store) from precomputed offsets.
+__global__ void __launch_bounds__(256) stem_im2col_krsc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols,
+                                                               int C, int H, int W, int R, int stride, int pad, int Ho,
+                                                               int Wo, int kpad) {
+  extern __shared__ float rows[];  // [R][W + 2*pad][C]
+  const int Wp = W + 2 * pad;
+  const int p = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  const int K = C * R * R, SC = R * C;
+  for (int i = threadIdx.x; i < C * R * Wp; i += blockDim.x) {
+    const int wv = i % Wp, cr = i / Wp;
+    const int r = cr % R, c = cr / R;
+    const int ih = p * stride - pad + r, iw = wv - pad;
+    rows[(r * Wp + wv) * C + c] =
+        (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + (((long long)n * C + c) * H + ih) * W + iw) : 0.f;
+  }
+  __syncthreads();
+  const int groups = kpad >> 3;                 // 8-column groups per pixel
+  const int ppi = blockDim.x / groups;          // pixels per iteration
+  const int kg = threadIdx.x % groups, ql = threadIdx.x / groups;
+  if (ql >= ppi) return;
+  int off[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = 8 * kg + e;
+    const int r = k / SC;
+    off[e] = k < K ? r * Wp * C + (k - r * SC) : -1;
+  }
+  __nv_bfloat16* out = cols + ((long long)n * Ho + p) * Wo * kpad + 8 * kg;
+  const int qstep = stride * C;
+  for (int q = ql; q < Wo; q += ppi) {
+    const float* base = rows + q * qstep;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? base[off[e]] : 0.f;
+    *reinterpret_cast<uint4*>(out + (long long)q * kpad) = pack8m(v);
+  }
+}
+
 // --------------------------------------------------------------------------------- max-pool
 // first maximum in row-major window order wins (ATen max_pool2d semantics); argmax stores the window slot.
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
@@ -102,43 +142,52 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
   }
 }
 
-// gather form: every input pixel sums the output gradients of the windows that selected it
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ arg,
-                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int k,
-                                   int stride, int pad) {
+// gather form: every input pixel sums the output gradients of the windows that selected it.  One CTA per input row:
+// the (at most 8) output rows whose windows cover it are resolved once, the inner loop is 32-bit arithmetic only.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const unsigned char* __restrict__ arg,
+                                                          __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C,
+                                                          int Ho, int Wo, int k, int stride, int pad) {
   const int vpc = C >> 3;
-  const long long total = (long long)N * H * W * vpc;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % vpc) << 3;
-    const long long m = i / vpc;
-    const int w = (int)(m % W), h = (int)((m / W) % H), n = (int)(m / ((long long)W * H));
+  const int h = blockIdx.x % H, n = blockIdx.x / H;
+  int prow[8], rsel[8], np = 0;
+  for (int r = 0; r < k; ++r) {
+    const int t = h + pad - r;
+    if (t < 0 || t % stride) continue;
+    const int p = t / stride;
+    if (p < Ho && np < 8) {
+      prow[np] = p;
+      rsel[np] = r;
+      ++np;
+    }
+  }
+  const int rowlen = W * vpc;
+  __nv_bfloat16* drow = dx + ((long long)n * H + h) * W * C;
+  for (int i = threadIdx.x; i < rowlen; i += blockDim.x) {
+    const int w = i / vpc, c = (i - w * vpc) << 3;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int r = 0; r < k; ++r) {
-      const int t = h + pad - r;
-      if (t < 0 || t % stride) continue;
-      const int p = t / stride;
-      if (p >= Ho) continue;
+    for (int a = 0; a < np; ++a) {
+      const long long obase = ((long long)n * Ho + prow[a]) * Wo;
       for (int s = 0; s < k; ++s) {
         const int u = w + pad - s;
         if (u < 0 || u % stride) continue;
         const int q = u / stride;
         if (q >= Wo) continue;
-        const long long mo = ((long long)n * Ho + p) * Wo + q;
-        const uint2 a = *reinterpret_cast<const uint2*>(arg + mo * C + c);
+        const long long mo = (obase + q) * C + c;
+        const uint2 sel2 = *reinterpret_cast<const uint2*>(arg + mo);
         float g[8];
-        unpack8m(*reinterpret_cast<const uint4*>(dy + mo * C + c), g);
-        const int slot = r * k + s;
+        unpack8m(*reinterpret_cast<const uint4*>(dy + mo), g);
+        const unsigned slot = (unsigned)(rsel[a] * k + s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int sel = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xFF;
+          const unsigned sel = ((j < 4 ? sel2.x : sel2.y) >> (8 * (j & 3))) & 0xFFu;
           if (sel == slot) acc[j] += g[j];
         }
       }
     }
-    *reinterpret_cast<uint4*>(dx + m * C + c) = pack8m(acc);
+    *reinterpret_cast<uint4*>(drow + (long long)w * C + c) = pack8m(acc);
   }
 }
 
@@ -404,8 +453,8 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logit, const float* __re
 // The training step never needs the full-resolution class scores themselves: loss = CE(upsample(x), target).  These
 // two kernels evaluate the bilinear upsample on the fly (same blend order as upsample_logits_fwd_kernel: vertical
 // into fp32, then horizontal), so the [N][C][Ho][Wo] fp32 logits and their gradient (2 x 354 MB at bs=16, 513x513)
-// are never written to or read from HBM.  C <= 32 classes live in registers.
-constexpr int CE_MAX_C = 32;
+// are never written to or read from HBM.  C <= 24 classes live in registers (VOC: 21).
+constexpr int CE_MAX_C = 24;
 
 __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                               const float* __restrict__ target,
@@ -464,17 +513,19 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const __nv_bfloat1
 // h-1, h, h+1 are staged in shared memory (every contributing output row blends two of them); stage 1 recomputes the
 // softmax per (oh, ow) and accumulates vertically into v[c][ow], stage 2 reduces horizontally (as in
 // upsample_logits_bwd_kernel).
-__global__ void __launch_bounds__(512) upsample_ce_bwd_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              const float* __restrict__ target,
-                                                              const float* __restrict__ weight, int C, int Hi, int Wi,
-                                                              int cs, int Ho, int Wo, float sh, float sw, int ignore,
-                                                              const double* __restrict__ accum, float div,
-                                                              const float* __restrict__ gout,
-                                                              __nv_bfloat16* __restrict__ dx, int max_rows) {
+__global__ void __launch_bounds__(640) upsample_ce_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ target,
+                                                               const float* __restrict__ weight, int C, int Hi, int Wi,
+                                                               int cs, int Ho, int Wo, float sh, float sw, int ignore,
+                                                               const double* __restrict__ accum, float div,
+                                                               const float* __restrict__ gout,
+                                                               __nv_bfloat16* __restrict__ dx, int max_rows) {
+  // blockDim.x >= Wo (one output column per thread, so the per-class accumulators stay in registers across rows)
   extern __shared__ float smem_f[];
   const int ldi = Wi + 1, ldo = Wo + 1;
   float* xs = smem_f;                 // [3][C][Wi+1]: input rows h-1, h, h+1
-  float* v = smem_f + 3 * C * ldi;    // [C][Wo+1]
+  float* bl = xs + 3 * C * ldi;       // [C][Wi+1]: the two input rows of the current output row, blended vertically
+  float* v = bl + C * ldi;            // [C][Wo+1]
   unsigned char* tg = reinterpret_cast<unsigned char*>(v + C * ldo);  // [max_rows][Wo] labels (255 = no gradient)
   const int h = blockIdx.x % Hi, n = blockIdx.x / Hi;
   const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
@@ -492,49 +543,54 @@ __global__ void __launch_bounds__(512) upsample_ce_bwd_kernel(const __nv_bfloat1
     xs[(slot * C + c) * ldi + w] =
         (row >= 0 && row < Hi) ? __bfloat162float(x[(((long long)n * Hi + row) * Wi + w) * cs + c]) : 0.f;
   }
-  __syncthreads();
   const float g = gout[0] / ((float)accum[1] * div);
-  for (int ow = threadIdx.x; ow < Wo; ow += blockDim.x) {
-    int x0, x1; float lx;
-    bl_coord(ow, sw, Wi, x0, x1, lx);
-    float acc[CE_MAX_C];
+  const int ow = threadIdx.x;
+  int x0 = 0, x1 = 0; float lx = 0.f;
+  if (ow < Wo) bl_coord(ow, sw, Wi, x0, x1, lx);
+  float acc[CE_MAX_C];
 #pragma unroll
-    for (int c = 0; c < CE_MAX_C; ++c) acc[c] = 0.f;
-    for (int r = 0; r < rows; ++r) {
-      const int oh = oh_lo + r;
-      int y0, y1; float ly;
-      bl_coord(oh, sh, Hi, y0, y1, ly);
-      const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
-      const int t = tg[r * Wo + ow];
-      if (wy == 0.f || t == 255) continue;
-      const float* s0 = xs + (y0 - (h - 1)) * C * ldi;
-      const float* s1 = xs + (y1 - (h - 1)) * C * ldi;
-      float lg[CE_MAX_C];
-      float mx = -INFINITY;
+  for (int c = 0; c < CE_MAX_C; ++c) acc[c] = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    int y0, y1; float ly;
+    bl_coord(oh_lo + r, sh, Hi, y0, y1, ly);
+    const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
+    if (wy == 0.f) continue;  // CTA-uniform
+    __syncthreads();          // xs staged (first pass) / previous row's readers of bl are done
+    const float* s0 = xs + (y0 - (h - 1)) * C * ldi;
+    const float* s1 = xs + (y1 - (h - 1)) * C * ldi;
+    for (int i = threadIdx.x; i < C * Wi; i += blockDim.x) {
+      const int c = i / Wi, w = i - c * Wi;
+      bl[c * ldi + w] = (1.f - ly) * s0[c * ldi + w] + ly * s1[c * ldi + w];
+    }
+    __syncthreads();
+    if (ow >= Wo) continue;
+    const int t = tg[r * Wo + ow];
+    if (t == 255) continue;
+    float lg[CE_MAX_C];
+    float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < CE_MAX_C; ++c) {
-        if (c < C) {
-          const float a0 = (1.f - ly) * s0[c * ldi + x0] + ly * s1[c * ldi + x0];
-          const float a1 = (1.f - ly) * s0[c * ldi + x1] + ly * s1[c * ldi + x1];
-          lg[c] = (1.f - lx) * a0 + lx * a1;
-          mx = fmaxf(mx, lg[c]);
-        }
-      }
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < CE_MAX_C; ++c) {
-        if (c < C) {
-          lg[c] = __expf(lg[c] - mx);
-          s += lg[c];
-        }
-      }
-      const float coef = wy * g * (weight ? weight[t] : 1.f);
-      const float inv = coef / s;
-#pragma unroll
-      for (int c = 0; c < CE_MAX_C; ++c) {
-        if (c < C) acc[c] += lg[c] * inv - (c == t ? coef : 0.f);
+    for (int c = 0; c < CE_MAX_C; ++c) {
+      if (c < C) {
+        lg[c] = (1.f - lx) * bl[c * ldi + x0] + lx * bl[c * ldi + x1];
+        mx = fmaxf(mx, lg[c]);
       }
     }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CE_MAX_C; ++c) {
+      if (c < C) {
+        lg[c] = __expf(lg[c] - mx);
+        s += lg[c];
+      }
+    }
+    const float coef = wy * g * (weight ? weight[t] : 1.f);
+    const float inv = coef / s;
+#pragma unroll
+    for (int c = 0; c < CE_MAX_C; ++c) {
+      if (c < C) acc[c] += lg[c] * inv - (c == t ? coef : 0.f);
+    }
+  }
+  if (ow < Wo) {
 #pragma unroll
     for (int c = 0; c < CE_MAX_C; ++c) {
       if (c < C) v[c * ldo + ow] = acc[c];
@@ -548,11 +604,11 @@ __global__ void __launch_bounds__(512) upsample_ce_bwd_kernel(const __nv_bfloat1
     if (c < C) {
       int ow_lo = sw > 0.f ? (int)floorf((w - 1) * isw) - 1 : 0, ow_hi = sw > 0.f ? (int)ceilf((w + 1) * isw) + 1 : Wo - 1;
       ow_lo = max(ow_lo, 0); ow_hi = min(ow_hi, Wo - 1);
-      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-        int x0, x1; float lx;
-        bl_coord(ow, sw, Wi, x0, x1, lx);
-        const float wx = (x0 == w ? 1.f - lx : 0.f) + (x1 == w ? lx : 0.f);
-        if (wx != 0.f) a += wx * v[c * ldo + ow];
+      for (int o = ow_lo; o <= ow_hi; ++o) {
+        int xa, xb; float l;
+        bl_coord(o, sw, Wi, xa, xb, l);
+        const float wx = (xa == w ? 1.f - l : 0.f) + (xb == w ? l : 0.f);
+        if (wx != 0.f) a += wx * v[c * ldo + o];
       }
     }
     out[(long long)w * cs + c] = __float2bfloat16(a);
@@ -615,7 +671,14 @@ extern "C" int zs3_stem_im2col(const float* x, void* cols, int N, int C, int H, 
   const size_t smem = (size_t)C * R * (W + 2 * pad) * sizeof(float);
   ZS3_CHECK_ARG(smem <= 200 * 1024, "stem_im2col: input rows do not fit in shared memory");
   if (smem > 48 * 1024) cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  stem_im2col_kernel<<<N * Ho, 192, smem, ST(stream)>>>(x, BF(cols), C, H, W, R, stride, pad, Ho, Wo, kpad, krsc);
+  if (krsc) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(stem_im2col_krsc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int threads = (256 / (kpad / 8)) * (kpad / 8);  // whole pixels per iteration
+    stem_im2col_krsc_kernel<<<N * Ho, threads, smem, ST(stream)>>>(x, BF(cols), C, H, W, R, stride, pad, Ho, Wo, kpad);
+  } else {
+    stem_im2col_kernel<<<N * Ho, 192, smem, ST(stream)>>>(x, BF(cols), C, H, W, R, stride, pad, Ho, Wo, kpad, krsc);
+  }
   ZS3_CHECK_LAUNCH("stem_im2col");
   return ZS3_OK;
 }
@@ -632,8 +695,8 @@ extern "C" int zs3_maxpool_fwd(const void* x, void* y, unsigned char* argmax, in
 extern "C" int zs3_maxpool_bwd(const void* dy, const unsigned char* argmax, void* dx, int N, int H, int W, int C,
                                int Ho, int Wo, int k, int stride, int pad, void* stream) {
   ZS3_CHECK_ARG(dy && dx && argmax && C % 8 == 0, "maxpool_bwd: bad args");
-  maxpool_bwd_kernel<<<ew_blocks((long long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(dy), argmax, BF(dx), N, H, W, C, Ho, Wo, k, stride, pad);
+  ZS3_CHECK_ARG(k >= 1 && k <= 8 && stride >= 1, "maxpool_bwd: kernel size %d outside [1, 8]", k);
+  maxpool_bwd_kernel<<<N * H, 256, 0, ST(stream)>>>(CBF(dy), argmax, BF(dx), N, H, W, C, Ho, Wo, k, stride, pad);
   ZS3_CHECK_LAUNCH("maxpool_bwd");
   return ZS3_OK;
 }
@@ -746,12 +809,14 @@ extern "C" int zs3_upsample_ce_bwd(const void* x, const float* target, const flo
   // output rows whose bilinear footprint can touch one input row: (h-1)/sh - 1 .. (h+1)/sh + 1
   const float shf = bl_scale(Hi, Ho);
   const int max_rows = shf > 0.f ? (int)ceilf(2.f / shf) + 6 : Ho;
-  const size_t smem = ((size_t)3 * C * (Wi + 1) + (size_t)C * (Wo + 1)) * sizeof(float) + (size_t)max_rows * Wo;
+  const size_t smem = ((size_t)4 * C * (Wi + 1) + (size_t)C * (Wo + 1)) * sizeof(float) + (size_t)max_rows * Wo;
   ZS3_CHECK_ARG(smem <= 200 * 1024, "upsample_ce_bwd: rows do not fit in shared memory");
+  ZS3_CHECK_ARG(Wo <= 640, "upsample_ce_bwd: output width %d > 640 (use the unfused upsample + CE kernels)", Wo);
   if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  upsample_ce_bwd_kernel<<<N * Hi, 512, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, shf,
-                                                            bl_scale(Wi, Wo), ignore_index, accum2, div, grad_out, BF(dx),
-                                                            max_rows);
+  const int threads = ((Wo + 31) / 32) * 32;  // one output column per thread
+  upsample_ce_bwd_kernel<<<N * Hi, threads, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, shf,
+                                                                bl_scale(Wi, Wo), ignore_index, accum2, div, grad_out,
+                                                                BF(dx), max_rows);
   ZS3_CHECK_LAUNCH("upsample_ce_bwd");
   return ZS3_OK;
 }

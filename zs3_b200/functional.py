@@ -233,7 +233,7 @@ def _bn_forward_coeffs(bn, stats, count, cs):
 class _Saved:
     """what a conv->BN->act forward keeps for its backward"""
     __slots__ = ("conv", "bn", "relu", "p", "training", "ranges", "has_res", "geom", "flops_per_cin", "mask_from_y",
-                 "y", "out", "mean", "invstd", "scale", "shift", "xs")
+                 "y", "out", "mean", "invstd", "scale", "shift", "xs", "relu_bits")
 
 
 def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, channels, need_backward=True):

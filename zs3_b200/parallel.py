@@ -200,7 +200,8 @@ class DataParallelTrainer:
         owner = getattr(self.criterion, "__self__", None)
         fusable = (self.fuse_loss and hasattr(self.model, "forward_scores")
                    and getattr(self.criterion, "__func__", None) is getattr(type(owner), "CrossEntropyLoss", None)
-                   and hasattr(owner, "UpsampledCrossEntropyLoss") and getattr(self.model, "num_classes", 99) <= 32)
+                   and hasattr(owner, "UpsampledCrossEntropyLoss") and getattr(self.model, "num_classes", 99) <= 24
+                   and target.shape[-1] <= 640)  # limits of zs3_upsample_ce_* (classes in registers, a column per thread)
         if fusable:
             return owner.UpsampledCrossEntropyLoss(self.model.forward_scores(image), self.model.num_classes, target)
         return self.criterion(self.model(image), target)
