@@ -271,8 +271,16 @@ def run_ours(args):
         fl_all = sum(sum(f for _, _, f in evs) for evs in prof.values()) / 2
         peak, how = measured_peaks()
         ach = fl_all / (ms_all * 1e-3) / 1e12
+        # DRAM bytes per conv launch from the committed ncu capture of the same step (bench.py cannot run under ncu)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic, traffic_src = tj.get("conv_dram_bytes_per_launch_avg"), "profiles/r01_conv_traffic.json: " + tj.get("source", "")
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "kernel": "conv_fprop_kernel/conv_wgrad_kernel (tcgen05 implicit GEMM; fprop+dgrad+wgrad)",
+                    "traffic": traffic, "traffic_unit": "bytes per conv launch (average over the step's conv launches)",
+                    "traffic_source": traffic_src, "kernel": "conv_fprop_kernel/conv_wgrad_kernel (tcgen05 implicit GEMM; fprop+dgrad+wgrad)",
                     "peak_source": how, "conv_ms_per_step": ms_all, "conv_share_of_step": ms_all / ms_step,
                     "nominal_tflop_per_step": fl_all / 1e12, "by_kind": per_kind}
 

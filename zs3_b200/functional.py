@@ -462,6 +462,67 @@ class BottleneckFn(torch.autograd.Function):
         return (None, dx, *[grads[k] for k in order])
 
 
+class ASPPFn(torch.autograd.Function):
+    """The whole ASPP head (zs3/modeling/aspp.py:103-116) as ONE autograd node.  Forward = the five branches and the
+    1280->256 projection (five K-segments, concat never materialised).  The point is the backward: the five branch
+    gradients meet at the backbone output and are summed by the data-gradient convs' TMA reduce-add epilogue
+    (and the pooling branch by an accumulating broadcast) instead of four elementwise adds by the autograd engine."""
+
+    @staticmethod
+    def forward(ctx, aspp, keep_mask, x, *params):
+        nb = any(ctx.needs_input_grad)
+        n, h, w, _ = x.shape
+        cin = aspp.inplanes
+        branches, outs = [], []
+        for i in range(1, 5):
+            m = getattr(aspp, f"aspp{i}")
+            o, sv = cba_forward(m.atrous_conv, m.bn, True, 0.0, False, None, None, [x], [cin], nb)
+            branches.append(sv)
+            outs.append(o)
+        width = aspp.conv1.out_channels
+        norm = aspp.global_avg_pool[2] if aspp.global_avg_pool_bn else IdentityBN(width, x.device)
+        pooled = K.spatial_sum(x, 1.0 / (h * w))
+        pg, sg = cba_forward(aspp.global_avg_pool[1], norm, True, 0.0, False, None, None, [pooled], [cin], nb)
+        outs.append(K.spatial_broadcast(pg, h, w, 1.0))
+        out, sp = cba_forward(aspp.conv1, aspp.bn1, True, aspp.dropout.p, aspp.dropout.training, keep_mask, None, outs,
+                              [width] * 5, nb)
+        ctx.saved = (branches, sg, sp, (h, w), aspp.global_avg_pool_bn)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        branches, sg, sp, (h, w), gap_bn = ctx.saved
+        ctx.saved = None
+        need_x = ctx.needs_input_grad[2]
+        need_p = any(ctx.needs_input_grad[3:])
+        douts, gw, gg, gb, _ = cba_backward(sp, dout, [True] * 5, need_p, need_p)
+        proj = [gw, gg, gb]
+        dpg = K.spatial_sum(douts[4].contiguous(), 1.0)
+        (dpooled,), pw, pgm, pbt, _ = cba_backward(sg, dpg, [need_x], need_p, need_p and gap_bn)
+        dx, grads = None, []
+        for sv, d in zip(branches, douts[:4]):
+            into = [(dx, True)] if dx is not None else None
+            (dxi,), bw, bg, bb, _ = cba_backward(sv, d, [need_x], need_p, need_p, dx_into=into)
+            dx = dx if dx is not None else dxi
+            grads += [bw, bg, bb]
+        if need_x:
+            K.spatial_broadcast(dpooled, h, w, 1.0 / (h * w), out=dx, accumulate=True)
+        grads += [pw] + ([pgm, pbt] if gap_bn else []) + proj
+        return (None, None, dx, *grads)
+
+
+def aspp_head(aspp, x, keep_mask=None):
+    params = []
+    for i in range(1, 5):
+        m = getattr(aspp, f"aspp{i}")
+        params += [m.atrous_conv.weight, m.bn.weight, m.bn.bias]
+    params.append(aspp.global_avg_pool[1].weight)
+    if aspp.global_avg_pool_bn:
+        params += [aspp.global_avg_pool[2].weight, aspp.global_avg_pool[2].bias]
+    params += [aspp.conv1.weight, aspp.bn1.weight, aspp.bn1.bias]
+    return ASPPFn.apply(aspp, keep_mask, x, *params)
+
+
 def bottleneck(blk, x):
     params = [blk.conv1.weight, blk.bn1.weight, blk.bn1.bias, blk.conv2.weight, blk.bn2.weight, blk.bn2.bias,
               blk.conv3.weight, blk.bn3.weight, blk.bn3.bias]

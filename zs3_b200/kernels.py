@@ -399,12 +399,13 @@ def spatial_sum(x, scale):
     return y
 
 
-def spatial_broadcast(x, h, w, scale):
-    """[N,1,1,C] -> [N,h,w,C], y = scale * x."""
+def spatial_broadcast(x, h, w, scale, out=None, accumulate=False):
+    """[N,1,1,C] -> [N,h,w,C], y = scale * x  (accumulate: out += scale * x)."""
     n, _, _, c = x.shape
-    y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
-    L.check(L.lib().zs3_spatial_broadcast(L.ptr(x), L.ptr(y), n, h * w, c, c, c, float(scale), 0, L.stream_ptr()),
-            "zs3_spatial_broadcast")
+    y = out if out is not None else torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _chk_act(y, "spatial_broadcast out")
+    L.check(L.lib().zs3_spatial_broadcast(L.ptr(x), L.ptr(y), n, h * w, c, x.shape[3], y.shape[3], float(scale),
+                                          int(bool(accumulate)), L.stream_ptr()), "zs3_spatial_broadcast")
     return y
 
 

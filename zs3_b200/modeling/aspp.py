@@ -46,16 +46,10 @@ class ASPP(nn.Module):
         B.init_kaiming_(self)
 
     def forward(self, x, keep_mask=None):
-        n, h, w, _ = x.shape
-        pyramid = [getattr(self, f"aspp{i}")(x) for i in range(1, 5)]
-        # image-level branch: global mean -> 1x1 conv (-> BN) -> ReLU; its bilinear "upsampling" from 1x1 is a broadcast
-        pooled = ZF.SpatialMean.apply(x)
-        norm = self.global_avg_pool[2] if self.global_avg_pool_bn else ZF.IdentityBN(ASPP_WIDTH, x.device)
-        pooled = ZF.conv_bn_act([pooled], [self.inplanes], self.global_avg_pool[1], norm, relu=True)
-        pyramid.append(ZF.SpatialBroadcast.apply(pooled, h, w))
-        # concat + 1x1 projection: five K-segments of one implicit GEMM, the concat is never materialised
-        return ZF.conv_bn_act(pyramid, [ASPP_WIDTH] * 5, self.conv1, self.bn1, relu=True, drop_p=self.dropout.p,
-                              drop_training=self.dropout.training, keep_mask=keep_mask)
+        """x: NHWC bf16 backbone features.  One fused autograd node: four atrous branches + image-level branch (global
+        mean -> 1x1 conv (-> BN) -> ReLU -> broadcast, the bilinear "upsampling" from 1x1) -> concat + 1x1 projection
+        as five K-segments of one implicit GEMM -> BN -> ReLU -> Dropout."""
+        return ZF.aspp_head(self, x, keep_mask)
 
 
 def build_aspp(output_stride, BatchNorm, global_avg_pool_bn=True):
