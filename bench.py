@@ -329,7 +329,9 @@ def run_ours(args):
                        "num_classes": NUM_CLASSES, "per_gpu_batch": B, "global_batch": B * world, "input": f"{HW}x{HW}",
                        "parallelism": f"dp{world}", "bn": "rank-local batch statistics", "launch_mode": args.mode,
                        "l2_policy": "inputs+activations per step (>6 GB) exceed the 126 MB L2; 2 alternating input batches",
-                       "optimizer": "fused SGD momentum 0.9 wd 5e-4, lr 0.007/0.07"},
+                       "optimizer": "fused SGD momentum 0.9 wd 5e-4, lr 0.007/0.07",
+                       "loss": "weighted CE with ignore_index, /batch; final x4 bilinear upsample fused into the loss "
+                               "kernels (same value as criterion(model(image), target))"},
             "achieved_tflops_nominal": value * FWDBWD_GFLOP_PER_IMG / 1e3,
             "final_loss": final_loss,
             "clocks": sampler.summary(),
