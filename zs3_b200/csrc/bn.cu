@@ -604,8 +604,14 @@ static int stream_grid_cap(long long M, int rows_per_block, int ctas_per_sm, int
   return (int)b;
 }
 
-static int stream_grid(long long M, int rows_per_block) {
-  static const int per_sm = env_int("ZS3_BN_MAP_CTAS", 8);
+// map kernels: measured on the full training step (profiles/r01_bn_grid_experiment.md) 2 CTAs/SM beat 1, 3, 4 and 8
+// (854 -> 874 img/s from 8 to 2): fewer CTAs mean fewer per-CTA coefficient prologues and a shorter tail, and
+// 2 x 256 threads x 4 rows in flight already cover the L2/HBM latency; only the > 96 MB tensors (stem, layer1's
+// 256-channel outputs) keep 4 CTAs/SM, which streams them 10 % faster (tools/bn_bench.py)
+static int stream_grid(long long M, int rows_per_block, long long bytes = 0) {
+  static const int forced = env_int("ZS3_BN_MAP_CTAS", -1);
+  int per_sm = bytes >= (96ll << 20) ? 4 : 2;
+  if (forced > 0) per_sm = forced;
   return stream_grid_cap(M, rows_per_block, per_sm, UNROLL);
 }
 
@@ -706,7 +712,7 @@ extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
   ZS3_CHECK_ARG(a->C <= 2048, "bn_apply: C=%d > 2048", a->C);
   p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
   const size_t smem = a->stat_sum ? (size_t)2 * a->C * sizeof(float) : 0;
-  launch_pdl(PDL_BN, bn_apply_kernel, dim3(stream_grid(a->M, p.rows_per_block)), dim3(256), smem, static_cast<cudaStream_t>(stream),
+  launch_pdl(PDL_BN, bn_apply_kernel, dim3(stream_grid(a->M, p.rows_per_block, a->M * a->C * 2)), dim3(256), smem, static_cast<cudaStream_t>(stream),
              p);
   ZS3_CHECK_LAUNCH("bn_apply");
   return ZS3_OK;
@@ -766,7 +772,7 @@ extern "C" int zs3_bn_bwd_apply(const zs3_bn_bwd_args* a, void* stream) {
                 "bn_bwd_apply: bad parameter gradient buffers");
   if (a->M <= 0) return ZS3_OK;
   p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
-  launch_pdl(PDL_BN, bn_bwd_apply_kernel, dim3(stream_grid(a->M, p.rows_per_block)), dim3(256), (size_t)3 * a->C * sizeof(float),
+  launch_pdl(PDL_BN, bn_bwd_apply_kernel, dim3(stream_grid(a->M, p.rows_per_block, a->M * a->C * 2)), dim3(256), (size_t)3 * a->C * sizeof(float),
              static_cast<cudaStream_t>(stream), p);
   ZS3_CHECK_LAUNCH("bn_bwd_apply");
   return ZS3_OK;

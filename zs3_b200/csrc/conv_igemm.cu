@@ -1123,6 +1123,12 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
     if (ks < 1) ks = 1;
     const int max_ks = p.pblocks_total / 4 > 0 ? p.pblocks_total / 4 : 1;  // >= 4 k-blocks of 64 pixels per CTA
     if (ks > max_ks) ks = max_ks;
+    static int cap = -1;  // experiment knob: upper bound on the pixel splits (fewer splits = less fp32 reduce traffic)
+    if (cap < 0) {
+      const char* e = getenv("ZS3_WGRAD_MAX_SPLITS");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap > 0 && ks > cap) ks = cap;
   }
   if (ks > p.pblocks_total) ks = p.pblocks_total;
   p.k_splits = ks;

@@ -139,7 +139,7 @@ class DataParallelTrainer:
                  use_cuda_graph=False, fuse_loss=True):
         self.model, self.criterion, self.world = model, criterion, world_size
         self.fuse_loss = fuse_loss
-        self.use_cuda_graph, self.graph = use_cuda_graph, None
+        self.use_cuda_graph, self.graph, self.graph_tail = use_cuda_graph, None, None
         groups = [list(model.get_1x_lr_params()), list(model.get_10x_lr_params())]
         self.flat = FlatParams(groups)
         self.opt = FusedSGD(self.flat, [lr, lr * 10], momentum, weight_decay, nesterov)
@@ -155,6 +155,19 @@ class DataParallelTrainer:
                     co, ci, r, s = m.weight.shape
                     m.__dict__["_zs3_bf16_shadow"] = (self.shadow[off:off + m.weight.numel()].view(co, r * s, ci),
                                                       m.weight.data_ptr())
+        # parameters above the backbone cut (layer3 .. decoder): one contiguous range of the flat buffers, reduced
+        # while the rest of the backward still runs (see _finish_distributed)
+        self.early_range, self.early_params = None, []
+        bb = getattr(model, "backbone", None)
+        if world_size > 1 and bb is not None and hasattr(bb, "layer3"):
+            first = next(iter(bb.layer3.parameters()), None)
+            if first is not None and first.grad is not None:
+                a = (first.grad.data_ptr() - self.flat.grad.data_ptr()) // self.flat.grad.element_size()
+                below = {id(p) for m in (bb.conv1, bb.bn1, bb.layer1, bb.layer2) for p in m.parameters()}
+                self.early_params = [p for p in self.flat.params if id(p) not in below]
+                early_n = sum(p.numel() for p in self.early_params)
+                if 0 < a and a + early_n == self.flat.grad.numel():  # layout is [stem, layer1, layer2 | the rest]
+                    self.early_range = (a, self.flat.grad.numel())
         if world_size > 1:
             # identical replicas: broadcast rank 0's weights and BN buffers once
             dist.broadcast(self.flat.flat, 0)
@@ -162,8 +175,10 @@ class DataParallelTrainer:
                 dist.broadcast(b, 0)
 
     def train_step(self, image, target):
-        """One optimisation step; returns the (device) loss tensor.  With use_cuda_graph the whole step --
-        ~1.2k kernel launches, the NCCL all-reduce and the optimizer -- is captured once and replayed."""
+        """One optimisation step; returns the (device) loss tensor.  With use_cuda_graph the step is captured once
+        and replayed: on one GPU a single graph (forward, loss, backward, optimizer); with several ranks two graphs,
+        split inside the backward pass, with the NCCL all-reduces and the optimizer issued eagerly between/after
+        them (keeps NCCL out of stream capture and overlaps the big all-reduce with the tail of the backward)."""
         if not self.use_cuda_graph:
             return self._step(image, target)
         if self.graph is None:
@@ -172,7 +187,7 @@ class DataParallelTrainer:
         self.static_target.copy_(target, non_blocking=True)
         self.graph.replay()
         if self.world > 1:
-            self._reduce_and_update()  # the collective and the optimizer stay outside the captured graph
+            self._finish_distributed(self.graph_tail.replay if self.graph_tail is not None else None)
         return self.static_loss
 
     def _capture(self, image, target):
@@ -186,12 +201,72 @@ class DataParallelTrainer:
                 self._step(self.static_image, self.static_target)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        # single GPU: the whole step (forward, backward, optimizer) is one graph.  Multi-GPU: the graph holds
-        # forward+backward; the NCCL all-reduce and the two fused-SGD launches are issued eagerly after each replay
-        # (3 launches; keeps NCCL out of stream capture)
-        self.graph = torch.cuda.CUDAGraph()
+        self.graph, self.graph_tail = torch.cuda.CUDAGraph(), None
+        if self.world == 1:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._step(self.static_image, self.static_target)
+            return
         with torch.cuda.graph(self.graph):
-            self.static_loss = self._step(self.static_image, self.static_target, update=self.world == 1)
+            self.static_loss, tail = self._forward_backward_head(self.static_image, self.static_target)
+        if tail is not None:
+            self.graph_tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_tail, pool=self.graph.pool()):
+                tail()
+
+    # ------------------------------------------------------------------------------------------ one step
+    def _begin_step(self):
+        if ZF._RngState.device_counter is not None:
+            ZF._RngState.device_counter.add_(1 << 32)  # fresh dropout masks per step, also under graph replay
+        self.flat.zero_grad()
+        K.cast_f32_to_bf16(self.flat.flat, self.shadow)  # one launch refreshes every layer's bf16 forward weight
+
+    def _step(self, image, target):
+        if self.world > 1:
+            loss, tail = self._forward_backward_head(image, target)
+            self._finish_distributed(tail)
+            return loss
+        self._begin_step()
+        loss = self._forward_loss(image, target)
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    def _forward_backward_head(self, image, target):
+        """Forward, loss and the backward of everything ABOVE the backbone's cut (layer3, layer4, ASPP, decoder).
+        Returns (loss, tail) where tail() runs the rest of the backward (layer2, layer1, stem) -- or None when the
+        model exposes no cut, in which case the whole backward has run."""
+        self._begin_step()
+        loss = self._forward_loss(image, target)
+        cut = getattr(getattr(self.model, "backbone", None), "last_cut", None)
+        if self.early_range is None or cut is None or not all(t.requires_grad for t in cut):
+            loss.backward()
+            return loss, None
+        cut = list(cut)
+        for t in cut:
+            t.grad = None
+        torch.autograd.backward(loss, inputs=cut + self.early_params)
+        grads = [t.grad for t in cut]
+
+        def tail():
+            torch.autograd.backward(cut, grads)
+
+        return loss, tail
+
+    def _finish_distributed(self, tail):
+        """all-reduce (sum) + optimizer.  With a cut: the gradients above it (one contiguous range of the flat
+        buffer) are reduced on NCCL's stream WHILE the tail of the backward runs; the small remainder follows."""
+        if tail is None:
+            dist.all_reduce(self.flat.grad)
+        else:
+            a, b = self.early_range
+            early = dist.all_reduce(self.flat.grad[a:b], async_op=True)
+            tail()
+            late = [dist.all_reduce(self.flat.grad[lo:hi], async_op=True)
+                    for lo, hi in ((0, a), (b, self.flat.grad.numel())) if hi > lo]
+            early.wait()
+            for w in late:
+                w.wait()
+        self.opt.step(grad_scale=1.0 / self.world)
 
     def _forward_loss(self, image, target):
         """criterion(model(image), target) (base_trainer.py:17-18).  When the criterion is this package's
@@ -205,19 +280,3 @@ class DataParallelTrainer:
         if fusable:
             return owner.UpsampledCrossEntropyLoss(self.model.forward_scores(image), self.model.num_classes, target)
         return self.criterion(self.model(image), target)
-
-    def _reduce_and_update(self):
-        if self.world > 1:
-            dist.all_reduce(self.flat.grad)  # the one collective of the step
-        self.opt.step(grad_scale=1.0 / self.world)
-
-    def _step(self, image, target, update=True):
-        if ZF._RngState.device_counter is not None:
-            ZF._RngState.device_counter.add_(1 << 32)  # fresh dropout masks per step, also under graph replay
-        self.flat.zero_grad()
-        K.cast_f32_to_bf16(self.flat.flat, self.shadow)  # one launch refreshes every layer's bf16 forward weight
-        loss = self._forward_loss(image, target)
-        loss.backward()
-        if update:
-            self._reduce_and_update()
-        return loss
