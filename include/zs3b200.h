@@ -344,6 +344,53 @@ int zs3_mmd_bwd(const float* gen, const float* real, int M, int N, int D, const 
 int zs3_concat2(const float* a, int c1, const float* b, int c2, float* y, long long rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused generator update (csrc/gmmn_fused.cu): one persistent cooperative launch executes a work list of
+ * (image, class) iterations of the step-2 inner loop, zs3/train_pascal_GMMN.py:211-240 -- gather of the
+ * batch_size_generator sampled rows (`:229-237`), GMMNnetwork.forward (gmmn.py:43-49), GMMNLoss.moment_loss
+ * (utils/loss.py:92-115), its backward, and torch.optim.Adam.step (`:239-240`, Adam(lr 2e-4) `:65-67`) --
+ * sequentially (every update sees the weights left by the previous one, as in the reference) and without
+ * returning to the host in between.  Replaces ~25 forward + ~40 backward library launches per update.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* base;   /* element (r, k) = base[row(r) * row_stride + k * col_stride] */
+  const int* rows;     /* optional gather: row(r) = rows[r]; NULL: row(r) = r */
+  long long row_stride, col_stride; /* in elements; e.g. an NCHW feature map: row_stride 1, col_stride H*W */
+} zs3_row_source;
+
+typedef struct {
+  zs3_row_source emb;    /* [rows][embed_dim] class embedding of each sampled pixel (row_stride 0 = one shared row) */
+  zs3_row_source noise;  /* [rows][noise_dim] z ~ U[0,1) (train_pascal_GMMN.py:216) */
+  zs3_row_source real;   /* [rows][feat]      real decoder features of the sampled pixels */
+  const unsigned char* keep_mask; /* optional Dropout keep mask [*][hidden] (bytes); NULL = counter-based RNG */
+  const int* keep_rows;  /* optional row gather for keep_mask (and the RNG's row key) */
+  int rows;              /* M = N = number of sampled rows, 1..128 (batch_size_generator) */
+  int reserved;
+} zs3_gmmn_item;
+
+typedef struct {
+  const zs3_gmmn_item* items; /* DEVICE array [n_items] */
+  int n_items;
+  int max_rows;               /* host-side promise: every item has rows <= max_rows <= 128 */
+  int embed_dim, noise_dim, hidden, feat;
+  float* w1; float* b1;       /* model.0.weight [hidden][embed_dim+noise_dim], model.0.bias [hidden] */
+  float* w2; float* b2;       /* model.3.weight [feat][hidden], model.3.bias [feat] */
+  int apply_adam;             /* 1: update w/b and the Adam moments in place; 0: write gradients (n_items <= 1) */
+  float* adam_m[4];           /* exp_avg of w1, b1, w2, b2 */
+  float* adam_v[4];           /* exp_avg_sq */
+  float* grad[4];             /* gradient outputs (apply_adam == 0) */
+  float lr, beta1, beta2, eps;
+  long long step0;            /* item w performs Adam step number step0 + w + 1 */
+  float sigma[8]; int nsigma; /* MMD bandwidths (loss.py:86: [2, 5, 10, 20, 40, 80]) */
+  float slope, drop_p;        /* LeakyReLU slope 0.2, Dropout p 0.5 (0 = eval mode) */
+  unsigned long long seed, offset; /* counter RNG of the Dropout mask when keep_mask == NULL */
+  float* losses;              /* [n_items] moment_loss of every update */
+  void* workspace; unsigned long long workspace_bytes; /* >= zs3_gmmn_train_workspace_size(...), 16-byte aligned */
+} zs3_gmmn_train_args;
+
+unsigned long long zs3_gmmn_train_workspace_size(int embed_dim, int noise_dim, int hidden, int feat);
+int zs3_gmmn_train_fused(const zs3_gmmn_train_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fp32-grade parity mode (forward only; csrc/parity.cu).  An fp32 convolution is emulated on the bf16 tensor
  * cores by splitting both operands into three bf16 pieces and reducing the six significant cross products as
  * six K-segments of one fp32 TMEM accumulator (zs3_conv_fprop).  Activations stay fp32 NHWC between layers;

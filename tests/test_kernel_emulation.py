@@ -1,0 +1,229 @@
+"""CPU check of the fused generator-update kernel's LOGIC: csrc/gmmn_fused.cu is compiled for the host with
+-DZS3_HOST_EMULATION (tests/emul/cuda_emul.h: one thread block = 256 host threads) and run on host buffers through
+the same C structs, then compared with the oracle (forward, MMD loss, analytic gradients, sequential Adam steps).
+This is test infrastructure: it pins indexing / phase ordering / arithmetic of the kernel source without a GPU; the
+GPU parity tests proper are tests/test_gmmn_fused_gpu.py."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import rel_l2
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    out_dir = os.path.join(HERE, "emul", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libgmmn_emul.so")
+    src = os.path.join(ROOT, "zs3_b200", "csrc", "gmmn_fused.cu")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DZS3_HOST_EMULATION", "-I", os.path.join(HERE, "emul"),
+           "-x", "c++", src, "-o", so, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from zs3_b200 import _lib as L
+    lib = C.CDLL(so)
+    lib.zs3_emul_gmmn_train_fused.restype = C.c_int
+    lib.zs3_emul_gmmn_train_fused.argtypes = [C.POINTER(L.GmmnTrainArgs), C.c_void_p]
+    lib.zs3_emul_gmmn_train_workspace_size.restype = C.c_ulonglong
+    lib.zs3_emul_gmmn_train_workspace_size.argtypes = [C.c_int] * 4
+    return lib
+
+
+def _state(E, Z, H, F, seed):
+    import zs3_oracle as O
+    return O.init_gmmn_state(seed=seed, noise_dim=Z, embed_dim=E, hidden=H, feat=F)
+
+
+def _make_case(E, Z, H, F, n_src, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    emb = torch.randn(n_src, E, generator=g) * 0.06
+    z = torch.rand(n_src, Z, generator=g)
+    real = torch.relu(torch.randn(n_src, F, generator=g))
+    mask = (torch.rand(n_src, H, generator=g) > 0.5)
+    ridx = torch.randint(0, n_src, (B,), generator=g)
+    return emb, z, real, mask, ridx
+
+
+def _run_emul(lib, st, cases, dims, adam=None, step0=0, drop=True, blocks=1):
+    """cases: list of (emb, z, real, mask, ridx).  Returns (losses, grads or None); st is updated in place (adam).
+    blocks > 1 runs the grid as forked processes: everything the kernel writes sits in shared memory."""
+    from zs3_b200 import gmmn_fused as GF
+    E, Z, H, F = dims
+    keep, items = [], []
+    for emb, z, real, mask, ridx in cases:
+        r32 = ridx.to(torch.int32).contiguous()
+        m8 = mask.to(torch.uint8).contiguous()
+        # real features as an NCHW-like map: element (pixel, d) at real_t[d * n + pixel]
+        real_t = real.t().contiguous()
+        keep += [r32, m8, real_t, emb, z]
+        items.append(GF.pack_item(GF.row_source(emb, r32), GF.row_source(z, r32),
+                                  GF.row_source(real_t, r32, row_stride=1, col_stride=real.shape[0]),
+                                  len(ridx), keep_mask=m8 if drop else None, keep_rows=r32))
+    buf = torch.frombuffer(bytearray(GF.items_to_bytes(items)), dtype=torch.uint8)
+    ws = torch.zeros(lib.zs3_emul_gmmn_train_workspace_size(E, Z, H, F) + 64, dtype=torch.uint8).share_memory_()
+    losses = torch.zeros(len(items)).share_memory_()
+    params = tuple(st[k].share_memory_() for k in ("model.0.weight", "model.0.bias", "model.3.weight", "model.3.bias"))
+    grads = None if adam is not None else [torch.zeros_like(p).share_memory_() for p in params]
+    if adam is not None:
+        for t in adam[0] + adam[1]:
+            t.share_memory_()
+    a = GF.pack_args(buf.data_ptr(), len(items), dims, params, (2, 5, 10, 20, 40, 80), losses, ws, adam=adam,
+                     grads=grads, step0=step0, drop_p=0.5 if drop else 0.0)
+    assert lib.zs3_emul_gmmn_train_fused(C.byref(a), C.c_void_p(blocks if blocks > 1 else None)) == 0
+    return losses, grads
+
+
+def _oracle_loss(st, case, drop=True):
+    import zs3_oracle as O
+    emb, z, real, mask, ridx = case
+    fake = O.gmmn_forward(st, emb, z, training=drop, keep_mask=mask if drop else None)
+    return O.moment_loss(fake[ridx], real[ridx])
+
+
+@pytest.mark.parametrize("dims,n_src,B", [((300, 300, 256, 256), 150, 128), ((20, 13, 40, 50), 60, 37)])
+def test_fused_update_gradients_match_autograd_oracle(emul, dims, n_src, B):
+    E, Z, H, F = dims
+    st = {k: v.clone().requires_grad_(True) for k, v in _state(E, Z, H, F, seed=3).items()}
+    case = _make_case(E, Z, H, F, n_src, B, seed=5)
+    loss = _oracle_loss(st, case)
+    ref = torch.autograd.grad(loss, list(st.values()))
+    losses, grads = _run_emul(emul, {k: v.detach().clone() for k, v in st.items()}, [case], dims)
+    assert abs(losses[0].item() - loss.item()) < 1e-4 * abs(loss.item())
+    for g, r, k in zip(grads, ref, st):
+        assert rel_l2(g, r) < 1e-4, k
+
+
+def test_fused_update_eval_mode_no_dropout(emul):
+    dims = (20, 13, 40, 50)
+    st = {k: v.clone().requires_grad_(True) for k, v in _state(*dims, seed=2).items()}
+    case = _make_case(*dims, 40, 32, seed=9)
+    loss = _oracle_loss(st, case, drop=False)
+    ref = torch.autograd.grad(loss, list(st.values()))
+    losses, grads = _run_emul(emul, {k: v.detach().clone() for k, v in st.items()}, [case], dims, drop=False)
+    assert abs(losses[0].item() - loss.item()) < 1e-4 * abs(loss.item())
+    for g, r in zip(grads, ref):
+        assert rel_l2(g, r) < 1e-4
+
+
+@pytest.mark.parametrize("blocks", [1, 3])
+def test_fused_work_list_of_sequential_adam_updates(emul, blocks):
+    """three dependent updates in one launch == three oracle iterations (train_pascal_GMMN.py:211-240); with
+    blocks=3 the grid-wide barrier and the unit distribution over several thread blocks are exercised too"""
+    import zs3_oracle as O
+    dims = (300, 300, 256, 256)
+    st0 = _state(*dims, seed=3)
+    cases = [_make_case(*dims, 140 + 10 * i, 128 if i != 1 else 77, seed=20 + i) for i in range(3)]
+    # oracle
+    ref = {k: v.clone().requires_grad_(True) for k, v in st0.items()}
+    adam = {k: [torch.zeros_like(v), torch.zeros_like(v)] for k, v in ref.items()}
+    ref_losses = []
+    for t, case in enumerate(cases):
+        loss = _oracle_loss(ref, case)
+        ref_losses.append(loss.item())
+        grads = torch.autograd.grad(loss, list(ref.values()))
+        with torch.no_grad():
+            for (k, p), g in zip(ref.items(), grads):
+                O.adam_step(p, g, adam[k][0], adam[k][1], 5 + t + 1)
+    # emulated kernel
+    st = {k: v.clone() for k, v in st0.items()}
+    ms = [torch.zeros_like(v) for v in st.values()]
+    vs = [torch.zeros_like(v) for v in st.values()]
+    losses, _ = _run_emul(emul, st, cases, dims, adam=(ms, vs), step0=5, blocks=blocks)
+    assert torch.allclose(losses, torch.tensor(ref_losses), rtol=1e-4)
+    for k in st:
+        assert rel_l2(st[k], ref[k].detach()) < 1e-5, k
+        assert rel_l2(st[k] - st0[k], ref[k].detach() - st0[k]) < 2e-3, k   # the update itself, not just the weights
+    for m, (k, (rm, rv)) in zip(ms, adam.items()):
+        assert rel_l2(m, rm) < 1e-4, k
+
+
+def test_fused_step2_host_logic_against_step2_oracle(emul, monkeypatch):
+    """ZS3StepFused's HOST logic (device-side label sort / histogram, sampled-pixel gathers straight from the
+    full-resolution embedding map and the NCHW feature map, work-list flushes around unseen-class images, loss
+    bookkeeping) on CPU tensors: the kernel launch is redirected to the host emulation, the DeepLab head and the
+    generator forward are plain-torch stand-ins, and the result is held against oracle/zs3_step2_oracle.py."""
+    import torch.nn.functional as F
+    import zs3_oracle as O
+    import zs3_step2_oracle as S
+    from test_step2_gpu import Replay, _labels
+    from zs3_b200 import gmmn_fused as GF
+    from zs3_b200.step2 import ZS3StepFused
+
+    B, HW, NC = 3, 33, 21
+    fh = fw = 9
+    unseen, seen = [15, 16, 17, 18, 19], [c for c in range(21) if c not in (15, 16, 17, 18, 19)]
+    target = _labels(B, HW, [[0, 3, 7], [0, 17, 5], [2, 9]], seed=4)
+    emb_table = torch.randn(NC, 300, generator=torch.Generator().manual_seed(8)) * 0.06
+    embedding = emb_table[target.clamp(max=NC - 1).long()].permute(0, 3, 1, 2).contiguous()
+    image = torch.zeros(B, 3, HW, HW)
+    real = torch.relu(torch.randn(B, 256, fh, fw, generator=torch.Generator().manual_seed(2)))
+    gst = O.init_gmmn_state(seed=3)
+    g = torch.Generator().manual_seed(6)
+    st = {"decoder.pred_conv.weight": torch.randn(NC, 256, 1, 1, generator=g) * 0.05,
+          "decoder.pred_conv.bias": torch.zeros(NC)}
+
+    class Head(torch.nn.Module):           # decoder.pred_conv + final upsample (decoder.py:66-68, deeplab.py:53-56)
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(st["decoder.pred_conv.weight"].clone())
+            self.b = torch.nn.Parameter(st["decoder.pred_conv.bias"].clone())
+
+        def forward_class_prediction(self, x, size):
+            return F.interpolate(F.conv2d(x, self.w, self.b), size=size, mode="bilinear", align_corners=True)
+
+    class Gen(torch.nn.Module):            # gmmn.py:17-21 with an injectable Dropout mask
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Sequential(torch.nn.Linear(600, 256), torch.nn.LeakyReLU(0.2), torch.nn.Dropout(0.5),
+                                             torch.nn.Linear(256, 256))
+            self.load_state_dict(gst)
+
+        def forward(self, emb, z, keep_mask=None):
+            return O.gmmn_forward({k: v for k, v in self.state_dict().items()}, emb, z, training=True, keep_mask=keep_mask)
+
+    head, gen = Head(), Gen().train()
+    cw = torch.ones(NC)
+    cw[unseen] = 100.0
+    opt = torch.optim.SGD(head.parameters(), lr=0.07, momentum=0.9, weight_decay=5e-4)
+    opt_g = torch.optim.Adam(gen.parameters(), lr=2e-4)
+    rp = Replay(77)
+    step = ZS3StepFused(head, gen, lambda out, tg: O.cross_entropy(out, tg, weight=cw), None, opt, opt_g, seen, unseen,
+                        noise_fn=rp.noise, index_fn=rp.index, mask_fn=rp.mask)
+
+    def emul_run(items, E, Z, keepalive=()):
+        upd = step.updater
+        ms, vs, step0 = upd._adam_state()
+        for t in ms + vs:
+            t.share_memory_()
+        for p in upd.params:
+            p.data.share_memory_()
+        buf = torch.frombuffer(bytearray(GF.items_to_bytes(items)), dtype=torch.uint8)
+        ws = torch.zeros(emul.zs3_emul_gmmn_train_workspace_size(E, Z, 256, 256) + 64, dtype=torch.uint8).share_memory_()
+        losses = torch.zeros(len(items)).share_memory_()
+        a = GF.pack_args(buf.data_ptr(), len(items), (E, Z, 256, 256), tuple(p.data for p in upd.params), upd.sigma,
+                         losses, ws, adam=(ms, vs), step0=step0)
+        assert emul.zs3_emul_gmmn_train_fused(C.byref(a), C.c_void_p(2)) == 0
+        for p in upd.params:
+            upd.optimizer.state[p]["step"] += len(items)
+        return losses
+
+    monkeypatch.setattr(step.updater, "run", emul_run)
+    loss, glb, g_losses = step.training_step(image, target, embedding, real_features=real)
+
+    rp.reset()
+    ref = S.step2(st, gst, real, target, embedding, (HW, HW), set(seen), set(unseen), rp.noise, rp.index, rp.mask, cw)
+    assert len(g_losses) == len(ref["g_losses"]) == 5
+    assert torch.allclose(torch.tensor(g_losses), torch.tensor(ref["g_losses"]), rtol=1e-4)
+    assert abs(glb - ref["generator_loss_batch"]) < 1e-4 * abs(ref["generator_loss_batch"])
+    for k, p in gen.state_dict().items():
+        assert rel_l2(p, ref["generator"][k]) < 1e-5, k
+    assert abs(loss.item() - ref["loss"]) < 1e-4 * abs(ref["loss"])
+    assert rel_l2(head.w.detach(), ref["pred_conv.weight"]) < 1e-5

@@ -48,13 +48,14 @@ def _labels(n, hw, classes, seed):
     return lab
 
 
-def test_step2_iteration_matches_oracle():
+@pytest.mark.parametrize("fused", [False, True], ids=["modules", "fused_work_list"])
+def test_step2_iteration_matches_oracle(fused):
     import zs3_oracle as O
     import zs3_step2_oracle as S
     from zs3.modeling.deeplab import DeepLab
     from zs3.modeling.gmmn import GMMNnetwork
     from zs3.utils.loss import GMMNLoss, SegmentationLosses
-    from zs3_b200.step2 import ZS3Step
+    from zs3_b200.step2 import ZS3Step, ZS3StepFused
     B, HW, C = 3, 65, 21
     unseen, seen = [15, 16, 17, 18, 19], [c for c in range(21) if c not in (15, 16, 17, 18, 19)]
     # image 0: seen classes only (generator trains), image 1: contains unseen class 17 (features generated),
@@ -85,8 +86,8 @@ def test_step2_iteration_matches_oracle():
                            {"params": model.module.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
     opt_g = torch.optim.Adam(gen.parameters(), lr=2e-4)
     rp = Replay(77)
-    step = ZS3Step(model, gen, crit, crit_g, opt, opt_g, seen, unseen, noise_fn=rp.noise, index_fn=rp.index,
-                   mask_fn=rp.mask)
+    step = (ZS3StepFused if fused else ZS3Step)(model, gen, crit, crit_g, opt, opt_g, seen, unseen, noise_fn=rp.noise,
+                                                index_fn=rp.index, mask_fn=rp.mask)
     with torch.no_grad():
         real = model.module.forward_before_class_prediction(image.cuda())
         # frozen random-init BN leaves the features at magnitude ~1e3, where the reference's fp32 formula

@@ -91,6 +91,9 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.restype = i
         fn.argtypes = argtypes
+    lib.zs3_gmmn_train_workspace_size.restype = C.c_ulonglong
+    lib.zs3_gmmn_train_workspace_size.argtypes = [i, i, i, i]
+    sigs["zs3_gmmn_train_workspace_size"] = [i, i, i, i]
     return sigs
 
 
@@ -129,6 +132,35 @@ class BnBwdArgs(C.Structure):
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("C_real", C.c_int), ("param_accumulate", C.c_int),
         ("reset_sum_dz", C.c_void_p), ("reset_sum_dzx", C.c_void_p), ("reset_count", C.c_int),
         ("relu_mask", C.c_void_p),
+    ]
+
+
+class RowSource(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("rows", C.c_void_p), ("row_stride", C.c_longlong), ("col_stride", C.c_longlong)]
+
+
+class GmmnItem(C.Structure):
+    _fields_ = [
+        ("emb", RowSource), ("noise", RowSource), ("real", RowSource),
+        ("keep_mask", C.c_void_p), ("keep_rows", C.c_void_p),
+        ("rows", C.c_int), ("reserved", C.c_int),
+    ]
+
+
+class GmmnTrainArgs(C.Structure):
+    _fields_ = [
+        ("items", C.c_void_p), ("n_items", C.c_int), ("max_rows", C.c_int),
+        ("embed_dim", C.c_int), ("noise_dim", C.c_int), ("hidden", C.c_int), ("feat", C.c_int),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("apply_adam", C.c_int),
+        ("adam_m", C.c_void_p * 4), ("adam_v", C.c_void_p * 4), ("grad", C.c_void_p * 4),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("step0", C.c_longlong),
+        ("sigma", C.c_float * 8), ("nsigma", C.c_int),
+        ("slope", C.c_float), ("drop_p", C.c_float),
+        ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+        ("losses", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_ulonglong),
     ]
 
 
@@ -178,6 +210,7 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_mmd_fwd": [vp, vp, i, i, i, C.POINTER(C.c_float), i, vp, vp, vp, vp],
         "zs3_mmd_bwd": [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp],
         "zs3_concat2": [vp, i, vp, i, vp, ll, vp],
+        "zs3_gmmn_train_fused": [C.POINTER(GmmnTrainArgs), vp],
         "zs3_split3_f32": [vp, vp, vp, vp, ll, vp],
         "zs3_pack_weight_component": [vp, i, i, i, i, i, i, vp, i, i, i, i, vp],
         "zs3_bn_apply_f32": [vp, i, vp, i, vp, i, vp, vp, ll, i, i, vp],
