@@ -391,6 +391,29 @@ unsigned long long zs3_gmmn_train_workspace_size(int embed_dim, int noise_dim, i
 int zs3_gmmn_train_fused(const zs3_gmmn_train_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Semantic-cluster graph of a label map (csrc/graph.cu).  Replaces construct_adj_mat
+ * (zs3/train_context_GMMN_GCNcontext.py:33-102: pure-Python DFS on the host, called per image at `:307-321`).
+ * One thread block per image; 8-connected components of equal labels (255 included), node ids in raster
+ * order of each component's first pixel (`:55-62`), node label / seed pixel (`:58-61,72-74`), binary
+ * symmetric adjacency between touching components (`:78-88`).  Integer work: bit-exact.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* labels;    /* [B][*] class ids as floats (the reference keeps its label maps in float tensors) */
+  const int* src_index;   /* optional [h*w]: pixel q of the graph grid reads labels[b][src_index[q]] (the nearest
+                             down-sampling of train_context_GMMN_GCNcontext.py:293-298); NULL: labels is [B][h*w] */
+  long long image_stride; /* elements between consecutive images in `labels` */
+  int B, h, w;
+  int max_nodes;          /* capacity of the per-image outputs below */
+  int* n_nodes;           /* [B] number of components; > max_nodes means the outputs were truncated */
+  int* node_label;        /* [B][max_nodes] class id of every node */
+  int* node_seed;         /* [B][max_nodes] flat pixel index (graph grid) of every node's first pixel */
+  int* node_map;          /* optional [B][h*w] node id of every pixel (the reference's `flag` array) */
+  float* adj;             /* [B][max_nodes][max_nodes] 0/1, symmetric, zero diagonal (written in full) */
+} zs3_components_args;
+
+int zs3_label_components(const zs3_components_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fp32-grade parity mode (forward only; csrc/parity.cu).  An fp32 convolution is emulated on the bf16 tensor
  * cores by splitting both operands into three bf16 pieces and reducing the six significant cross products as
  * six K-segments of one fp32 TMEM accumulator (zs3_conv_fprop).  Activations stay fp32 NHWC between layers;

@@ -36,6 +36,12 @@ static thread_local EmulBlock* emul_block;
 static inline void __syncthreads() { pthread_barrier_wait(&emul_block->bar); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicMin(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+  return old;
+}
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }

@@ -227,3 +227,81 @@ def test_fused_step2_host_logic_against_step2_oracle(emul, monkeypatch):
         assert rel_l2(p, ref["generator"][k]) < 1e-5, k
     assert abs(loss.item() - ref["loss"]) < 1e-4 * abs(ref["loss"])
     assert rel_l2(head.w.detach(), ref["pred_conv.weight"]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ cluster graph (config 5)
+@pytest.fixture(scope="module")
+def graph_emul():
+    out_dir = os.path.join(HERE, "emul", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libgraph_emul.so")
+    src = os.path.join(ROOT, "zs3_b200", "csrc", "graph.cu")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DZS3_HOST_EMULATION", "-I", os.path.join(HERE, "emul"),
+           "-x", "c++", src, "-o", so, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from zs3_b200 import _lib as L
+    lib = C.CDLL(so)
+    lib.zs3_emul_label_components.restype = C.c_int
+    lib.zs3_emul_label_components.argtypes = [C.POINTER(L.ComponentsArgs), C.c_void_p]
+    return lib
+
+
+def _emul_components(lib, labels, h, w, src_index=None, max_nodes=64):
+    from zs3_b200 import _lib as L
+    B = labels.shape[0]
+    n_nodes = torch.zeros(B, dtype=torch.int32)
+    node_label = torch.zeros((B, max_nodes), dtype=torch.int32)
+    node_seed = torch.zeros((B, max_nodes), dtype=torch.int32)
+    node_map = torch.zeros((B, h * w), dtype=torch.int32)
+    adj = torch.full((B, max_nodes, max_nodes), -1.0)
+    a = L.ComponentsArgs()
+    a.labels, a.image_stride = labels.data_ptr(), labels.stride(0)
+    a.src_index = None if src_index is None else src_index.data_ptr()
+    a.B, a.h, a.w, a.max_nodes = B, h, w, max_nodes
+    a.n_nodes, a.node_label, a.node_seed, a.node_map = (t.data_ptr() for t in (n_nodes, node_label, node_seed, node_map))
+    a.adj = adj.data_ptr()
+    assert lib.zs3_emul_label_components(C.byref(a), None) == 0
+    return n_nodes, node_label, node_seed, node_map, adj
+
+
+def test_cluster_graph_kernel_source_matches_reference_golden(graph_emul):
+    import numpy as np
+    gold = np.load(os.path.join(HERE, "golden", "graph.npz"))
+    for name in sorted({k.split("/")[0] for k in gold.files}):
+        seg = torch.from_numpy(gold[name + "/seg"])
+        h, w = seg.shape
+        n_nodes, node_label, node_seed, node_map, adj = _emul_components(graph_emul, seg.reshape(1, -1).contiguous(), h, w)
+        n = int(n_nodes[0])
+        assert n == len(gold[name + "/node_label"]), name
+        assert np.array_equal(node_label[0, :n].numpy(), gold[name + "/node_label"].astype(np.int32)), name
+        assert np.array_equal(node_seed[0, :n].numpy(), gold[name + "/node_seed"]), name
+        assert np.array_equal(node_map[0].numpy().reshape(h, w), gold[name + "/node_map"]), name
+        assert np.array_equal(adj[0, :n, :n].numpy(), gold[name + "/adj"]), name
+        assert (adj[0] >= 0).all()          # the whole capacity is written (zero outside the n x n block)
+        assert adj[0, n:].abs().sum() == 0 and adj[0, :, n:].abs().sum() == 0
+
+
+def test_cluster_graph_kernel_source_nearest_gather_and_overflow(graph_emul):
+    """labels read through the nearest-neighbour source index (train_context_GMMN_GCNcontext.py:293-298) and a
+    batch of two images; a map with more clusters than max_nodes reports the true count"""
+    import numpy as np
+    import zs3_graph_oracle as GO
+    g = torch.Generator().manual_seed(3)
+    full = torch.randint(0, 3, (2, 6, 6), generator=g).float().repeat_interleave(5, 1).repeat_interleave(5, 2)[:, :29, :29]
+    idx = torch.arange(29 * 29, dtype=torch.float32).view(1, 1, 29, 29)
+    src = torch.nn.functional.interpolate(idx, size=(8, 8), mode="nearest").view(-1).to(torch.int32)
+    n_nodes, node_label, node_seed, node_map, adj = _emul_components(graph_emul, full.reshape(2, -1).contiguous(), 8, 8,
+                                                                     src_index=src)
+    small = torch.nn.functional.interpolate(full[:, None], size=(8, 8), mode="nearest")[:, 0]
+    for b in range(2):
+        nm, nl, ns, ad = GO.cluster_graph(small[b].numpy())
+        n = len(nl)
+        assert int(n_nodes[b]) == n
+        assert np.array_equal(node_map[b].numpy().reshape(8, 8), nm)
+        assert np.array_equal(node_label[b, :n].numpy(), nl.astype(np.int32))
+        assert np.array_equal(node_seed[b, :n].numpy(), ns)
+        assert np.array_equal(adj[b, :n, :n].numpy(), ad)
+    noisy = (torch.rand(1, 20 * 20, generator=g) < 0.3).float()
+    n_nodes, _, _, _, _ = _emul_components(graph_emul, noisy, 20, 20, max_nodes=8)
+    assert int(n_nodes[0]) == len(GO.cluster_graph(noisy.view(20, 20).numpy())[1]) > 8

@@ -151,3 +151,18 @@ def test_optimizer_restatements():
         opt.step()
         O.adam_step(q, g, m, v, step)
     assert torch.allclose(p.detach(), q, atol=1e-6)
+
+
+def test_graph_oracle_matches_reference_construct_adj_mat_golden():
+    """oracle/zs3_graph_oracle.py == the real construct_adj_mat (tests/golden/make_golden_graph.py) bit for bit"""
+    import numpy as np
+    import zs3_graph_oracle as GO
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph.npz"))
+    names = sorted({k.split("/")[0] for k in gold.files})
+    assert len(names) == 5
+    for name in names:
+        node_map, node_label, node_seed, adj = GO.cluster_graph(gold[name + "/seg"])
+        assert np.array_equal(node_map, gold[name + "/node_map"]), name
+        assert np.array_equal(node_label, gold[name + "/node_label"]), name
+        assert np.array_equal(node_seed, gold[name + "/node_seed"]), name
+        assert np.array_equal(adj, gold[name + "/adj"]), name

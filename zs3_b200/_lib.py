@@ -164,6 +164,15 @@ class GmmnTrainArgs(C.Structure):
     ]
 
 
+class ComponentsArgs(C.Structure):
+    _fields_ = [
+        ("labels", C.c_void_p), ("src_index", C.c_void_p), ("image_stride", C.c_longlong),
+        ("B", C.c_int), ("h", C.c_int), ("w", C.c_int), ("max_nodes", C.c_int),
+        ("n_nodes", C.c_void_p), ("node_label", C.c_void_p), ("node_seed", C.c_void_p), ("node_map", C.c_void_p),
+        ("adj", C.c_void_p),
+    ]
+
+
 class SgemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("lda", C.c_longlong), ("transA", C.c_int), ("idxA", C.c_void_p),
@@ -211,6 +220,7 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_mmd_bwd": [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp],
         "zs3_concat2": [vp, i, vp, i, vp, ll, vp],
         "zs3_gmmn_train_fused": [C.POINTER(GmmnTrainArgs), vp],
+        "zs3_label_components": [C.POINTER(ComponentsArgs), vp],
         "zs3_split3_f32": [vp, vp, vp, vp, ll, vp],
         "zs3_pack_weight_component": [vp, i, i, i, i, i, i, vp, i, i, i, i, vp],
         "zs3_bn_apply_f32": [vp, i, vp, i, vp, i, vp, vp, ll, i, i, vp],
