@@ -414,6 +414,18 @@ typedef struct {
 int zs3_label_components(const zs3_components_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Validation metrics (csrc/metrics.cu): np.argmax over the class axis + Evaluator._generate_matrix
+ * (zs3/train_pascal_GMMN.py:371-375, zs3/utils/metrics.py:73-82) without copying the logits to the host.
+ * logits [B][C][HW] fp32 (NCHW), target [B][HW] float class ids; pred [B][HW] bytes (optional);
+ * conf [C][C] 64-bit counters, conf[gt*C + pred] += 1 for pixels with 0 <= gt < C (optional, accumulated).
+ * ---------------------------------------------------------------------------------------------- */
+int zs3_argmax_confusion(const float* logits, const float* target, int B, int C, long long HW, unsigned char* pred,
+                         unsigned long long* conf, void* stream);
+/* Evaluator.add_batch(gt_image, pre_image) (metrics.py:79-81) for predictions computed elsewhere: pred [n] int32 */
+int zs3_confusion_from_pred(const int* pred, const float* target, long long n, int C, unsigned long long* conf,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fp32-grade parity mode (forward only; csrc/parity.cu).  An fp32 convolution is emulated on the bf16 tensor
  * cores by splitting both operands into three bf16 pieces and reducing the six significant cross products as
  * six K-segments of one fp32 TMEM accumulator (zs3_conv_fprop).  Activations stay fp32 NHWC between layers;

@@ -330,3 +330,35 @@ def adam_step(p, g, m, v, step, lr=2e-4, b1=0.9, b2=0.999, eps=1e-8):
     v.mul_(b2).addcmul_(g, g, value=1 - b2)
     bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
     p.addcdiv_(m, (v.sqrt() / math.sqrt(bc2)).add_(eps), value=-lr / bc1)
+
+
+# ------------------------------------------------------------------------------------------- metrics
+def confusion_matrix(gt, pred, num_class):
+    """zs3/utils/metrics.py:73-77 (Evaluator._generate_matrix): rows = ground truth, columns = prediction; pixels
+    whose label lies outside [0, num_class) (255 = ignore) are skipped.  numpy int64 [C, C]."""
+    import numpy as np
+    gt, pred = np.asarray(gt), np.asarray(pred)
+    keep = (gt >= 0) & (gt < num_class)
+    idx = num_class * gt[keep].astype(np.int64) + pred[keep].astype(np.int64)
+    return np.bincount(idx, minlength=num_class * num_class).reshape(num_class, num_class)
+
+
+def evaluator_scores(cm, seen=None, unseen=None):
+    """zs3/utils/metrics.py:11-71: (pixel acc, class acc, mIoU, fwIoU) overall, and over seen / unseen rows."""
+    import numpy as np
+    cm = np.asarray(cm, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.diag(cm)
+        acc_c = d / cm.sum(1)
+        iou = d / (cm.sum(1) + cm.sum(0) - d)
+        freq = cm.sum(1) / cm.sum()
+
+        def scores(idx):
+            rows = slice(None) if idx is None else idx
+            f, i = freq[rows], iou[rows]
+            return (d[rows].sum() / cm[rows, :].sum(), np.nanmean(np.nan_to_num(acc_c[rows])),
+                    np.nanmean(np.nan_to_num(i)), (f[f > 0] * i[f > 0]).sum())
+        out = {"all": scores(None)}
+        if seen and unseen:
+            out["seen"], out["unseen"] = scores(seen), scores(unseen)
+    return out

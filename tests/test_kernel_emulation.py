@@ -305,3 +305,43 @@ def test_cluster_graph_kernel_source_nearest_gather_and_overflow(graph_emul):
     noisy = (torch.rand(1, 20 * 20, generator=g) < 0.3).float()
     n_nodes, _, _, _, _ = _emul_components(graph_emul, noisy, 20, 20, max_nodes=8)
     assert int(n_nodes[0]) == len(GO.cluster_graph(noisy.view(20, 20).numpy())[1]) > 8
+
+
+# ------------------------------------------------------------------------------- validation metrics
+def test_argmax_confusion_kernel_source_vs_numpy(tmp_path):
+    """metrics.cu under host emulation == np.argmax + Evaluator._generate_matrix (ties -> first maximum,
+    255 / out-of-range labels skipped, accumulation over calls, several thread blocks)"""
+    import numpy as np
+    import zs3_oracle as O
+    out_dir = os.path.join(HERE, "emul", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libmetrics_emul.so")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DZS3_HOST_EMULATION", "-I", os.path.join(HERE, "emul"),
+           "-x", "c++", os.path.join(ROOT, "zs3_b200", "csrc", "metrics.cu"), "-o", so, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(so)
+    vp = C.c_void_p
+    lib.zs3_emul_argmax_confusion.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp, vp, vp]
+    lib.zs3_emul_confusion_from_pred.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp]
+    g = torch.Generator().manual_seed(4)
+    B, Cn, H, W = 3, 21, 17, 13
+    logits = torch.randn(B, Cn, H, W, generator=g)
+    logits[:, 5] = logits[:, 2]                      # exact ties: the first maximum wins
+    logits[0, :, 0, 0] = 1.0
+    target = torch.randint(0, Cn, (B, H, W), generator=g).float()
+    target[torch.rand(B, H, W, generator=g) < 0.1] = 255
+    target[0, 1, 1] = -1
+    pred = torch.full((B, H, W), 99, dtype=torch.uint8)
+    conf = torch.zeros(Cn, Cn, dtype=torch.int64)
+    for _ in range(2):
+        assert lib.zs3_emul_argmax_confusion(logits.data_ptr(), target.data_ptr(), B, Cn, H * W, pred.data_ptr(),
+                                             conf.data_ptr(), vp(3)) == 0
+    ref_pred = np.argmax(logits.numpy(), axis=1)
+    assert np.array_equal(pred.numpy(), ref_pred)
+    ref_cm = O.confusion_matrix(target.numpy(), ref_pred, Cn)
+    assert np.array_equal(conf.numpy(), 2 * ref_cm) and ref_cm.sum() < B * H * W
+    conf2 = torch.zeros(Cn, Cn, dtype=torch.int64)
+    p32 = torch.from_numpy(ref_pred.astype(np.int32)).contiguous()
+    assert lib.zs3_emul_confusion_from_pred(p32.data_ptr(), target.data_ptr(), p32.numel(), Cn, conf2.data_ptr(), None) == 0
+    assert np.array_equal(conf2.numpy(), ref_cm)

@@ -166,3 +166,17 @@ def test_graph_oracle_matches_reference_construct_adj_mat_golden():
         assert np.array_equal(node_label, gold[name + "/node_label"]), name
         assert np.array_equal(node_seed, gold[name + "/node_seed"]), name
         assert np.array_equal(adj, gold[name + "/adj"]), name
+
+
+def test_metrics_oracle_matches_reference_evaluator_golden():
+    """oracle confusion matrix / scores == the real Evaluator (tests/golden/make_golden_metrics.py)"""
+    import numpy as np
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.npz"))
+    cm = O.confusion_matrix(gold["gt"], gold["pred"], 21)
+    assert np.array_equal(cm, gold["confusion"].astype(np.int64))
+    sc = O.evaluator_scores(cm, seen=[c for c in range(21) if c not in (10, 14)], unseen=[10, 14])
+    for k, name in enumerate(["all", "seen", "unseen"]):
+        assert np.isclose(sc[name][0], gold["pixel_acc"][k], rtol=1e-12)
+        assert np.isclose(sc[name][1], gold["class_acc"][k], rtol=1e-12)
+        assert np.isclose(sc[name][2], gold["miou"][k], rtol=1e-12)
+        assert np.isclose(sc[name][3], gold["fwiou"][k], rtol=1e-12)

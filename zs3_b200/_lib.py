@@ -221,6 +221,8 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_concat2": [vp, i, vp, i, vp, ll, vp],
         "zs3_gmmn_train_fused": [C.POINTER(GmmnTrainArgs), vp],
         "zs3_label_components": [C.POINTER(ComponentsArgs), vp],
+        "zs3_argmax_confusion": [vp, vp, i, i, ll, vp, vp, vp],
+        "zs3_confusion_from_pred": [vp, vp, ll, i, vp, vp],
         "zs3_split3_f32": [vp, vp, vp, vp, ll, vp],
         "zs3_pack_weight_component": [vp, i, i, i, i, i, i, vp, i, i, i, i, vp],
         "zs3_bn_apply_f32": [vp, i, vp, i, vp, i, vp, vp, ll, i, i, vp],
