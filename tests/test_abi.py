@@ -60,3 +60,24 @@ def test_product_code_never_imports_the_oracle():
                     if "zs3_oracle" in txt or "import oracle" in txt or "from oracle" in txt:
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_zs3_shim_falls_through_to_a_reference_checkout(tmp_path):
+    """With this repo before a reference checkout on sys.path, hot-path modules resolve here and the rest of the
+    reference's namespace package (dataloaders, parsing, utils.saver, ...) stays importable."""
+    import subprocess
+    import sys
+    ref = tmp_path / "ref" / "zs3"
+    (ref / "utils").mkdir(parents=True)
+    (ref / "dataloaders").mkdir()
+    (ref / "parsing.py").write_text("WHO = 'reference parsing'\n")
+    (ref / "utils" / "lr_scheduler.py").write_text("WHO = 'reference lr_scheduler'\n")
+    (ref / "utils" / "loss.py").write_text("WHO = 'reference loss (must be shadowed)'\n")
+    (ref / "dataloaders" / "__init__.py").write_text("WHO = 'reference dataloaders'\n")
+    code = ("import zs3.parsing, zs3.utils.lr_scheduler, zs3.dataloaders, zs3.utils.loss, zs3.utils.metrics;"
+            "print(zs3.parsing.WHO, '|', zs3.utils.lr_scheduler.WHO, '|', zs3.dataloaders.WHO, '|',"
+            "hasattr(zs3.utils.loss, 'GMMNLoss'), hasattr(zs3.utils.metrics, 'Evaluator'))")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, str(tmp_path / "ref")]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "reference parsing | reference lr_scheduler | reference dataloaders | True True"
