@@ -187,6 +187,8 @@ def test_fused_step2_host_logic_against_step2_oracle(emul, monkeypatch):
             self.load_state_dict(gst)
 
         def forward(self, emb, z, keep_mask=None):
+            if keep_mask is None:
+                keep_mask = torch.rand(emb.shape[0], 256) > 0.5
             return O.gmmn_forward({k: v for k, v in self.state_dict().items()}, emb, z, training=True, keep_mask=keep_mask)
 
     head, gen = Head(), Gen().train()
@@ -198,8 +200,8 @@ def test_fused_step2_host_logic_against_step2_oracle(emul, monkeypatch):
     step = ZS3StepFused(head, gen, lambda out, tg: O.cross_entropy(out, tg, weight=cw), None, opt, opt_g, seen, unseen,
                         noise_fn=rp.noise, index_fn=rp.index, mask_fn=rp.mask)
 
-    def emul_run(items, E, Z, keepalive=()):
-        upd = step.updater
+    def emul_run(items, E, Z, keepalive=(), which=None):
+        upd = (which or step).updater
         ms, vs, step0 = upd._adam_state()
         for t in ms + vs:
             t.share_memory_()
@@ -209,7 +211,7 @@ def test_fused_step2_host_logic_against_step2_oracle(emul, monkeypatch):
         ws = torch.zeros(emul.zs3_emul_gmmn_train_workspace_size(E, Z, 256, 256) + 64, dtype=torch.uint8).share_memory_()
         losses = torch.zeros(len(items)).share_memory_()
         a = GF.pack_args(buf.data_ptr(), len(items), (E, Z, 256, 256), tuple(p.data for p in upd.params), upd.sigma,
-                         losses, ws, adam=(ms, vs), step0=step0)
+                         losses, ws, adam=(ms, vs), step0=step0, drop_p=0.5 if upd.generator.training else 0.0)
         assert emul.zs3_emul_gmmn_train_fused(C.byref(a), C.c_void_p(2)) == 0
         for p in upd.params:
             upd.optimizer.state[p]["step"] += len(items)
@@ -227,6 +229,12 @@ def test_fused_step2_host_logic_against_step2_oracle(emul, monkeypatch):
         assert rel_l2(p, ref["generator"][k]) < 1e-5, k
     assert abs(loss.item() - ref["loss"]) < 1e-4 * abs(ref["loss"])
     assert rel_l2(head.w.detach(), ref["pred_conv.weight"]) < 1e-5
+
+    # default randomness (noise drawn per sampled row on the device, counter-RNG Dropout): runs and stays finite
+    step_b = ZS3StepFused(head, gen, lambda out, tg: O.cross_entropy(out, tg, weight=cw), None, opt, opt_g, seen, unseen)
+    monkeypatch.setattr(step_b.updater, "run", lambda items, E, Z, keepalive=(): emul_run(items, E, Z, which=step_b))
+    loss_b, glb_b, g_b = step_b.training_step(image, target, embedding, real_features=real)
+    assert len(g_b) == 5 and all(v == v and v > 0 for v in g_b) and torch.isfinite(loss_b)
 
 
 # ------------------------------------------------------------------------------------ cluster graph (config 5)
@@ -345,3 +353,23 @@ def test_argmax_confusion_kernel_source_vs_numpy(tmp_path):
     p32 = torch.from_numpy(ref_pred.astype(np.int32)).contiguous()
     assert lib.zs3_emul_confusion_from_pred(p32.data_ptr(), target.data_ptr(), p32.numel(), Cn, conf2.data_ptr(), None) == 0
     assert np.array_equal(conf2.numpy(), ref_cm)
+
+
+def test_cluster_graph_kernel_source_random_maps_vs_oracle(graph_emul):
+    """random 2-4 label maps (dense noise exercises every branch of the union-pruning rules, incl. diagonal-only
+    contacts), batch of 48, vs the oracle"""
+    import numpy as np
+    import zs3_graph_oracle as GO
+    g = torch.Generator().manual_seed(11)
+    B, h, w = 48, 11, 13
+    maps = torch.stack([torch.randint(0, 2 + b % 3, (h, w), generator=g) for b in range(B)]).float()
+    maps[B // 2:] = maps[B // 2:].repeat_interleave(2, 1).repeat_interleave(2, 2)[:, :h, :w]   # blockier half
+    n_nodes, node_label, node_seed, node_map, adj = _emul_components(graph_emul, maps.reshape(B, -1).contiguous(), h, w,
+                                                                     max_nodes=160)
+    for b in range(B):
+        nm, nl, ns, ad = GO.cluster_graph(maps[b].numpy())
+        n = len(nl)
+        assert int(n_nodes[b]) == n, b
+        assert np.array_equal(node_map[b].numpy().reshape(h, w), nm), b
+        assert np.array_equal(node_seed[b, :n].numpy(), ns), b
+        assert np.array_equal(adj[b, :n, :n].numpy(), ad), b

@@ -110,3 +110,58 @@ def test_step2_iteration_matches_oracle(fused):
     # only pred_conv (and nothing in the frozen backbone) received a gradient: SURVEY 3.2
     others = [n for n, p in model.module.named_parameters() if p.grad is not None and "pred_conv" not in n]
     assert not others
+
+
+def test_fused_step_graph_features_and_fused_classifier_loss():
+    """ZS3StepFused options: feature extraction replayed from a CUDA graph == eager extraction, and the classifier
+    update through the fused upsample+CE loss == the unfused criterion(forward_class_prediction(...)) path"""
+    import copy
+    from zs3.modeling.deeplab import DeepLab
+    from zs3.modeling.gmmn import GMMNnetwork
+    from zs3.utils.loss import GMMNLoss, SegmentationLosses
+    from zs3_b200.step2 import ZS3StepFused
+    B, HW, C = 2, 65, 21
+    unseen, seen = [15, 16], [c for c in range(21) if c not in (15, 16)]
+    target = _labels(B, HW, [[0, 3, 7], [2, 9]], seed=4).cuda()
+    emb_table = torch.randn(C, 300, generator=torch.Generator().manual_seed(8)) * 0.06
+    embedding = emb_table[target.cpu().clamp(max=C - 1).long()].permute(0, 3, 1, 2).contiguous().cuda()
+    image = torch.randn(B, 3, HW, HW, generator=torch.Generator().manual_seed(1)).cuda()
+    torch.manual_seed(3)
+    base = DeepLab(num_classes=C, sync_bn=True, freeze_bn=True, pretrained=False).cuda()
+    for m in base.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    cw = torch.ones(C)
+    cw[unseen] = 100.0
+
+    def make(**kw):
+        model = copy.deepcopy(base).train()
+        model.freeze_bn()
+        gen = GMMNnetwork(300, 300, 256, 256).cuda().train()
+        crit = SegmentationLosses(weight=cw.cuda(), cuda=True).build_loss("ce")
+        crit_g = GMMNLoss(cuda=True).build_loss()
+        opt = torch.optim.SGD([{"params": model.get_1x_lr_params(), "lr": 0.007},
+                               {"params": model.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+        rp = Replay(5)
+        return model, ZS3StepFused(model, gen, crit, crit_g, opt, torch.optim.Adam(gen.parameters(), lr=2e-4), seen,
+                                   unseen, index_fn=rp.index, **kw)
+
+    model_g, step_g = make(graph_features=True)
+    with torch.no_grad():
+        eager = model_g.forward_before_class_prediction(image)
+    first = step_g._extract_features(model_g, image).clone()          # captures, then replays
+    second = step_g._extract_features(model_g, image).clone()         # pure replay
+    assert rel_l2(first, eager) < 1e-3 and rel_l2(second, eager) < 1e-3
+    real = eager / eager.std()
+    outs = []
+    for fuse in (True, False):
+        torch.manual_seed(9)
+        model, step = make(fuse_classifier_loss=fuse)
+        loss, glb, g_losses = step.training_step(image, target, embedding, real_features=real)
+        assert len(g_losses) == 5 and all(np.isfinite(g_losses))
+        outs.append((loss.item(), model.decoder.pred_conv.weight.detach().clone()))
+    assert abs(outs[0][0] - outs[1][0]) < 2e-3 * abs(outs[1][0])
+    assert rel_l2(outs[0][1], outs[1][1]) < 2e-3
+    # whole step with graph features (features computed inside): runs, trains the generator, finite losses
+    loss, glb, g_losses = step_g.training_step(image, target, embedding)
+    assert torch.isfinite(loss) and len(g_losses) == 5

@@ -11,8 +11,8 @@ timeout 240 python tools/ncu_new_kernels.py > gpurun_out/new_kernels_timing.json
 echo "== new kernel timings exit $?"; cat gpurun_out/new_kernels_timing.json; tail -n 5 gpurun_out/new_kernels_timing.err
 timeout 420 python tools/step2_bench.py --steps 4 --warmup 2 --out gpurun_out/step2_bench.json > gpurun_out/step2_bench.log 2>&1
 echo "== step2 bench exit $?"; tail -n 5 gpurun_out/step2_bench.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"gmmn_train_fused|label_components|argmax_confusion" \
-  --launch-skip 3 --launch-count 3 -o gpurun_out/new_kernels_full -f python tools/ncu_new_kernels.py > gpurun_out/ncu_new.log 2>&1
+ZS3_NCU=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"gmmn_train_fused|label_components|argmax_confusion" \
+  --launch-count 6 -o gpurun_out/new_kernels_full -f python tools/ncu_new_kernels.py > gpurun_out/ncu_new.log 2>&1
 echo "== ncu exit $?"; tail -n 3 gpurun_out/ncu_new.log
 python tools/ncu_summary.py gpurun_out/new_kernels_full.ncu-rep > gpurun_out/new_kernels_ncu_summary.md 2>&1; cat gpurun_out/new_kernels_ncu_summary.md
 timeout 600 python -m pytest tests -q -m gpu --tb=short -p no:cacheprovider --deselect tests/test_gmmn_fused_gpu.py \

@@ -66,7 +66,7 @@ def main():
     # per-pixel embedding map as the reference's dataloader builds it (dataloaders/datasets/base.py:45-51): 5 GB
     embedding = emb_table[target.clamp(max=C - 1).long()].permute(0, 3, 1, 2).contiguous()
 
-    def build(step_cls):
+    def build(step_cls, **kw):
         torch.manual_seed(1)
         model = DeepLab(num_classes=C, sync_bn=True, freeze_bn=False, pretrained=False)
         model = torch.nn.DataParallel(model.cuda(), device_ids=[0])
@@ -80,7 +80,7 @@ def main():
                                {"params": model.module.get_10x_lr_params(), "lr": 0.07}], momentum=0.9,
                               weight_decay=5e-4)
         opt_g = torch.optim.Adam(gen.parameters(), lr=2e-4)
-        return step_cls(model, gen, crit, crit_g, opt, opt_g, seen, UNSEEN)
+        return step_cls(model, gen, crit, crit_g, opt, opt_g, seen, UNSEEN, **kw)
 
     def time_steps(step, label):
         n0 = L.lib().zs3_launch_count()
@@ -108,6 +108,11 @@ def main():
                        f"{C} classes, unseen {UNSEEN}", "steps": args.steps, "warmup": args.warmup, "runs": []}
     fused = build(ZS3StepFused)
     res["runs"].append(time_steps(fused, "ZS3StepFused (device work list + zs3_gmmn_train_fused)"))
+    try:
+        res["runs"].append(time_steps(build(ZS3StepFused, graph_features=True),
+                                      "ZS3StepFused + feature extraction replayed from a CUDA graph"))
+    except Exception as e:  # the graph variant is opt-in; report instead of losing the other numbers
+        res["runs"].append({"impl": "ZS3StepFused graph_features", "error": repr(e)[:300]})
     if not args.skip_unfused:
         res["runs"].append(time_steps(build(ZS3Step), "ZS3Step (module by module)"))
 

@@ -14,9 +14,9 @@
 // is staged through shared memory ([k][32] panels) and consumed by 8 warps that split the k range of the tile
 // (in-CTA split-K, fixed-order reduction through shared memory => bit-reproducible results).  The phases of one
 // iteration are separated by a grid-wide barrier (the kernel is launched cooperatively, all CTAs co-resident):
-//   P1 Hd = dropout(leaky(Xin W1^T + b1))           P4 dY_i = 1/loss * sum_j P_ij (x_j - x_i)
+//   P1 Hd = dropout(leaky(Xin W1^T + b1)) + gather of item w+1 (idle CTAs)     P4 dY_i = 1/loss * sum_j P_ij (x_j - x_i)
 //   P2 Y  = Hd W2^T + b2  -> X[0:B]                 P5 dH  = (dY W2) * f'(Hd)
-//   P3 P_ij, loss^2 partials (difference form)      P6 dW1, db1, dW2, db2 -> Adam in the epilogue; gather of item w+1
+//   P3 P_ij, loss^2 partials (difference form)      P6 dW1, db1, dW2, db2 -> Adam in the epilogue
 // fp32 SIMT on purpose (the MMD exponent cancels catastrophically in reduced precision); the whole
 // iteration is 90 MFMA -- the cost is latency (6 barriers + operand staging), not arithmetic.
 //
@@ -39,7 +39,7 @@ constexpr int FKC = 128;        // k extent staged per chunk: 8 warps x 16
 constexpr int FLD = 36;         // pitch of a staged [k][32] panel (floats); keeps rows 16-byte aligned
 constexpr int FTHREADS = 256;
 constexpr int FMAXB = 128;      // max sampled rows per item
-constexpr int FGATHER_UNITS = 8;
+constexpr int FGATHER_ROWS = 2;   // rows per gather unit (64 units for a 128-row item)
 
 struct Opnd {
   const float* p;
@@ -102,9 +102,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
   __syncthreads();
 }
 
-// Stage the [FKC k][32 rows] panel of an operand (rows r0.., k range k0..) into S, zero filled outside [R) x [K).
-__device__ __forceinline__ void stage_panel(float* __restrict__ S, const Opnd o, int r0, int R, int k0, int K) {
-  float v[16];
+// Panel staging, split in two halves so that the global loads of chunk c+1 are in flight while chunk c is being
+// consumed: panel_load reads this thread's 16 elements of the [FKC k][32 rows] panel (rows r0.., k range k0..; zero
+// outside [R) x [K)) into registers, panel_store writes them to shared memory as S[k][row].
+__device__ __forceinline__ void panel_load(float (&v)[16], const Opnd o, int r0, int R, int k0, int K) {
   if (o.kcontig) {
     const int k = threadIdx.x & (FKC - 1);
     const int rb = threadIdx.x >> 7;  // 0..1
@@ -114,8 +115,6 @@ __device__ __forceinline__ void stage_panel(float* __restrict__ S, const Opnd o,
       const int r = rb + 2 * e;
       v[e] = (kin && (r0 + r) < R) ? __ldcg(o.p + (long long)(r0 + r) * o.ld + (k0 + k)) : 0.f;
     }
-#pragma unroll
-    for (int e = 0; e < 16; ++e) S[k * FLD + rb + 2 * e] = v[e];
   } else {
     const int r = threadIdx.x & 31;
     const int kb = threadIdx.x >> 5;  // 0..7
@@ -125,6 +124,18 @@ __device__ __forceinline__ void stage_panel(float* __restrict__ S, const Opnd o,
       const int k = kb + 8 * e;
       v[e] = (rin && (k0 + k) < K) ? __ldcg(o.p + (long long)(k0 + k) * o.ld + (r0 + r)) : 0.f;
     }
+  }
+}
+
+__device__ __forceinline__ void panel_store(float* __restrict__ S, const float (&v)[16], const Opnd o) {
+  if (o.kcontig) {
+    const int k = threadIdx.x & (FKC - 1);
+    const int rb = threadIdx.x >> 7;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) S[k * FLD + rb + 2 * e] = v[e];
+  } else {
+    const int r = threadIdx.x & 31;
+    const int kb = threadIdx.x >> 5;
 #pragma unroll
     for (int e = 0; e < 16; ++e) S[(kb + 8 * e) * FLD + r] = v[e];
   }
@@ -158,11 +169,18 @@ __device__ __forceinline__ void tile32(float* __restrict__ sm, const Opnd A, int
         if (i < M && j < N) c[x][y] = __ldcg(Cmat + (long long)i * ldc + j);
       }
   }
+  float va[16], vb[16];
+  panel_load(va, A, i0, M, 0, K);
+  panel_load(vb, B, j0, N, 0, K);
   for (int k0 = 0; k0 < K; k0 += FKC) {
     __syncthreads();  // the previous chunk (or the previous tile's reduction buffer) is no longer being read
-    stage_panel(As, A, i0, M, k0, K);
-    stage_panel(Bs, B, j0, N, k0, K);
+    panel_store(As, va, A);
+    panel_store(Bs, vb, B);
     __syncthreads();
+    if (k0 + FKC < K) {  // next chunk's loads overlap this chunk's arithmetic
+      panel_load(va, A, i0, M, k0 + FKC, K);
+      panel_load(vb, B, j0, N, k0 + FKC, K);
+    }
     if (k0 + warp * 16 < K) {
 #pragma unroll 4
       for (int kk = 0; kk < 16; ++kk) {
@@ -209,19 +227,36 @@ __device__ __forceinline__ void tile32(float* __restrict__ sm, const Opnd A, int
   // the next tile32 call starts with __syncthreads() before it overwrites `red`
 }
 
-__device__ __forceinline__ float src_elem(const zs3_row_source& s, int r, int k) {
-  const long long row = s.rows ? (long long)__ldg(s.rows + r) : (long long)r;
-  return __ldg(s.base + row * s.row_stride + (long long)k * s.col_stride);
-}
-
-// Gather unit `u` of FGATHER_UNITS: rows r = u, u + 8, ... of item `it` into the packed input / sample buffers.
+// Gather unit `u`: rows [u*FGATHER_ROWS, +FGATHER_ROWS) of item `it` into the packed input / sample buffers.  Every
+// thread first issues all of its (independent) loads, then stores: the row indirection + strided feature reads
+// are latency, not bandwidth.
 __device__ __forceinline__ void gather_rows(const FusedP& p, const zs3_gmmn_item& it, int u, float* __restrict__ Xin,
                                             float* __restrict__ X) {
-  const int K1 = p.E + p.Z, B = min(it.rows, FMAXB);
-  for (int r = u; r < B; r += FGATHER_UNITS) {
-    for (int k = threadIdx.x; k < K1; k += FTHREADS)
-      Xin[(long long)r * K1 + k] = k < p.E ? src_elem(it.emb, r, k) : src_elem(it.noise, r, k - p.E);
-    for (int d = threadIdx.x; d < p.F; d += FTHREADS) X[(long long)(B + r) * p.F + d] = src_elem(it.real, r, d);
+  const int K1 = p.E + p.Z, B = min(it.rows, FMAXB), F = p.F;
+  const int r0 = u * FGATHER_ROWS, r1 = min(r0 + FGATHER_ROWS, B);
+  for (int r = r0; r < r1; ++r) {
+    const long long er = it.emb.rows ? (long long)__ldg(it.emb.rows + r) : (long long)r;
+    const long long zr = it.noise.rows ? (long long)__ldg(it.noise.rows + r) : (long long)r;
+    const long long fr = it.real.rows ? (long long)__ldg(it.real.rows + r) : (long long)r;
+    const float* eb = it.emb.base + er * it.emb.row_stride;
+    const float* zb = it.noise.base + zr * it.noise.row_stride;
+    const float* fb = it.real.base + fr * it.real.row_stride;
+    for (int k0 = 0; k0 < K1; k0 += 4 * FTHREADS) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + e * FTHREADS + threadIdx.x;
+        v[e] = k < p.E ? __ldg(eb + (long long)k * it.emb.col_stride)
+                       : (k < K1 ? __ldg(zb + (long long)(k - p.E) * it.noise.col_stride) : 0.f);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + e * FTHREADS + threadIdx.x;
+        if (k < K1) Xin[(long long)r * K1 + k] = v[e];
+      }
+    }
+    for (int d = threadIdx.x; d < F; d += FTHREADS)
+      X[(long long)(B + r) * F + d] = __ldg(fb + (long long)d * it.real.col_stride);
   }
 }
 
@@ -255,7 +290,10 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
   if (p.n_items <= 0) return;
   if (threadIdx.x == 0) sh_item[0] = p.items[0];
   __syncthreads();
-  for (int u = blockIdx.x; u < FGATHER_UNITS; u += gridDim.x) gather_rows(p, sh_item[0], u, p.Xin, p.X);
+  {
+    const int ng0 = (min(sh_item[0].rows, FMAXB) + FGATHER_ROWS - 1) / FGATHER_ROWS;
+    for (int u = blockIdx.x; u < ng0; u += gridDim.x) gather_rows(p, sh_item[0], u, p.Xin, p.X);
+  }
   grid_barrier(p.barrier, bar_target);
 
   for (int w = 0; w < p.n_items; ++w) {
@@ -275,8 +313,15 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     const int tB = (B + FT - 1) / FT, tL = (L + FT - 1) / FT, tH = (H + FT - 1) / FT, tF = (F + FT - 1) / FT;
     const int tK1 = (K1 + FT - 1) / FT;
 
-    // ---- P1: Hd = dropout(leaky(Xin W1^T + b1))
-    for (int u = blockIdx.x; u < tB * tH; u += gridDim.x) {
+    // ---- P1: Hd = dropout(leaky(Xin W1^T + b1)); the CTAs without a tile gather the rows of item w+1 into the
+    //          other Xin / X buffers (last read in P6 of item w-1, i.e. before the previous grid barrier)
+    const int ng = (w + 1 < p.n_items) ? (min(sh_item[1].rows, FMAXB) + FGATHER_ROWS - 1) / FGATHER_ROWS : 0;
+    for (int u = blockIdx.x; u < tB * tH + ng; u += gridDim.x) {
+      if (u >= tB * tH) {
+        gather_rows(p, sh_item[1], u - tB * tH, p.Xin + (size_t)((w + 1) & 1) * FMAXB * K1,
+                    p.X + (size_t)((w + 1) & 1) * 2 * FMAXB * F);
+        continue;
+      }
       const int i0 = (u / tH) * FT, j0 = (u % tH) * FT;
       tile32<OP_DOT>(sm, Opnd{Xin, K1, 1}, i0, B, Opnd{p.W1, K1, 1}, j0, H, K1, nullptr, 0,
                      [&](int i, int j, float v) {
@@ -368,12 +413,11 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     }
     grid_barrier(p.barrier, bar_target);
 
-    // ---- P6: dW1 = dH^T Xin, dW2 = dY^T Hd, db1, db2 -> Adam; plus the gather of item w+1 into the other buffers
+    // ---- P6: dW1 = dH^T Xin, dW2 = dY^T Hd, db1, db2 -> Adam
     {
       const float bc1 = sh_scalar[1], bc2s = sh_scalar[2];
       const int n1 = tH * tK1, n2 = tF * tH;
-      const int ng = (w + 1 < p.n_items) ? FGATHER_UNITS : 0;
-      const int total = n1 + n2 + 2 + ng;
+      const int total = n1 + n2 + 2;
       for (int u = blockIdx.x; u < total; u += gridDim.x) {
         if (u < n1) {
           const int i0 = (u / tK1) * FT, j0 = (u % tK1) * FT;
@@ -391,18 +435,17 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
         } else if (u == n1 + n2) {
           for (int h = threadIdx.x; h < H; h += FTHREADS) {
             float s = 0.f;
+#pragma unroll 8
             for (int r = 0; r < B; ++r) s += __ldcg(p.dH + (long long)r * H + h);
             apply_grad(p, p.b1, p.mb1, p.vb1, p.gb1, h, s, bc1, bc2s);
           }
-        } else if (u == n1 + n2 + 1) {
+        } else {
           for (int o = threadIdx.x; o < F; o += FTHREADS) {
             float s = 0.f;
+#pragma unroll 8
             for (int r = 0; r < B; ++r) s += __ldcg(p.dY + (long long)r * F + o);
             apply_grad(p, p.b2, p.mb2, p.vb2, p.gb2, o, s, bc1, bc2s);
           }
-        } else {
-          gather_rows(p, sh_item[1], u - (n1 + n2 + 2), p.Xin + (size_t)((w + 1) & 1) * FMAXB * K1,
-                      p.X + (size_t)((w + 1) & 1) * 2 * FMAXB * F);
         }
       }
     }

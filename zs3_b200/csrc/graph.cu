@@ -88,17 +88,49 @@ __global__ void __launch_bounds__(CC_THREADS) label_components_kernel(const Comp
   for (int q = tid; q < p.max_nodes * p.max_nodes; q += CC_THREADS) adj[q] = 0.f;
   __syncthreads();
 
-  // union with the already-visited half of the 8-neighbourhood: W, NW, N, NE
+  // horizontal runs first: link every pixel to its left neighbour of equal label, then pointer-jump until each
+  // pixel points at the first pixel of its run (ceil(log2 w) rounds; unsynchronised reads only ever see a pointer
+  // that is already further up the same chain).  The unions below then start from trees of depth <= 1 instead
+  // of w-long chains.
+  for (int q = tid; q < npix; q += CC_THREADS) {
+    const int j = q % w;
+    if (j > 0 && lab[q - 1] == lab[q]) parent[q] = q - 1;
+  }
+  __syncthreads();
+  for (int span = 1; span < w; span <<= 1) {
+    for (int q = tid; q < npix; q += CC_THREADS) {
+      const volatile int* vp = parent;
+      parent[q] = vp[vp[q]];
+    }
+    __syncthreads();
+  }
+  // union with the previous row's part of the 8-neighbourhood (NW, N, NE).  Runs are already connected, so one
+  // union per maximal overlap of two runs suffices; a pixel skips the unions that a row neighbour performs:
+  //   N  is implied when the left neighbour and NW carry the label too (the left pixel's N-union + the two runs),
+  //   NW / NE only matter when N differs, and are implied when the left / right neighbour carries the label
+  //   (that pixel sees the same upper-row pixel as its own N).
   for (int q = tid; q < npix; q += CC_THREADS) {
     const int i = q / w, j = q - i * w, l = lab[q];
-    if (j > 0 && lab[q - 1] == l) cc_unite(parent, q, q - 1);
-    if (i > 0) {
-      if (j > 0 && lab[q - w - 1] == l) cc_unite(parent, q, q - w - 1);
-      if (lab[q - w] == l) cc_unite(parent, q, q - w);
-      if (j + 1 < w && lab[q - w + 1] == l) cc_unite(parent, q, q - w + 1);
+    if (i == 0) continue;
+    const bool left = j > 0 && lab[q - 1] == l, right = j + 1 < w && lab[q + 1] == l;
+    const bool up = lab[q - w] == l;
+    const bool upl = j > 0 && lab[q - w - 1] == l, upr = j + 1 < w && lab[q - w + 1] == l;
+    if (up) {
+      if (!(left && upl)) cc_unite(parent, q, q - w);
+    } else {
+      if (upl && !left) cc_unite(parent, q, q - w - 1);
+      if (upr && !right) cc_unite(parent, q, q - w + 1);
     }
   }
   __syncthreads();
+  // flatten: a few pointer-jumping rounds take the bulk of the depth out, the exact walk finishes
+  for (int r = 0; r < 6; ++r) {
+    for (int q = tid; q < npix; q += CC_THREADS) {
+      const volatile int* vp = parent;
+      parent[q] = vp[vp[q]];
+    }
+    __syncthreads();
+  }
   for (int q = tid; q < npix; q += CC_THREADS) parent[q] = cc_find(parent, q);
   __syncthreads();
 

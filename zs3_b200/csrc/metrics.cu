@@ -24,6 +24,7 @@ namespace zs3 {
 
 constexpr int AM_THREADS = 256;
 constexpr int AM_MAXC = 64;
+constexpr int AM_PIX = 4;
 
 struct ArgmaxP {
   const float* logits;   // [B][C][HW], or null when pred_in is given
@@ -43,30 +44,57 @@ __global__ void __launch_bounds__(AM_THREADS) argmax_confusion_kernel(const Argm
     for (int i = threadIdx.x; i < C * C; i += AM_THREADS) hist[i] = 0;
     __syncthreads();
   }
+  // AM_PIX pixels per thread (block-strided, so every class-plane read stays coalesced): AM_PIX independent
+  // load chains per class step, a few class steps unrolled -> enough bytes in flight to approach the HBM rate
   const long long total = (long long)p.B * p.HW;
-  for (long long q = (long long)blockIdx.x * AM_THREADS + threadIdx.x; q < total; q += (long long)gridDim.x * AM_THREADS) {
-    const long long b = q / p.HW, px = q - b * p.HW;
-    int arg = 0;
+  for (long long base = (long long)blockIdx.x * (AM_THREADS * AM_PIX); base < total;
+       base += (long long)gridDim.x * (AM_THREADS * AM_PIX)) {
+    long long q[AM_PIX];
+    const float* src[AM_PIX];
+    bool ok[AM_PIX];
+    int arg[AM_PIX];
+#pragma unroll
+    for (int e = 0; e < AM_PIX; ++e) {
+      q[e] = base + e * AM_THREADS + threadIdx.x;
+      ok[e] = q[e] < total;
+      const long long qq = ok[e] ? q[e] : 0;
+      const long long b = qq / p.HW, px = qq - b * p.HW;
+      src[e] = p.logits ? p.logits + b * C * p.HW + px : nullptr;
+      arg[e] = 0;
+    }
     if (p.logits) {
-      const float* src = p.logits + b * C * p.HW + px;
-      float best = __ldg(src);
+      float best[AM_PIX];
+#pragma unroll
+      for (int e = 0; e < AM_PIX; ++e) best[e] = __ldg(src[e]);
 #pragma unroll 4
       for (int c = 1; c < C; ++c) {
-        const float v = __ldg(src + (long long)c * p.HW);
-        if (v > best) {
-          best = v;
-          arg = c;
-        }
+        float v[AM_PIX];
+#pragma unroll
+        for (int e = 0; e < AM_PIX; ++e) v[e] = __ldg(src[e] + (long long)c * p.HW);
+#pragma unroll
+        for (int e = 0; e < AM_PIX; ++e)
+          if (v[e] > best[e]) {   // strict: the first maximum wins, like np.argmax
+            best[e] = v[e];
+            arg[e] = c;
+          }
       }
-      if (p.pred) p.pred[q] = (unsigned char)arg;
+#pragma unroll
+      for (int e = 0; e < AM_PIX; ++e)
+        if (ok[e] && p.pred) p.pred[q[e]] = (unsigned char)arg[e];
     } else {
-      arg = __ldg(p.pred_in + q);
+#pragma unroll
+      for (int e = 0; e < AM_PIX; ++e)
+        if (ok[e]) arg[e] = __ldg(p.pred_in + q[e]);
     }
     if (count) {
-      const float g = __ldg(p.target + q);
-      // metrics.py:74-75: mask = (gt >= 0) & (gt < num_class); gt.astype(int) truncates; a prediction outside
-      // [0, C) cannot come from an argmax and is skipped here (np.bincount would spill it into the next row)
-      if (g >= 0.f && g < (float)C && arg >= 0 && arg < C) atomicAdd(&hist[(int)g * C + arg], 1);
+#pragma unroll
+      for (int e = 0; e < AM_PIX; ++e) {
+        if (!ok[e]) continue;
+        const float g = __ldg(p.target + q[e]);
+        // metrics.py:74-75: mask = (gt >= 0) & (gt < num_class); gt.astype(int) truncates; a prediction outside
+        // [0, C) cannot come from an argmax and is skipped here (np.bincount would spill it into the next row)
+        if (g >= 0.f && g < (float)C && arg[e] >= 0 && arg[e] < C) atomicAdd(&hist[(int)g * C + arg[e]], 1);
+      }
     }
   }
   if (count) {
@@ -94,7 +122,7 @@ extern "C" int zs3_argmax_confusion(const float* logits, const float* target, in
   ArgmaxP p;
   p.logits = logits; p.pred_in = nullptr; p.target = target; p.pred = pred; p.conf = conf; p.B = B; p.C = C; p.HW = HW;
   const long long total = (long long)B * HW;
-  long long blocks = (total + AM_THREADS - 1) / AM_THREADS;
+  long long blocks = (total + AM_THREADS * AM_PIX - 1) / (AM_THREADS * AM_PIX);
 #ifdef ZS3_HOST_EMULATION
   const int nb = stream ? (int)reinterpret_cast<intptr_t>(stream) : 1;
   for (int b = 0; b < nb; ++b) emul_run_block<ArgmaxP>(argmax_confusion_kernel, p, AM_THREADS, b, nb);
@@ -124,7 +152,7 @@ extern "C" int zs3_confusion_from_pred(const int* pred, const float* target, lon
   emul_run_block<ArgmaxP>(argmax_confusion_kernel, p, AM_THREADS, 0, 1);
   return ZS3_OK;
 #else
-  long long blocks = (n + AM_THREADS - 1) / AM_THREADS;
+  long long blocks = (n + AM_THREADS * AM_PIX - 1) / (AM_THREADS * AM_PIX);
   if (blocks > 148 * 8) blocks = 148 * 8;
   argmax_confusion_kernel<<<(int)blocks, AM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   ZS3_CHECK_LAUNCH("confusion_from_pred");

@@ -93,10 +93,14 @@ class ZS3StepFused(ZS3Step):
         values on the host and copies them, `:216-218`); pass `noise_fn` to reproduce the reference's stream.
     """
 
-    def __init__(self, *args, noise_fn=None, **kw):
+    def __init__(self, *args, noise_fn=None, graph_features=False, fuse_classifier_loss=True, **kw):
         super().__init__(*args, noise_fn=noise_fn, **kw)
         from .gmmn_fused import FusedGeneratorUpdater
         self._device_noise = noise_fn is None
+        self.fuse_classifier_loss = fuse_classifier_loss
+        # graph_features: capture the (frozen-weight, no_grad) feature extraction in a CUDA graph on first use and
+        # replay it afterwards -- ~350 launches per step issued by one graph launch instead of by the interpreter
+        self.graph_features, self._feat_graph, self._feat_in, self._feat_out = graph_features, None, None, None
         # criterion_generator is GMMNLoss(...).build_loss(), a bound method of the loss object holding `sigma`
         sigma = getattr(getattr(self.criterion_generator, "__self__", None), "sigma", None) or (2, 5, 10, 20, 40, 80)
         self.updater = FusedGeneratorUpdater(self.generator, self.optimizer_generator, sigma=sigma)
@@ -111,27 +115,111 @@ class ZS3StepFused(ZS3Step):
             self._src_index[key] = nn.functional.interpolate(idx, size=out_hw, mode="nearest").view(-1).to(torch.int32)
         return self._src_index[key]
 
+    def _extract_features(self, model, image):
+        """model.forward_before_class_prediction(image) under no_grad (`:154-157`), optionally through a CUDA graph"""
+        if not self.graph_features:
+            with torch.no_grad():
+                return model.forward_before_class_prediction(image)
+        from . import functional as ZF
+        dev = image.device
+        if self._feat_graph is None or self._feat_in.shape != image.shape:
+            if ZF._RngState.device_counter is None:
+                ZF._RngState.device_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._feat_in = image.clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):          # lazy initialisations (function attributes, scratch) outside the capture
+                    model.forward_before_class_prediction(self._feat_in)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self._feat_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._feat_graph), torch.no_grad():
+                self._feat_out = model.forward_before_class_prediction(self._feat_in)
+        ZF._RngState.device_counter.add_(1 << 32)  # fresh Dropout masks per replay
+        self._feat_in.copy_(image, non_blocking=True)
+        self._feat_graph.replay()
+        return self._feat_out
+
+    def _classifier_loss(self, model, features, image, target):
+        """criterion(forward_class_prediction(features, input_size), target).  When the criterion is this package's
+        cross entropy, the x4 bilinear upsample is evaluated inside the loss kernels from the low-resolution class
+        scores (SegmentationLosses.UpsampledCrossEntropyLoss: same value, the 354 MB logits are never written)."""
+        from .utils.loss import SegmentationLosses
+        owner = getattr(self.criterion, "__self__", None)
+        if (self.fuse_classifier_loss and isinstance(owner, SegmentationLosses)
+                and getattr(self.criterion, "__func__", None) is SegmentationLosses.CrossEntropyLoss
+                and tuple(target.shape[1:]) == tuple(image.shape[2:])):
+            scores = model.decoder.forward_class_prediction(features)
+            return owner.UpsampledCrossEntropyLoss(scores, model.num_classes, target)
+        return self.criterion(model.forward_class_prediction(features, image.size()[2:]), target)
+
+    @staticmethod
+    def _feature_grid(h, w):
+        """spatial size of forward_before_class_prediction's output: stem conv 7x7/2 pad 3, max-pool 3x3/2 pad 1
+        (resnet.py:79-82); the decoder works at that low-level resolution (decoder.py:33-37)"""
+        def down(n):
+            return (n - 1) // 2 + 1
+        return down(down(h)), down(down(w))
+
     def training_step(self, image, target, embedding, real_features=None):
         from . import gmmn_fused as GF
         model = self.model.module if hasattr(self.model, "module") else self.model
         dev = image.device
-        if real_features is None:
-            with torch.no_grad():
-                real_features = model.forward_before_class_prediction(image)
-        real_features = real_features.contiguous().float()
-        embedding = embedding.contiguous().float()
-        nb, fd, fh, fw = real_features.shape
+        nb = image.shape[0]
+        in_hw = tuple(target.shape[1:])
+        fh, fw = self._feature_grid(*in_hw) if real_features is None else tuple(real_features.shape[2:])
         hw = fh * fw
-        in_hw = target.shape[1:]
+        # ---- label work list first: its one host sync then overlaps nothing, and the feature extraction enqueued
+        # right after it runs on the GPU while the host plans the updates below
         src = self._nearest_source_index(in_hw, (fh, fw), dev)                          # [hw] int32
         tg = target.reshape(nb, -1)[:, src.long()].long()                               # nearest down-sampling `:175-179`
         hist = torch.zeros((nb, 256), dtype=torch.int32, device=dev)
         hist.scatter_add_(1, tg.clamp(0, 255), torch.ones_like(tg, dtype=torch.int32))
         order = torch.argsort(tg, dim=1, stable=True).to(torch.int32)                   # raster order inside a class
         hist_h = hist.cpu().numpy()                                                     # the step's one label sync
+        if real_features is None:
+            real_features = self._extract_features(model, image)                       # `:154-157`
+        real_features = real_features.contiguous().float()
+        embedding = embedding.contiguous().float()
+        fd = real_features.shape[1]
+        assert tuple(real_features.shape[2:]) == (fh, fw), (real_features.shape, fh, fw)
+
+        # ---- host plan: the (image, class) visits in the reference's order, drawing the injected randomness in the
+        # reference's order (noise, [mask], indices); entries are executed in this order below
+        plan, n_unique, image_has_unseen = [], [], []
+        for i in range(nb):
+            classes = [c for c in range(256) if hist_h[i, c] > 0]                       # == torch.unique (sorted)
+            n_unique.append(len(classes))
+            has_unseen = any(c in self.unseen for c in classes)
+            image_has_unseen.append(has_unseen)
+            need_fake = has_unseen or not self.real_seen_features
+            off = 0
+            for c in classes:
+                n_c, start = int(hist_h[i, c]), off
+                off += n_c
+                if c == 255:
+                    continue
+                z_full = None if self._device_noise else self.noise_fn(n_c)
+                m_full = None if self.mask_fn is None else self.mask_fn(n_c)
+                if need_fake:
+                    plan.append(("bulk", i, n_c, start, z_full, m_full, None))
+                if c in self.seen and not has_unseen:
+                    plan.append(("item", i, n_c, start, z_full, m_full, self.index_fn(n_c)))
+
+        # ---- device side of all updates at once: sampled pixels in the feature grid and in the input grid, noise
+        upd = [e for e in plan if e[0] == "item"]
+        if upd:
+            ridx_all = torch.stack([e[6].to(torch.int32) for e in upd]).to(dev)          # [n, rows] one H2D
+            base = torch.tensor([e[1] * hw + e[3] for e in upd], dtype=torch.int64).to(dev)
+            pix_all = order.view(-1)[base[:, None] + ridx_all.long()].contiguous()      # [n, rows] feature-grid pixels
+            spix_all = src[pix_all.long()].contiguous()                                  # same pixels, input grid
+            rows = ridx_all.shape[1]
+            z_all = torch.rand((len(upd), rows, self.noise_dim), device=dev) if self._device_noise else None
+
         fake_features = torch.zeros(real_features.shape, device=dev)
-        queue, keep, owners = [], [], []          # owners[k] = image index of queued / executed update k
-        loss_chunks = []
+        fake_by_image = {}
+        queue, keep, owners, loss_chunks = [], [], [], []
 
         def flush():
             if queue:
@@ -139,63 +227,45 @@ class ZS3StepFused(ZS3Step):
                 queue.clear()
                 keep.clear()
 
-        n_unique = []
-        for i in range(nb):
-            classes = [c for c in range(256) if hist_h[i, c] > 0]                       # == torch.unique (sorted)
-            n_unique.append(len(classes))
-            starts = {}
-            off = 0
-            for c in classes:
-                starts[c] = off
-                off += int(hist_h[i, c])
-            has_unseen = any(c in self.unseen for c in classes)
-            need_fake = has_unseen or not self.real_seen_features
-            fake_i = torch.zeros((hw, fd), device=dev) if need_fake else None
-            for c in classes:
-                if c == 255:
-                    continue
-                n_c = int(hist_h[i, c])
-                pix_c = order[i, starts[c]:starts[c] + n_c]                              # pixels of the class, raster order
-                z_full = None if self._device_noise else self.noise_fn(n_c).to(dev).float().contiguous()
-                m_full = None if self.mask_fn is None else self.mask_fn(n_c).to(dev).to(torch.uint8).contiguous()
-                if need_fake:
-                    flush()                                                              # weights as of this point
-                    with torch.no_grad():
-                        emb_c = embedding[i].reshape(self.embed_dim, -1)[:, src[pix_c.long()].long()].t().contiguous()
-                        z_gen = z_full if z_full is not None else torch.rand((n_c, self.noise_dim), device=dev)
-                        if m_full is not None:
-                            fake_c = self.generator(emb_c, z_gen, keep_mask=m_full)
-                        else:
-                            fake_c = self.generator(emb_c, z_gen)
-                        fake_i[pix_c.long()] = fake_c
-                if c in self.seen and not has_unseen:
-                    ridx = self.index_fn(n_c).to(dev).to(torch.int32).contiguous()
-                    rows = int(ridx.numel())
-                    pix = pix_c[ridx.long()].contiguous()                                # sampled pixels (feature grid)
-                    spix = src[pix.long()].contiguous()                                  # same pixels in the input grid
-                    emb_src = GF.row_source(embedding[i], spix, row_stride=1, col_stride=in_hw[0] * in_hw[1])
-                    if z_full is not None:
-                        noise_src = GF.row_source(z_full, ridx)
+        k = 0
+        for kind, i, n_c, start, z_full, m_full, _ in plan:
+            z_dev = None if z_full is None else z_full.to(dev).float().contiguous()
+            m_dev = None if m_full is None else m_full.to(dev).to(torch.uint8).contiguous()
+            if kind == "bulk":
+                flush()                                                                  # weights as of this point
+                pix_c = order[i, start:start + n_c].long()
+                if i not in fake_by_image:
+                    fake_by_image[i] = torch.zeros((hw, fd), device=dev)
+                with torch.no_grad():
+                    emb_c = embedding[i].reshape(self.embed_dim, -1)[:, src[pix_c].long()].t().contiguous()
+                    z_gen = z_dev if z_dev is not None else torch.rand((n_c, self.noise_dim), device=dev)
+                    if m_dev is not None:
+                        fake_c = self.generator(emb_c, z_gen, keep_mask=m_dev)
                     else:
-                        z_full = torch.rand((rows, self.noise_dim), device=dev)
-                        noise_src = GF.row_source(z_full)
-                    real_src = GF.row_source(real_features[i], pix, row_stride=1, col_stride=hw)
-                    queue.append(GF.pack_item(emb_src, noise_src, real_src, rows, keep_mask=m_full, keep_rows=ridx))
-                    keep.extend([ridx, pix, spix, z_full, m_full])
-                    owners.append(i)
-            if self.real_seen_features and not has_unseen:
+                        fake_c = self.generator(emb_c, z_gen)                           # `:220-222`
+                    fake_by_image[i][pix_c] = fake_c                                     # `:242`
+                continue
+            ridx, pix, spix = ridx_all[k], pix_all[k], spix_all[k]
+            emb_src = GF.row_source(embedding[i], spix, row_stride=1, col_stride=in_hw[0] * in_hw[1])
+            noise_src = GF.row_source(z_all[k]) if z_dev is None else GF.row_source(z_dev, ridx)
+            real_src = GF.row_source(real_features[i], pix, row_stride=1, col_stride=hw)
+            queue.append(GF.pack_item(emb_src, noise_src, real_src, rows, keep_mask=m_dev, keep_rows=ridx))
+            keep.extend([z_dev, m_dev])
+            owners.append(i)
+            k += 1
+        flush()
+        for i in range(nb):                                                              # `:244-259`
+            if self.real_seen_features and not image_has_unseen[i]:
                 fake_features[i] = real_features[i]
             else:
-                fake_features[i] = fake_i.view(fh, fw, fd).permute(2, 0, 1)
-        flush()
+                fake_features[i] = fake_by_image[i].view(fh, fw, fd).permute(2, 0, 1) if i in fake_by_image else 0
         self.optimizer.zero_grad()
-        output = model.forward_class_prediction(fake_features.detach(), image.size()[2:])
-        loss = self.criterion(output, target)
+        loss = self._classifier_loss(model, fake_features.detach(), image, target)      # `:261-264`
         loss.backward()
         self.optimizer.step()
         g_losses = torch.cat(loss_chunks).tolist() if loss_chunks else []
         per_image = [0.0] * nb
-        for k, v in enumerate(g_losses):
-            per_image[owners[k]] += v
+        for j, v in enumerate(g_losses):
+            per_image[owners[j]] += v
         generator_loss_batch = sum(per_image[i] / n_unique[i] for i in range(nb))
         return loss, generator_loss_batch, g_losses
