@@ -319,6 +319,14 @@ def run_ours(args):
                         "sample": f"2 steps of bs=2 {HW}x{HW} fwd+CE+bwd+SGD with the oracle port on {cores} threads "
                                   f"({s:.2f} s/step; host has {os.cpu_count()} cores)"}
 
+    # ---- BASELINE configs[2]: the ZS3Net step-2 iteration (feature extraction + generator updates + classifier)
+    step2 = None
+    if rank == 0 and world == 1 and not args.no_step2:
+        try:
+            step2 = step2_rate(dev, B, HW, steps=min(args.steps, 10))
+        except Exception as e:  # reported, never fatal for the headline line
+            step2 = {"error": repr(e)[:300]}
+
     if rank == 0:
         sampler.join(timeout=2)
         line = {
@@ -340,12 +348,71 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "forward_only": forward_only,
+            "step2": step2,
             "cpu_baseline": cpu_baseline,
         }
         emit(line)
     phase("done")
     if world > 1:
         dist.destroy_process_group()
+
+
+def step2_rate(dev, B, HW, steps, warmup=3):
+    """images/sec of one ZS3Net step-2 iteration (train_pascal_GMMN.py:152-268; BASELINE configs[2]): DeepLab feature
+    extraction under no_grad (CUDA graph), the per-(image, class) generator updates as ONE work-list launch of the
+    fused MLP + MMD + backward + Adam kernel, and the pred_conv update with the fused upsample + CE loss."""
+    from zs3_b200 import _lib as L
+    from zs3_b200.modeling.deeplab import DeepLab
+    from zs3_b200.modeling.gmmn import GMMNnetwork
+    from zs3_b200.step2 import ZS3StepFused
+    from zs3_b200.utils.loss import GMMNLoss, SegmentationLosses
+    unseen = [10, 14]
+    seen = [c for c in range(NUM_CLASSES) if c not in unseen]
+    g = torch.Generator().manual_seed(7)
+    lab = torch.zeros(B, HW, HW)
+    cell = (HW + 7) // 8
+    for i in range(B):  # blocky maps with 2-5 classes; ~25 % of the images hold an unseen class; 2 % ignore pixels
+        k = int(torch.randint(2, 6, (1,), generator=g))
+        cls = [seen[j] for j in torch.randperm(len(seen), generator=g)[:k].tolist()]
+        if torch.rand(1, generator=g).item() < 0.25:
+            cls[-1] = unseen[int(torch.randint(0, 2, (1,), generator=g))]
+        grid = torch.randint(0, k, (8, 8), generator=g)
+        lab[i] = torch.tensor(cls, dtype=torch.float32)[grid].repeat_interleave(cell, 0).repeat_interleave(cell, 1)[:HW, :HW]
+    lab[torch.rand(B, HW, HW, generator=g) < 0.02] = 255
+    target = lab.to(dev)
+    image = torch.randn(B, 3, HW, HW, generator=g).to(dev)
+    table = (torch.randn(NUM_CLASSES, 300, generator=g) * 0.06).to(dev)
+    # the per-pixel embedding map the reference's dataloader builds (dataloaders/datasets/base.py:45-51)
+    embedding = table[target.clamp(max=NUM_CLASSES - 1).long()].permute(0, 3, 1, 2).contiguous()
+    model = DeepLab(num_classes=NUM_CLASSES, sync_bn=True, pretrained=False).to(dev).train()
+    gen = GMMNnetwork(300, 300, 256, 256).to(dev).train()
+    cw = torch.ones(NUM_CLASSES)
+    cw[unseen] = 100.0
+    crit = SegmentationLosses(weight=cw.to(dev), cuda=True).build_loss("ce")
+    crit_g = GMMNLoss(cuda=True).build_loss()
+    opt = torch.optim.SGD([{"params": model.get_1x_lr_params(), "lr": 0.007},
+                           {"params": model.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+    step = ZS3StepFused(model, gen, crit, crit_g, opt, torch.optim.Adam(gen.parameters(), lr=2e-4), seen, unseen,
+                        graph_features=True)
+    for _ in range(warmup):
+        step.training_step(image, target, embedding)
+    torch.cuda.synchronize()
+    n0 = L.lib().zs3_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    updates = 0
+    for _ in range(steps):
+        loss, _, g_losses = step.training_step(image, target, embedding)
+        updates += len(g_losses)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "ZS3Net train_pascal_GMMN step (BASELINE configs[2]): frozen-feature extraction + GMMN "
+                        f"generator updates + 21-class classifier update, bs={B} {HW}x{HW}, unseen classes {unseen}",
+            "value": B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps,
+            "generator_updates_per_step": updates / steps, "final_loss": float(loss.item()),
+            "final_generator_loss": g_losses[-1] if g_losses else None,
+            "launch_calls_per_step_outside_the_feature_graph": (L.lib().zs3_launch_count() - n0) / steps}
 
 
 _RESULT_FD = None
@@ -379,6 +446,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE: 16)")
     ap.add_argument("--size", type=int, default=513, help="input height=width (BASELINE: 513)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-step2", action="store_true", help="skip the configs[2] (ZS3Net step-2 iteration) measurement")
     ap.add_argument("--layer-table", default="", help="write a per-conv-shape timing table (markdown) to this path")
     ap.add_argument("--mode", default="graph", choices=["eager", "graph"],
                     help="graph: capture the whole training step in one CUDA graph and replay it")

@@ -385,6 +385,8 @@ typedef struct {
   unsigned long long seed, offset; /* counter RNG of the Dropout mask when keep_mask == NULL */
   float* losses;              /* [n_items] moment_loss of every update */
   void* workspace; unsigned long long workspace_bytes; /* >= zs3_gmmn_train_workspace_size(...), 16-byte aligned */
+  unsigned long long* phase_stamps; /* optional [n_items][8]: %globaltimer (ns) at the start of each update and after
+                                       each of its six phases, written by CTA 0 (profiling aid); NULL = off */
 } zs3_gmmn_train_args;
 
 unsigned long long zs3_gmmn_train_workspace_size(int embed_dim, int noise_dim, int hidden, int feat);

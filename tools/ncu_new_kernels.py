@@ -51,6 +51,15 @@ for k in range(16):
                               GF.row_source(feats[k], pix, row_stride=1, col_stride=hw), 128))
 us = timed(lambda: upd.run(items, 300, 300, keepalive=keep))
 res["gmmn_train_fused"] = {"updates": 16, "us_per_launch": us, "us_per_update": us / 16}
+stamps = torch.zeros((16, 8), dtype=torch.int64, device=dev)
+upd.run(items, 300, 300, keepalive=keep, phase_stamps=stamps)
+torch.cuda.synchronize()
+st = stamps.cpu().double()
+names = ["P1 hidden layer (+gather of the next item)", "P2 output layer", "P3 pairwise kernel + loss partials",
+         "P4 loss + dY", "P5 dH", "P6 weight gradients + Adam"]
+res["gmmn_train_fused"]["phase_us_mean_over_updates_1_15"] = {
+    n: float((st[1:, k + 1] - st[1:, k]).mean() / 1e3) for k, n in enumerate(names)}
+res["gmmn_train_fused"]["update_us_from_stamps"] = float((st[1:, 6] - st[1:, 0]).mean() / 1e3)
 
 # cluster graph: 16 Voronoi label maps at 129 x 129
 rng = np.random.RandomState(3)

@@ -161,6 +161,7 @@ class GmmnTrainArgs(C.Structure):
         ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
         ("losses", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_ulonglong),
+        ("phase_stamps", C.c_void_p),
     ]
 
 

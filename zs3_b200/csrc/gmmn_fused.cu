@@ -58,7 +58,7 @@ struct FusedP {
   int apply_adam;
   float lr, beta1, beta2, eps;
   long long step0;
-  float sigma[8];
+  float inv_sigma[8];
   int nsigma;
   float slope, drop_p;
   unsigned long long seed, offset;
@@ -71,6 +71,7 @@ struct FusedP {
   float* dH;      // [FMAXB][H]
   double* lossp;  // [64] per-tile partial sums of loss^2
   unsigned* barrier;
+  unsigned long long* stamps;  // optional [n_items][8] %globaltimer at the phase boundaries
 };
 
 enum { OP_DOT = 0, OP_DIST = 1, OP_WDIFF = 2 };
@@ -83,23 +84,36 @@ __device__ __forceinline__ uint64_t splitmix64f(uint64_t x) {
 }
 
 // All CTAs of the (cooperatively launched) grid arrive; `target` is the running arrival count to wait for.
+// bar.sync orders the CTA's writes before thread 0's release-add (cumulativity), the acquire poll orders the other
+// CTAs' writes before everything after the second bar.sync; cross-CTA data is read with ld.cg (L2) throughout.
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
   target += gridDim.x;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
     unsigned v;
-    do {
 #ifdef ZS3_HOST_EMULATION
+    atomicAdd(ctr, 1u);
+    do {
       v = emul_ld_acquire(ctr);
-#else
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-#endif
     } while ((int)(v - target) < 0);
-    __threadfence();
+#else
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0);
+#endif
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void phase_stamp(unsigned long long* stamps, int w, int slot) {
+#ifndef ZS3_HOST_EMULATION
+  if (stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    stamps[w * 8 + slot] = t;
+  }
+#endif
 }
 
 // Panel staging, split in two halves so that the global loads of chunk c+1 are in flight while chunk c is being
@@ -108,11 +122,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
 __device__ __forceinline__ void panel_load(float (&v)[16], const Opnd o, int r0, int R, int k0, int K) {
   if (o.kcontig) {
     const int k = threadIdx.x & (FKC - 1);
-    const int rb = threadIdx.x >> 7;  // 0..1
+    const int rb = (threadIdx.x >> 7) * 16;  // rows rb .. rb+15 (lanes of a warp: consecutive k -> coalesced)
     const bool kin = (k0 + k) < K;
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-      const int r = rb + 2 * e;
+      const int r = rb + e;
       v[e] = (kin && (r0 + r) < R) ? __ldcg(o.p + (long long)(r0 + r) * o.ld + (k0 + k)) : 0.f;
     }
   } else {
@@ -129,10 +143,13 @@ __device__ __forceinline__ void panel_load(float (&v)[16], const Opnd o, int r0,
 
 __device__ __forceinline__ void panel_store(float* __restrict__ S, const float (&v)[16], const Opnd o) {
   if (o.kcontig) {
+    // one thread = 16 consecutive rows of one k: four 128-bit stores; a quarter warp (8 consecutive k, pitch 36)
+    // covers all 32 banks exactly once
     const int k = threadIdx.x & (FKC - 1);
-    const int rb = threadIdx.x >> 7;
+    const int rb = (threadIdx.x >> 7) * 16;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) S[k * FLD + rb + 2 * e] = v[e];
+    for (int e = 0; e < 4; ++e)
+      *reinterpret_cast<float4*>(S + k * FLD + rb + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
   } else {
     const int r = threadIdx.x & 31;
     const int kb = threadIdx.x >> 5;
@@ -306,6 +323,7 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
       sh_scalar[2] = (float)sqrt(1.0 - pow((double)p.beta2, t));
     }
     __syncthreads();
+    phase_stamp(p.stamps, w, 0);
     const zs3_gmmn_item& it = sh_item[0];
     const int B = min(it.rows, FMAXB), L = 2 * B;
     float* Xin = p.Xin + (size_t)(w & 1) * FMAXB * K1;
@@ -344,6 +362,7 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
                      });
     }
     grid_barrier(p.barrier, bar_target);
+    phase_stamp(p.stamps, w, 1);
 
     // ---- P2: Y = Hd W2^T + b2 -> X[0:B]
     for (int u = blockIdx.x; u < tB * tF; u += gridDim.x) {
@@ -352,6 +371,7 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
                      [&](int i, int j, float v) { X[(long long)i * F + j] = v + __ldcg(p.b2 + j); });
     }
     grid_barrier(p.barrier, bar_target);
+    phase_stamp(p.stamps, w, 2);
 
     // ---- P3: P_ij = s_i s_j sum_sigma exp(e_ij/sigma)/sigma, loss^2 partial per tile; e_ij = -|x_i - x_j|^2 / 2.
     // get_scale_matrix quirk (loss.py:92-97): the FIRST N rows carry +1/N, the last M rows -1/M (M = N = B here).
@@ -364,9 +384,9 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
         const float e = -0.5f * d2;
         float kv = 0.f, kp = 0.f;
         for (int s = 0; s < p.nsigma; ++s) {
-          const float ex = expf(e / p.sigma[s]);
+          const float ex = expf(e * p.inv_sigma[s]);
           kv += ex;
-          kp += ex / p.sigma[s];
+          kp += ex * p.inv_sigma[s];
         }
         part += si * sj * kv;
         p.P[(long long)i * L + j] = si * sj * kp;
@@ -382,6 +402,7 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
       __syncthreads();
     }
     grid_barrier(p.barrier, bar_target);
+    phase_stamp(p.stamps, w, 3);
 
     // ---- P4: loss = sqrt(sum of partials) (NaN for a negative sum, like the reference: loss.py:114);
     //          dY_i = 1/loss * sum_j P_ij (x_j - x_i), i < B
@@ -402,6 +423,7 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
       }
     }
     grid_barrier(p.barrier, bar_target);
+    phase_stamp(p.stamps, w, 4);
 
     // ---- P5: dH = (dY W2) * d/dh[dropout(leaky(h))], reconstructed from the forward output Hd
     for (int u = blockIdx.x; u < tB * tH; u += gridDim.x) {
@@ -412,6 +434,7 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
       });
     }
     grid_barrier(p.barrier, bar_target);
+    phase_stamp(p.stamps, w, 5);
 
     // ---- P6: dW1 = dH^T Xin, dW2 = dY^T Hd, db1, db2 -> Adam
     {
@@ -450,6 +473,7 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
       }
     }
     grid_barrier(p.barrier, bar_target);
+    phase_stamp(p.stamps, w, 6);
   }
 }
 
@@ -523,7 +547,7 @@ extern "C" int zs3_gmmn_train_fused(const zs3_gmmn_train_args* a, void* stream) 
   p.gW1 = a->grad[0]; p.gb1 = a->grad[1]; p.gW2 = a->grad[2]; p.gb2 = a->grad[3];
   p.apply_adam = a->apply_adam;
   p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps; p.step0 = a->step0;
-  for (int i = 0; i < 8; ++i) p.sigma[i] = i < a->nsigma ? a->sigma[i] : 1.f;
+  for (int i = 0; i < 8; ++i) p.inv_sigma[i] = i < a->nsigma ? 1.f / a->sigma[i] : 1.f;
   p.nsigma = a->nsigma;
   p.slope = a->slope; p.drop_p = a->drop_p; p.seed = a->seed; p.offset = a->offset;
   p.losses = a->losses;
@@ -536,6 +560,7 @@ extern "C" int zs3_gmmn_train_fused(const zs3_gmmn_train_args* a, void* stream) 
   p.dH = reinterpret_cast<float*>(ws + l.dh);
   p.lossp = reinterpret_cast<double*>(ws + l.lossp);
   p.barrier = reinterpret_cast<unsigned*>(ws + l.barrier);
+  p.stamps = a->phase_stamps;
 
 #ifdef ZS3_HOST_EMULATION
   // `stream` carries the number of emulated thread blocks (tests/test_kernel_emulation.py)

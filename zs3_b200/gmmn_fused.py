@@ -49,7 +49,8 @@ def items_to_bytes(items):
 
 
 def pack_args(items_ptr, n_items, dims, params, sigma, losses, workspace, *, adam=None, grads=None, lr=2e-4,
-              betas=(0.9, 0.999), eps=1e-8, step0=0, slope=0.2, drop_p=0.5, seed=0, offset=0, max_rows=MAX_ROWS):
+              betas=(0.9, 0.999), eps=1e-8, step0=0, slope=0.2, drop_p=0.5, seed=0, offset=0, max_rows=MAX_ROWS,
+              phase_stamps=None):
     """dims = (embed_dim, noise_dim, hidden, feat); params = (w1, b1, w2, b2) fp32 contiguous tensors;
     adam = ([exp_avg x4], [exp_avg_sq x4]) for in-place Adam, or grads = [g x4] for gradient output."""
     a = L.GmmnTrainArgs()
@@ -75,6 +76,7 @@ def pack_args(items_ptr, n_items, dims, params, sigma, losses, workspace, *, ada
     a.slope, a.drop_p, a.seed, a.offset = slope, drop_p, int(seed), int(offset)
     a.losses = losses.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    a.phase_stamps = None if phase_stamps is None else phase_stamps.data_ptr()   # int64 [n_items, 8]
     return a
 
 
@@ -123,8 +125,9 @@ class FusedGeneratorUpdater:
                 raise RuntimeError("Adam step counters of the generator parameters disagree")
         return ms, vs, step
 
-    def run(self, items, embed_dim, noise_dim, keepalive=()):
-        """items: list of zs3_gmmn_item (pack_item); returns the device tensor of their moment losses."""
+    def run(self, items, embed_dim, noise_dim, keepalive=(), phase_stamps=None):
+        """items: list of zs3_gmmn_item (pack_item); returns the device tensor of their moment losses.
+        phase_stamps: optional int64 CUDA tensor [len(items), 8] receiving %globaltimer at the phase boundaries."""
         dev = self.params[0].device
         if dev.type != "cuda":
             raise RuntimeError("zs3_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
@@ -148,7 +151,7 @@ class FusedGeneratorUpdater:
                       tuple(p.data for p in self.params), self.sigma, losses, self._workspace, adam=(ms, vs),
                       lr=float(g["lr"]), betas=tuple(g["betas"]), eps=float(g["eps"]), step0=step,
                       slope=float(self.act.negative_slope), drop_p=float(self.drop.p) if training else 0.0,
-                      seed=torch.initial_seed() & 0xFFFFFFFFFFFF, offset=self._calls << 44)
+                      seed=torch.initial_seed() & 0xFFFFFFFFFFFF, offset=self._calls << 44, phase_stamps=phase_stamps)
         L.check(lib.zs3_gmmn_train_fused(C.byref(a), L.stream_ptr()), "zs3_gmmn_train_fused")
         for p in self.params:
             st = self.optimizer.state[p]
