@@ -109,8 +109,13 @@ def main():
     fused = build(ZS3StepFused)
     res["runs"].append(time_steps(fused, "ZS3StepFused (device work list + zs3_gmmn_train_fused)"))
     try:
-        res["runs"].append(time_steps(build(ZS3StepFused, graph_features=True),
-                                      "ZS3StepFused + feature extraction replayed from a CUDA graph"))
+        gstep = build(ZS3StepFused, graph_features=True)
+        res["runs"].append(time_steps(gstep, "ZS3StepFused + feature extraction replayed from a CUDA graph"))
+        gstep.profile = {}
+        gstep.training_step(image, target, embedding)
+        torch.cuda.synchronize()
+        res["segments_of_one_graph_step"] = gstep.profile_summary()
+        gstep.profile = None
     except Exception as e:  # the graph variant is opt-in; report instead of losing the other numbers
         res["runs"].append({"impl": "ZS3StepFused graph_features", "error": repr(e)[:300]})
     if not args.skip_unfused:

@@ -980,7 +980,19 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
 
   FpropParams p;
   memset(&p, 0, sizeof(p));
-  const int BN = a->cout_pad >= 256 ? 256 : (a->cout_pad >= 128 ? 128 : 64);
+  int BN = a->cout_pad >= 256 ? 256 : (a->cout_pad >= 128 ? 128 : 64);
+  {
+    // A 256-channel output whose 128-row tiles fit in ONE wave (layer3's 33x33 maps: 137 tiles on 148 SMs) gives every
+    // CTA a single tile: prologue, pipeline fill and the whole epilogue are exposed.  With 128-column tiles each CTA
+    // runs two half-width tiles and the epilogue of the first overlaps the main loop of the second (the A tile is
+    // read twice, from L2).  ZS3_FPROP_SPLIT_N=0/1; see profiles/ for the measurement behind the default.
+    static int split_n = -1;
+    if (split_n < 0) {
+      const char* env = getenv("ZS3_FPROP_SPLIT_N");
+      split_n = env ? atoi(env) : 0;
+    }
+    if (split_n && a->cout_pad == 256 && ceil_div_ll(M, BLOCK_M) <= num_sms()) BN = 128;
+  }
   // cluster size: CTAs of a cluster share (multicast) the weight tile.  Measured on B200 (profiles/r01_cluster_*):
   // multicast at cluster sizes <= 4 does not reduce L2->SM traffic and the lock step costs 8-60 %, so the default is
   // 1; ZS3_CLUSTER=2|4 keeps the path testable.

@@ -98,6 +98,7 @@ class ZS3StepFused(ZS3Step):
         from .gmmn_fused import FusedGeneratorUpdater
         self._device_noise = noise_fn is None
         self.fuse_classifier_loss = fuse_classifier_loss
+        self.profile = None   # set to {} to collect per-segment (host ms, CUDA events) of the next training_step
         # graph_features: capture the (frozen-weight, no_grad) feature extraction in a CUDA graph on first use and
         # replay it afterwards -- ~350 launches per step issued by one graph launch instead of by the interpreter
         self.graph_features, self._feat_graph, self._feat_in, self._feat_out = graph_features, None, None, None
@@ -141,6 +142,18 @@ class ZS3StepFused(ZS3Step):
         self._feat_graph.replay()
         return self._feat_out
 
+    def _mark(self, name):
+        if self.profile is not None:
+            import time
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.profile.setdefault("marks", []).append((name, time.perf_counter(), ev))
+
+    def profile_summary(self):
+        """per-segment host and device milliseconds of the profiled step (call after torch.cuda.synchronize())"""
+        marks = self.profile["marks"]
+        return {b[0]: {"host_ms": (b[1] - a[1]) * 1e3, "gpu_ms": a[2].elapsed_time(b[2])} for a, b in zip(marks, marks[1:])}
+
     def _classifier_loss(self, model, features, image, target):
         """criterion(forward_class_prediction(features, input_size), target).  When the criterion is this package's
         cross entropy, the x4 bilinear upsample is evaluated inside the loss kernels from the low-resolution class
@@ -168,6 +181,8 @@ class ZS3StepFused(ZS3Step):
         dev = image.device
         nb = image.shape[0]
         in_hw = tuple(target.shape[1:])
+        mark = self._mark
+        mark("start")
         fh, fw = self._feature_grid(*in_hw) if real_features is None else tuple(real_features.shape[2:])
         hw = fh * fw
         # ---- label work list first: its one host sync then overlaps nothing, and the feature extraction enqueued
@@ -178,8 +193,10 @@ class ZS3StepFused(ZS3Step):
         hist.scatter_add_(1, tg.clamp(0, 255), torch.ones_like(tg, dtype=torch.int32))
         order = torch.argsort(tg, dim=1, stable=True).to(torch.int32)                   # raster order inside a class
         hist_h = hist.cpu().numpy()                                                     # the step's one label sync
+        mark("labels")
         if real_features is None:
             real_features = self._extract_features(model, image)                       # `:154-157`
+        mark("features")
         real_features = real_features.contiguous().float()
         embedding = embedding.contiguous().float()
         fd = real_features.shape[1]
@@ -217,6 +234,7 @@ class ZS3StepFused(ZS3Step):
             rows = ridx_all.shape[1]
             z_all = torch.rand((len(upd), rows, self.noise_dim), device=dev) if self._device_noise else None
 
+        mark("plan+index")
         fake_features = torch.zeros(real_features.shape, device=dev)
         fake_by_image = {}
         queue, keep, owners, loss_chunks = [], [], [], []
@@ -254,6 +272,7 @@ class ZS3StepFused(ZS3Step):
             owners.append(i)
             k += 1
         flush()
+        mark("generator")
         for i in range(nb):                                                              # `:244-259`
             if self.real_seen_features and not image_has_unseen[i]:
                 fake_features[i] = real_features[i]
@@ -263,6 +282,7 @@ class ZS3StepFused(ZS3Step):
         loss = self._classifier_loss(model, fake_features.detach(), image, target)      # `:261-264`
         loss.backward()
         self.optimizer.step()
+        mark("classifier")
         g_losses = torch.cat(loss_chunks).tolist() if loss_chunks else []
         per_image = [0.0] * nb
         for j, v in enumerate(g_losses):
