@@ -373,3 +373,27 @@ def test_cluster_graph_kernel_source_random_maps_vs_oracle(graph_emul):
         assert np.array_equal(node_map[b].numpy().reshape(h, w), nm), b
         assert np.array_equal(node_seed[b, :n].numpy(), ns), b
         assert np.array_equal(adj[b, :n, :n].numpy(), ad), b
+
+
+def test_vectorized_item_packing_equals_per_item_packing():
+    """pack_items_vectorized (numpy pointer arithmetic over the whole work list) == pack_item per update, byte for
+    byte (host logic only: pointers of CPU tensors are as good as device pointers here)"""
+    from zs3_b200 import gmmn_fused as GF
+    n, rows, E, Z, F, hw_in, hw = 5, 128, 300, 300, 256, 33 * 33, 9 * 9
+    embedding = torch.zeros(3, E, hw_in)
+    real = torch.zeros(3, F, hw)
+    images = [0, 0, 2, 1, 2]
+    g = torch.Generator().manual_seed(1)
+    spix = torch.randint(0, hw_in, (n, rows), generator=g, dtype=torch.int32)
+    pix = torch.randint(0, hw, (n, rows), generator=g, dtype=torch.int32)
+    ridx = torch.randint(0, 50, (n, rows), generator=g, dtype=torch.int32)
+    z = torch.rand(n, rows, Z, generator=g)
+    import numpy as np
+    arr = GF.pack_items_vectorized(images=np.array(images, dtype=np.int64), rows=rows,
+                                   emb=(embedding.data_ptr(), embedding.stride(0) * 4, hw_in), emb_rows=spix, noise=z,
+                                   real=(real.data_ptr(), real.stride(0) * 4, hw), real_rows=pix, keep_rows=ridx)
+    items = [GF.pack_item(GF.row_source(embedding[i], spix[k], row_stride=1, col_stride=hw_in), GF.row_source(z[k]),
+                          GF.row_source(real[i], pix[k], row_stride=1, col_stride=hw), rows, keep_rows=ridx[k])
+             for k, i in enumerate(images)]
+    assert GF.items_to_bytes(arr) == GF.items_to_bytes(items)
+    assert GF.items_to_bytes(arr[1:3]) == GF.items_to_bytes(items[1:3])

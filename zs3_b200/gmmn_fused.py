@@ -7,6 +7,7 @@ launches on the current CUDA stream and refuses anything that is not a CUDA tens
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -44,8 +45,40 @@ def pack_item(emb, noise, real, rows, keep_mask=None, keep_rows=None):
 
 
 def items_to_bytes(items):
+    """list of zs3_gmmn_item, or the numpy structured array of pack_items_vectorized"""
+    if isinstance(items, np.ndarray):
+        return items.tobytes()
     arr = (L.GmmnItem * len(items))(*items)
     return bytes(memoryview(arr).cast("B"))
+
+
+ITEM_DTYPE = np.dtype(L.GmmnItem)   # numpy mirror of zs3_gmmn_item (same offsets: derived from the ctypes struct)
+
+
+def pack_items_vectorized(images, rows, emb, emb_rows, noise, real, real_rows, keep_rows):
+    """A whole work list at once.  Update k belongs to image images[k]; `emb` / `real` = (base pointer, bytes per
+    image, column stride in elements) of an NCHW-like map whose rows are gathered through emb_rows[k] / real_rows[k]
+    (int32 [n, rows] CUDA tensors, row stride 1); noise [n, rows, Z] fp32 (dense); keep_rows int32 [n, rows]."""
+    n = len(images)
+    a = np.zeros(n, dtype=ITEM_DTYPE)
+    k = np.arange(n, dtype=np.int64)
+    for name, (base, img_bytes, cs), idx in (("emb", emb, emb_rows), ("real", real, real_rows)):
+        if idx.dtype != torch.int32 or not idx.is_contiguous():
+            raise TypeError("row gathers are contiguous int32 tensors")
+        a[name]["base"] = (base + images * img_bytes).astype(np.uint64)
+        a[name]["rows"] = (idx.data_ptr() + k * (rows * 4)).astype(np.uint64)
+        a[name]["row_stride"], a[name]["col_stride"] = 1, cs
+    if noise.dtype != torch.float32 or not noise.is_contiguous():
+        raise TypeError("noise is a contiguous fp32 tensor [n, rows, Z]")
+    a["noise"]["base"] = (noise.data_ptr() + k * (rows * noise.shape[2] * 4)).astype(np.uint64)
+    a["noise"]["rows"] = 0
+    a["noise"]["row_stride"], a["noise"]["col_stride"] = noise.shape[2], 1
+    a["keep_mask"] = 0
+    a["keep_rows"] = (keep_rows.data_ptr() + k * (rows * 4)).astype(np.uint64)
+    if not 1 <= rows <= MAX_ROWS:
+        raise ValueError(f"a generator update samples 1..{MAX_ROWS} rows, got {rows}")
+    a["rows"] = rows
+    return a
 
 
 def pack_args(items_ptr, n_items, dims, params, sigma, losses, workspace, *, adam=None, grads=None, lr=2e-4,

@@ -5,6 +5,7 @@ frozen-backbone feature extraction, per-(image, class) generator updates on 128 
 loss, fake/real feature assembly, classifier (pred_conv) update.  The reference trainer can drive the same
 modules unchanged; this class is the in-repo runner used by tests and benchmarks.
 """
+import numpy as np
 import torch
 from torch import nn
 
@@ -90,11 +91,15 @@ class ZS3StepFused(ZS3Step):
       * the sequential updates of consecutive images are queued and executed by one launch; the queue is flushed
         before anything that reads the generator weights;
       * `noise_fn=None` draws z ~ U[0,1) for the 128 sampled rows on the device (the reference draws n_c x 300
-        values on the host and copies them, `:216-218`); pass `noise_fn` to reproduce the reference's stream.
+        values on the host and copies them, `:216-218`), `index_fn=None` draws the sampled row indices of all
+        updates on the device in one call (the reference: one host `torch.randint` per class, `:229`); pass
+        `noise_fn` / `index_fn` to reproduce the reference's host streams.  With both defaults and no injected
+        mask, the work list is packed with a handful of numpy vector operations instead of per-update Python.
     """
 
-    def __init__(self, *args, noise_fn=None, graph_features=False, fuse_classifier_loss=True, **kw):
-        super().__init__(*args, noise_fn=noise_fn, **kw)
+    def __init__(self, *args, noise_fn=None, index_fn=None, graph_features=False, fuse_classifier_loss=True, **kw):
+        super().__init__(*args, noise_fn=noise_fn, index_fn=index_fn, **kw)
+        self._device_index = index_fn is None     # default: sampled row indices drawn on the device for all updates
         from .gmmn_fused import FusedGeneratorUpdater
         self._device_noise = noise_fn is None
         self.fuse_classifier_loss = fuse_classifier_loss
@@ -206,7 +211,7 @@ class ZS3StepFused(ZS3Step):
         # reference's order (noise, [mask], indices); entries are executed in this order below
         plan, n_unique, image_has_unseen = [], [], []
         for i in range(nb):
-            classes = [c for c in range(256) if hist_h[i, c] > 0]                       # == torch.unique (sorted)
+            classes = np.nonzero(hist_h[i])[0].tolist()                                  # == torch.unique (sorted)
             n_unique.append(len(classes))
             has_unseen = any(c in self.unseen for c in classes)
             image_has_unseen.append(has_unseen)
@@ -222,30 +227,49 @@ class ZS3StepFused(ZS3Step):
                 if need_fake:
                     plan.append(("bulk", i, n_c, start, z_full, m_full, None))
                 if c in self.seen and not has_unseen:
-                    plan.append(("item", i, n_c, start, z_full, m_full, self.index_fn(n_c)))
+                    plan.append(("item", i, n_c, start, z_full, m_full, None if self._device_index else self.index_fn(n_c)))
 
         # ---- device side of all updates at once: sampled pixels in the feature grid and in the input grid, noise
         upd = [e for e in plan if e[0] == "item"]
+        rows = self.batch_size_generator
         if upd:
-            ridx_all = torch.stack([e[6].to(torch.int32) for e in upd]).to(dev)          # [n, rows] one H2D
             base = torch.tensor([e[1] * hw + e[3] for e in upd], dtype=torch.int64).to(dev)
+            if self._device_index:   # floor(u * n_c), u ~ U[0,1): uniform over the class's pixels, with replacement
+                n_c_all = torch.tensor([e[2] for e in upd], dtype=torch.float32).to(dev)
+                u = torch.rand((len(upd), rows), device=dev)
+                ridx_all = torch.minimum((u * n_c_all[:, None]).floor(), n_c_all[:, None] - 1).to(torch.int32)
+            else:
+                ridx_all = torch.stack([e[6].to(torch.int32) for e in upd]).to(dev)      # [n, rows] one H2D
+                rows = ridx_all.shape[1]
             pix_all = order.view(-1)[base[:, None] + ridx_all.long()].contiguous()      # [n, rows] feature-grid pixels
             spix_all = src[pix_all.long()].contiguous()                                  # same pixels, input grid
-            rows = ridx_all.shape[1]
             z_all = torch.rand((len(upd), rows, self.noise_dim), device=dev) if self._device_noise else None
 
         mark("plan+index")
         fake_features = torch.zeros(real_features.shape, device=dev)
         fake_by_image = {}
-        queue, keep, owners, loss_chunks = [], [], [], []
+        queue, keep, owners, loss_chunks = [], [], [e[1] for e in upd], []
+        # nothing injected per update: the whole work list is packed with a handful of numpy vector operations
+        vec = self._device_noise and self.mask_fn is None and bool(upd)
+        if vec:
+            arr = GF.pack_items_vectorized(
+                images=np.array([e[1] for e in upd], dtype=np.int64), rows=rows,
+                emb=(embedding.data_ptr(), embedding.stride(0) * 4, in_hw[0] * in_hw[1]), emb_rows=spix_all,
+                noise=z_all, real=(real_features.data_ptr(), real_features.stride(0) * 4, hw), real_rows=pix_all,
+                keep_rows=ridx_all)
+        done = [0, 0]   # [updates launched, updates visited]
 
         def flush():
-            if queue:
+            if vec:
+                if done[1] > done[0]:
+                    loss_chunks.append(self.updater.run(arr[done[0]:done[1]], self.embed_dim, self.noise_dim,
+                                                        keepalive=[spix_all, pix_all, ridx_all, z_all]))
+                    done[0] = done[1]
+            elif queue:
                 loss_chunks.append(self.updater.run(list(queue), self.embed_dim, self.noise_dim, keepalive=list(keep)))
                 queue.clear()
                 keep.clear()
 
-        k = 0
         for kind, i, n_c, start, z_full, m_full, _ in plan:
             z_dev = None if z_full is None else z_full.to(dev).float().contiguous()
             m_dev = None if m_full is None else m_full.to(dev).to(torch.uint8).contiguous()
@@ -263,14 +287,16 @@ class ZS3StepFused(ZS3Step):
                         fake_c = self.generator(emb_c, z_gen)                           # `:220-222`
                     fake_by_image[i][pix_c] = fake_c                                     # `:242`
                 continue
+            k = done[1]
+            done[1] += 1
+            if vec:
+                continue
             ridx, pix, spix = ridx_all[k], pix_all[k], spix_all[k]
             emb_src = GF.row_source(embedding[i], spix, row_stride=1, col_stride=in_hw[0] * in_hw[1])
             noise_src = GF.row_source(z_all[k]) if z_dev is None else GF.row_source(z_dev, ridx)
             real_src = GF.row_source(real_features[i], pix, row_stride=1, col_stride=hw)
             queue.append(GF.pack_item(emb_src, noise_src, real_src, rows, keep_mask=m_dev, keep_rows=ridx))
             keep.extend([z_dev, m_dev])
-            owners.append(i)
-            k += 1
         flush()
         mark("generator")
         for i in range(nb):                                                              # `:244-259`
