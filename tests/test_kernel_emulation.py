@@ -231,7 +231,8 @@ def test_fused_step2_host_logic_against_step2_oracle(emul, monkeypatch):
     assert rel_l2(head.w.detach(), ref["pred_conv.weight"]) < 1e-5
 
     # default randomness (noise drawn per sampled row on the device, counter-RNG Dropout): runs and stays finite
-    step_b = ZS3StepFused(head, gen, lambda out, tg: O.cross_entropy(out, tg, weight=cw), None, opt, opt_g, seen, unseen)
+    step_b = ZS3StepFused(head, gen, lambda out, tg: O.cross_entropy(out, tg, weight=cw), None, opt, opt_g, seen, unseen,
+                          tensor_core_bulk=False)   # the image-level tcgen05 generation is GPU-only (test_step2_gpu.py)
     monkeypatch.setattr(step_b.updater, "run", lambda items, E, Z, keepalive=(): emul_run(items, E, Z, which=step_b))
     loss_b, glb_b, g_b = step_b.training_step(image, target, embedding, real_features=real)
     assert len(g_b) == 5 and all(v == v and v > 0 for v in g_b) and torch.isfinite(loss_b)

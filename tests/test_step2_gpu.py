@@ -165,3 +165,41 @@ def test_fused_step_graph_features_and_fused_classifier_loss():
     # whole step with graph features (features computed inside): runs, trains the generator, finite losses
     loss, glb, g_losses = step_g.training_step(image, target, embedding)
     assert torch.isfinite(loss) and len(g_losses) == 5
+
+
+def test_image_level_generation_on_tensor_cores_matches_per_class_generator():
+    """ZS3StepFused._generate_image (whole image, tcgen05 fp32x3 1x1 convs) == GMMNnetwork called per class on the
+    fp32 SIMT kernels with the same noise and Dropout mask (zs3/train_pascal_GMMN.py:211-222,242); 255 stays zero"""
+    import zs3_oracle as O
+    from zs3.modeling.deeplab import DeepLab
+    from zs3.modeling.gmmn import GMMNnetwork
+    from zs3.utils.loss import GMMNLoss, SegmentationLosses
+    from zs3_b200.step2 import ZS3StepFused
+    HW, C, fh = 65, 21, 17
+    target = _labels(1, HW, [[0, 17, 5]], seed=4).cuda()
+    emb_table = torch.randn(C, 300, generator=torch.Generator().manual_seed(8)) * 0.06
+    embedding = emb_table[target.cpu().clamp(max=C - 1).long()].permute(0, 3, 1, 2).contiguous().cuda()
+    model = DeepLab(num_classes=C, pretrained=False).cuda()
+    gen = GMMNnetwork(300, 300, 256, 256)
+    gen.load_state_dict(O.init_gmmn_state(seed=3))
+    gen = gen.cuda().train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    step = ZS3StepFused(model, gen, SegmentationLosses(cuda=True).build_loss("ce"), GMMNLoss(cuda=True).build_loss(), opt,
+                        torch.optim.Adam(gen.parameters(), lr=2e-4), list(range(15)), [15, 16, 17, 18, 19])
+    src = step._nearest_source_index((HW, HW), (fh, fh), target.device)
+    tg = target.reshape(1, -1)[:, src.long()].long()[0]
+    g = torch.Generator().manual_seed(2)
+    z = torch.rand(fh * fh, 300, generator=g).cuda()
+    mask = (torch.rand(fh * fh, 256, generator=g) > 0.5).to(torch.uint8).cuda()
+    fake = step._generate_image(embedding[0], src, tg, fh, fh, noise=z, keep_mask=mask)
+    emb_rows = embedding[0].reshape(300, -1)[:, src.long()].t().contiguous()
+    with torch.no_grad():
+        ref = gen(emb_rows, z, keep_mask=mask)
+    ref[tg == 255] = 0
+    assert (tg == 255).any() and float(fake[tg == 255].abs().max()) == 0.0
+    assert rel_l2(fake, ref) < 1e-4
+    # and against the CPU oracle
+    st = {k: v.detach().cpu() for k, v in gen.state_dict().items()}
+    cpu = O.gmmn_forward(st, emb_rows.cpu(), z.cpu(), training=True, keep_mask=mask.cpu().bool())
+    cpu[(tg == 255).cpu()] = 0
+    assert rel_l2(fake.cpu(), cpu) < 1e-4

@@ -118,6 +118,8 @@ def main():
         gstep.profile = None
     except Exception as e:  # the graph variant is opt-in; report instead of losing the other numbers
         res["runs"].append({"impl": "ZS3StepFused graph_features", "error": repr(e)[:300]})
+    res["runs"].append(time_steps(build(ZS3StepFused, graph_features=True, tensor_core_bulk=False),
+                                  "ZS3StepFused + graph, unseen-image features per class on the fp32 SIMT GEMM"))
     if not args.skip_unfused:
         res["runs"].append(time_steps(build(ZS3Step), "ZS3Step (module by module)"))
 

@@ -97,12 +97,16 @@ class ZS3StepFused(ZS3Step):
         mask, the work list is packed with a handful of numpy vector operations instead of per-update Python.
     """
 
-    def __init__(self, *args, noise_fn=None, index_fn=None, graph_features=False, fuse_classifier_loss=True, **kw):
+    def __init__(self, *args, noise_fn=None, index_fn=None, graph_features=False, fuse_classifier_loss=True,
+                 tensor_core_bulk=True, **kw):
         super().__init__(*args, noise_fn=noise_fn, index_fn=index_fn, **kw)
         self._device_index = index_fn is None     # default: sampled row indices drawn on the device for all updates
         from .gmmn_fused import FusedGeneratorUpdater
         self._device_noise = noise_fn is None
         self.fuse_classifier_loss = fuse_classifier_loss
+        # features for whole unseen-class images: one image-level generator pass on the tcgen05 kernel (fp32x3)
+        # instead of one fp32 SIMT GEMM pair per class
+        self.tensor_core_bulk = tensor_core_bulk
         self.profile = None   # set to {} to collect per-segment (host ms, CUDA events) of the next training_step
         # graph_features: capture the (frozen-weight, no_grad) feature extraction in a CUDA graph on first use and
         # replay it afterwards -- ~350 launches per step issued by one graph launch instead of by the interpreter
@@ -158,6 +162,38 @@ class ZS3StepFused(ZS3Step):
         """per-segment host and device milliseconds of the profiled step (call after torch.cuda.synchronize())"""
         marks = self.profile["marks"]
         return {b[0]: {"host_ms": (b[1] - a[1]) * 1e3, "gpu_ms": a[2].elapsed_time(b[2])} for a, b in zip(marks, marks[1:])}
+
+    @torch.no_grad()
+    def _generate_image(self, emb_map, src, tg_i, fh, fw, noise=None, keep_mask=None):
+        """Generated features for EVERY pixel of one image (`:211-222,242`: the reference calls the generator once
+        per class; rows are independent, so one call over all pixels with each pixel's own class embedding is the
+        same map), as two 1x1 "convolutions" over the fh x fw grid on the tcgen05 implicit-GEMM kernel in fp32x3
+        mode (zs3_b200/parity.py: three-way bf16 operand split, fp32 TMEM accumulation, ~2e-6 of an fp32 GEMM).
+        Pixels labelled 255 keep zeros, as in the reference.  `noise` [hw, noise_dim] / `keep_mask` [hw, hidden] are
+        injectable for tests (default: drawn on the device).  Returns fp32 [fh*fw, feature_dim]."""
+        from . import gmmn_ops as G
+        from . import kernels as K
+        from . import parity as P
+        upd = self.updater
+        dev = emb_map.device
+        hw, kin = fh * fw, self.embed_dim + self.noise_dim
+        x = torch.zeros((1, fh, fw, K.cpad(kin)), dtype=torch.float32, device=dev)
+        xv = x.view(hw, -1)
+        xv[:, :self.embed_dim] = emb_map.reshape(self.embed_dim, -1)[:, src.long()].t()
+        xv[:, self.embed_dim:kin] = torch.rand((hw, self.noise_dim), device=dev) if noise is None else noise
+        w1, b1, w2, b2 = (t.detach() for t in upd.params)
+        h1 = P.conv_fp32([x], [kin], w1.view(upd.hidden, kin, 1, 1), 1, 1, 1, 0, 1, upd.hidden, bias=self._pad_bias(b1))
+        hd = G.LeakyDropout.apply(h1.view(hw, -1), upd.act.negative_slope, upd.drop.p, self.generator.training, keep_mask)
+        y = P.conv_fp32([hd.view(1, fh, fw, -1)], [upd.hidden], w2.view(upd.feat, upd.hidden, 1, 1), 1, 1, 1, 0, 1,
+                        upd.feat, bias=self._pad_bias(b2))
+        out = y.view(hw, -1)[:, :upd.feat]
+        return torch.where((tg_i == 255)[:, None], torch.zeros_like(out), out)
+
+    @staticmethod
+    def _pad_bias(b):
+        from . import kernels as K
+        n = K.cpad(b.numel())
+        return b if n == b.numel() else torch.cat([b, b.new_zeros(n - b.numel())])
 
     def _classifier_loss(self, model, features, image, target):
         """criterion(forward_class_prediction(features, input_size), target).  When the criterion is this package's
@@ -216,6 +252,10 @@ class ZS3StepFused(ZS3Step):
             has_unseen = any(c in self.unseen for c in classes)
             image_has_unseen.append(has_unseen)
             need_fake = has_unseen or not self.real_seen_features
+            # nothing injected and no update interleaved with the generation: one image-level generator call
+            image_level = need_fake and has_unseen and self._device_noise and self.mask_fn is None and self.tensor_core_bulk
+            if image_level:
+                plan.append(("image", i, hw, 0, None, None, None))
             off = 0
             for c in classes:
                 n_c, start = int(hist_h[i, c]), off
@@ -224,7 +264,7 @@ class ZS3StepFused(ZS3Step):
                     continue
                 z_full = None if self._device_noise else self.noise_fn(n_c)
                 m_full = None if self.mask_fn is None else self.mask_fn(n_c)
-                if need_fake:
+                if need_fake and not image_level:
                     plan.append(("bulk", i, n_c, start, z_full, m_full, None))
                 if c in self.seen and not has_unseen:
                     plan.append(("item", i, n_c, start, z_full, m_full, None if self._device_index else self.index_fn(n_c)))
@@ -273,6 +313,10 @@ class ZS3StepFused(ZS3Step):
         for kind, i, n_c, start, z_full, m_full, _ in plan:
             z_dev = None if z_full is None else z_full.to(dev).float().contiguous()
             m_dev = None if m_full is None else m_full.to(dev).to(torch.uint8).contiguous()
+            if kind == "image":
+                flush()                                                                  # weights as of this point
+                fake_by_image[i] = self._generate_image(embedding[i], src, tg[i], fh, fw)
+                continue
             if kind == "bulk":
                 flush()                                                                  # weights as of this point
                 pix_c = order[i, start:start + n_c].long()
