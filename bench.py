@@ -306,6 +306,41 @@ def run_ours(args):
                     "frac_of_measured_bf16_peak": ftf / peak}
 
         forward_only = {"train_mode_bn": time_forward()}  # batch statistics: conv + statistics + normalisation passes
+
+        def time_forward_graph(nf=5):
+            """the same forward replayed from a CUDA graph: launch gaps out, programmatic dependent launch edges in"""
+            from zs3_b200 import functional as ZF
+            if ZF._RngState.device_counter is None:
+                ZF._RngState.device_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            static_in = devb[0][0].clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad():
+                model(static_in)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr), torch.no_grad():
+                model(static_in)
+            gr.replay()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(nf):
+                static_in.copy_(devb[i % nbuf][0], non_blocking=True)
+                ZF._RngState.device_counter.add_(1 << 32)
+                gr.replay()
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / nf
+            ftf = B * FWD_GFLOP_PER_IMG / 1e3 / (fms * 1e-3)
+            return {"ms": fms, "images_per_sec": B / (fms * 1e-3), "nominal_tflops": ftf,
+                    "frac_of_measured_bf16_peak": ftf / peak}
+
+        try:
+            forward_only["train_mode_bn_cuda_graph"] = time_forward_graph()
+        except Exception as e:  # reported, never fatal
+            forward_only["train_mode_bn_cuda_graph"] = {"error": repr(e)[:200]}
         model.eval()                                      # running statistics: BN/ReLU/residual folded into the convs
         forward_only["eval_mode_bn_fused_epilogue"] = time_forward()
         model.train()
