@@ -25,6 +25,7 @@
 
 struct emul_dim3 { unsigned x, y, z; };
 struct float4 { float x, y, z, w; } __attribute__((aligned(16)));
+struct float2 { float x, y; } __attribute__((aligned(8)));
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 struct EmulWarp { pthread_barrier_t bar; float fbuf[32]; int ibuf[32]; };

@@ -35,6 +35,7 @@
 namespace zs3 {
 
 constexpr int FT = 32;          // output tile edge
+constexpr int FTR = 16;         // rows of the tiles of P1-P5 (their 32-row tiling leaves >= half of the grid idle)
 constexpr int FKC = 128;        // k extent staged per chunk: 8 warps x 16
 constexpr int FLD = 36;         // pitch of a staged [k][32] panel (floats); keeps rows 16-byte aligned
 constexpr int FTHREADS = 256;
@@ -69,7 +70,7 @@ struct FusedP {
   float* P;       // [2*FMAXB][2*FMAXB]
   float* dY;      // [FMAXB][F]
   float* dH;      // [FMAXB][H]
-  double* lossp;  // [64] per-tile partial sums of loss^2
+  double* lossp;  // [128] per-tile partial sums of loss^2 (P3: 16 x 8 tiles at most)
   unsigned* barrier;
   unsigned long long* stamps;  // optional [n_items][8] %globaltimer at the phase boundaries
 };
@@ -117,61 +118,65 @@ __device__ __forceinline__ void phase_stamp(unsigned long long* stamps, int w, i
 }
 
 // Panel staging, split in two halves so that the global loads of chunk c+1 are in flight while chunk c is being
-// consumed: panel_load reads this thread's 16 elements of the [FKC k][32 rows] panel (rows r0.., k range k0..; zero
-// outside [R) x [K)) into registers, panel_store writes them to shared memory as S[k][row].
-__device__ __forceinline__ void panel_load(float (&v)[16], const Opnd o, int r0, int R, int k0, int K) {
+// consumed: panel_load reads this thread's PR/2 elements of the [FKC k][PR rows] panel (rows r0.., k range k0..; zero
+// outside [R) x [K)) into registers, panel_store writes them to shared memory as S[k][row].  PR = 32 or 16.
+template <int PR>
+__device__ __forceinline__ void panel_load(float (&v)[PR / 2], const Opnd o, int r0, int R, int k0, int K) {
   if (o.kcontig) {
     const int k = threadIdx.x & (FKC - 1);
-    const int rb = (threadIdx.x >> 7) * 16;  // rows rb .. rb+15 (lanes of a warp: consecutive k -> coalesced)
+    const int rb = (threadIdx.x >> 7) * (PR / 2);  // PR/2 consecutive rows (lanes of a warp: consecutive k -> coalesced)
     const bool kin = (k0 + k) < K;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
+    for (int e = 0; e < PR / 2; ++e) {
       const int r = rb + e;
       v[e] = (kin && (r0 + r) < R) ? __ldcg(o.p + (long long)(r0 + r) * o.ld + (k0 + k)) : 0.f;
     }
   } else {
-    const int r = threadIdx.x & 31;
-    const int kb = threadIdx.x >> 5;  // 0..7
+    const int r = threadIdx.x & (PR - 1);
+    const int kb = threadIdx.x / PR;  // 0 .. 256/PR - 1
     const bool rin = (r0 + r) < R;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int k = kb + 8 * e;
+    for (int e = 0; e < PR / 2; ++e) {
+      const int k = kb + (FTHREADS / PR) * e;
       v[e] = (rin && (k0 + k) < K) ? __ldcg(o.p + (long long)(k0 + k) * o.ld + (r0 + r)) : 0.f;
     }
   }
 }
 
-__device__ __forceinline__ void panel_store(float* __restrict__ S, const float (&v)[16], const Opnd o) {
+template <int PR>
+__device__ __forceinline__ void panel_store(float* __restrict__ S, const float (&v)[PR / 2], const Opnd o) {
   if (o.kcontig) {
-    // one thread = 16 consecutive rows of one k: four 128-bit stores; a quarter warp (8 consecutive k, pitch 36)
+    // one thread = PR/2 consecutive rows of one k: 128-bit stores; a quarter warp (8 consecutive k, pitch 36)
     // covers all 32 banks exactly once
     const int k = threadIdx.x & (FKC - 1);
-    const int rb = (threadIdx.x >> 7) * 16;
+    const int rb = (threadIdx.x >> 7) * (PR / 2);
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
+    for (int e = 0; e < PR / 8; ++e)
       *reinterpret_cast<float4*>(S + k * FLD + rb + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
   } else {
-    const int r = threadIdx.x & 31;
-    const int kb = threadIdx.x >> 5;
+    const int r = threadIdx.x & (PR - 1);
+    const int kb = threadIdx.x / PR;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) S[(kb + 8 * e) * FLD + r] = v[e];
+    for (int e = 0; e < PR / 2; ++e) S[(kb + (FTHREADS / PR) * e) * FLD + r] = v[e];
   }
 }
 
-// One 32x32 output tile: out(i, j) = sum_k f(A(i,k), B(j,k)) with
+// One RT x 32 output tile (RT = 32 or 16 rows): out(i, j) = sum_k f(A(i,k), B(j,k)) with
 //   OP_DOT   f = a*b            OP_DIST  f = (a-b)^2            OP_WDIFF f = a*(b - Cmat[i][j])
 // 8 warps split every staged k chunk (16 k each); warp partials are summed in warp order through shared memory and
-// epi(i, j, value) is called once per in-range output element (consecutive threads = consecutive j).
-template <int OP, class Epi>
+// epi(i, j, value) is called once per in-range output element (consecutive threads = consecutive j).  The 16-row
+// variant doubles the number of tiles of a phase whose 32-row tiling would leave most of the grid without work.
+template <int OP, int RT, class Epi>
 __device__ __forceinline__ void tile32(float* __restrict__ sm, const Opnd A, int i0, int M, const Opnd B, int j0, int N,
                                        int K, const float* __restrict__ Cmat, int ldc, Epi epi) {
+  constexpr int RX = RT / 8;  // rows per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int li = lane >> 2, lj = lane & 3;
   float* As = sm;
   float* Bs = sm + FKC * FLD;
-  float acc[4][8], c[4][8];
+  float acc[RX][8], c[RX][8];
 #pragma unroll
-  for (int x = 0; x < 4; ++x)
+  for (int x = 0; x < RX; ++x)
 #pragma unroll
     for (int y = 0; y < 8; ++y) {
       acc[x][y] = 0.f;
@@ -179,36 +184,42 @@ __device__ __forceinline__ void tile32(float* __restrict__ sm, const Opnd A, int
     }
   if (OP == OP_WDIFF) {
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < RX; ++x)
 #pragma unroll
       for (int y = 0; y < 8; ++y) {
-        const int i = i0 + li * 4 + x, j = j0 + lj * 8 + y;
+        const int i = i0 + li * RX + x, j = j0 + lj * 8 + y;
         if (i < M && j < N) c[x][y] = __ldcg(Cmat + (long long)i * ldc + j);
       }
   }
-  float va[16], vb[16];
-  panel_load(va, A, i0, M, 0, K);
-  panel_load(vb, B, j0, N, 0, K);
+  float va[RT / 2], vb[16];
+  panel_load<RT>(va, A, i0, M, 0, K);
+  panel_load<32>(vb, B, j0, N, 0, K);
   for (int k0 = 0; k0 < K; k0 += FKC) {
     __syncthreads();  // the previous chunk (or the previous tile's reduction buffer) is no longer being read
-    panel_store(As, va, A);
-    panel_store(Bs, vb, B);
+    panel_store<RT>(As, va, A);
+    panel_store<32>(Bs, vb, B);
     __syncthreads();
     if (k0 + FKC < K) {  // next chunk's loads overlap this chunk's arithmetic
-      panel_load(va, A, i0, M, k0 + FKC, K);
-      panel_load(vb, B, j0, N, k0 + FKC, K);
+      panel_load<RT>(va, A, i0, M, k0 + FKC, K);
+      panel_load<32>(vb, B, j0, N, k0 + FKC, K);
     }
     if (k0 + warp * 16 < K) {
 #pragma unroll 4
       for (int kk = 0; kk < 16; ++kk) {
         const int k = warp * 16 + kk;
-        const float4 a4 = *reinterpret_cast<const float4*>(As + k * FLD + li * 4);
+        float av[RX];
+        if (RX == 4) {
+          const float4 a4 = *reinterpret_cast<const float4*>(As + k * FLD + li * 4);
+          av[0] = a4.x; av[1] = a4.y; av[RX - 2] = a4.z; av[RX - 1] = a4.w;
+        } else {
+          const float2 a2 = *reinterpret_cast<const float2*>(As + k * FLD + li * 2);
+          av[0] = a2.x; av[1] = a2.y;
+        }
         const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * FLD + lj * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * FLD + lj * 8 + 4);
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < RX; ++x)
 #pragma unroll
           for (int y = 0; y < 8; ++y) {
             if (OP == OP_DOT) {
@@ -224,20 +235,20 @@ __device__ __forceinline__ void tile32(float* __restrict__ sm, const Opnd A, int
     }
   }
   __syncthreads();  // every warp is done with the staged panels: reuse the buffer for the reduction
-  float* red = sm;  // [8 warps][32][32]
+  float* red = sm;  // [8 warps][RT][32]
 #pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    float* dst = red + warp * (FT * FT) + (li * 4 + x) * FT + lj * 8;
+  for (int x = 0; x < RX; ++x) {
+    float* dst = red + warp * (RT * FT) + (li * RX + x) * FT + lj * 8;
     *reinterpret_cast<float4*>(dst) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
     *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[x][4], acc[x][5], acc[x][6], acc[x][7]);
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < RT / 8; ++q) {
     const int e = threadIdx.x + FTHREADS * q;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w * (FT * FT) + e];
+    for (int w = 0; w < 8; ++w) s += red[w * (RT * FT) + e];
     const int i = i0 + (e >> 5), j = j0 + (e & 31);
     if (i < M && j < N) epi(i, j, s);
   }
@@ -328,20 +339,21 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     const int B = min(it.rows, FMAXB), L = 2 * B;
     float* Xin = p.Xin + (size_t)(w & 1) * FMAXB * K1;
     float* X = p.X + (size_t)(w & 1) * 2 * FMAXB * F;
-    const int tB = (B + FT - 1) / FT, tL = (L + FT - 1) / FT, tH = (H + FT - 1) / FT, tF = (F + FT - 1) / FT;
+    const int tL = (L + FT - 1) / FT, tH = (H + FT - 1) / FT, tF = (F + FT - 1) / FT;
     const int tK1 = (K1 + FT - 1) / FT;
+    const int tBr = (B + FTR - 1) / FTR, tLr = (L + FTR - 1) / FTR;  // row tiles of P1-P5
 
     // ---- P1: Hd = dropout(leaky(Xin W1^T + b1)); the CTAs without a tile gather the rows of item w+1 into the
     //          other Xin / X buffers (last read in P6 of item w-1, i.e. before the previous grid barrier)
     const int ng = (w + 1 < p.n_items) ? (min(sh_item[1].rows, FMAXB) + FGATHER_ROWS - 1) / FGATHER_ROWS : 0;
-    for (int u = blockIdx.x; u < tB * tH + ng; u += gridDim.x) {
-      if (u >= tB * tH) {
-        gather_rows(p, sh_item[1], u - tB * tH, p.Xin + (size_t)((w + 1) & 1) * FMAXB * K1,
+    for (int u = blockIdx.x; u < tBr * tH + ng; u += gridDim.x) {
+      if (u >= tBr * tH) {
+        gather_rows(p, sh_item[1], u - tBr * tH, p.Xin + (size_t)((w + 1) & 1) * FMAXB * K1,
                     p.X + (size_t)((w + 1) & 1) * 2 * FMAXB * F);
         continue;
       }
-      const int i0 = (u / tH) * FT, j0 = (u % tH) * FT;
-      tile32<OP_DOT>(sm, Opnd{Xin, K1, 1}, i0, B, Opnd{p.W1, K1, 1}, j0, H, K1, nullptr, 0,
+      const int i0 = (u / tH) * FTR, j0 = (u % tH) * FT;
+      tile32<OP_DOT, FTR>(sm, Opnd{Xin, K1, 1}, i0, B, Opnd{p.W1, K1, 1}, j0, H, K1, nullptr, 0,
                      [&](int i, int j, float v) {
                        v += __ldcg(p.b1 + j);
                        v = v > 0.f ? v : v * p.slope;
@@ -365,9 +377,9 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     phase_stamp(p.stamps, w, 1);
 
     // ---- P2: Y = Hd W2^T + b2 -> X[0:B]
-    for (int u = blockIdx.x; u < tB * tF; u += gridDim.x) {
-      const int i0 = (u / tF) * FT, j0 = (u % tF) * FT;
-      tile32<OP_DOT>(sm, Opnd{p.Hd, H, 1}, i0, B, Opnd{p.W2, H, 1}, j0, F, H, nullptr, 0,
+    for (int u = blockIdx.x; u < tBr * tF; u += gridDim.x) {
+      const int i0 = (u / tF) * FTR, j0 = (u % tF) * FT;
+      tile32<OP_DOT, FTR>(sm, Opnd{p.Hd, H, 1}, i0, B, Opnd{p.W2, H, 1}, j0, F, H, nullptr, 0,
                      [&](int i, int j, float v) { X[(long long)i * F + j] = v + __ldcg(p.b2 + j); });
     }
     grid_barrier(p.barrier, bar_target);
@@ -375,10 +387,10 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
 
     // ---- P3: P_ij = s_i s_j sum_sigma exp(e_ij/sigma)/sigma, loss^2 partial per tile; e_ij = -|x_i - x_j|^2 / 2.
     // get_scale_matrix quirk (loss.py:92-97): the FIRST N rows carry +1/N, the last M rows -1/M (M = N = B here).
-    for (int u = blockIdx.x; u < tL * tL; u += gridDim.x) {
-      const int i0 = (u / tL) * FT, j0 = (u % tL) * FT;
+    for (int u = blockIdx.x; u < tLr * tL; u += gridDim.x) {
+      const int i0 = (u / tL) * FTR, j0 = (u % tL) * FT;
       float part = 0.f;
-      tile32<OP_DIST>(sm, Opnd{X, F, 1}, i0, L, Opnd{X, F, 1}, j0, L, F, nullptr, 0, [&](int i, int j, float d2) {
+      tile32<OP_DIST, FTR>(sm, Opnd{X, F, 1}, i0, L, Opnd{X, F, 1}, j0, L, F, nullptr, 0, [&](int i, int j, float d2) {
         const float si = i < B ? 1.f / B : -1.f / B;
         const float sj = j < B ? 1.f / B : -1.f / B;
         const float e = -0.5f * d2;
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     //          dY_i = 1/loss * sum_j P_ij (x_j - x_i), i < B
     if (threadIdx.x == 0) {
       double s = 0;
-      for (int t = 0; t < tL * tL; ++t) s += __ldcg(p.lossp + t);
+      for (int t = 0; t < tLr * tL; ++t) s += __ldcg(p.lossp + t);
       const float loss = sqrtf((float)s);
       sh_scalar[0] = loss;
       if (blockIdx.x == 0) p.losses[w] = loss;
@@ -416,9 +428,9 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     __syncthreads();
     {
       const float inv_loss = 1.f / sh_scalar[0];
-      for (int u = blockIdx.x; u < tB * tF; u += gridDim.x) {
-        const int i0 = (u / tF) * FT, j0 = (u % tF) * FT;
-        tile32<OP_WDIFF>(sm, Opnd{p.P, L, 1}, i0, B, Opnd{X, F, 0}, j0, F, L, X, F,
+      for (int u = blockIdx.x; u < tBr * tF; u += gridDim.x) {
+        const int i0 = (u / tF) * FTR, j0 = (u % tF) * FT;
+        tile32<OP_WDIFF, FTR>(sm, Opnd{p.P, L, 1}, i0, B, Opnd{X, F, 0}, j0, F, L, X, F,
                          [&](int i, int j, float v) { p.dY[(long long)i * F + j] = inv_loss * v; });
       }
     }
@@ -426,9 +438,9 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     phase_stamp(p.stamps, w, 4);
 
     // ---- P5: dH = (dY W2) * d/dh[dropout(leaky(h))], reconstructed from the forward output Hd
-    for (int u = blockIdx.x; u < tB * tH; u += gridDim.x) {
-      const int i0 = (u / tH) * FT, j0 = (u % tH) * FT;
-      tile32<OP_DOT>(sm, Opnd{p.dY, F, 1}, i0, B, Opnd{p.W2, H, 0}, j0, H, F, nullptr, 0, [&](int i, int j, float v) {
+    for (int u = blockIdx.x; u < tBr * tH; u += gridDim.x) {
+      const int i0 = (u / tH) * FTR, j0 = (u % tH) * FT;
+      tile32<OP_DOT, FTR>(sm, Opnd{p.dY, F, 1}, i0, B, Opnd{p.W2, H, 0}, j0, H, F, nullptr, 0, [&](int i, int j, float v) {
         const float hv = __ldcg(p.Hd + (long long)i * H + j);
         p.dH[(long long)i * H + j] = v * (hv > 0.f ? ks : (hv < 0.f ? p.slope * ks : 0.f));
       });
@@ -444,14 +456,14 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
       for (int u = blockIdx.x; u < total; u += gridDim.x) {
         if (u < n1) {
           const int i0 = (u / tK1) * FT, j0 = (u % tK1) * FT;
-          tile32<OP_DOT>(sm, Opnd{p.dH, H, 0}, i0, H, Opnd{Xin, K1, 0}, j0, K1, B, nullptr, 0,
+          tile32<OP_DOT, FT>(sm, Opnd{p.dH, H, 0}, i0, H, Opnd{Xin, K1, 0}, j0, K1, B, nullptr, 0,
                          [&](int i, int j, float v) {
                            apply_grad(p, p.W1, p.mW1, p.vW1, p.gW1, (long long)i * K1 + j, v, bc1, bc2s);
                          });
         } else if (u < n1 + n2) {
           const int t = u - n1;
           const int i0 = (t / tH) * FT, j0 = (t % tH) * FT;
-          tile32<OP_DOT>(sm, Opnd{p.dY, F, 0}, i0, F, Opnd{p.Hd, H, 0}, j0, H, B, nullptr, 0,
+          tile32<OP_DOT, FT>(sm, Opnd{p.dY, F, 0}, i0, F, Opnd{p.Hd, H, 0}, j0, H, B, nullptr, 0,
                          [&](int i, int j, float v) {
                            apply_grad(p, p.W2, p.mW2, p.vW2, p.gW2, (long long)i * H + j, v, bc1, bc2s);
                          });
@@ -492,7 +504,7 @@ static FusedLayout fused_layout(int E, int Z, int H, int F) {
   l.pm = o; o += align256(sizeof(float) * 4 * FMAXB * FMAXB);
   l.dy = o; o += align256(sizeof(float) * FMAXB * (size_t)F);
   l.dh = o; o += align256(sizeof(float) * FMAXB * (size_t)H);
-  l.lossp = o; o += align256(sizeof(double) * 64);
+  l.lossp = o; o += align256(sizeof(double) * 128);
   l.barrier = o; o += 256;
   l.total = o;
   return l;
