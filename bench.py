@@ -337,10 +337,11 @@ def run_ours(args):
             return {"ms": fms, "images_per_sec": B / (fms * 1e-3), "nominal_tflops": ftf,
                     "frac_of_measured_bf16_peak": ftf / peak}
 
-        try:
-            forward_only["train_mode_bn_cuda_graph"] = time_forward_graph()
-        except Exception as e:  # reported, never fatal
-            forward_only["train_mode_bn_cuda_graph"] = {"error": repr(e)[:200]}
+        if world == 1:  # (stream capture next to other ranks' NCCL teardown is not worth the risk for a side figure)
+            try:
+                forward_only["train_mode_bn_cuda_graph"] = time_forward_graph()
+            except Exception as e:  # reported, never fatal
+                forward_only["train_mode_bn_cuda_graph"] = {"error": repr(e)[:200]}
         model.eval()                                      # running statistics: BN/ReLU/residual folded into the convs
         forward_only["eval_mode_bn_fused_epilogue"] = time_forward()
         model.train()

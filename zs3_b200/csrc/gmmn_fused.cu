@@ -418,14 +418,20 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
 
     // ---- P4: loss = sqrt(sum of partials) (NaN for a negative sum, like the reference: loss.py:114);
     //          dY_i = 1/loss * sum_j P_ij (x_j - x_i), i < B
-    if (threadIdx.x == 0) {
-      double s = 0;
-      for (int t = 0; t < tLr * tL; ++t) s += __ldcg(p.lossp + t);
-      const float loss = sqrtf((float)s);
-      sh_scalar[0] = loss;
-      if (blockIdx.x == 0) p.losses[w] = loss;
+    {  // the <= 128 partials are fetched by 128 threads at once (one L2 round trip instead of 128 dependent ones)
+       // and summed from shared memory in index order, so every CTA derives the same bits
+      double* part = reinterpret_cast<double*>(sm);  // the staging buffer is free between phases
+      if (threadIdx.x < 128) part[threadIdx.x] = threadIdx.x < tLr * tL ? __ldcg(p.lossp + threadIdx.x) : 0.0;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0;
+        for (int t = 0; t < tLr * tL; ++t) s += part[t];
+        const float loss = sqrtf((float)s);
+        sh_scalar[0] = loss;
+        if (blockIdx.x == 0) p.losses[w] = loss;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     {
       const float inv_loss = 1.f / sh_scalar[0];
       for (int u = blockIdx.x; u < tBr * tF; u += gridDim.x) {
