@@ -458,35 +458,38 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     {
       const float bc1 = sh_scalar[1], bc2s = sh_scalar[2];
       const int n1 = tH * tK1, n2 = tF * tH;
-      const int total = n1 + n2 + 2;
+      const int total = 2 + n1 + n2;
+      // units 0 / 1 = the bias gradients (column sums over the B rows: 32 independent loads in flight per thread,
+      // 4 round trips instead of B dependent ones); they come first so that they never queue behind a tile
       for (int u = blockIdx.x; u < total; u += gridDim.x) {
-        if (u < n1) {
-          const int i0 = (u / tK1) * FT, j0 = (u % tK1) * FT;
+        if (u == 0) {
+          for (int h = threadIdx.x; h < H; h += FTHREADS) {
+            float s = 0.f;
+#pragma unroll 32
+            for (int r = 0; r < B; ++r) s += __ldcg(p.dH + (long long)r * H + h);
+            apply_grad(p, p.b1, p.mb1, p.vb1, p.gb1, h, s, bc1, bc2s);
+          }
+        } else if (u == 1) {
+          for (int o = threadIdx.x; o < F; o += FTHREADS) {
+            float s = 0.f;
+#pragma unroll 32
+            for (int r = 0; r < B; ++r) s += __ldcg(p.dY + (long long)r * F + o);
+            apply_grad(p, p.b2, p.mb2, p.vb2, p.gb2, o, s, bc1, bc2s);
+          }
+        } else if (u < 2 + n1) {
+          const int t = u - 2;
+          const int i0 = (t / tK1) * FT, j0 = (t % tK1) * FT;
           tile32<OP_DOT, FT>(sm, Opnd{p.dH, H, 0}, i0, H, Opnd{Xin, K1, 0}, j0, K1, B, nullptr, 0,
                          [&](int i, int j, float v) {
                            apply_grad(p, p.W1, p.mW1, p.vW1, p.gW1, (long long)i * K1 + j, v, bc1, bc2s);
                          });
-        } else if (u < n1 + n2) {
-          const int t = u - n1;
+        } else {
+          const int t = u - 2 - n1;
           const int i0 = (t / tH) * FT, j0 = (t % tH) * FT;
           tile32<OP_DOT, FT>(sm, Opnd{p.dY, F, 0}, i0, F, Opnd{p.Hd, H, 0}, j0, H, B, nullptr, 0,
                          [&](int i, int j, float v) {
                            apply_grad(p, p.W2, p.mW2, p.vW2, p.gW2, (long long)i * H + j, v, bc1, bc2s);
                          });
-        } else if (u == n1 + n2) {
-          for (int h = threadIdx.x; h < H; h += FTHREADS) {
-            float s = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < B; ++r) s += __ldcg(p.dH + (long long)r * H + h);
-            apply_grad(p, p.b1, p.mb1, p.vb1, p.gb1, h, s, bc1, bc2s);
-          }
-        } else {
-          for (int o = threadIdx.x; o < F; o += FTHREADS) {
-            float s = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < B; ++r) s += __ldcg(p.dY + (long long)r * F + o);
-            apply_grad(p, p.b2, p.mb2, p.vb2, p.gb2, o, s, bc1, bc2s);
-          }
         }
       }
     }
