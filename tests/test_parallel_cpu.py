@@ -94,3 +94,66 @@ def test_two_rank_gloo_allreduce_matches_full_batch():
     full = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     assert torch.allclose(got[0], got[1])
     assert torch.allclose(got[0], full, atol=1e-6)
+
+
+class _FreeingBlock(torch.autograd.Function):
+    """y = tanh(x * w); drops its saved state after backward like the fused network nodes (functional.BottleneckFn),
+    so a node that is run twice fails loudly.  in_place=True mimics the nodes that add the weight gradient into
+    w.grad themselves and return None for it (KRSC conv weights, functional.py)."""
+
+    @staticmethod
+    def forward(ctx, x, w, in_place):
+        ctx.saved = (x, w, in_place)
+        return torch.tanh(x * w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, in_place = ctx.saved
+        ctx.saved = None
+        d = g * (1 - torch.tanh(x * w) ** 2)
+        gw = (d * x).sum().reshape(w.shape)
+        if in_place:
+            w.grad = gw if w.grad is None else w.grad + gw
+            gw = None
+        return d * w, gw, None
+
+
+def _toy_forward(ws, inp, alias):
+    """stem -> layer1 (= low-level feature) -> layer2 (= x) | layer3(x) + decoder(low) -> loss: the shape of the
+    DeepLab graph around the backbone cut (zs3_b200/modeling/backbone/resnet.py)"""
+    h = _FreeingBlock.apply(inp, ws[0], False)
+    low = _FreeingBlock.apply(h, ws[1], True)
+    x = _FreeingBlock.apply(low, ws[2], False)
+    low_dec = low.view_as(low) if alias else low
+    out = _FreeingBlock.apply(x, ws[3], True) + _FreeingBlock.apply(low_dec, ws[4], False)
+    return (out ** 2).mean(), (x, low_dec)
+
+
+def test_cut_backward_two_stage_equals_single_pass():
+    """parallel.cut_backward: gradients above the cut first (so their all-reduce can start), the rest in tail();
+    the cut has to be an antichain -- naming layer1's output itself (upstream of layer2's output) would hand the
+    decoder's gradient AND layer2's gradient to the same tensor, i.e. stage 1 would have to run layer2"""
+    from zs3_b200.parallel import cut_backward
+    torch.manual_seed(0)
+    inp = torch.randn(4, 5)
+    w0 = [torch.randn(1).requires_grad_(True) for _ in range(5)]
+    loss, _ = _toy_forward(w0, inp, alias=True)
+    loss.backward()
+    ref = [w.grad.clone() for w in w0]
+
+    w1 = [w.detach().clone().requires_grad_(True) for w in w0]
+    loss, cut = _toy_forward(w1, inp, alias=True)
+    tail = cut_backward(loss, list(cut), [w1[3], w1[4]])
+    assert w1[3].grad is not None and w1[4].grad is not None           # above the cut: ready before the tail
+    assert all(w.grad is None for w in w1[:3])                        # below the cut: untouched so far
+    assert torch.allclose(w1[3].grad, ref[3]) and torch.allclose(w1[4].grad, ref[4])
+    tail()
+    for a, b in zip(w1, ref):
+        assert torch.allclose(a.grad, b, atol=1e-7)
+    # a second step accumulates onto existing .grad buffers (the flat gradient buffer is zeroed, not dropped)
+    for w in w1:
+        w.grad.zero_()
+    loss, cut = _toy_forward(w1, inp, alias=True)
+    cut_backward(loss, list(cut), [w1[3], w1[4]])()
+    for a, b in zip(w1, ref):
+        assert torch.allclose(a.grad, b, atol=1e-7)

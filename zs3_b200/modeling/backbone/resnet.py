@@ -4,6 +4,8 @@ Parameter names, shapes, initialisation and the output-stride handling follow zs
 (so state_dict()s are interchangeable); the tree is generated from the tables in modeling/_build.py and every
 block executes as ONE fused autograd node (functional.BottleneckFn) on NHWC bf16 activations.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -30,6 +32,8 @@ class Bottleneck(nn.Module):
         """x: NHWC bf16 [N, H, W, cpad(inplanes)]"""
         return ZF.bottleneck(self, x)
 
+
+_DP_CUT = os.environ.get("ZS3_DP_CUT", "0") == "1"
 
 class ResNet(nn.Module):
     """stem + 4 residual stages; returns (stage-4 features, stage-1 'low level' features), reference resnet.py:56-226"""
@@ -75,7 +79,13 @@ class ResNet(nn.Module):
         # the activations that separate {stem, layer1, layer2} from the rest of the network: the data-parallel
         # runtime cuts the backward pass here to overlap the gradient all-reduce of everything above the cut
         # (97 % of the parameters) with the backward of everything below it
-        self.last_cut = (x, low_level_feat)
+        # (opt-in, ZS3_DP_CUT=1, see parallel.py.  The decoder then consumes an ALIAS of layer1's output:
+        # low_level_feat itself is upstream of x, and a cut must be an antichain -- with the alias, the decoder's
+        # gradient arrives at a node of its own.)
+        self.last_cut = None
+        if _DP_CUT:
+            low_level_feat = low_level_feat.view_as(low_level_feat)
+            self.last_cut = (x, low_level_feat)
         x = self.layer4(self.layer3(x))
         return x, low_level_feat
 

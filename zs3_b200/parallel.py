@@ -132,6 +132,32 @@ class HostPrefetcher:
         self.consumed[k] = ev
 
 
+def cut_backward(loss, cut, early_params):
+    """Two-stage backward.  Stage 1 (run here): gradients of `loss` w.r.t. the `cut` activations and the parameters
+    above them (`early_params`; accumulated into .grad -- by the fused nodes themselves where they write the weight
+    gradient in place, otherwise here).  Returns tail(), which backpropagates the cut gradients through everything
+    below.  Two requirements, both learnt from the first 2-GPU run of this path:
+      * the cut must be an antichain of the autograd graph (no cut tensor upstream of another);
+      * stage 1 must CAPTURE the gradients at the cut (torch.autograd.grad): `backward(inputs=[non-leaf])` executes
+        the node that produced the tensor, which the tail then finds already run (and, for the fused nodes, freed)."""
+    early_params = list(early_params)
+    got = torch.autograd.grad(loss, list(cut) + early_params, allow_unused=True)
+    grads = list(got[:len(cut)])
+    with torch.no_grad():
+        for p, g in zip(early_params, got[len(cut):]):
+            if g is not None:  # (None: the node accumulated into p.grad itself)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.add_(g)
+
+    def tail():
+        live = [(t, g) for t, g in zip(cut, grads) if g is not None]
+        torch.autograd.backward([t for t, _ in live], [g for _, g in live])
+
+    return tail
+
+
 class DataParallelTrainer:
     """step-1 training step of zs3/base_trainer.py:16-20 (zero_grad, forward, CE, backward, SGD) for one rank."""
 
@@ -157,9 +183,16 @@ class DataParallelTrainer:
                                                       m.weight.data_ptr())
         # parameters above the backbone cut (layer3 .. decoder): one contiguous range of the flat buffers, reduced
         # while the rest of the backward still runs (see _finish_distributed)
+        # Status: OFF unless ZS3_DP_CUT=1.  The first version failed its 2-GPU run (profiles/r01_dp_cut_failure.md):
+        # stage 1 used backward(inputs=[cut tensors]), which executes the nodes that PRODUCED the cut tensors, and the
+        # cut named low_level_feat, which is upstream of layer2's output.  cut_backward() now captures the cut
+        # gradients with torch.autograd.grad and the backbone hands the decoder an alias of low_level_feat; the
+        # two-stage logic is CPU-tested (tests/test_parallel_cpu.py) but not re-validated on GPUs, so the default is
+        # the flow measured in profiles/r01_bench_dp{2,4,8}.json: the whole backward from the graph, then ONE
+        # all-reduce over the flat gradient buffer.
         self.early_range, self.early_params = None, []
         bb = getattr(model, "backbone", None)
-        if world_size > 1 and bb is not None and hasattr(bb, "layer3"):
+        if world_size > 1 and bb is not None and hasattr(bb, "layer3") and os.environ.get("ZS3_DP_CUT", "0") == "1":
             first = next(iter(bb.layer3.parameters()), None)
             if first is not None and first.grad is not None:
                 a = (first.grad.data_ptr() - self.flat.grad.data_ptr()) // self.flat.grad.element_size()
@@ -241,16 +274,7 @@ class DataParallelTrainer:
         if self.early_range is None or cut is None or not all(t.requires_grad for t in cut):
             loss.backward()
             return loss, None
-        cut = list(cut)
-        for t in cut:
-            t.grad = None
-        torch.autograd.backward(loss, inputs=cut + self.early_params)
-        grads = [t.grad for t in cut]
-
-        def tail():
-            torch.autograd.backward(cut, grads)
-
-        return loss, tail
+        return loss, cut_backward(loss, list(cut), self.early_params)
 
     def _finish_distributed(self, tail):
         """all-reduce (sum) + optimizer.  With a cut: the gradients above it (one contiguous range of the flat
