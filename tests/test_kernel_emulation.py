@@ -398,3 +398,110 @@ def test_vectorized_item_packing_equals_per_item_packing():
              for k, i in enumerate(images)]
     assert GF.items_to_bytes(arr) == GF.items_to_bytes(items)
     assert GF.items_to_bytes(arr[1:3]) == GF.items_to_bytes(items[1:3])
+
+
+def test_gcn_context_step_host_logic_against_oracle(emul, graph_emul, monkeypatch):
+    """ZS3StepGCN (config 5, zs3/train_context_GMMN_GCNcontext.py:270-460) on CPU tensors: cluster graphs from the
+    host-emulated zs3_label_components, generator updates through the host-emulated fused kernel, plain-torch
+    stand-ins for the DeepLab head and the two generators; held against oracle step2(..., gcn=...)."""
+    import torch.nn.functional as F
+    import zs3_oracle as O
+    import zs3_step2_oracle as S
+    from test_step2_gpu import Replay, _labels
+    from zs3_b200 import gmmn_fused as GF
+    from zs3_b200 import graph as ZG
+    from zs3_b200.modeling.gmmn import GMMNnetwork_GCN
+    from zs3_b200.step2 import ZS3StepGCN
+
+    B, HW, NC, fh = 3, 33, 21, 9
+    unseen, seen = [15, 16, 17, 18, 19], [c for c in range(21) if c not in (15, 16, 17, 18, 19)]
+    target = _labels(B, HW, [[0, 3, 7], [0, 17, 5], [2, 9]], seed=4)
+    emb_table = torch.randn(NC, 300, generator=torch.Generator().manual_seed(8)) * 0.06
+    embedding = emb_table[target.clamp(max=NC - 1).long()].permute(0, 3, 1, 2).contiguous()
+    image = torch.zeros(B, 3, HW, HW)
+    real = torch.relu(torch.randn(B, 256, fh, fh, generator=torch.Generator().manual_seed(2)))
+    gst = O.init_gmmn_state(seed=3)
+    torch.manual_seed(12)
+    gcn_state = {k: v.detach().clone() for k, v in GMMNnetwork_GCN().state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    st = {"decoder.pred_conv.weight": torch.randn(NC, 256, 1, 1, generator=g) * 0.05,
+          "decoder.pred_conv.bias": torch.zeros(NC)}
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(st["decoder.pred_conv.weight"].clone())
+            self.b = torch.nn.Parameter(st["decoder.pred_conv.bias"].clone())
+
+        def forward_class_prediction(self, x, size):
+            return F.interpolate(F.conv2d(x, self.w, self.b), size=tuple(size), mode="bilinear", align_corners=True)
+
+    class Gen(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Sequential(torch.nn.Linear(600, 256), torch.nn.LeakyReLU(0.2), torch.nn.Dropout(0.5),
+                                             torch.nn.Linear(256, 256))
+            self.load_state_dict(gst)
+
+        def forward(self, emb, z, keep_mask=None):
+            return O.gmmn_forward(dict(self.state_dict()), emb, z, training=True, keep_mask=keep_mask)
+
+    class GenGCN(torch.nn.Module):         # gmmn.py:52-67 on the oracle's graph convolution (differentiable torch ops)
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.ParameterDict({k.replace(".", "_"): torch.nn.Parameter(v.clone()) for k, v in gcn_state.items()})
+
+        def forward(self, emb, z, adj, keep_mask=None):
+            stt = {k.replace("_", ".", 1): v for k, v in self.p.items()}
+            return O.gmmn_gcn_forward(stt, emb, z, adj, training=True, keep_mask=keep_mask)
+
+    head, gen, gen_gcn = Head(), Gen().train(), GenGCN()
+    cw = torch.ones(NC)
+    cw[unseen] = 100.0
+    opt = torch.optim.SGD(head.parameters(), lr=0.07, momentum=0.9, weight_decay=5e-4)
+    rp, rp_gcn = Replay(77), Replay(91)
+    step = ZS3StepGCN(head, gen, lambda out, tg: O.cross_entropy(out, tg, weight=cw), O.moment_loss, opt,
+                      torch.optim.Adam(gen.parameters(), lr=2e-4), seen, unseen, noise_fn=rp.noise, index_fn=rp.index,
+                      mask_fn=rp.mask, generator_gcn=gen_gcn,
+                      optimizer_generator_gcn=torch.optim.Adam(gen_gcn.parameters(), lr=2e-4), gcn_weight=0.1,
+                      gcn_noise_fn=rp_gcn.noise, gcn_mask_fn=rp_gcn.mask, max_nodes=64)
+
+    def emul_run(items, E, Z, keepalive=()):
+        upd = step.updater
+        ms, vs, step0 = upd._adam_state()
+        for t in ms + vs:
+            t.share_memory_()
+        for p in upd.params:
+            p.data.share_memory_()
+        buf = torch.frombuffer(bytearray(GF.items_to_bytes(items)), dtype=torch.uint8)
+        ws = torch.zeros(emul.zs3_emul_gmmn_train_workspace_size(E, Z, 256, 256) + 64, dtype=torch.uint8).share_memory_()
+        losses = torch.zeros(len(items)).share_memory_()
+        a = GF.pack_args(buf.data_ptr(), len(items), (E, Z, 256, 256), tuple(p.data for p in upd.params), upd.sigma,
+                         losses, ws, adam=(ms, vs), step0=step0)
+        assert emul.zs3_emul_gmmn_train_fused(C.byref(a), C.c_void_p(2)) == 0
+        for p in upd.params:
+            upd.optimizer.state[p]["step"] += len(items)
+        return losses
+
+    def emul_components(labels, h, w, src_index=None, max_nodes=256, want_node_map=False):
+        n_nodes, node_label, node_seed, node_map, adj = _emul_components(graph_emul, labels.contiguous(), h, w,
+                                                                         src_index=src_index, max_nodes=max_nodes)
+        return n_nodes, node_label, node_seed, adj, node_map
+
+    monkeypatch.setattr(step.updater, "run", emul_run)
+    monkeypatch.setattr(ZG, "label_components", emul_components)
+    loss, glb, g_losses = step.training_step(image, target, embedding, real_features=real)
+
+    rp.reset()
+    rp_gcn.reset()
+    ref = S.step2(st, gst, real, target, embedding, (HW, HW), set(seen), set(unseen), rp.noise, rp.index, rp.mask, cw,
+                  gcn=dict(state=gcn_state, noise_fn=rp_gcn.noise, mask_fn=rp_gcn.mask, weight=0.1))
+    assert torch.allclose(torch.tensor(g_losses), torch.tensor(ref["g_losses"]), rtol=1e-4)
+    assert len(ref["gcn_losses"]) == 2 == len(step.last_gcn_losses)          # images 0 and 2 (image 1 holds an unseen class)
+    assert torch.allclose(torch.stack(step.last_gcn_losses), torch.tensor(ref["gcn_losses"]), rtol=1e-5)
+    for k, v in ref["gcn_generator"].items():
+        assert rel_l2(gen_gcn.p[k.replace(".", "_")].detach(), v) < 1e-6, k
+    assert abs(loss.item() - ref["loss"]) < 1e-4 * abs(ref["loss"])
+    assert rel_l2(head.w.detach(), ref["pred_conv.weight"]) < 1e-5          # includes the cluster-level CE gradient
+    assert rel_l2(head.w.detach() - st["decoder.pred_conv.weight"],
+                  ref["pred_conv.weight"] - st["decoder.pred_conv.weight"]) < 1e-4

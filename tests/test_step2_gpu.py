@@ -203,3 +203,65 @@ def test_image_level_generation_on_tensor_cores_matches_per_class_generator():
     cpu = O.gmmn_forward(st, emb_rows.cpu(), z.cpu(), training=True, keep_mask=mask.cpu().bool())
     cpu[(tg == 255).cpu()] = 0
     assert rel_l2(fake.cpu(), cpu) < 1e-4
+
+
+@pytest.mark.skipif(os.environ.get("ZS3_EXPERIMENTAL") != "1",
+                    reason="ZS3StepGCN is CPU-validated only (tests/test_kernel_emulation.py); set ZS3_EXPERIMENTAL=1 "
+                           "to run its first GPU validation")
+def test_gcn_context_step_matches_oracle():
+    """config 5 (zs3/train_context_GMMN_GCNcontext.py:270-460): ZS3StepGCN on the CUDA modules vs oracle step2(gcn=...)"""
+    import zs3_oracle as O
+    import zs3_step2_oracle as S
+    from zs3.modeling.deeplab import DeepLab
+    from zs3.modeling.gmmn import GMMNnetwork, GMMNnetwork_GCN
+    from zs3.utils.loss import GMMNLoss, SegmentationLosses
+    from zs3_b200.step2 import ZS3StepGCN
+    B, HW, C = 3, 65, 21
+    unseen, seen = [15, 16, 17, 18, 19], [c for c in range(21) if c not in (15, 16, 17, 18, 19)]
+    target = _labels(B, HW, [[0, 3, 7], [0, 17, 5], [2, 9]], seed=4)
+    emb_table = torch.randn(C, 300, generator=torch.Generator().manual_seed(8)) * 0.06
+    embedding = emb_table[target.clamp(max=C - 1).long()].permute(0, 3, 1, 2).contiguous()
+    image = torch.randn(B, 3, HW, HW, generator=torch.Generator().manual_seed(1))
+    st = O.init_deeplab_state(seed=1, randomize_bn=True)
+    gst = O.init_gmmn_state(seed=3)
+    model = DeepLab(num_classes=C, sync_bn=True, freeze_bn=True, pretrained=False)
+    model.load_state_dict(st)
+    model = model.cuda().train()
+    model.freeze_bn()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    gen = GMMNnetwork(300, 300, 256, 256)
+    gen.load_state_dict(gst)
+    gen = gen.cuda().train()
+    torch.manual_seed(12)
+    gen_gcn = GMMNnetwork_GCN()
+    gcn_state = {k: v.detach().clone() for k, v in gen_gcn.state_dict().items()}
+    gen_gcn = gen_gcn.cuda().train()
+    cw = torch.ones(C)
+    cw[unseen] = 100.0
+    crit = SegmentationLosses(weight=cw.cuda(), cuda=True).build_loss("ce")
+    crit_g = GMMNLoss(cuda=True).build_loss()
+    opt = torch.optim.SGD([{"params": model.get_1x_lr_params(), "lr": 0.007},
+                           {"params": model.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+    rp, rp_gcn = Replay(77), Replay(91)
+    step = ZS3StepGCN(model, gen, crit, crit_g, opt, torch.optim.Adam(gen.parameters(), lr=2e-4), seen, unseen,
+                      noise_fn=rp.noise, index_fn=rp.index, mask_fn=rp.mask, generator_gcn=gen_gcn,
+                      optimizer_generator_gcn=torch.optim.Adam(gen_gcn.parameters(), lr=2e-4), gcn_weight=0.1,
+                      gcn_noise_fn=rp_gcn.noise, gcn_mask_fn=rp_gcn.mask)
+    with torch.no_grad():
+        real = model.forward_before_class_prediction(image.cuda())
+        real = real / real.std()
+    loss, glb, g_losses = step.training_step(image.cuda(), target.cuda(), embedding.cuda(), real_features=real)
+    torch.cuda.synchronize()
+    rp.reset()
+    rp_gcn.reset()
+    ref = S.step2(st, gst, real.cpu(), target, embedding, (HW, HW), set(seen), set(unseen), rp.noise, rp.index, rp.mask,
+                  cw, gcn=dict(state=gcn_state, noise_fn=rp_gcn.noise, mask_fn=rp_gcn.mask, weight=0.1))
+    assert np.allclose(g_losses, ref["g_losses"], rtol=1e-3)
+    assert len(step.last_gcn_losses) == len(ref["gcn_losses"]) > 0
+    assert np.allclose([v.item() for v in step.last_gcn_losses], ref["gcn_losses"], rtol=1e-3)
+    for k, p in gen_gcn.state_dict().items():
+        assert rel_l2(p.cpu(), ref["gcn_generator"][k]) < 1e-4, k
+    assert abs(loss.item() - ref["loss"]) < 2e-2 * abs(ref["loss"])
+    assert rel_l2(model.decoder.pred_conv.weight.detach().cpu(), ref["pred_conv.weight"]) < 2e-2

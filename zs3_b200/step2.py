@@ -195,6 +195,9 @@ class ZS3StepFused(ZS3Step):
         n = K.cpad(b.numel())
         return b if n == b.numel() else torch.cat([b, b.new_zeros(n - b.numel())])
 
+    def _extra_classifier_backward(self, model, state):
+        """hook between the classifier's backward and optimizer.step() (used by ZS3StepGCN)"""
+
     def _classifier_loss(self, model, features, image, target):
         """criterion(forward_class_prediction(features, input_size), target).  When the criterion is this package's
         cross entropy, the x4 bilinear upsample is evaluated inside the loss kernels from the low-resolution class
@@ -351,6 +354,8 @@ class ZS3StepFused(ZS3Step):
         self.optimizer.zero_grad()
         loss = self._classifier_loss(model, fake_features.detach(), image, target)      # `:261-264`
         loss.backward()
+        self._extra_classifier_backward(model, dict(real_features=real_features, labels=tg, embedding=embedding,
+                                                    src=src, grid=(fh, fw), image_has_unseen=image_has_unseen))
         self.optimizer.step()
         mark("classifier")
         g_losses = torch.cat(loss_chunks).tolist() if loss_chunks else []
@@ -359,3 +364,77 @@ class ZS3StepFused(ZS3Step):
             per_image[owners[j]] += v
         generator_loss_batch = sum(per_image[i] / n_unique[i] for i in range(nb))
         return loss, generator_loss_batch, g_losses
+
+
+class ZS3StepGCN(ZS3StepFused):
+    """Step-2 iteration of the GCN-context variant (zs3/train_context_GMMN_GCNcontext.py:270-460; BASELINE configs[4]):
+    the ZS3Net iteration of `ZS3StepFused` plus, per image, the semantic-cluster graph of its label map, one update of
+    the graph generator (`GMMNnetwork_GCN`, MMD between generated and real node features) and a cluster-level
+    cross-entropy term on the classifier (`GCN_weight`).
+
+    EXPERIMENTAL in round 1: host logic and arithmetic are checked on the CPU against the oracle
+    (tests/test_kernel_emulation.py); the GPU test is gated (ZS3_EXPERIMENTAL=1) until it has run on a B200.
+    Differences from the reference's host code: the cluster graphs of all images come from ONE launch of
+    `zs3_label_components` (`:307-321` runs a Python DFS per image after three D2H copies), node embeddings / features
+    are gathered on the device at the seed pixels, and the nodes of the batch are laid out on an [n/8, 8] grid (padded
+    with ignore labels) for the classifier instead of [n, 1]."""
+
+    def __init__(self, *args, generator_gcn=None, optimizer_generator_gcn=None, gcn_weight=0.1, gcn_noise_fn=None,
+                 gcn_mask_fn=None, max_nodes=256, **kw):
+        super().__init__(*args, **kw)
+        if generator_gcn is None or optimizer_generator_gcn is None:
+            raise ValueError("ZS3StepGCN needs generator_gcn and optimizer_generator_gcn")
+        self.generator_gcn, self.optimizer_generator_gcn = generator_gcn, optimizer_generator_gcn
+        self.gcn_weight, self.max_nodes = float(gcn_weight), max_nodes
+        self.gcn_noise_fn = gcn_noise_fn      # optional: n -> [n, noise_dim] (tests); default torch.rand on the device
+        self.gcn_mask_fn = gcn_mask_fn        # optional: n -> [n, hidden] Dropout keep mask of the graph generator (tests)
+        self.last_gcn_losses = []
+
+    def _extra_classifier_backward(self, model, state):
+        from . import graph as ZG
+        real, labels, embedding, src = state["real_features"], state["labels"], state["embedding"], state["src"]
+        fh, fw = state["grid"]
+        nb, fd, hw = real.shape[0], real.shape[1], fh * fw
+        dev = real.device
+        n_nodes, node_label, node_seed, adj, _ = ZG.label_components(labels.float(), fh, fw, max_nodes=self.max_nodes)
+        counts = n_nodes.tolist()                                                   # one sync for the batch
+        feats, targets, self.last_gcn_losses = [], [], []
+        for i, n in enumerate(counts):
+            if n > self.max_nodes:
+                raise RuntimeError(f"image {i}: {n} clusters exceed max_nodes={self.max_nodes}")
+            if n <= 1:                                                              # adj_mat is None (`:93-97,323`)
+                continue
+            seeds = node_seed[i, :n].long()
+            targets.append(node_label[i, :n].float())                               # `:323-324`
+            emb_n = embedding[i].reshape(self.embed_dim, -1)[:, src[seeds].long()].t().contiguous()   # seed embeddings `:58`
+            real_n = real[i].reshape(fd, -1)[:, seeds].t().contiguous()             # seed features `:72-74`
+            z = (torch.rand((n, self.noise_dim), device=dev) if self.gcn_noise_fn is None
+                 else self.gcn_noise_fn(n).to(dev).float())                         # `:404`
+            self.optimizer_generator_gcn.zero_grad()                                # `:402`
+            if self.gcn_mask_fn is not None:
+                fake_n = self.generator_gcn(emb_n, z, adj[i, :n, :n].contiguous(),
+                                            keep_mask=self.gcn_mask_fn(n).to(dev).to(torch.uint8).contiguous())
+            else:
+                fake_n = self.generator_gcn(emb_n, z, adj[i, :n, :n].contiguous())  # `:407-409`
+            if not state["image_has_unseen"][i]:                                    # `:413-419`
+                g_loss = self.criterion_generator(fake_n, real_n)
+                g_loss.backward()
+                self.optimizer_generator_gcn.step()
+                self.last_gcn_losses.append(g_loss.detach())
+            keep_real = self.real_seen_features and not state["image_has_unseen"][i]
+            feats.append(real_n if keep_real else fake_n.detach())                  # `:421-428`
+        if not feats:
+            return
+        x = torch.cat(feats, 0)                                                     # [N, fd]
+        t = torch.cat(targets, 0)
+        pad = (-x.shape[0]) % 8
+        if pad:
+            x = torch.cat([x, x.new_zeros(pad, fd)], 0)
+            t = torch.cat([t, t.new_full((pad,), 255.0)], 0)                        # ignored by the loss
+        grid = (x.shape[0] // 8, 8)
+        x = x.t().reshape(1, fd, *grid).contiguous()                                # `:439-443` ([1, fd, N, 1] there)
+        out = model.forward_class_prediction(x, grid)                               # same-size "upsample" = identity
+        loss_gcn = self.gcn_weight * self.criterion(out, t.view(1, *grid))          # `:444-453`
+        loss_gcn.backward()
+        self.last_gcn_cluster_loss = loss_gcn.detach()
+
