@@ -82,3 +82,40 @@ def test_zs3_shim_falls_through_to_a_reference_checkout(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() == "reference parsing | reference lr_scheduler | reference dataloaders | True True"
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """argument checks of the round-1b entry points happen before any CUDA call (usable on the CPU box)"""
+    import ctypes as C
+    from zs3_b200 import _lib
+    lib = _lib.lib()
+    err = lambda: lib.zs3_last_error().decode()  # noqa: E731
+    # fused generator update: null args, bad dims, workspace too small
+    assert lib.zs3_gmmn_train_fused(None, None) == -1 and "null args" in err()
+    a = _lib.GmmnTrainArgs()
+    assert lib.zs3_gmmn_train_fused(C.byref(a), None) == -1 and "bad dims" in err()
+    need = lib.zs3_gmmn_train_workspace_size(300, 300, 256, 256)
+    assert 1_000_000 < need < 4_000_000
+    assert lib.zs3_gmmn_train_workspace_size(0, 300, 256, 256) == 0
+    buf = (C.c_float * 16)()
+    a.embed_dim, a.noise_dim, a.hidden, a.feat, a.nsigma, a.max_rows, a.apply_adam = 300, 300, 256, 256, 6, 128, 0
+    for name in ("w1", "b1", "w2", "b2", "losses", "workspace"):
+        setattr(a, name, C.addressof(buf))
+    for i in range(4):
+        a.grad[i] = C.addressof(buf)
+    a.workspace_bytes = 64
+    assert lib.zs3_gmmn_train_fused(C.byref(a), None) == -1 and "workspace too small" in err()
+    a.max_rows = 129
+    assert lib.zs3_gmmn_train_fused(C.byref(a), None) == -1 and "max_rows" in err()
+    # cluster graph: a map that does not fit in shared memory; null pointers
+    c = _lib.ComponentsArgs()
+    assert lib.zs3_label_components(C.byref(c), None) == -1 and "null pointer" in err()
+    for name in ("labels", "n_nodes", "node_label", "node_seed", "adj"):
+        setattr(c, name, C.addressof(buf))
+    c.B, c.h, c.w, c.max_nodes = 1, 400, 400, 8
+    assert lib.zs3_label_components(C.byref(c), None) == -1 and "shared memory" in err()
+    # metrics: more classes than the per-CTA histogram holds; nothing to compute
+    p = C.addressof(buf)
+    assert lib.zs3_argmax_confusion(p, p, 1, 65, 10, p, p, None) == -1 and "1 <= C <= 64" in err()
+    assert lib.zs3_argmax_confusion(p, None, 1, 21, 10, None, None, None) == -1 and "nothing to compute" in err()
+    assert lib.zs3_confusion_from_pred(None, p, 10, 21, p, None) == -1

@@ -505,3 +505,19 @@ def test_gcn_context_step_host_logic_against_oracle(emul, graph_emul, monkeypatc
     assert rel_l2(head.w.detach(), ref["pred_conv.weight"]) < 1e-5          # includes the cluster-level CE gradient
     assert rel_l2(head.w.detach() - st["decoder.pred_conv.weight"],
                   ref["pred_conv.weight"] - st["decoder.pred_conv.weight"]) < 1e-4
+
+
+@pytest.mark.parametrize("n_src,B", [(5, 1), (3, 128)])
+def test_fused_update_edge_cases(emul, n_src, B):
+    """one sampled row (M = N = 1) and 128 samples drawn from only three source rows (heavy duplication, as when a
+    class covers a handful of pixels: train_pascal_GMMN.py:229 samples with replacement)"""
+    dims = (300, 300, 256, 256)
+    st = {k: v.clone().requires_grad_(True) for k, v in _state(*dims, seed=3).items()}
+    case = _make_case(*dims, n_src, B, seed=31)
+    loss = _oracle_loss(st, case)
+    ref = torch.autograd.grad(loss, list(st.values()))
+    losses, grads = _run_emul(emul, {k: v.detach().clone() for k, v in st.items()}, [case], dims)
+    assert torch.isfinite(loss) and abs(losses[0].item() - loss.item()) < 1e-3 * abs(loss.item()) + 1e-6
+    for g, r, k in zip(grads, ref, st):
+        assert torch.isfinite(g).all()
+        assert rel_l2(g, r) < 2e-3 or float(r.norm()) < 1e-6, k
