@@ -37,6 +37,19 @@ int zs3_abi_version(void);
 unsigned long long zs3_launch_count(void);
 /* 1 if the current device is compute capability 10.x, else 0 (kernels are sm_100a only) */
 int zs3_device_supported(void);
+/* sizeof() of the argument struct `which` as THIS library was compiled (a binding checks its own mirror against it
+ * before the first call; a short struct handed to a kernel is an out-of-bounds read).  Unknown id: returns 0. */
+#define ZS3_STRUCT_CONV_ARGS 1
+#define ZS3_STRUCT_WGRAD_ARGS 2
+#define ZS3_STRUCT_BN_APPLY_ARGS 3
+#define ZS3_STRUCT_BN_BWD_ARGS 4
+#define ZS3_STRUCT_SGEMM_ARGS 5
+#define ZS3_STRUCT_GMMN_ITEM 6
+#define ZS3_STRUCT_GMMN_TRAIN_ARGS 7
+#define ZS3_STRUCT_COMPONENTS_ARGS 8
+#define ZS3_STRUCT_CONV_SEGMENT 9
+#define ZS3_STRUCT_ROW_SOURCE 10
+unsigned long long zs3_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolution as implicit GEMM on tcgen05 (TMA im2col A-tiles, TMA weight tiles, TMEM accumulator).
@@ -282,7 +295,7 @@ int zs3_ce_bwd(const float* logit, const float* target, const float* weight, int
 
 /* Training-loss fusion of deeplab.py:44 (F.interpolate(x, size=input, bilinear, align_corners=True)) with
  * SegmentationLosses.CrossEntropyLoss (loss.py:31-46): loss = CE(upsample(x), target) straight from the low-resolution
- * class scores x (NHWC bf16 [N][Hi][Wi][cs], C <= 24 real classes), without materialising the [N][C][Ho][Wo] fp32
+ * class scores x (NHWC bf16 [N][Hi][Wi][cs], C <= 64 real classes: VOC 21, Pascal-Context 60), without materialising the [N][C][Ho][Wo] fp32
  * logits or their gradient.  Same arguments/semantics as zs3_ce_fwd/bwd; the backward returns d loss / d x (NHWC bf16,
  * padding channels zeroed; Wo <= 640).  Models that must RETURN the logits (evaluation) use zs3_upsample_logits_* +
  * zs3_ce_*. */
@@ -299,6 +312,11 @@ int zs3_upsample_ce_bwd(const void* x, const float* target, const float* weight,
 int zs3_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 int zs3_sgd_step(float* p, const float* g, float* momentum_buf, long long n, float lr, float momentum,
                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
+/* same update with the learning rate read from DEVICE memory when the kernel runs (one float): a CUDA graph that
+ * captured the step keeps following the poly LR schedule the reference applies every iteration
+ * (zs3/utils/lr_scheduler.py:46-67, zs3/base_trainer.py:15) */
+int zs3_sgd_step_lrdev(float* p, const float* g, float* momentum_buf, long long n, const float* lr_dev, float momentum,
+                       float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 int zs3_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, int step, float grad_scale, void* stream);
 

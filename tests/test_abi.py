@@ -38,6 +38,21 @@ def test_binding_covers_header_and_reports_errors():
     assert rc == -1 and b"num_segments" in lib.zs3_last_error()
 
 
+def test_binding_struct_sizes_match_the_library():
+    """every ctypes mirror has the size the library was compiled with (a stale stub is an OOB read)"""
+    from zs3_b200 import _lib
+    lib = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "zs3b200.h")).read()
+    ids = dict((int(v), k) for k, v in re.findall(r"#define (ZS3_STRUCT_[A-Z_]+) (\d+)", hdr))
+    assert sorted(ids) == sorted(_lib.STRUCT_IDS), (ids, _lib.STRUCT_IDS)
+    for which, mirror in _lib.STRUCT_IDS.items():
+        assert lib.zs3_sizeof(which) == ctypes.sizeof(mirror) > 0, (ids[which], mirror)
+    assert lib.zs3_sizeof(999) == 0
+    # the stub printed in INTEGRATION.md is the binding's own struct, not a hand copy
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert "from zs3_b200._lib import ConvArgs" in doc and "class ConvArgs(C.Structure)" not in doc
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import importlib
     from zs3_b200 import _lib

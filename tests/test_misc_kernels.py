@@ -110,7 +110,8 @@ def test_cross_entropy(C, weighted):
     assert abs(l2.item() - r2.item()) < 1e-5 * abs(r2.item())
 
 
-@pytest.mark.parametrize("C,hi,ho,weighted", [(21, 33, 129, False), (21, 17, 65, True), (5, 9, 33, True), (21, 129, 513, False)])
+@pytest.mark.parametrize("C,hi,ho,weighted", [(21, 33, 129, False), (21, 17, 65, True), (5, 9, 33, True), (21, 129, 513, False),
+                                              (60, 17, 65, True), (60, 129, 513, False), (33, 33, 129, True)])
 def test_fused_upsample_cross_entropy(C, hi, ho, weighted):
     """loss = CE(interpolate(scores)) straight from the low-resolution NHWC bf16 scores (training-loss fusion) against
     torch's interpolate + cross_entropy in fp32 on the same bf16-representable scores; tolerances: loss 1e-5 rel,
@@ -132,7 +133,7 @@ def test_fused_upsample_cross_entropy(C, hi, ho, weighted):
     ref = F.cross_entropy(up, target.long(), weight=w, ignore_index=255) / N
     (g_ref,) = torch.autograd.grad(ref, x)
     losses = SegmentationLosses(weight=w, cuda=True)
-    xh = K.nchw_to_nhwc(x.detach(), 64).requires_grad_(True)
+    xh = K.nchw_to_nhwc(x.detach(), 64).requires_grad_(True)   # C = 60 is Pascal-Context (the C <= 64 instantiation)
     loss = losses.UpsampledCrossEntropyLoss(xh, C, target)
     loss.backward()
     assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())

@@ -79,6 +79,8 @@ def _declare(lib):
     lib.zs3_device_supported.restype = i
     lib.zs3_launch_count.restype = C.c_ulonglong
     lib.zs3_launch_count.argtypes = []
+    lib.zs3_sizeof.restype = C.c_ulonglong
+    lib.zs3_sizeof.argtypes = [i]
     sigs = {
         "zs3_conv_fprop": [C.POINTER(ConvArgs), vp],
         "zs3_conv_wgrad": [C.POINTER(WgradArgs), vp],
@@ -211,6 +213,7 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_upsample_ce_bwd": [vp, vp, vp, i, i, i, i, i, i, i, i, f, vp, vp, vp, vp],
         "zs3_cast_f32_to_bf16": [vp, vp, ll, vp],
         "zs3_sgd_step": [vp, vp, vp, ll, f, f, f, i, i, f, vp],
+        "zs3_sgd_step_lrdev": [vp, vp, vp, ll, vp, f, f, i, i, f, vp],
         "zs3_adam_step": [vp, vp, vp, vp, ll, f, f, f, f, i, f, vp],
         "zs3_sgemm": [C.POINTER(SgemmArgs), vp],
         "zs3_find_active_rows": [vp, i, i, vp, vp, vp],
@@ -236,6 +239,11 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
     }
 
 
+# ids of include/zs3b200.h (ZS3_STRUCT_*) -> ctypes mirror; checked against zs3_sizeof() when the library loads
+STRUCT_IDS = {1: ConvArgs, 2: WgradArgs, 3: BnApplyArgs, 4: BnBwdArgs, 5: SgemmArgs, 6: GmmnItem, 7: GmmnTrainArgs,
+              8: ComponentsArgs, 9: ConvSegment, 10: RowSource}
+
+
 def lib():
     """Load (once) and return the native library; raises if it is absent."""
     global _lib
@@ -247,7 +255,11 @@ def lib():
         l = C.CDLL(LIB_PATH)
         declared = _declare(l)
         l._zs3_declared = sorted(declared) + ["zs3_last_error", "zs3_abi_version", "zs3_device_supported",
-                                                "zs3_launch_count"]
+                                                "zs3_launch_count", "zs3_sizeof"]
+        for which, mirror in STRUCT_IDS.items():
+            if l.zs3_sizeof(which) != C.sizeof(mirror):
+                raise Zs3NativeError(f"ctypes mirror {mirror.__name__} is {C.sizeof(mirror)} bytes, the library's "
+                                     f"struct is {l.zs3_sizeof(which)}: binding and libzs3b200.so are out of step")
         _lib = l
     return _lib
 

@@ -172,6 +172,22 @@ const char* zs3_last_error(void) { return zs3::g_err; }
 
 int zs3_abi_version(void) { return 1; }
 
+unsigned long long zs3_sizeof(int which) {
+  switch (which) {
+    case ZS3_STRUCT_CONV_ARGS: return sizeof(zs3_conv_args);
+    case ZS3_STRUCT_WGRAD_ARGS: return sizeof(zs3_wgrad_args);
+    case ZS3_STRUCT_BN_APPLY_ARGS: return sizeof(zs3_bn_apply_args);
+    case ZS3_STRUCT_BN_BWD_ARGS: return sizeof(zs3_bn_bwd_args);
+    case ZS3_STRUCT_SGEMM_ARGS: return sizeof(zs3_sgemm_args);
+    case ZS3_STRUCT_GMMN_ITEM: return sizeof(zs3_gmmn_item);
+    case ZS3_STRUCT_GMMN_TRAIN_ARGS: return sizeof(zs3_gmmn_train_args);
+    case ZS3_STRUCT_COMPONENTS_ARGS: return sizeof(zs3_components_args);
+    case ZS3_STRUCT_CONV_SEGMENT: return sizeof(zs3_conv_segment);
+    case ZS3_STRUCT_ROW_SOURCE: return sizeof(zs3_row_source);
+    default: return 0;
+  }
+}
+
 unsigned long long zs3_launch_count(void) { return zs3::g_launch_count; }
 
 int zs3_device_supported(void) {

@@ -453,8 +453,10 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logit, const float* __re
 // The training step never needs the full-resolution class scores themselves: loss = CE(upsample(x), target).  These
 // two kernels evaluate the bilinear upsample on the fly (same blend order as upsample_logits_fwd_kernel: vertical
 // into fp32, then horizontal), so the [N][C][Ho][Wo] fp32 logits and their gradient (2 x 354 MB at bs=16, 513x513)
-// are never written to or read from HBM.  C <= 24 classes live in registers (VOC: 21).
-constexpr int CE_MAX_C = 24;
+// are never written to or read from HBM.  The backward keeps one accumulator per class in registers: instantiated for
+// C <= 24 (VOC: 21; softmax terms also stay in registers) and C <= 64 (Pascal-Context: 60; softmax terms re-read from
+// the blended row in shared memory).
+constexpr int CE_MAX_C = 64;
 
 __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                               const float* __restrict__ target,
@@ -513,6 +515,7 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const __nv_bfloat1
 // h-1, h, h+1 are staged in shared memory (every contributing output row blends two of them); stage 1 recomputes the
 // softmax per (oh, ow) and accumulates vertically into v[c][ow], stage 2 reduces horizontally (as in
 // upsample_logits_bwd_kernel).
+template <int MAXC>
 __global__ void __launch_bounds__(640) upsample_ce_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                                const float* __restrict__ target,
                                                                const float* __restrict__ weight, int C, int Hi, int Wi,
@@ -525,8 +528,9 @@ __global__ void __launch_bounds__(640) upsample_ce_bwd_kernel(const __nv_bfloat1
   const int ldi = Wi + 1, ldo = Wo + 1;
   float* xs = smem_f;                 // [3][C][Wi+1]: input rows h-1, h, h+1
   float* bl = xs + 3 * C * ldi;       // [C][Wi+1]: the two input rows of the current output row, blended vertically
-  float* v = bl + C * ldi;            // [C][Wo+1]
-  unsigned char* tg = reinterpret_cast<unsigned char*>(v + C * ldo);  // [max_rows][Wo] labels (255 = no gradient)
+  float* v = smem_f;                  // [C][Wo+1]: ALIASES xs/bl (only written after the row loop is done with them)
+  const int fl_words = max(4 * C * ldi, C * ldo);
+  unsigned char* tg = reinterpret_cast<unsigned char*>(smem_f + fl_words);  // [max_rows][Wo] labels (255 = no gradient)
   const int h = blockIdx.x % Hi, n = blockIdx.x / Hi;
   const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
   int oh_lo = sh > 0.f ? (int)floorf((h - 1) * ish) - 1 : 0, oh_hi = sh > 0.f ? (int)ceilf((h + 1) * ish) + 1 : Ho - 1;
@@ -547,9 +551,10 @@ __global__ void __launch_bounds__(640) upsample_ce_bwd_kernel(const __nv_bfloat1
   const int ow = threadIdx.x;
   int x0 = 0, x1 = 0; float lx = 0.f;
   if (ow < Wo) bl_coord(ow, sw, Wi, x0, x1, lx);
-  float acc[CE_MAX_C];
+  constexpr bool KEEP = MAXC <= 24;  // softmax terms in registers next to the accumulators
+  float acc[MAXC];
 #pragma unroll
-  for (int c = 0; c < CE_MAX_C; ++c) acc[c] = 0.f;
+  for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
   for (int r = 0; r < rows; ++r) {
     int y0, y1; float ly;
     bl_coord(oh_lo + r, sh, Hi, y0, y1, ly);
@@ -566,33 +571,39 @@ __global__ void __launch_bounds__(640) upsample_ce_bwd_kernel(const __nv_bfloat1
     if (ow >= Wo) continue;
     const int t = tg[r * Wo + ow];
     if (t == 255) continue;
-    float lg[CE_MAX_C];
+    float lg[KEEP ? MAXC : 1];
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < CE_MAX_C; ++c) {
+    for (int c = 0; c < MAXC; ++c) {
       if (c < C) {
-        lg[c] = (1.f - lx) * bl[c * ldi + x0] + lx * bl[c * ldi + x1];
-        mx = fmaxf(mx, lg[c]);
+        const float l = (1.f - lx) * bl[c * ldi + x0] + lx * bl[c * ldi + x1];
+        if (KEEP) lg[c] = l;
+        mx = fmaxf(mx, l);
       }
     }
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < CE_MAX_C; ++c) {
+    for (int c = 0; c < MAXC; ++c) {
       if (c < C) {
-        lg[c] = __expf(lg[c] - mx);
-        s += lg[c];
+        const float e = __expf((KEEP ? lg[c] : (1.f - lx) * bl[c * ldi + x0] + lx * bl[c * ldi + x1]) - mx);
+        if (KEEP) lg[c] = e;
+        s += e;
       }
     }
     const float coef = wy * g * (weight ? weight[t] : 1.f);
     const float inv = coef / s;
 #pragma unroll
-    for (int c = 0; c < CE_MAX_C; ++c) {
-      if (c < C) acc[c] += lg[c] * inv - (c == t ? coef : 0.f);
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        const float e = KEEP ? lg[c] : __expf((1.f - lx) * bl[c * ldi + x0] + lx * bl[c * ldi + x1] - mx);
+        acc[c] += e * inv - (c == t ? coef : 0.f);
+      }
     }
   }
+  __syncthreads();  // every reader of xs / bl is done: v (same shared memory) may be written
   if (ow < Wo) {
 #pragma unroll
-    for (int c = 0; c < CE_MAX_C; ++c) {
+    for (int c = 0; c < MAXC; ++c) {
       if (c < C) v[c * ldo + ow] = acc[c];
     }
   }
@@ -633,7 +644,9 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 // -------------------------------------------------------------------------------- optimizers
 // torch.optim.SGD: d = g*gscale + wd*p; buf = first ? d : mom*buf + d; p -= lr * (nesterov ? d + mom*buf : buf)
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
-                           float lr, float mom, float wd, int nesterov, int first, float gscale) {
+                           float lr, float mom, float wd, int nesterov, int first, float gscale,
+                           const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = *lr_dev;  // learning rate read at RUN time: a captured CUDA graph follows the LR schedule
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float w = p[i];
     float d = g[i] * gscale + wd * w;
@@ -809,14 +822,25 @@ extern "C" int zs3_upsample_ce_bwd(const void* x, const float* target, const flo
   // output rows whose bilinear footprint can touch one input row: (h-1)/sh - 1 .. (h+1)/sh + 1
   const float shf = bl_scale(Hi, Ho);
   const int max_rows = shf > 0.f ? (int)ceilf(2.f / shf) + 6 : Ho;
-  const size_t smem = ((size_t)4 * C * (Wi + 1) + (size_t)C * (Wo + 1)) * sizeof(float) + (size_t)max_rows * Wo;
-  ZS3_CHECK_ARG(smem <= 200 * 1024, "upsample_ce_bwd: rows do not fit in shared memory");
+  // staging rows (xs, bl) and the vertical accumulators v share one region (the kernel aliases them)
+  const size_t fl_words = (size_t)4 * C * (Wi + 1) > (size_t)C * (Wo + 1) ? (size_t)4 * C * (Wi + 1) : (size_t)C * (Wo + 1);
+  const size_t smem = fl_words * sizeof(float) + (size_t)max_rows * Wo;
+  ZS3_CHECK_ARG(smem <= 220 * 1024, "upsample_ce_bwd: rows do not fit in shared memory");
   ZS3_CHECK_ARG(Wo <= 640, "upsample_ce_bwd: output width %d > 640 (use the unfused upsample + CE kernels)", Wo);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int threads = ((Wo + 31) / 32) * 32;  // one output column per thread
-  upsample_ce_bwd_kernel<<<N * Hi, threads, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, shf,
-                                                                bl_scale(Wi, Wo), ignore_index, accum2, div, grad_out,
-                                                                BF(dx), max_rows);
+  if (C <= 24) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(upsample_ce_bwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    upsample_ce_bwd_kernel<24><<<N * Hi, threads, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, shf,
+                                                                      bl_scale(Wi, Wo), ignore_index, accum2, div,
+                                                                      grad_out, BF(dx), max_rows);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(upsample_ce_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    upsample_ce_bwd_kernel<64><<<N * Hi, threads, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, shf,
+                                                                      bl_scale(Wi, Wo), ignore_index, accum2, div,
+                                                                      grad_out, BF(dx), max_rows);
+  }
   ZS3_CHECK_LAUNCH("upsample_ce_bwd");
   return ZS3_OK;
 }
@@ -836,8 +860,19 @@ extern "C" int zs3_sgd_step(float* p, const float* g, float* buf, long long n, f
   ZS3_CHECK_ARG(p && g && buf && n >= 0, "sgd_step: bad args");
   if (n == 0) return ZS3_OK;
   sgd_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(p, g, buf, n, lr, momentum, weight_decay, nesterov, first_step,
-                                                        grad_scale);
+                                                        grad_scale, nullptr);
   ZS3_CHECK_LAUNCH("sgd_step");
+  return ZS3_OK;
+}
+
+extern "C" int zs3_sgd_step_lrdev(float* p, const float* g, float* buf, long long n, const float* lr_dev,
+                                  float momentum, float weight_decay, int nesterov, int first_step, float grad_scale,
+                                  void* stream) {
+  ZS3_CHECK_ARG(p && g && buf && lr_dev && n >= 0, "sgd_step_lrdev: bad args");
+  if (n == 0) return ZS3_OK;
+  sgd_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(p, g, buf, n, 0.f, momentum, weight_decay, nesterov,
+                                                        first_step, grad_scale, lr_dev);
+  ZS3_CHECK_LAUNCH("sgd_step_lrdev");
   return ZS3_OK;
 }
 

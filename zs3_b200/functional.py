@@ -146,7 +146,9 @@ class _RngState:
 
     @classmethod
     def next(cls, numel):
-        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        # the data-parallel rank is mixed into the seed: replicas must not draw identical Dropout masks
+        rank = int(os.environ.get("RANK", "0"))
+        seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
         off = cls.offset
         cls.offset += numel
         return seed, off

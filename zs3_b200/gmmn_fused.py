@@ -113,6 +113,18 @@ def pack_args(items_ptr, n_items, dims, params, sigma, losses, workspace, *, ada
     return a
 
 
+def _launch_seed(calls):
+    """64-bit Dropout seed of one launch: splitmix64 of (torch seed, launch counter).  The kernel adds
+    (item << 40) + element/4 to the offset, so the launch counter must not share those bits (round 1 passed it as
+    offset = calls << 44: item 16 of launch c drew the masks of item 0 of launch c+1, and it wrapped after 2^20
+    launches)."""
+    m = 0xFFFFFFFFFFFFFFFF
+    z = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (calls + 1)) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)
+
+
 class FusedGeneratorUpdater:
     """Runs work lists of generator updates for a `GMMNnetwork` (hidden_size > 0) and its torch.optim.Adam.
     The Adam state (`exp_avg`, `exp_avg_sq`, `step`) stays in `optimizer.state`, so checkpoints and a later
@@ -184,7 +196,7 @@ class FusedGeneratorUpdater:
                       tuple(p.data for p in self.params), self.sigma, losses, self._workspace, adam=(ms, vs),
                       lr=float(g["lr"]), betas=tuple(g["betas"]), eps=float(g["eps"]), step0=step,
                       slope=float(self.act.negative_slope), drop_p=float(self.drop.p) if training else 0.0,
-                      seed=torch.initial_seed() & 0xFFFFFFFFFFFF, offset=self._calls << 44, phase_stamps=phase_stamps)
+                      seed=_launch_seed(self._calls), offset=0, phase_stamps=phase_stamps)
         L.check(lib.zs3_gmmn_train_fused(C.byref(a), L.stream_ptr()), "zs3_gmmn_train_fused")
         for p in self.params:
             st = self.optimizer.state[p]
@@ -212,6 +224,6 @@ class FusedGeneratorUpdater:
                       tuple(p.data for p in self.params), self.sigma, losses, self._workspace, grads=grads,
                       slope=float(self.act.negative_slope),
                       drop_p=float(self.drop.p) if self.generator.training else 0.0,
-                      seed=torch.initial_seed() & 0xFFFFFFFFFFFF, offset=self._calls << 44)
+                      seed=_launch_seed(self._calls), offset=0)
         L.check(lib.zs3_gmmn_train_fused(C.byref(a), L.stream_ptr()), "zs3_gmmn_train_fused")
         return losses[0], grads

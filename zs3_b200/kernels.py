@@ -432,6 +432,12 @@ def cast_f32_to_bf16(src, dst):
 
 
 def sgd_step(p, g, buf, lr, momentum, weight_decay, nesterov, first_step, grad_scale=1.0):
+    """lr: a Python float, or a 1-element fp32 CUDA tensor read by the kernel at run time (CUDA-graph safe)"""
+    if isinstance(lr, torch.Tensor):
+        L.check(L.lib().zs3_sgd_step_lrdev(L.ptr(p), L.ptr(g), L.ptr(buf), p.numel(), L.ptr(lr), float(momentum),
+                                           float(weight_decay), int(nesterov), int(first_step), float(grad_scale),
+                                           L.stream_ptr()), "zs3_sgd_step_lrdev")
+        return
     L.check(L.lib().zs3_sgd_step(L.ptr(p), L.ptr(g), L.ptr(buf), p.numel(), float(lr), float(momentum),
                                  float(weight_decay), int(nesterov), int(first_step), float(grad_scale),
                                  L.stream_ptr()), "zs3_sgd_step")

@@ -83,15 +83,38 @@ class FusedSGD:
     """torch.optim.SGD semantics (momentum, weight decay, nesterov, per-group lr) over FlatParams ranges."""
 
     def __init__(self, flat, lrs, momentum=0.9, weight_decay=5e-4, nesterov=False):
-        self.flat, self.lrs = flat, list(lrs)
+        self.flat = flat
         self.momentum, self.weight_decay, self.nesterov = momentum, weight_decay, nesterov
         self.buf = torch.zeros_like(flat.flat)
         self.steps = 0
+        # per-group learning rates live in device memory and are read by the kernel when it RUNS, so a step captured in
+        # a CUDA graph keeps following set_lr() (the reference applies its poly schedule every iteration,
+        # base_trainer.py:15 -> lr_scheduler.py:46-67: group 0 = lr, groups > 0 = 10 * lr)
+        self._lrs = [float(v) for v in lrs]
+        self.lr_dev = torch.tensor(self._lrs, dtype=torch.float32, device=flat.flat.device)
+
+    @property
+    def lrs(self):
+        return list(self._lrs)
+
+    @lrs.setter
+    def lrs(self, values):
+        self.set_lr(values)
+
+    def set_lr(self, values):
+        """per-group learning rates (a list, or one float = the schedule's lr: group 0 gets lr, the others 10 * lr as
+        LR_Scheduler.__call__ does).  Takes effect on the next step, also under CUDA-graph replay."""
+        if not isinstance(values, (list, tuple)):
+            values = [float(values)] + [float(values) * 10.0] * (len(self._lrs) - 1)
+        if len(values) != len(self._lrs):
+            raise ValueError(f"{len(self._lrs)} parameter groups, {len(values)} learning rates")
+        self._lrs = [float(v) for v in values]
+        self.lr_dev.copy_(torch.tensor(self._lrs, dtype=torch.float32), non_blocking=True)
 
     def step(self, grad_scale=1.0):
-        for (a, b), lr in zip(self.flat.group_ranges, self.lrs):
-            K.sgd_step(self.flat.flat[a:b], self.flat.grad[a:b], self.buf[a:b], lr, self.momentum, self.weight_decay,
-                       self.nesterov, self.steps == 0, grad_scale)
+        for gi, (a, b) in enumerate(self.flat.group_ranges):
+            K.sgd_step(self.flat.flat[a:b], self.flat.grad[a:b], self.buf[a:b], self.lr_dev[gi:gi + 1], self.momentum,
+                       self.weight_decay, self.nesterov, False, grad_scale)  # buf starts at 0: mom*0 + d == torch's first-step buf = d
         self.steps += 1
         ZF.invalidate_weight_caches()
 
@@ -229,11 +252,22 @@ class DataParallelTrainer:
         ZF._RngState.device_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        # the warm-up steps below are real optimisation steps on the first batch; the training state (parameters,
+        # momentum, BatchNorm running statistics, step counter) is put back afterwards so that capture is invisible
+        snap = (self.flat.flat.clone(), self.opt.buf.clone(), [b.clone() for b in self.model.buffers()], self.opt.steps)
         with torch.cuda.stream(side):
             for _ in range(2):  # warm-up outside capture: lazy inits (cudaFuncSetAttribute, scratch buffers, NCCL)
                 self._step(self.static_image, self.static_target)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            self.flat.flat.copy_(snap[0])
+            self.opt.buf.copy_(snap[1])
+            for b, s0 in zip(self.model.buffers(), snap[2]):
+                b.copy_(s0)
+        self.opt.steps = snap[3]
+        ZF.invalidate_weight_caches()
+        del snap
         self.graph, self.graph_tail = torch.cuda.CUDAGraph(), None
         if self.world == 1:
             with torch.cuda.graph(self.graph):
@@ -299,7 +333,7 @@ class DataParallelTrainer:
         owner = getattr(self.criterion, "__self__", None)
         fusable = (self.fuse_loss and hasattr(self.model, "forward_scores")
                    and getattr(self.criterion, "__func__", None) is getattr(type(owner), "CrossEntropyLoss", None)
-                   and hasattr(owner, "UpsampledCrossEntropyLoss") and getattr(self.model, "num_classes", 99) <= 24
+                   and hasattr(owner, "UpsampledCrossEntropyLoss") and getattr(self.model, "num_classes", 99) <= 64
                    and target.shape[-1] <= 640)  # limits of zs3_upsample_ce_* (classes in registers, a column per thread)
         if fusable:
             return owner.UpsampledCrossEntropyLoss(self.model.forward_scores(image), self.model.num_classes, target)

@@ -206,7 +206,8 @@ class ZS3StepFused(ZS3Step):
         owner = getattr(self.criterion, "__self__", None)
         if (self.fuse_classifier_loss and isinstance(owner, SegmentationLosses)
                 and getattr(self.criterion, "__func__", None) is SegmentationLosses.CrossEntropyLoss
-                and tuple(target.shape[1:]) == tuple(image.shape[2:])):
+                and tuple(target.shape[1:]) == tuple(image.shape[2:])
+                and model.num_classes <= 64 and target.shape[-1] <= 640):   # limits of zs3_upsample_ce_*
             scores = model.decoder.forward_class_prediction(features)
             return owner.UpsampledCrossEntropyLoss(scores, model.num_classes, target)
         return self.criterion(model.forward_class_prediction(features, image.size()[2:]), target)

@@ -79,6 +79,17 @@ class Evaluator:
             return np.zeros((self.num_class,) * 2)
         return self._conf.cpu().numpy().astype(np.float64)
 
+    @confusion_matrix.setter
+    def confusion_matrix(self, value):
+        """the reference's attribute is a plain ndarray callers may assign (metrics.py:9,85)"""
+        value = np.asarray(value)
+        if value.shape != (self.num_class, self.num_class):
+            raise ValueError(f"confusion matrix must be [{self.num_class}, {self.num_class}]")
+        if not torch.cuda.is_available():
+            raise RuntimeError("zs3_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        dev = self._conf.device if self._conf is not None else torch.device("cuda")
+        self._conf = torch.from_numpy(np.ascontiguousarray(value).astype(np.int64)).to(dev)
+
     # ---------------------------------------------------------------------------------------- scores
     def _split(self):
         return bool(self.seen_classes_idx) and bool(self.unseen_classes_idx)
@@ -123,3 +134,50 @@ class Evaluator:
         if not self._split():
             return fw(None)
         return fw(None), fw(self.seen_classes_idx), fw(self.unseen_classes_idx)
+
+
+class Evaluator_seen_unseen:
+    """zs3/utils/metrics.py:88-200 (used by eval_pascal.py:83 / eval_context.py).  Same constructor and
+    `label_accuracy_score(label_trues, label_preds, by_class=False)` return structure.  The reference builds up to
+    3 + num_class masked histograms per image on the host; every one of those masks selects ROWS of the one
+    confusion matrix (they only test the ground-truth label), so here the matrix is accumulated once on the device
+    (`zs3_confusion_from_pred`) and the seen / unseen / per-class histograms are row selections of it."""
+
+    def __init__(self, num_class, unseen_classes_idx):
+        self.num_class = num_class
+        self.unseen_classes_idx = unseen_classes_idx
+
+    @staticmethod
+    def _hist_to_metrics(hist):
+        """metrics.py:127-139: (overall acc, mean class acc, mean IoU, frequency-weighted IoU); NaN classes skipped"""
+        d = np.diag(hist)
+        total = hist.sum()
+        acc = 0.0 if total == 0 else d.sum() / total
+        acc_cls = np.nanmean(_ratio(d, hist.sum(axis=1)))
+        iu = _ratio(d, hist.sum(axis=1) + hist.sum(axis=0) - d)
+        freq = _ratio(hist.sum(axis=1), total)
+        pos = freq > 0
+        return acc, acc_cls, np.nanmean(iu), (freq[pos] * iu[pos]).sum()
+
+    def _rows(self, hist, rows):
+        out = np.zeros_like(hist)
+        rows = [r for r in rows if 0 <= r < self.num_class]
+        out[rows] = hist[rows]
+        return out
+
+    def label_accuracy_score(self, label_trues, label_preds, by_class=False):
+        ev = Evaluator(self.num_class)
+        for lt, lp in zip(label_trues, label_preds):
+            ev.add_batch(np.asarray(lt).reshape(-1), np.asarray(lp).reshape(-1))
+        hist = ev.confusion_matrix
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)  # nanmean of an all-NaN slice, as in the reference
+            metrics = self._hist_to_metrics(hist)
+            if self.unseen_classes_idx:
+                unseen = list(self.unseen_classes_idx)
+                seen = [c for c in range(self.num_class) if c not in unseen]
+                metrics = metrics, self._hist_to_metrics(self._rows(hist, seen)), self._hist_to_metrics(self._rows(hist, unseen))
+            if by_class:
+                return metrics, [self._hist_to_metrics(self._rows(hist, [c])) for c in range(self.num_class)]
+        return metrics
