@@ -99,7 +99,7 @@ def cpu_reference_step_rate(batch, hw, steps, warmup, threads):
         t0 = time.perf_counter()
         for p in params:
             p.grad = None
-        out = O.deeplab_forward(st, img, training=True, drop_p=(0.0, 0.0, 0.0))
+        out = O.deeplab_forward(st, img, training=True, masks="torch")   # Dropout 0.5/0.5/0.1 active, as in the reference
         loss = O.cross_entropy(out, lab)
         loss.backward()
         with torch.no_grad():
@@ -130,13 +130,214 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DeepLabv3+ ResNet-101 fwd+bwd+SGD, 513x513 synthetic (BASELINE configs[1])",
-                   "num_classes": NUM_CLASSES, "per_gpu_batch": 16, "input": "513x513"},
+                   "num_classes": NUM_CLASSES, "per_gpu_batch": 16, "input": "513x513",
+                   "bounded": f"each step is a {batch}-image sample of the 16-image batch (train-mode BN, Dropout on, "
+                              "SGD momentum 0.9 wd 5e-4): a 16-image CPU step takes ~10 s"},
         "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                          "sample": f"bs={batch} 513x513 fwd+CE+bwd+SGD steps of the oracle port on {cores} threads "
                                    f"(host has {os.cpu_count()} cores)"},
         "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+
+# ------------------------------------------------------------------------------------------ library baseline (GPU)
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zs3_oracle as O
+    return O
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten().to(a.device)
+    return float(torch.linalg.norm(a - b) / (torch.linalg.norm(b) + 1e-300))
+
+
+def _global_rel(ga, gb):
+    num = sum(float(((ga[k].double() - gb[k].double().to(ga[k].device)) ** 2).sum()) for k in gb)
+    den = sum(float((gb[k].double() ** 2).sum()) for k in gb)
+    return (num / max(den, 1e-300)) ** 0.5
+
+
+LIB_ARMS = {
+    # the reference's own GPU path: eager PyTorch, NCHW fp32 tensors, cuDNN with TF32 allowed (torch's default), no
+    # cudnn.benchmark, no AMP (nothing in zs3/*.py touches torch.backends or autocast)
+    "tf32_reference_defaults": dict(autocast=False, channels_last=False, benchmark=False, tf32=True),
+    # the same with the knobs a user would turn first
+    "tf32_cudnn_benchmark_channels_last": dict(autocast=False, channels_last=True, benchmark=True, tf32=True),
+    "bf16_autocast_channels_last": dict(autocast=True, channels_last=True, benchmark=True, tf32=True),
+}
+
+
+def _lib_state(O, dev, channels_last, seed=1, randomize_bn=False, dtype=torch.float32):
+    st = O.init_deeplab_state(seed=seed, randomize_bn=randomize_bn)
+    out = {}
+    for k, v in st.items():
+        v = v.to(dev)
+        if v.is_floating_point():
+            v = v.to(dtype)
+            if channels_last and v.dim() == 4:
+                v = v.contiguous(memory_format=torch.channels_last)
+            if "running" not in k:
+                v.requires_grad_(True)
+        out[k] = v
+    return out
+
+
+def _lib_forward_loss(O, st, img, lab, cfg, training=True, masks="torch", drop_p=(0.5, 0.5, 0.1)):
+    if cfg["channels_last"]:
+        img = img.contiguous(memory_format=torch.channels_last)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg["autocast"]):
+        out = O.deeplab_forward(st, img, training=training, masks=masks, drop_p=drop_p)
+    return O.cross_entropy(out.float(), lab), out
+
+
+def _set_backend(cfg):
+    torch.backends.cudnn.benchmark = bool(cfg["benchmark"])
+    torch.backends.cudnn.allow_tf32 = bool(cfg["tf32"])
+
+
+def library_step1_rate(dev, B, HW, batches, arm, steps=5, warmup=3):
+    """img/s of the step-1 iteration (zero_grad, forward, CE, backward, SGD; base_trainer.py:16-20) on STOCK PyTorch
+    kernels (cuDNN / cuBLAS / ATen) on this GPU: the oracle restatement is plain F.conv2d / F.batch_norm / F.relu /
+    F.dropout / F.interpolate, i.e. the kernels the reference's nn.Modules launch."""
+    O = _oracle()
+    cfg = LIB_ARMS[arm]
+    _set_backend(cfg)
+    st = _lib_state(O, dev, cfg["channels_last"])
+    p1 = [v for k, v in st.items() if v.requires_grad and k.startswith("backbone.")]
+    p10 = [v for k, v in st.items() if v.requires_grad and not k.startswith("backbone.")]
+    opt = torch.optim.SGD([{"params": p1, "lr": 0.007}, {"params": p10, "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        img, lab = batches[i % len(batches)]
+        opt.zero_grad(set_to_none=True)
+        loss, _ = _lib_forward_loss(O, st, img, lab, cfg)
+        loss.backward()
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fin = float(loss.item())
+    del st, opt, p1, p10, loss
+    torch.cuda.empty_cache()
+    _set_backend(dict(benchmark=False, tf32=True))
+    return {"value": B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps, "final_loss": fin,
+            "flags": cfg}
+
+
+def numerics_table(dev, hw=513):
+    """rel-L2 distance to the fp64 evaluation of the reference's arithmetic (the oracle in float64 on this GPU), same
+    weights and inputs for every arm.  Two regimes: BASELINE configs[0] (1 x 3 x 513 x 513, eval-mode BatchNorm,
+    forward logits) and one training step at 2 x 3 x 513 x 513 (train-mode BatchNorm at random init, Dropout off:
+    logits and the global relative error over all 312 parameter gradients)."""
+    O = _oracle()
+    from zs3_b200 import parity_train as PT
+    from zs3_b200.modeling.deeplab import DeepLab
+    from zs3_b200.utils.loss import SegmentationLosses
+    g = torch.Generator().manual_seed(1)
+    x1 = torch.randn(1, 3, hw, hw, generator=g).to(dev)
+    x2, t2 = synth_batch(2, hw, 5)
+    x2, t2 = x2.to(dev), t2.to(dev)
+    st_e = O.init_deeplab_state(seed=1, randomize_bn=True)
+    st_t = O.init_deeplab_state(seed=1)
+    plain = dict(autocast=False, channels_last=False, benchmark=False, tf32=True)
+
+    def lib(st0, x, t, training, cfg, dtype):
+        _set_backend(cfg)
+        st = {k: (v.to(dev).to(dtype) if v.is_floating_point() else v.to(dev)) for k, v in st0.items()}
+        for k, v in st.items():
+            if v.is_floating_point() and "running" not in k and t is not None:
+                v.requires_grad_(True)
+        if t is None:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg["autocast"]):
+                return O.deeplab_forward(st, x.to(dtype), training=False).float(), None
+        loss, out = _lib_forward_loss(O, st, x.to(dtype), t, cfg, training=training, masks=None, drop_p=(0.0, 0.0, 0.0))
+        loss.backward()
+        return out.detach().float(), {k: v.grad for k, v in st.items() if v.requires_grad}
+
+    ref_e, _ = lib(st_e, x1, None, False, plain, torch.float64)
+    ref_t, gref_t = lib(st_t, x2, t2, True, plain, torch.float64)
+    rows = {}
+    arms = {"torch_fp32_no_tf32": (dict(plain, tf32=False), torch.float32),
+            "torch_tf32_reference_defaults": (plain, torch.float32),
+            "torch_bf16_autocast": (dict(plain, autocast=True), torch.float32)}
+    for name, (cfg, dt) in arms.items():
+        le, _ = lib(st_e, x1, None, False, cfg, dt)
+        lt, gt = lib(st_t, x2, t2, True, cfg, dt)
+        rows[name] = {"logits_eval_configs0": _rel(le, ref_e), "logits_train": _rel(lt, ref_t), "grads_train": _global_rel(gt, gref_t)}
+    _set_backend(dict(benchmark=False, tf32=True))
+
+    def ours(pieces):
+        def build(st, training):
+            m = DeepLab(num_classes=NUM_CLASSES, sync_bn=True, pretrained=False)
+            m.load_state_dict({k: v.clone() for k, v in st.items()})
+            m = m.to(dev)
+            m.train() if training else m.eval()
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.Dropout):
+                    mod.p = 0.0
+            return m
+        me, mt = build(st_e, False), build(st_t, True)
+        if pieces == 0:   # the bf16 throughput path through the module API
+            with torch.no_grad():
+                le = me(x1)
+            lt = mt(x2)
+            SegmentationLosses(weight=None, cuda=True).build_loss("ce")(lt, t2).backward()
+            lt = lt.detach()
+        else:
+            with torch.no_grad():
+                le, _ = PT.SplitPrecisionTrainer(me, pieces=pieces, optimizer=False).forward(x1)
+            _, lt = PT.SplitPrecisionTrainer(mt, pieces=pieces, optimizer=False).loss_and_grads(x2, t2, return_logits=True)
+        gt = {k: p.grad for k, p in mt.named_parameters()}
+        return {"logits_eval_configs0": _rel(le, ref_e), "logits_train": _rel(lt, ref_t), "grads_train": _global_rel(gt, gref_t)}
+
+    rows["zs3_b200_bf16"] = ours(0)
+    for pcs in (1, 2, 3):
+        rows[f"zs3_b200_split{pcs}"] = ours(pcs)
+    torch.cuda.empty_cache()
+    return {"what": "relative L2 distance to the float64 evaluation of the reference's arithmetic on identical weights and inputs",
+            "regimes": {"logits_eval_configs0": f"1x3x{hw}x{hw}, eval-mode BN (BASELINE configs[0])",
+                        "logits_train / grads_train": f"2x3x{hw}x{hw}, train-mode BN at random init, Dropout off; grads = all 312 parameter gradients, global rel-L2"},
+            "north_star_tolerance": 1e-3, "arms": rows}
+
+
+def split_precision_rate(dev, B, HW, batches, pieces, steps=5, warmup=3):
+    """img/s of the SAME step (zero_grad, forward, CE, backward, fused SGD; Dropout on) in the split-precision mode
+    (zs3_b200/parity_train.py): fp32 activations / gradients, every conv operand as `pieces` bf16 pieces on tcgen05."""
+    from zs3_b200 import _lib as L
+    from zs3_b200 import parity_train as PT
+    from zs3_b200.modeling.deeplab import DeepLab
+    torch.manual_seed(1)
+    model = DeepLab(num_classes=NUM_CLASSES, output_stride=16, sync_bn=True, pretrained=False).to(dev).train()
+    eng = PT.SplitPrecisionTrainer(model, pieces=pieces, lr=0.007)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = 0
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            n0 = L.lib().zs3_launch_count()
+            e0.record()
+        loss = eng.train_step(*batches[i % len(batches)])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (L.lib().zs3_launch_count() - n0) / steps
+    peak, _ = measured_peaks()
+    nom = B * FWDBWD_GFLOP_PER_IMG / 1e3 / (ms * 1e-3)
+    npairs = pieces * (pieces + 1) // 2
+    res = {"value": B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps, "pieces": pieces,
+           "dtype": f"f32 activations/gradients, {pieces}x bf16 operand pieces ({8 * pieces} mantissa bits), fp32 accumulate",
+           "products_per_conv": npairs, "launches_per_step": launches, "final_loss": float(loss.item()),
+           "nominal_tflops": nom, "tensor_tflops_executed": nom * npairs,
+           "roofline_frac_nominal": nom / peak, "roofline_frac_executed": nom * npairs / peak}
+    del eng, model
+    torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -363,6 +564,36 @@ def run_ours(args):
         except Exception as e:  # reported, never fatal for the headline line
             step2 = {"error": repr(e)[:300]}
 
+    # ---- the same step on stock PyTorch (cuDNN/cuBLAS/ATen) on THIS GPU, the split-precision (tolerance-meeting) mode
+    # of this repo, and every arm's distance to the fp64 evaluation of the reference's arithmetic
+    library_baseline = parity_mode = numerics = None
+    if rank == 0 and world == 1:
+        def guarded(fn, *a, **kw):
+            try:
+                return fn(*a, **kw)
+            except Exception as e:  # reported, never fatal for the headline line
+                torch.cuda.empty_cache()
+                return {"error": repr(e)[:300]}
+        if not args.no_library_baseline:
+            phase("library baseline (stock PyTorch on this GPU)")
+            library_baseline = {arm: guarded(library_step1_rate, dev, B, HW, devb, arm) for arm in LIB_ARMS}
+            library_baseline["what"] = ("zero_grad + forward + CE + backward + SGD of the same DeepLabv3+ step on stock PyTorch "
+                                        f"{torch.__version__} kernels (cuDNN {torch.backends.cudnn.version()}), eager, same "
+                                        "batch / resolution / Dropout / optimizer; the reference's own GPU path is the first arm")
+            for arm in LIB_ARMS:
+                if isinstance(library_baseline[arm], dict) and "value" in library_baseline[arm]:
+                    library_baseline[arm]["zs3_b200_bf16_speedup"] = value / library_baseline[arm]["value"]
+        if not args.no_parity:
+            phase("split-precision mode")
+            parity_mode = {f"split{pcs}": guarded(split_precision_rate, dev, B, HW, devb, pcs) for pcs in (2, 3, 1)}
+            if library_baseline and "value" in library_baseline.get("tf32_reference_defaults", {}):
+                for k, v in parity_mode.items():
+                    if "value" in v:
+                        v["speedup_vs_reference_gpu_path_tf32"] = v["value"] / library_baseline["tf32_reference_defaults"]["value"]
+        if not args.no_numerics:
+            phase("numerics table")
+            numerics = guarded(numerics_table, dev, HW)
+
     if rank == 0:
         sampler.join(timeout=2)
         line = {
@@ -385,6 +616,9 @@ def run_ours(args):
             "roofline": roofline,
             "forward_only": forward_only,
             "step2": step2,
+            "library_baseline": library_baseline,
+            "parity_mode": parity_mode,
+            "numerics_vs_fp64": numerics,
             "cpu_baseline": cpu_baseline,
         }
         emit(line)
@@ -483,6 +717,9 @@ def main():
     ap.add_argument("--size", type=int, default=513, help="input height=width (BASELINE: 513)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-step2", action="store_true", help="skip the configs[2] (ZS3Net step-2 iteration) measurement")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU arms")
+    ap.add_argument("--no-parity", action="store_true", help="skip the split-precision (tolerance-meeting) training mode")
+    ap.add_argument("--no-numerics", action="store_true", help="skip the distance-to-fp64 table")
     ap.add_argument("--layer-table", default="", help="write a per-conv-shape timing table (markdown) to this path")
     ap.add_argument("--mode", default="graph", choices=["eager", "graph"],
                     help="graph: capture the whole training step in one CUDA graph and replay it")

@@ -49,6 +49,8 @@ int zs3_device_supported(void);
 #define ZS3_STRUCT_COMPONENTS_ARGS 8
 #define ZS3_STRUCT_CONV_SEGMENT 9
 #define ZS3_STRUCT_ROW_SOURCE 10
+#define ZS3_STRUCT_BN_ACT_F32_ARGS 11
+#define ZS3_STRUCT_BN_BWD_F32_ARGS 12
 unsigned long long zs3_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
@@ -468,6 +470,61 @@ int zs3_spatial_broadcast_f32(const float* x, float* y, int N, int HW, int C, vo
 int zs3_nchw_to_nhwc_f32(const float* src, float* dst, int N, int C, long long HW, int cs, void* stream);
 int zs3_stem_im2col_f32(const float* x, float* cols, int N, int C, int H, int W, int R, int stride, int pad, int Ho,
                         int Wo, int kpad, int krsc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Split-precision TRAINING mode (csrc/parity_train.cu; host side zs3_b200/parity_train.py): fp32 activations and
+ * gradients, every conv operand fed to tcgen05 as P bf16 pieces (P = 1, 2, 3: 8, 16, 24 mantissa bits; cuDNN's
+ * default TF32 path that the reference runs on a GPU carries 10).  fprop/dgrad: the P(P+1)/2 significant cross
+ * products are K-segments of one zs3_conv_fprop launch (fp32 output); wgrad: one zs3_conv_wgrad launch per product,
+ * reduce-added into the same gradient.  Below: the HBM-bound glue of that mode, forward and backward.
+ * Same reference call sites as the bf16 kernels above (zs3/base_trainer.py:16-20 drives them).
+ * ---------------------------------------------------------------------------------------------- */
+/* x[n] fp32 (n % 8 == 0, 16-byte aligned) -> n_pieces bf16 tensors with x = sum of pieces (+ dropped tail) */
+int zs3_split_f32(const float* x, void* const* pieces, int n_pieces, long long n, void* stream);
+
+typedef struct {
+  const float* y; long long y_cstride;              /* conv output [M][y_cstride], pre-normalisation */
+  const float* residual; long long res_cstride;     /* optional fp32 residual added before the ReLU */
+  const float* scale; const float* shift;           /* per-channel affine (zs3_bn_finalize / zs3_bn_eval_coeffs) */
+  float* out; long long out_cstride;                /* fp32 result (optional if pieces are written) */
+  void* pieces[3]; int n_pieces; long long piece_cstride; /* bf16 pieces of the result: the next conv's operand */
+  long long M; int C;                               /* rows, channels (multiple of 8; padding channels included) */
+  int relu;
+  int drop_mode; float drop_p;                      /* 0 none, 1 counter-based RNG (bn.cu's stream), 2 keep_mask */
+  unsigned long long seed, offset; const void* offset_dev; const void* keep_mask;
+} zs3_bn_act_f32_args;
+/* out = dropout(relu(y * scale + shift + residual)), written as fp32 and/or as bf16 pieces, one pass */
+int zs3_bn_act_f32(const zs3_bn_act_f32_args* a, void* stream);
+
+typedef struct {
+  const float* dout; long long dout_cstride;        /* gradient w.r.t. the layer output */
+  const float* act; long long act_cstride;          /* forward output (fp32) for the ReLU/Dropout mask, or ... */
+  const void* act_hi; long long act_hi_cstride;     /* ... its first bf16 piece (same sign) */
+  const float* y; long long y_cstride;              /* saved conv output */
+  const float* mean; const float* invstd; const float* scale;
+  long long M; int C;                               /* C: power of two >= 64 */
+  int relu; float grad_scale; int training;         /* grad_scale = 1/(1-p) of a Dropout layer; training: batch stats */
+  double* sum_dz; double* sum_dzx;                  /* [C] scratch, zeroed by the call */
+  float* dy; long long dy_cstride;                  /* fp32 gradient w.r.t. y (optional if pieces are written) */
+  void* dy_pieces[3]; int n_pieces; long long piece_cstride;  /* bf16 pieces of dy: operands of dgrad / wgrad */
+  float* dres; long long dres_cstride;              /* optional: gradient w.r.t. the residual input */
+  float* dgamma; float* dbeta; int C_real; int param_accumulate;
+} zs3_bn_bwd_f32_args;
+/* BatchNorm(+ReLU/Dropout/residual) backward: per-channel sums, then dy (memset + two kernels on `stream`) */
+int zs3_bn_bwd_f32(const zs3_bn_bwd_f32_args* a, void* stream);
+/* out[c] = sum over rows of x[m][c] in fp64 (bias gradients); C a power of two >= 64 */
+int zs3_channel_sums_f32(const float* x, long long x_cstride, long long M, int C, double* out, void* stream);
+int zs3_maxpool_arg_f32(const float* x, float* y, unsigned char* argmax, int N, int H, int W, int C, int Ho, int Wo,
+                        int k, int stride, int pad, void* stream);
+int zs3_maxpool_bwd_f32(const float* dy, const unsigned char* argmax, float* dx, int N, int H, int W, int C, int Ho,
+                        int Wo, int k, int stride, int pad, void* stream);
+/* backward of zs3_bilinear_f32: dy NHWC [N][Ho][Wo][dy_cs] (from_nchw = 0) or NCHW [N][C][Ho][Wo] (from_nchw = 1,
+ * the logits gradient) -> dx NHWC [N][Hi][Wi][dx_cs], channels < C written */
+int zs3_bilinear_bwd_f32(const float* dy, float* dx, int N, int Hi, int Wi, int Ho, int Wo, int C, int dy_cs, int dx_cs,
+                         int from_nchw, void* stream);
+/* y[n][p][c] (+)= scale * x[n][c]: backward of the global average pool (aspp.py:84) */
+int zs3_spatial_broadcast_acc_f32(const float* x, float* y, int N, int HW, int C, float scale, int accumulate,
+                                  void* stream);
 
 /* debug: one im2col TMA load dumped raw (tests/test_tma_probe.py) */
 int zs3_debug_im2col_probe(const void* x, int N, int H, int W, int C, int pad, int upper, int stride, int cpp, int ppc,

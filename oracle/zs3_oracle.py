@@ -153,6 +153,8 @@ def dropout(x, p, training, masks, name):
     """nn.Dropout with an injectable keep-mask (masks[name], same shape as x, 1 = keep)."""
     if not training or p == 0.0:
         return x
+    if masks == "torch":  # stock nn.Dropout (bench.py's library baseline: the reference's own GPU path, RNG not injected)
+        return F.dropout(x, p, True)
     if masks is None or name not in masks:
         raise ValueError(f"oracle dropout '{name}' needs an explicit keep mask in training mode")
     return x * masks[name].to(x.dtype) / (1.0 - p)
@@ -258,7 +260,7 @@ def moment_loss(gen_samples, x, sigma=(2, 5, 10, 20, 40, 80)):
     X2 = torch.sum(X * X, 1, keepdim=True)
     exp = XX - 0.5 * X2 - 0.5 * X2.t()
     M, N = gen_samples.shape[0], x.shape[0]
-    s = torch.cat((torch.ones(N, 1, dtype=X.dtype) / N, -torch.ones(M, 1, dtype=X.dtype) / M), 0)
+    s = torch.cat((torch.ones(N, 1, dtype=X.dtype) / N, -torch.ones(M, 1, dtype=X.dtype) / M), 0).to(X.device)  # loss.py:93-96 builds it on the host, then .cuda()
     S = s @ s.t()
     loss = 0
     for v in sigma:

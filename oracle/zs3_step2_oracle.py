@@ -41,11 +41,12 @@ def step2(st_deeplab, st_gen, real_features, target, embedding, input_size, seen
                 continue
             sel = tg == c
             real_c, emb_c = rf[sel], emb[sel]
-            z = noise_fn(emb_c.shape[0])
-            mask = mask_fn(emb_c.shape[0])
+            dev = emb_c.device                                 # (CPU in the tests; bench.py's library baseline runs it on cuda)
+            z = noise_fn(emb_c.shape[0]).to(dev)               # :216-218 draws on the host, then .cuda()
+            mask = mask_fn(emb_c.shape[0]).to(dev)
             fake_c = O.gmmn_forward(gen, emb_c, z.float(), training=True, keep_mask=mask)
             if int(c) in seen and not has_unseen:
-                ridx = index_fn(fake_c.shape[0])
+                ridx = index_fn(fake_c.shape[0]).to(dev)
                 loss = O.moment_loss(fake_c[ridx], real_c[ridx])
                 g_losses.append(loss.item())
                 sample_loss += loss.item()

@@ -43,7 +43,7 @@ def test_binding_struct_sizes_match_the_library():
     from zs3_b200 import _lib
     lib = _lib.lib()
     hdr = open(os.path.join(ROOT, "include", "zs3b200.h")).read()
-    ids = dict((int(v), k) for k, v in re.findall(r"#define (ZS3_STRUCT_[A-Z_]+) (\d+)", hdr))
+    ids = dict((int(v), k) for k, v in re.findall(r"#define (ZS3_STRUCT_[A-Z0-9_]+) (\d+)", hdr))
     assert sorted(ids) == sorted(_lib.STRUCT_IDS), (ids, _lib.STRUCT_IDS)
     for which, mirror in _lib.STRUCT_IDS.items():
         assert lib.zs3_sizeof(which) == ctypes.sizeof(mirror) > 0, (ids[which], mirror)

@@ -187,6 +187,37 @@ class SgemmArgs(C.Structure):
     ]
 
 
+class BnActF32Args(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p), ("y_cstride", C.c_longlong),
+        ("residual", C.c_void_p), ("res_cstride", C.c_longlong),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("out", C.c_void_p), ("out_cstride", C.c_longlong),
+        ("pieces", C.c_void_p * 3), ("n_pieces", C.c_int), ("piece_cstride", C.c_longlong),
+        ("M", C.c_longlong), ("C", C.c_int),
+        ("relu", C.c_int),
+        ("drop_mode", C.c_int), ("drop_p", C.c_float),
+        ("seed", C.c_ulonglong), ("offset", C.c_ulonglong), ("offset_dev", C.c_void_p), ("keep_mask", C.c_void_p),
+    ]
+
+
+class BnBwdF32Args(C.Structure):
+    _fields_ = [
+        ("dout", C.c_void_p), ("dout_cstride", C.c_longlong),
+        ("act", C.c_void_p), ("act_cstride", C.c_longlong),
+        ("act_hi", C.c_void_p), ("act_hi_cstride", C.c_longlong),
+        ("y", C.c_void_p), ("y_cstride", C.c_longlong),
+        ("mean", C.c_void_p), ("invstd", C.c_void_p), ("scale", C.c_void_p),
+        ("M", C.c_longlong), ("C", C.c_int),
+        ("relu", C.c_int), ("grad_scale", C.c_float), ("training", C.c_int),
+        ("sum_dz", C.c_void_p), ("sum_dzx", C.c_void_p),
+        ("dy", C.c_void_p), ("dy_cstride", C.c_longlong),
+        ("dy_pieces", C.c_void_p * 3), ("n_pieces", C.c_int), ("piece_cstride", C.c_longlong),
+        ("dres", C.c_void_p), ("dres_cstride", C.c_longlong),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("C_real", C.c_int), ("param_accumulate", C.c_int),
+    ]
+
+
 def _EXTRA_SIGS(vp, i, ll, f, d):
     return {
         "zs3_debug_im2col_probe": [vp, i, i, i, i, i, i, i, i, i, i, i, i, i, i, i, vp, vp],
@@ -236,12 +267,20 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_spatial_broadcast_f32": [vp, vp, i, i, i, vp],
         "zs3_nchw_to_nhwc_f32": [vp, vp, i, i, ll, i, vp],
         "zs3_stem_im2col_f32": [vp, vp, i, i, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_split_f32": [vp, C.POINTER(C.c_void_p), i, ll, vp],
+        "zs3_bn_act_f32": [C.POINTER(BnActF32Args), vp],
+        "zs3_bn_bwd_f32": [C.POINTER(BnBwdF32Args), vp],
+        "zs3_channel_sums_f32": [vp, ll, ll, i, vp, vp],
+        "zs3_maxpool_arg_f32": [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_maxpool_bwd_f32": [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_bilinear_bwd_f32": [vp, vp, i, i, i, i, i, i, i, i, i, vp],
+        "zs3_spatial_broadcast_acc_f32": [vp, vp, i, i, i, f, i, vp],
     }
 
 
 # ids of include/zs3b200.h (ZS3_STRUCT_*) -> ctypes mirror; checked against zs3_sizeof() when the library loads
 STRUCT_IDS = {1: ConvArgs, 2: WgradArgs, 3: BnApplyArgs, 4: BnBwdArgs, 5: SgemmArgs, 6: GmmnItem, 7: GmmnTrainArgs,
-              8: ComponentsArgs, 9: ConvSegment, 10: RowSource}
+              8: ComponentsArgs, 9: ConvSegment, 10: RowSource, 11: BnActF32Args, 12: BnBwdF32Args}
 
 
 def lib():

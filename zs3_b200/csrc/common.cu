@@ -184,6 +184,8 @@ unsigned long long zs3_sizeof(int which) {
     case ZS3_STRUCT_COMPONENTS_ARGS: return sizeof(zs3_components_args);
     case ZS3_STRUCT_CONV_SEGMENT: return sizeof(zs3_conv_segment);
     case ZS3_STRUCT_ROW_SOURCE: return sizeof(zs3_row_source);
+    case ZS3_STRUCT_BN_ACT_F32_ARGS: return sizeof(zs3_bn_act_f32_args);
+    case ZS3_STRUCT_BN_BWD_F32_ARGS: return sizeof(zs3_bn_bwd_f32_args);
     default: return 0;
   }
 }
