@@ -180,3 +180,32 @@ def test_metrics_oracle_matches_reference_evaluator_golden():
         assert np.isclose(sc[name][1], gold["class_acc"][k], rtol=1e-12)
         assert np.isclose(sc[name][2], gold["miou"][k], rtol=1e-12)
         assert np.isclose(sc[name][3], gold["fwiou"][k], rtol=1e-12)
+
+
+def test_step2_loop_oracle_matches_the_real_trainer_iteration():
+    """oracle/zs3_step2_oracle.step2 against ONE iteration of the REAL `Trainer.training`
+    (train_pascal_GMMN.py:134-311, compiled from the reference file by tests/golden/make_golden_step2.py) with the
+    recorded randomness replayed: per-update generator losses, the generator after five sequential Adam steps and
+    pred_conv after its SGD step.  This pins the LOOP (class order, seen/unseen gating, sampled rows, update order)."""
+    import step2_golden as G
+    import zs3_step2_oracle as S
+    torch.set_num_threads(8)
+    image, target, embedding, feats, _ = G.inputs()
+    rp = G.Replay()
+    gold = rp.gold
+    st = O.init_deeplab_state(seed=1, randomize_bn=True)
+    gst = O.init_gmmn_state(seed=3)
+    cw = torch.ones(G.C)
+    cw[G.UNSEEN] = 100.0
+    ref = S.step2(st, gst, feats, target, embedding, (65, 65), set(G.SEEN), set(G.UNSEEN), rp.noise, rp.index, rp.mask, cw)
+    assert rp.nk == int(gold["n_noise_draws"]) and rp.ik == int(gold["n_index_draws"]) == len(ref["g_losses"])
+    assert np.allclose(ref["g_losses"], gold["g_losses"], rtol=2e-5), (ref["g_losses"], gold["g_losses"])
+    for k, v in ref["generator"].items():
+        a = v.numpy()
+        assert _rel(a[::4, ::4] if a.ndim == 2 else a, gold["generator/" + k]) < 1e-6, k
+        assert abs(np.linalg.norm(a.astype(np.float64)) - float(gold["generator_norm/" + k])) < 1e-5 * float(gold["generator_norm/" + k])
+        # the accumulated UPDATE (5 Adam steps of 2e-4), not just the weights it sits on
+        d = np.linalg.norm((a - gst[k].numpy()).astype(np.float64))
+        assert abs(d - float(gold["generator_delta_norm/" + k])) < 2e-3 * float(gold["generator_delta_norm/" + k]), k
+    assert _rel(ref["pred_conv.weight"].numpy(), gold["pred_conv.weight"]) < 1e-6
+    assert _rel(ref["pred_conv.bias"].numpy(), gold["pred_conv.bias"]) < 1e-6

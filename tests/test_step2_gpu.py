@@ -265,3 +265,51 @@ def test_gcn_context_step_matches_oracle():
         assert rel_l2(p.cpu(), ref["gcn_generator"][k]) < 1e-4, k
     assert abs(loss.item() - ref["loss"]) < 2e-2 * abs(ref["loss"])
     assert rel_l2(model.decoder.pred_conv.weight.detach().cpu(), ref["pred_conv.weight"]) < 2e-2
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["modules", "fused_work_list"])
+def test_step2_iteration_matches_the_real_trainer_golden(fused):
+    """Both runners against tests/golden/step2.npz = one iteration of the REAL reference `Trainer.training`
+    (train_pascal_GMMN.py:134-311; tests/golden/make_golden_step2.py) with its recorded randomness replayed: per-update
+    generator losses 1e-3 (north-star tolerance on the GMMN loss), generator weights after five sequential Adam steps
+    1e-4, accumulated update 1 %, pred_conv after SGD 2e-2 (the classifier runs on bf16 tensor-core operands)."""
+    import step2_golden as G
+    import zs3_oracle as O
+    from zs3.modeling.deeplab import DeepLab
+    from zs3.modeling.gmmn import GMMNnetwork
+    from zs3.utils.loss import GMMNLoss, SegmentationLosses
+    from zs3_b200.step2 import ZS3Step, ZS3StepFused
+    image, target, embedding, feats, _ = G.inputs()
+    rp = G.Replay()
+    gold = rp.gold
+    st = O.init_deeplab_state(seed=1, randomize_bn=True)
+    gst = O.init_gmmn_state(seed=3)
+    model = DeepLab(num_classes=G.C, sync_bn=True, pretrained=False)
+    model.load_state_dict(st)
+    model = torch.nn.DataParallel(model.cuda(), device_ids=[0])
+    model.train()
+    gen = GMMNnetwork(300, 300, 256, 256)
+    gen.load_state_dict(gst)
+    gen = gen.cuda().train()
+    cw = torch.ones(G.C)
+    cw[G.UNSEEN] = 100.0
+    crit = SegmentationLosses(weight=cw.cuda(), cuda=True).build_loss("ce")
+    crit_g = GMMNLoss(sigma=[2, 5, 10, 20, 40, 80], cuda=True).build_loss()
+    opt = torch.optim.SGD([{"params": model.module.get_1x_lr_params(), "lr": 0.007},
+                           {"params": model.module.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+    opt_g = torch.optim.Adam(gen.parameters(), lr=2e-4)
+    step = (ZS3StepFused if fused else ZS3Step)(model, gen, crit, crit_g, opt, opt_g, G.SEEN, G.UNSEEN, noise_fn=rp.noise,
+                                                index_fn=rp.index, mask_fn=rp.mask)
+    loss, glb, g_losses = step.training_step(image.cuda(), target.cuda(), embedding.cuda(), real_features=feats.cuda())
+    torch.cuda.synchronize()
+    print("g_losses gpu", np.round(g_losses, 5), "reference", np.round(gold["g_losses"], 5))
+    assert len(g_losses) == len(gold["g_losses"]) == 5
+    assert np.allclose(g_losses, gold["g_losses"], rtol=1e-3)
+    for k, p in gen.state_dict().items():
+        a = p.detach().cpu().numpy()
+        sub = a[::4, ::4] if a.ndim == 2 else a
+        assert rel_l2(torch.from_numpy(np.ascontiguousarray(sub)), torch.from_numpy(gold["generator/" + k])) < 1e-4, k
+        d = np.linalg.norm((a - gst[k].numpy()).astype(np.float64))
+        assert abs(d - float(gold["generator_delta_norm/" + k])) < 1e-2 * float(gold["generator_delta_norm/" + k]), k
+    assert rel_l2(model.module.decoder.pred_conv.weight.detach().cpu(), torch.from_numpy(gold["pred_conv.weight"])) < 2e-2
+    assert rel_l2(model.module.decoder.pred_conv.bias.detach().cpu(), torch.from_numpy(gold["pred_conv.bias"])) < 2e-2
