@@ -230,12 +230,28 @@ def test_fused_step2_host_logic_against_step2_oracle(emul, monkeypatch):
     assert abs(loss.item() - ref["loss"]) < 1e-4 * abs(ref["loss"])
     assert rel_l2(head.w.detach(), ref["pred_conv.weight"]) < 1e-5
 
+    # the [C, E] class-embedding table instead of the per-pixel map (rows gathered as table[label]): same iteration
+    head_t, gen_t = Head(), Gen().train()
+    rp.reset()
+    step_t = ZS3StepFused(head_t, gen_t, lambda out, tg: O.cross_entropy(out, tg, weight=cw), None,
+                          torch.optim.SGD(head_t.parameters(), lr=0.07, momentum=0.9, weight_decay=5e-4),
+                          torch.optim.Adam(gen_t.parameters(), lr=2e-4), seen, unseen, noise_fn=rp.noise, index_fn=rp.index,
+                          mask_fn=rp.mask)
+    monkeypatch.setattr(step_t.updater, "run", lambda items, E, Z, keepalive=(): emul_run(items, E, Z, which=step_t))
+    loss_t, glb_t, g_t = step_t.training_step(image, target, real_features=real, class_embeddings=emb_table)
+    assert torch.allclose(torch.tensor(g_t), torch.tensor(ref["g_losses"]), rtol=1e-4)
+    for k, p in gen_t.state_dict().items():
+        assert rel_l2(p, ref["generator"][k]) < 1e-5, k
+    assert abs(loss_t.item() - ref["loss"]) < 1e-4 * abs(ref["loss"])
+
     # default randomness (noise drawn per sampled row on the device, counter-RNG Dropout): runs and stays finite
     step_b = ZS3StepFused(head, gen, lambda out, tg: O.cross_entropy(out, tg, weight=cw), None, opt, opt_g, seen, unseen,
                           tensor_core_bulk=False)   # the image-level tcgen05 generation is GPU-only (test_step2_gpu.py)
     monkeypatch.setattr(step_b.updater, "run", lambda items, E, Z, keepalive=(): emul_run(items, E, Z, which=step_b))
     loss_b, glb_b, g_b = step_b.training_step(image, target, embedding, real_features=real)
     assert len(g_b) == 5 and all(v == v and v > 0 for v in g_b) and torch.isfinite(loss_b)
+    loss_c, _, g_c = step_b.training_step(image, target, real_features=real, class_embeddings=emb_table)   # vectorised packing
+    assert len(g_c) == 5 and all(v == v and v > 0 for v in g_c) and torch.isfinite(loss_c)
 
 
 # ------------------------------------------------------------------------------------ cluster graph (config 5)

@@ -205,9 +205,6 @@ def test_image_level_generation_on_tensor_cores_matches_per_class_generator():
     assert rel_l2(fake.cpu(), cpu) < 1e-4
 
 
-@pytest.mark.skipif(os.environ.get("ZS3_EXPERIMENTAL") != "1",
-                    reason="ZS3StepGCN is CPU-validated only (tests/test_kernel_emulation.py); set ZS3_EXPERIMENTAL=1 "
-                           "to run its first GPU validation")
 def test_gcn_context_step_matches_oracle():
     """config 5 (zs3/train_context_GMMN_GCNcontext.py:270-460): ZS3StepGCN on the CUDA modules vs oracle step2(gcn=...)"""
     import zs3_oracle as O
@@ -313,3 +310,40 @@ def test_step2_iteration_matches_the_real_trainer_golden(fused):
         assert abs(d - float(gold["generator_delta_norm/" + k])) < 1e-2 * float(gold["generator_delta_norm/" + k]), k
     assert rel_l2(model.module.decoder.pred_conv.weight.detach().cpu(), torch.from_numpy(gold["pred_conv.weight"])) < 2e-2
     assert rel_l2(model.module.decoder.pred_conv.bias.detach().cpu(), torch.from_numpy(gold["pred_conv.bias"])) < 2e-2
+
+
+def test_class_embedding_table_equals_per_pixel_map():
+    """training_step(image, target, class_embeddings=E) gathers E[label] on the device; same losses and weights as
+    the reference-shaped call with the [B, E, H, W] map built as E[label] (dataloaders/datasets/base.py:45-51)"""
+    import step2_golden as G
+    import zs3_oracle as O
+    from zs3.modeling.deeplab import DeepLab
+    from zs3.modeling.gmmn import GMMNnetwork
+    from zs3.utils.loss import GMMNLoss, SegmentationLosses
+    from zs3_b200.step2 import ZS3StepFused
+    image, target, embedding, feats, table = G.inputs()
+    results = []
+    for use_table in (False, True):
+        rp = G.Replay()
+        model = DeepLab(num_classes=G.C, sync_bn=True, pretrained=False)
+        model.load_state_dict(O.init_deeplab_state(seed=1, randomize_bn=True))
+        model = model.cuda().train()
+        gen = GMMNnetwork(300, 300, 256, 256)
+        gen.load_state_dict(O.init_gmmn_state(seed=3))
+        gen = gen.cuda().train()
+        cw = torch.ones(G.C)
+        cw[G.UNSEEN] = 100.0
+        opt = torch.optim.SGD([{"params": model.get_1x_lr_params(), "lr": 0.007},
+                               {"params": model.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+        step = ZS3StepFused(model, gen, SegmentationLosses(weight=cw.cuda(), cuda=True).build_loss("ce"),
+                            GMMNLoss(cuda=True).build_loss(), opt, torch.optim.Adam(gen.parameters(), lr=2e-4), G.SEEN, G.UNSEEN,
+                            noise_fn=rp.noise, index_fn=rp.index, mask_fn=rp.mask)
+        kw = dict(class_embeddings=table.cuda()) if use_table else dict(embedding=embedding.cuda())
+        loss, glb, g_losses = step.training_step(image.cuda(), target.cuda(), real_features=feats.cuda(), **kw)
+        results.append((loss.item(), g_losses, {k: v.detach().clone() for k, v in gen.state_dict().items()}))
+    (l0, g0, w0), (l1, g1, w1) = results
+    assert g0 == g1 and l0 == l1
+    for k in w0:
+        assert torch.equal(w0[k], w1[k]), k
+    with pytest.raises(ValueError):
+        step.training_step(image.cuda(), target.cuda())

@@ -58,16 +58,19 @@ ITEM_DTYPE = np.dtype(L.GmmnItem)   # numpy mirror of zs3_gmmn_item (same offset
 def pack_items_vectorized(images, rows, emb, emb_rows, noise, real, real_rows, keep_rows):
     """A whole work list at once.  Update k belongs to image images[k]; `emb` / `real` = (base pointer, bytes per
     image, column stride in elements) of an NCHW-like map whose rows are gathered through emb_rows[k] / real_rows[k]
-    (int32 [n, rows] CUDA tensors, row stride 1); noise [n, rows, Z] fp32 (dense); keep_rows int32 [n, rows]."""
+    (int32 [n, rows] CUDA tensors, row stride 1; an optional 4th tuple entry overrides the row stride, e.g. a
+    [C, E] class-embedding table gathered by class id); noise [n, rows, Z] fp32 (dense); keep_rows int32 [n, rows]."""
     n = len(images)
     a = np.zeros(n, dtype=ITEM_DTYPE)
     k = np.arange(n, dtype=np.int64)
-    for name, (base, img_bytes, cs), idx in (("emb", emb, emb_rows), ("real", real, real_rows)):
+    for name, src, idx in (("emb", emb, emb_rows), ("real", real, real_rows)):
+        base, img_bytes, cs = src[:3]
+        rs = src[3] if len(src) > 3 else 1     # row stride in elements (a [C, E] class-embedding table: E, with cs = 1)
         if idx.dtype != torch.int32 or not idx.is_contiguous():
             raise TypeError("row gathers are contiguous int32 tensors")
         a[name]["base"] = (base + images * img_bytes).astype(np.uint64)
         a[name]["rows"] = (idx.data_ptr() + k * (rows * 4)).astype(np.uint64)
-        a[name]["row_stride"], a[name]["col_stride"] = 1, cs
+        a[name]["row_stride"], a[name]["col_stride"] = rs, cs
     if noise.dtype != torch.float32 or not noise.is_contiguous():
         raise TypeError("noise is a contiguous fp32 tensor [n, rows, Z]")
     a["noise"]["base"] = (noise.data_ptr() + k * (rows * noise.shape[2] * 4)).astype(np.uint64)

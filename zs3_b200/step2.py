@@ -164,7 +164,7 @@ class ZS3StepFused(ZS3Step):
         return {b[0]: {"host_ms": (b[1] - a[1]) * 1e3, "gpu_ms": a[2].elapsed_time(b[2])} for a, b in zip(marks, marks[1:])}
 
     @torch.no_grad()
-    def _generate_image(self, emb_map, src, tg_i, fh, fw, noise=None, keep_mask=None):
+    def _generate_image(self, emb_map, src, tg_i, fh, fw, noise=None, keep_mask=None, table=None):
         """Generated features for EVERY pixel of one image (`:211-222,242`: the reference calls the generator once
         per class; rows are independent, so one call over all pixels with each pixel's own class embedding is the
         same map), as two 1x1 "convolutions" over the fh x fw grid on the tcgen05 implicit-GEMM kernel in fp32x3
@@ -179,7 +179,10 @@ class ZS3StepFused(ZS3Step):
         hw, kin = fh * fw, self.embed_dim + self.noise_dim
         x = torch.zeros((1, fh, fw, K.cpad(kin)), dtype=torch.float32, device=dev)
         xv = x.view(hw, -1)
-        xv[:, :self.embed_dim] = emb_map.reshape(self.embed_dim, -1)[:, src.long()].t()
+        if table is None:
+            xv[:, :self.embed_dim] = emb_map.reshape(self.embed_dim, -1)[:, src.long()].t()
+        else:
+            xv[:, :self.embed_dim] = self._table_rows(table, tg_i)
         xv[:, self.embed_dim:kin] = torch.rand((hw, self.noise_dim), device=dev) if noise is None else noise
         w1, b1, w2, b2 = (t.detach() for t in upd.params)
         h1 = P.conv_fp32([x], [kin], w1.view(upd.hidden, kin, 1, 1), 1, 1, 1, 0, 1, upd.hidden, bias=self._pad_bias(b1))
@@ -188,6 +191,13 @@ class ZS3StepFused(ZS3Step):
                         upd.feat, bias=self._pad_bias(b2))
         out = y.view(hw, -1)[:, :upd.feat]
         return torch.where((tg_i == 255)[:, None], torch.zeros_like(out), out)
+
+    @staticmethod
+    def _table_rows(table, labels):
+        """E_table[label] as the reference's dataloader builds the per-pixel map (dataloaders/datasets/base.py:45-51):
+        ignore pixels (255) carry the embedding of class 0"""
+        lab = labels.long()
+        return table[torch.where((lab < 0) | (lab >= table.shape[0]), torch.zeros_like(lab), lab)].contiguous()
 
     @staticmethod
     def _pad_bias(b):
@@ -220,10 +230,17 @@ class ZS3StepFused(ZS3Step):
             return (n - 1) // 2 + 1
         return down(down(h)), down(down(w))
 
-    def training_step(self, image, target, embedding, real_features=None):
+    def training_step(self, image, target, embedding=None, real_features=None, class_embeddings=None):
+        """embedding: the reference's per-pixel map [B, E, H, W] (dataloaders/datasets/base.py:45-51 builds it as
+        E_table[label]; 5.05 GB per bs=16 513x513 batch), OR class_embeddings: the [C, E] table itself -- every row the
+        step needs is then gathered as table[label of the pixel] on the device and the map never exists (labels outside
+        [0, C) -- 255 -- never reach the generator)."""
         from . import gmmn_fused as GF
         model = self.model.module if hasattr(self.model, "module") else self.model
         dev = image.device
+        if (embedding is None) == (class_embeddings is None):
+            raise ValueError("pass exactly one of embedding (per-pixel map) and class_embeddings ([C, E] table)")
+        table = None if class_embeddings is None else class_embeddings.to(dev).float().contiguous()
         nb = image.shape[0]
         in_hw = tuple(target.shape[1:])
         mark = self._mark
@@ -243,7 +260,8 @@ class ZS3StepFused(ZS3Step):
             real_features = self._extract_features(model, image)                       # `:154-157`
         mark("features")
         real_features = real_features.contiguous().float()
-        embedding = embedding.contiguous().float()
+        if embedding is not None:
+            embedding = embedding.contiguous().float()
         fd = real_features.shape[1]
         assert tuple(real_features.shape[2:]) == (fh, fw), (real_features.shape, fh, fw)
 
@@ -286,7 +304,11 @@ class ZS3StepFused(ZS3Step):
                 ridx_all = torch.stack([e[6].to(torch.int32) for e in upd]).to(dev)      # [n, rows] one H2D
                 rows = ridx_all.shape[1]
             pix_all = order.view(-1)[base[:, None] + ridx_all.long()].contiguous()      # [n, rows] feature-grid pixels
-            spix_all = src[pix_all.long()].contiguous()                                  # same pixels, input grid
+            if table is None:
+                spix_all = src[pix_all.long()].contiguous()                              # same pixels, input grid
+            else:   # rows of the class table: the label of each sampled pixel (constant per update)
+                img_of = torch.tensor([e[1] for e in upd], dtype=torch.int64).to(dev)
+                spix_all = tg[img_of[:, None], pix_all.long()].to(torch.int32).contiguous()
             z_all = torch.rand((len(upd), rows, self.noise_dim), device=dev) if self._device_noise else None
 
         mark("plan+index")
@@ -298,7 +320,8 @@ class ZS3StepFused(ZS3Step):
         if vec:
             arr = GF.pack_items_vectorized(
                 images=np.array([e[1] for e in upd], dtype=np.int64), rows=rows,
-                emb=(embedding.data_ptr(), embedding.stride(0) * 4, in_hw[0] * in_hw[1]), emb_rows=spix_all,
+                emb=((embedding.data_ptr(), embedding.stride(0) * 4, in_hw[0] * in_hw[1]) if table is None else
+                     (table.data_ptr(), 0, 1, table.stride(0))), emb_rows=spix_all,
                 noise=z_all, real=(real_features.data_ptr(), real_features.stride(0) * 4, hw), real_rows=pix_all,
                 keep_rows=ridx_all)
         done = [0, 0]   # [updates launched, updates visited]
@@ -319,7 +342,8 @@ class ZS3StepFused(ZS3Step):
             m_dev = None if m_full is None else m_full.to(dev).to(torch.uint8).contiguous()
             if kind == "image":
                 flush()                                                                  # weights as of this point
-                fake_by_image[i] = self._generate_image(embedding[i], src, tg[i], fh, fw)
+                fake_by_image[i] = self._generate_image(None if table is not None else embedding[i], src, tg[i], fh, fw,
+                                                        table=table)
                 continue
             if kind == "bulk":
                 flush()                                                                  # weights as of this point
@@ -327,7 +351,10 @@ class ZS3StepFused(ZS3Step):
                 if i not in fake_by_image:
                     fake_by_image[i] = torch.zeros((hw, fd), device=dev)
                 with torch.no_grad():
-                    emb_c = embedding[i].reshape(self.embed_dim, -1)[:, src[pix_c].long()].t().contiguous()
+                    if table is None:
+                        emb_c = embedding[i].reshape(self.embed_dim, -1)[:, src[pix_c].long()].t().contiguous()
+                    else:
+                        emb_c = self._table_rows(table, tg[i][pix_c])
                     z_gen = z_dev if z_dev is not None else torch.rand((n_c, self.noise_dim), device=dev)
                     if m_dev is not None:
                         fake_c = self.generator(emb_c, z_gen, keep_mask=m_dev)
@@ -340,7 +367,8 @@ class ZS3StepFused(ZS3Step):
             if vec:
                 continue
             ridx, pix, spix = ridx_all[k], pix_all[k], spix_all[k]
-            emb_src = GF.row_source(embedding[i], spix, row_stride=1, col_stride=in_hw[0] * in_hw[1])
+            emb_src = (GF.row_source(embedding[i], spix, row_stride=1, col_stride=in_hw[0] * in_hw[1]) if table is None
+                       else GF.row_source(table, spix))
             noise_src = GF.row_source(z_all[k]) if z_dev is None else GF.row_source(z_dev, ridx)
             real_src = GF.row_source(real_features[i], pix, row_stride=1, col_stride=hw)
             queue.append(GF.pack_item(emb_src, noise_src, real_src, rows, keep_mask=m_dev, keep_rows=ridx))
@@ -356,7 +384,8 @@ class ZS3StepFused(ZS3Step):
         loss = self._classifier_loss(model, fake_features.detach(), image, target)      # `:261-264`
         loss.backward()
         self._extra_classifier_backward(model, dict(real_features=real_features, labels=tg, embedding=embedding,
-                                                    src=src, grid=(fh, fw), image_has_unseen=image_has_unseen))
+                                                    table=table, src=src, grid=(fh, fw),
+                                                    image_has_unseen=image_has_unseen))
         self.optimizer.step()
         mark("classifier")
         g_losses = torch.cat(loss_chunks).tolist() if loss_chunks else []
@@ -373,8 +402,8 @@ class ZS3StepGCN(ZS3StepFused):
     the graph generator (`GMMNnetwork_GCN`, MMD between generated and real node features) and a cluster-level
     cross-entropy term on the classifier (`GCN_weight`).
 
-    EXPERIMENTAL in round 1: host logic and arithmetic are checked on the CPU against the oracle
-    (tests/test_kernel_emulation.py); the GPU test is gated (ZS3_EXPERIMENTAL=1) until it has run on a B200.
+    Host logic and arithmetic are checked on the CPU against the oracle (tests/test_kernel_emulation.py) and on the GPU
+    by tests/test_step2_gpu.py::test_gcn_context_step_matches_oracle.
     Differences from the reference's host code: the cluster graphs of all images come from ONE launch of
     `zs3_label_components` (`:307-321` runs a Python DFS per image after three D2H copies), node embeddings / features
     are gathered on the device at the seed pixels, and the nodes of the batch are laid out on an [n/8, 8] grid (padded
@@ -407,7 +436,10 @@ class ZS3StepGCN(ZS3StepFused):
                 continue
             seeds = node_seed[i, :n].long()
             targets.append(node_label[i, :n].float())                               # `:323-324`
-            emb_n = embedding[i].reshape(self.embed_dim, -1)[:, src[seeds].long()].t().contiguous()   # seed embeddings `:58`
+            if state.get("table") is None:
+                emb_n = embedding[i].reshape(self.embed_dim, -1)[:, src[seeds].long()].t().contiguous()   # seed embeddings `:58`
+            else:   # 255-regions are nodes too; the reference's map holds E[0] there (datasets/base.py:46-50)
+                emb_n = self._table_rows(state["table"], labels[i][seeds])
             real_n = real[i].reshape(fd, -1)[:, seeds].t().contiguous()             # seed features `:72-74`
             z = (torch.rand((n, self.noise_dim), device=dev) if self.gcn_noise_fn is None
                  else self.gcn_noise_fn(n).to(dev).float())                         # `:404`
