@@ -558,10 +558,17 @@ def run_ours(args):
 
     # ---- BASELINE configs[2]: the ZS3Net step-2 iteration (feature extraction + generator updates + classifier)
     step2 = None
-    if rank == 0 and world == 1 and not args.no_step2:
+    if world == 1 and not args.no_step2:
         try:
             step2 = step2_rate(dev, B, HW, steps=min(args.steps, 10))
         except Exception as e:  # reported, never fatal for the headline line
+            step2 = {"error": repr(e)[:300]}
+    elif world > 1 and not args.no_step2:
+        # every rank takes part (the iteration holds a collective); a failure on any rank would hang the others, so
+        # the block is entered by all ranks unconditionally and only caught around the whole thing
+        try:
+            step2 = step2_rate(dev, B, HW, steps=min(args.steps, 10), baselines=False, world=world, rank=rank)
+        except Exception as e:
             step2 = {"error": repr(e)[:300]}
 
     # ---- the same step on stock PyTorch (cuDNN/cuBLAS/ATen) on THIS GPU, the split-precision (tolerance-meeting) mode
@@ -627,7 +634,64 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def step2_rate(dev, B, HW, steps, warmup=3):
+def step2_inputs(B, HW, dev=None):
+    """synthetic configs[2] batch: blocky label maps with 2-5 classes per image, ~25 % of the images holding an unseen class
+    (10 or 14), 2 % ignore pixels; class-embedding table [21, 300]; returns CPU tensors"""
+    unseen = [10, 14]
+    seen = [c for c in range(NUM_CLASSES) if c not in unseen]
+    g = torch.Generator().manual_seed(7)
+    lab = torch.zeros(B, HW, HW)
+    cell = (HW + 7) // 8
+    for i in range(B):
+        k = int(torch.randint(2, 6, (1,), generator=g))
+        cls = [seen[j] for j in torch.randperm(len(seen), generator=g)[:k].tolist()]
+        if torch.rand(1, generator=g).item() < 0.25:
+            cls[-1] = unseen[int(torch.randint(0, 2, (1,), generator=g))]
+        grid = torch.randint(0, k, (8, 8), generator=g)
+        lab[i] = torch.tensor(cls, dtype=torch.float32)[grid].repeat_interleave(cell, 0).repeat_interleave(cell, 1)[:HW, :HW]
+    lab[torch.rand(B, HW, HW, generator=g) < 0.02] = 255
+    image = torch.randn(B, 3, HW, HW, generator=g)
+    table = torch.randn(NUM_CLASSES, 300, generator=g) * 0.06
+    return image, lab, table, seen, unseen
+
+
+def embedding_map(table, target):
+    """the per-pixel embedding map the reference's dataloader builds (dataloaders/datasets/base.py:45-51): E[label],
+    ignore pixels carry E[0]; [B, 300, H, W] fp32 (5.05 GB at bs=16 513x513)"""
+    lab = target.long()
+    lab = torch.where(lab == 255, torch.zeros_like(lab), lab)
+    return table[lab].permute(0, 3, 1, 2).contiguous()
+
+
+def oracle_step2_iteration(dev, image, target, embedding, table_seen_unseen, threads=None):
+    """ONE step-2 iteration with the reference's semantics on stock torch ops (the oracle restatement of
+    train_pascal_GMMN.py:152-268 on `dev`): train-mode feature extraction under no_grad, the per-(image, class) Python
+    loop with a host sync per update, classifier update.  Returns seconds."""
+    O = _oracle()
+    import zs3_step2_oracle as S
+    seen, unseen = table_seen_unseen
+    if threads:
+        torch.set_num_threads(threads)
+    st = {k: v.to(dev) for k, v in O.init_deeplab_state(seed=1).items()}
+    gst = {k: v.to(dev) for k, v in O.init_gmmn_state(seed=3).items()}
+    cw = torch.ones(NUM_CLASSES)
+    cw[unseen] = 100.0
+    cw = cw.to(dev)
+    sync = torch.cuda.synchronize if dev != "cpu" and str(dev) != "cpu" else (lambda: None)
+    sync()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        f, low = O.backbone(st, image, True)
+        a = O.aspp(st, f, True, masks="torch")
+        feat = O.decoder_features(st, a, low, True, masks="torch")
+    res = S.step2(st, gst, feat, target, embedding, tuple(image.shape[2:]), set(seen), set(unseen),
+                  lambda n: torch.rand((n, 300)), lambda n: torch.randint(low=0, high=n, size=(128,)),
+                  lambda n: torch.rand((n, 256)) > 0.5, cw)
+    sync()
+    return time.perf_counter() - t0, len(res["g_losses"])
+
+
+def step2_rate(dev, B, HW, steps, warmup=3, baselines=True, world=1, rank=0):
     """images/sec of one ZS3Net step-2 iteration (train_pascal_GMMN.py:152-268; BASELINE configs[2]): DeepLab feature
     extraction under no_grad (CUDA graph), the per-(image, class) generator updates as ONE work-list launch of the
     fused MLP + MMD + backward + Adam kernel, and the pred_conv update with the fused upsample + CE loss."""
@@ -636,24 +700,12 @@ def step2_rate(dev, B, HW, steps, warmup=3):
     from zs3_b200.modeling.gmmn import GMMNnetwork
     from zs3_b200.step2 import ZS3StepFused
     from zs3_b200.utils.loss import GMMNLoss, SegmentationLosses
-    unseen = [10, 14]
-    seen = [c for c in range(NUM_CLASSES) if c not in unseen]
-    g = torch.Generator().manual_seed(7)
-    lab = torch.zeros(B, HW, HW)
-    cell = (HW + 7) // 8
-    for i in range(B):  # blocky maps with 2-5 classes; ~25 % of the images hold an unseen class; 2 % ignore pixels
-        k = int(torch.randint(2, 6, (1,), generator=g))
-        cls = [seen[j] for j in torch.randperm(len(seen), generator=g)[:k].tolist()]
-        if torch.rand(1, generator=g).item() < 0.25:
-            cls[-1] = unseen[int(torch.randint(0, 2, (1,), generator=g))]
-        grid = torch.randint(0, k, (8, 8), generator=g)
-        lab[i] = torch.tensor(cls, dtype=torch.float32)[grid].repeat_interleave(cell, 0).repeat_interleave(cell, 1)[:HW, :HW]
-    lab[torch.rand(B, HW, HW, generator=g) < 0.02] = 255
-    target = lab.to(dev)
-    image = torch.randn(B, 3, HW, HW, generator=g).to(dev)
-    table = (torch.randn(NUM_CLASSES, 300, generator=g) * 0.06).to(dev)
-    # the per-pixel embedding map the reference's dataloader builds (dataloaders/datasets/base.py:45-51)
-    embedding = table[target.clamp(max=NUM_CLASSES - 1).long()].permute(0, 3, 1, 2).contiguous()
+    image_h, target_h, table_h, seen, unseen = step2_inputs(B, HW)
+    if world > 1:   # every rank trains on its own images (weak scaling): rotate the batch and re-draw the pixels
+        image_h = torch.randn(image_h.shape, generator=torch.Generator().manual_seed(500 + rank))
+        target_h = target_h.roll(rank, 0)
+    target, image, table = target_h.to(dev), image_h.to(dev), table_h.to(dev)
+    embedding = embedding_map(table, target)
     model = DeepLab(num_classes=NUM_CLASSES, sync_bn=True, pretrained=False).to(dev).train()
     gen = GMMNnetwork(300, 300, 256, 256).to(dev).train()
     cw = torch.ones(NUM_CLASSES)
@@ -662,27 +714,123 @@ def step2_rate(dev, B, HW, steps, warmup=3):
     crit_g = GMMNLoss(cuda=True).build_loss()
     opt = torch.optim.SGD([{"params": model.get_1x_lr_params(), "lr": 0.007},
                            {"params": model.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+    if world > 1:
+        import torch.distributed as dist
+        for t in list(model.parameters()) + list(model.buffers()) + list(gen.parameters()):
+            dist.broadcast(t.data, 0)           # identical replicas
     step = ZS3StepFused(model, gen, crit, crit_g, opt, torch.optim.Adam(gen.parameters(), lr=2e-4), seen, unseen,
-                        graph_features=True)
-    for _ in range(warmup):
+                        graph_features=True, world_size=world)
+
+    def timed(fn, n):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        n0 = L.lib().zs3_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, out, (L.lib().zs3_launch_count() - n0) / n
+
+    if world > 1:   # data parallel: one <1 MB all-reduce per iteration (parallel.exchange_step2); the caller takes the
+        import torch.distributed as dist        # max over ranks
+        dist.barrier()
+        ms, (loss, _, g_losses), launches = timed(lambda: step.training_step(image, target, class_embeddings=table), steps)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"workload": f"ZS3Net step-2 iteration, bs={B}/GPU {HW}x{HW}, data parallel over {world} GPUs: per-rank "
+                            "generator chains, ONE all-reduce of [generator delta | pred_conv gradients] per iteration",
+                "value": world * B / (t.item() * 1e-3), "unit": "images/sec", "ms_per_step": t.item(), "steps": steps,
+                "n_gpus": world, "generator_updates_per_step_rank0": len(g_losses), "final_loss_rank0": float(loss.item())}
+    ms, (loss, _, g_losses), launches = timed(lambda: step.training_step(image, target, embedding), steps)
+    ms_t, _, _ = timed(lambda: step.training_step(image, target, class_embeddings=table), steps)
+    res = {"workload": "ZS3Net train_pascal_GMMN step (BASELINE configs[2]): frozen-feature extraction + GMMN "
+                       f"generator updates + 21-class classifier update, bs={B} {HW}x{HW}, unseen classes {unseen}",
+           "value": B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps,
+           "value_label_table_api": B / (ms_t * 1e-3),
+           "generator_updates_per_step": len(g_losses), "final_loss": float(loss.item()),
+           "final_generator_loss": g_losses[-1] if g_losses else None,
+           "launch_calls_per_step_outside_the_feature_graph": launches}
+    # ---- end to end with HOST buffers: the reference-shaped call uploads image + label + the 300-channel per-pixel
+    # embedding map every step (train_pascal_GMMN.py:146-151); the table call uploads image + label only
+    img_p, tgt_p = image_h.pin_memory(), target_h.pin_memory()
+    e2e_steps = max(2, min(steps, 4))
+
+    def e2e_table():
+        i_d, t_d = img_p.to(dev, non_blocking=True), tgt_p.to(dev, non_blocking=True)
+        l, _, _ = step.training_step(i_d, t_d, class_embeddings=table)
+        return l.item()
+    ms_e, _, _ = timed(e2e_table, e2e_steps)
+    res["e2e_label_table_api"] = {"value": B / (ms_e * 1e-3), "unit": "images/sec", "ms_per_step": ms_e,
+                                  "h2d_bytes_per_step": img_p.numel() * 4 + tgt_p.numel() * 4, "d2h_bytes_per_step": 4}
+    try:
+        emb_p = embedding.cpu().pin_memory()
+
+        def e2e_map():
+            i_d, t_d = img_p.to(dev, non_blocking=True), tgt_p.to(dev, non_blocking=True)
+            e_d = emb_p.to(dev, non_blocking=True)
+            l, _, _ = step.training_step(i_d, t_d, e_d)
+            return l.item()
+        ms_m, _, _ = timed(e2e_map, e2e_steps)
+        res["e2e"] = {"value": B / (ms_m * 1e-3), "unit": "images/sec", "ms_per_step": ms_m,
+                      "h2d_bytes_per_step": img_p.numel() * 4 + tgt_p.numel() * 4 + emb_p.numel() * 4, "d2h_bytes_per_step": 4,
+                      "note": "the reference's call shape: the [B,300,H,W] fp32 embedding map crosses PCIe every step"}
+        del emb_p
+    except Exception as e:
+        res["e2e"] = {"error": repr(e)[:200]}
+    # ---- roofline of the step's dominant kernels: the tcgen05 feature-extraction convs and the fused generator update
+    peak, how = measured_peaks()
+    try:
+        from zs3_b200 import kernels as K
+        K.PROFILE = {}
+        with torch.no_grad():
+            torch.cuda._sleep(int(1.2e8))
+            model.forward_before_class_prediction(image)
+        torch.cuda.synchronize()
+        prof, K.PROFILE = K.PROFILE, None
+        prof.pop("_tags", None)
+        cms = sum(a.elapsed_time(b) for evs in prof.values() for a, b, _ in evs)
+        cfl = sum(f for evs in prof.values() for _, _, f in evs)
+        step.profile = {}
         step.training_step(image, target, embedding)
-    torch.cuda.synchronize()
-    n0 = L.lib().zs3_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    updates = 0
-    for _ in range(steps):
-        loss, _, g_losses = step.training_step(image, target, embedding)
-        updates += len(g_losses)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"workload": "ZS3Net train_pascal_GMMN step (BASELINE configs[2]): frozen-feature extraction + GMMN "
-                        f"generator updates + 21-class classifier update, bs={B} {HW}x{HW}, unseen classes {unseen}",
-            "value": B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps,
-            "generator_updates_per_step": updates / steps, "final_loss": float(loss.item()),
-            "final_generator_loss": g_losses[-1] if g_losses else None,
-            "launch_calls_per_step_outside_the_feature_graph": (L.lib().zs3_launch_count() - n0) / steps}
+        torch.cuda.synchronize()
+        seg = step.profile_summary()
+        step.profile = None
+        res["segments_ms"] = {k: round(v["gpu_ms"], 3) for k, v in seg.items()}
+        res["roofline"] = {"bound": "tensor", "kernel": "conv_fprop_kernel (feature extraction, 113 launches)",
+                           "achieved": cfl / (cms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                           "frac": cfl / (cms * 1e-3) / 1e12 / peak, "peak_source": how, "conv_ms_per_step": cms,
+                           "conv_share_of_step": cms / ms, "traffic": None}
+    except Exception as e:
+        res["roofline"] = {"error": repr(e)[:200]}
+    if baselines:
+        # ---- the same iteration on stock PyTorch on this GPU (the reference's own path) and on the host cores
+        try:
+            dt, nupd = min((oracle_step2_iteration(dev, image, target, embedding, (seen, unseen)) for _ in range(2)),
+                           key=lambda t: t[0])
+            res["library_baseline"] = {"value": B / dt, "unit": "images/sec", "ms_per_step": dt * 1e3,
+                                       "generator_updates": nupd,
+                                       "what": "oracle restatement of train_pascal_GMMN.py:152-268 on stock torch/cuDNN on "
+                                               "this GPU (TF32 default, eager, per-update host syncs as in the reference)",
+                                       "zs3_b200_speedup": (B / (ms * 1e-3)) / (B / dt)}
+        except Exception as e:
+            res["library_baseline"] = {"error": repr(e)[:200]}
+        try:
+            nb = 2
+            cores = cpu_threads()
+            emb_c = embedding[:nb].cpu()
+            dt, nupd = oracle_step2_iteration("cpu", image_h[:nb], target_h[:nb], emb_c, (seen, unseen), threads=cores)
+            res["cpu_baseline"] = {"value": nb / dt, "unit": "images/sec", "cores": cores, "kind": "port",
+                                   "sample": f"one step-2 iteration on the first {nb} images of the batch with the oracle "
+                                             f"port on {cores} threads ({dt:.2f} s, {nupd} generator updates)"}
+        except Exception as e:
+            res["cpu_baseline"] = {"error": repr(e)[:200]}
+    del step, model, gen, embedding
+    torch.cuda.empty_cache()
+    return res
 
 
 _RESULT_FD = None

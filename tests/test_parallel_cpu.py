@@ -96,6 +96,69 @@ def test_two_rank_gloo_allreduce_matches_full_batch():
     assert torch.allclose(got[0], full, atol=1e-6)
 
 
+def _worker_step2(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from zs3_b200.parallel import exchange_step2, init_distributed
+    init_distributed()
+    torch.manual_seed(0)
+    gen = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.LeakyReLU(0.2), torch.nn.Linear(4, 3))
+    head = torch.nn.Linear(3, 2)
+    gp = list(gen.parameters())
+    snap = torch.cat([p.detach().reshape(-1) for p in gp])
+    # each rank's own chain of sequential generator updates (different data per rank), then its classifier backward
+    opt = torch.optim.Adam(gp, lr=1e-2)
+    g = torch.Generator().manual_seed(100 + rank)
+    for _ in range(3):
+        opt.zero_grad()
+        (gen(torch.randn(5, 6, generator=g)) ** 2).mean().backward()
+        opt.step()
+    head(torch.randn(4, 3, generator=g)).pow(2).mean().backward()
+    local_delta = torch.cat([p.detach().reshape(-1) for p in gp]) - snap
+    local_grad = torch.cat([p.grad.reshape(-1) for p in head.parameters()])
+    exchange_step2(gp, snap, list(head.parameters()), world)
+    q.put((rank,) + tuple(t.numpy().copy() for t in (       # by value: the worker may exit before the parent reads
+        local_delta, local_grad, torch.cat([p.detach().reshape(-1) for p in gp]),
+        torch.cat([p.grad.reshape(-1) for p in head.parameters()]), snap)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_step2_exchange_averages_generator_delta_and_classifier_gradients():
+    """step 2 shards by image; ONE message [generator delta | pred_conv gradients] per iteration.  After the
+    exchange both ranks hold snapshot + mean(delta) and the mean classifier gradient (gloo, world_size 2)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_step2, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r[0]: tuple(torch.from_numpy(a) for a in r[1:]) for r in (q.get(timeout=90) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (d0, g0, w0, cg0, snap), (d1, g1, w1, cg1, _) = got[0], got[1]
+    assert not torch.allclose(d0, d1)                         # the ranks really diverged before the exchange
+    assert torch.allclose(w0, w1) and torch.allclose(cg0, cg1)
+    assert torch.allclose(w0, snap + (d0 + d1) / 2, atol=1e-7)
+    assert torch.allclose(cg0, (g0 + g1) / 2, atol=1e-7)
+
+
+def test_step2_exchange_single_rank_is_identity():
+    from zs3_b200.parallel import exchange_step2
+    torch.manual_seed(1)
+    gen, head = torch.nn.Linear(4, 4), torch.nn.Linear(4, 2)
+    snap = torch.cat([p.detach().reshape(-1) for p in gen.parameters()]) - 0.5
+    head(torch.randn(3, 4)).sum().backward()
+    before = [p.detach().clone() for p in gen.parameters()], [p.grad.clone() for p in head.parameters()]
+    exchange_step2(list(gen.parameters()), snap, list(head.parameters()), 1)
+    for a, b in zip(gen.parameters(), before[0]):
+        assert torch.allclose(a, b, atol=1e-7)
+    for a, b in zip(head.parameters(), before[1]):
+        assert torch.equal(a.grad, b)
+
+
 class _FreeingBlock(torch.autograd.Function):
     """y = tanh(x * w); drops its saved state after backward like the fused network nodes (functional.BottleneckFn),
     so a node that is run twice fails loudly.  in_place=True mimics the nodes that add the weight gradient into

@@ -45,6 +45,34 @@ def shard_batch(n_total, rank, world):
     return begin, begin + per + (1 if rank < rem else 0)
 
 
+def exchange_step2(generator_params, snapshot, classifier_params, world):
+    """The ONE collective of a data-parallel ZS3Net step-2 iteration (the reference runs step 2 on a single
+    GPU, train_pascal_GMMN.py:155,262, so these semantics are this repository's, stated in DESIGN.md "Multi-GPU"):
+    every rank has run its own sequential generator chain on its own images from the same starting weights
+    (`snapshot`, one flat tensor) and the classifier backward on its own batch.  One all-reduce(sum) over
+    [generator delta | classifier gradients] (220 k + 5.4 k floats at 21 classes: < 1 MB); afterwards every rank holds
+    generator = snapshot + mean delta and classifier .grad = mean gradient.  Adam moments stay rank-local.
+    Returns the flat message (for tests)."""
+    with torch.no_grad():
+        cur = torch.cat([p.detach().reshape(-1) for p in generator_params])
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in classifier_params]
+        msg = torch.cat([cur - snapshot] + [g.reshape(-1).to(cur.dtype) for g in grads])
+        if world > 1:
+            dist.all_reduce(msg)
+            msg /= world
+        off = 0
+        for p in generator_params:
+            n = p.numel()
+            p.copy_((snapshot[off:off + n] + msg[off:off + n]).view_as(p))
+            off += n
+        for p, g in zip(classifier_params, grads):
+            n = p.numel()
+            g.copy_(msg[off:off + n].view_as(g))
+            p.grad = g
+            off += n
+    return msg
+
+
 class FlatParams:
     """Re-homes the parameters of `param_groups` (list of lists) into one flat buffer (+ a flat grad buffer)."""
 

@@ -98,8 +98,11 @@ class ZS3StepFused(ZS3Step):
     """
 
     def __init__(self, *args, noise_fn=None, index_fn=None, graph_features=False, fuse_classifier_loss=True,
-                 tensor_core_bulk=True, **kw):
+                 tensor_core_bulk=True, world_size=1, **kw):
         super().__init__(*args, noise_fn=noise_fn, index_fn=index_fn, **kw)
+        # data parallel (one process per GPU, images sharded): ONE all-reduce per iteration over
+        # [generator delta | pred_conv gradients], see parallel.exchange_step2
+        self.world_size = int(world_size)
         self._device_index = index_fn is None     # default: sampled row indices drawn on the device for all updates
         from .gmmn_fused import FusedGeneratorUpdater
         self._device_noise = noise_fn is None
@@ -312,6 +315,9 @@ class ZS3StepFused(ZS3Step):
             z_all = torch.rand((len(upd), rows, self.noise_dim), device=dev) if self._device_noise else None
 
         mark("plan+index")
+        gen_snapshot = None
+        if self.world_size > 1:
+            gen_snapshot = torch.cat([p.detach().reshape(-1) for p in self.updater.params])
         fake_features = torch.zeros(real_features.shape, device=dev)
         fake_by_image = {}
         queue, keep, owners, loss_chunks = [], [], [e[1] for e in upd], []
@@ -386,6 +392,10 @@ class ZS3StepFused(ZS3Step):
         self._extra_classifier_backward(model, dict(real_features=real_features, labels=tg, embedding=embedding,
                                                     table=table, src=src, grid=(fh, fw),
                                                     image_has_unseen=image_has_unseen))
+        if self.world_size > 1:
+            from .parallel import exchange_step2
+            head = [p for g in self.optimizer.param_groups for p in g["params"] if p.grad is not None]
+            exchange_step2(self.updater.params, gen_snapshot, head, self.world_size)
         self.optimizer.step()
         mark("classifier")
         g_losses = torch.cat(loss_chunks).tolist() if loss_chunks else []
