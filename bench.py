@@ -601,6 +601,14 @@ def run_ours(args):
             phase("numerics table")
             numerics = guarded(numerics_table, dev, HW)
 
+    # ---- BASELINE configs[4]: Pascal-Context + GCN-context step, bs=8 per GPU (all ranks take part when world > 1)
+    config5 = None
+    if not args.no_config5:
+        try:
+            config5 = config5_rate(dev, 8, HW, steps=min(args.steps, 5), world=world, rank=rank)
+        except Exception as e:
+            config5 = {"error": repr(e)[:300]}
+
     if rank == 0:
         sampler.join(timeout=2)
         line = {
@@ -623,6 +631,7 @@ def run_ours(args):
             "roofline": roofline,
             "forward_only": forward_only,
             "step2": step2,
+            "config5": config5,
             "library_baseline": library_baseline,
             "parity_mode": parity_mode,
             "numerics_vs_fp64": numerics,
@@ -833,6 +842,77 @@ def step2_rate(dev, B, HW, steps, warmup=3, baselines=True, world=1, rank=0):
     return res
 
 
+def config5_rate(dev, B, HW, steps, warmup=3, world=1, rank=0):
+    """BASELINE configs[4]: Pascal-Context (60 logits) ZS3Net step with the GCN-context encoder
+    (train_context_GMMN_GCNcontext.py:270-460), bs=8 per GPU: frozen-feature extraction, per-(image, class) generator
+    updates, per-image cluster graph (ONE device launch for the batch) + graph-generator update + cluster-level CE
+    (GCN_weight 0.1), 60-class classifier update with the fused upsample + CE loss."""
+    from zs3_b200.modeling.deeplab import DeepLab
+    from zs3_b200.modeling.gmmn import GMMNnetwork, GMMNnetwork_GCN
+    from zs3_b200.step2 import ZS3StepGCN
+    from zs3_b200.utils.loss import GMMNLoss, SegmentationLosses
+    C = 60
+    unseen = [14, 36]                 # two unseen classes ("cow", "motorbike" in the reference's default split)
+    seen = [c for c in range(C) if c not in unseen]
+    g = torch.Generator().manual_seed(900 + rank)
+    lab = torch.zeros(B, HW, HW)
+    cell = (HW + 7) // 8
+    for i in range(B):   # 4-10 classes per image on an 8x8 block grid: 5-40 connected components at 129x129
+        k = int(torch.randint(4, 11, (1,), generator=g))
+        cls = [seen[j] for j in torch.randperm(len(seen), generator=g)[:k].tolist()]
+        if torch.rand(1, generator=g).item() < 0.25:
+            cls[-1] = unseen[int(torch.randint(0, 2, (1,), generator=g))]
+        coarse = torch.randint(0, k, (4, 4), generator=g).repeat_interleave(2, 0).repeat_interleave(2, 1)
+        noise = torch.randint(0, k, (8, 8), generator=g)
+        grid = torch.where(torch.rand(8, 8, generator=g) < 0.25, noise, coarse)
+        lab[i] = torch.tensor(cls, dtype=torch.float32)[grid].repeat_interleave(cell, 0).repeat_interleave(cell, 1)[:HW, :HW]
+    lab[torch.rand(B, HW, HW, generator=g) < 0.002] = 255
+    image = torch.randn(B, 3, HW, HW, generator=g).to(dev)
+    target = lab.to(dev)
+    table = (torch.randn(C, 300, generator=torch.Generator().manual_seed(901)) * 0.17).to(dev)   # row norms ~2.9 (SURVEY 2.1 #18)
+    torch.manual_seed(1)
+    model = DeepLab(num_classes=C, sync_bn=True, pretrained=False).to(dev).train()
+    gen = GMMNnetwork(300, 300, 256, 256).to(dev).train()
+    gen_gcn = GMMNnetwork_GCN().to(dev).train()
+    if world > 1:
+        import torch.distributed as dist
+        for t in list(model.parameters()) + list(model.buffers()) + list(gen.parameters()) + list(gen_gcn.parameters()):
+            dist.broadcast(t.data, 0)
+    cw = torch.ones(C)
+    cw[unseen] = 100.0
+    crit = SegmentationLosses(weight=cw.to(dev), cuda=True).build_loss("ce")
+    opt = torch.optim.SGD([{"params": model.get_1x_lr_params(), "lr": 0.007},
+                           {"params": model.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+    step = ZS3StepGCN(model, gen, crit, GMMNLoss(cuda=True).build_loss(), opt, torch.optim.Adam(gen.parameters(), lr=2e-4),
+                      seen, unseen, graph_features=True, generator_gcn=gen_gcn,
+                      optimizer_generator_gcn=torch.optim.Adam(gen_gcn.parameters(), lr=2e-4), gcn_weight=0.1,
+                      max_nodes=256, world_size=world)
+    for _ in range(warmup):
+        step.training_step(image, target, class_embeddings=table)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _, g_losses = step.training_step(image, target, class_embeddings=table)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    res = {"workload": f"Pascal-Context (60 logits) ZS3Net + GCN-context step (BASELINE configs[4]), bs={B}/GPU {HW}x{HW}, "
+                       f"{world} GPU(s), 4-10 classes and 5-40 clusters per image, unseen {unseen}, GCN_weight 0.1",
+           "value": world * B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+           "generator_updates_per_step": len(g_losses), "graph_generator_updates_per_step": len(step.last_gcn_losses),
+           "final_loss": float(loss.item())}
+    del step, model, gen, gen_gcn
+    torch.cuda.empty_cache()
+    return res
+
+
 _RESULT_FD = None
 
 
@@ -865,6 +945,7 @@ def main():
     ap.add_argument("--size", type=int, default=513, help="input height=width (BASELINE: 513)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-step2", action="store_true", help="skip the configs[2] (ZS3Net step-2 iteration) measurement")
+    ap.add_argument("--no-config5", action="store_true", help="skip the configs[4] (Pascal-Context + GCN) measurement")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU arms")
     ap.add_argument("--no-parity", action="store_true", help="skip the split-precision (tolerance-meeting) training mode")
     ap.add_argument("--no-numerics", action="store_true", help="skip the distance-to-fp64 table")

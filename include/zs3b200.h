@@ -199,6 +199,9 @@ typedef struct {
   int reset_count;      /* number of leading entries of reset_sum/reset_sqsum to zero */
   unsigned char* relu_mask_out; /* optional [M][C/8]: bit j of byte (m, c/8) = [out[m][c+j] > 0]; lets the backward of
                                  * residual layers read 1 bit instead of 16 per element for the ReLU mask */
+  int sync_clamp;       /* fused finalize: invstd = max(var, eps)^-1/2 instead of (var + eps)^-1/2 -- the multi-replica
+                         * formula of the reference's SynchronizedBatchNorm (sync_batchnorm/batchnorm.py:124-142); the
+                         * caller has all-reduced stat_sum / stat_sqsum over the ranks and passes the GLOBAL count */
 } zs3_bn_apply_args;
 
 /* out = dropout(relu?(scale*y + shift (+ residual))) */
@@ -238,6 +241,7 @@ typedef struct {
   double* reset_sum_dzx;/* sums buffer the NEXT layer's reduce phase will accumulate into; two buffers alternate) */
   int reset_count;
   const unsigned char* relu_mask; /* relu == 3: the bit mask written by zs3_bn_apply (relu_mask_out); `out` unused */
+  long long stat_count; /* 0: M.  Synchronised BatchNorm: the GLOBAL element count the (all-reduced) sums range over */
 } zs3_bn_bwd_args;
 
 /* phase 1: sum_dz += sum(dz), sum_dzx += sum(dz * xhat) with dz = dout * [out > 0] * grad_scale */

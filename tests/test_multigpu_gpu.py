@@ -1,0 +1,125 @@
+"""Hardware tests of the data-parallel runtime on >= 2 GPUs of one box (NCCL): skipped on a single-GPU box.
+Run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py -m gpu -q -s`.
+
+  * 2 ranks x 4 images with frozen BatchNorm reproduce the flat gradient of 1 rank x 8 images (test
+    pyramid item 4; VERDICT r1 "missing hardware test"): all-reduce(sum) x 1/world^2 == the global-batch gradient;
+  * 2 ranks x 4 images with SYNCHRONISED train-mode BatchNorm (sync_batchnorm/batchnorm.py:60-142) reproduce 1 rank x 8
+    images with ordinary train-mode BatchNorm: same statistics, same running buffers, same gradients;
+  * the step-2 exchange on NCCL.
+Tolerances: both sides run the bf16 tensor-core path, but on differently composed batches (different tile
+boundaries, different split-K partitions), so they agree to bf16 rounding, not bit for bit: 3e-2 global rel-L2."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _data(n=8, hw=65):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, 3, hw, hw, generator=g)
+    t = torch.randint(0, 21, (n, hw, hw), generator=g).float()      # no ignore pixels: equal weight sums per shard
+    return x, t
+
+
+def _build(train_bn, dev):
+    import zs3_oracle as O
+    from zs3_b200.modeling.deeplab import DeepLab
+    m = DeepLab(num_classes=21, sync_bn=True, pretrained=False)
+    m.load_state_dict(O.init_deeplab_state(seed=1, randomize_bn=True))
+    m = m.to(dev)
+    m.train()
+    if not train_bn:
+        m.freeze_bn()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return m
+
+
+def _worker(rank, world, port, train_bn, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from zs3_b200.parallel import DataParallelTrainer, init_distributed, shard_batch, exchange_step2
+    from zs3_b200.utils.loss import SegmentationLosses
+    _, local, _ = init_distributed()
+    dev = torch.device("cuda", local)
+    model = _build(train_bn, dev)
+    crit = SegmentationLosses(weight=None, cuda=True).build_loss("ce")
+    tr = DataParallelTrainer(model, crit, world_size=world, sync_bn=train_bn)
+    x, t = _data()
+    a, b = shard_batch(x.shape[0], rank, world)
+    tr._begin_step()
+    loss = tr._forward_loss(x[a:b].to(dev), t[a:b].to(dev))
+    loss.backward()
+    dist.all_reduce(tr.flat.grad)
+    tr.flat.grad.mul_(tr.grad_scale)
+    # step-2 exchange over NCCL: every rank moves its generator copy by rank+1, the mean delta is 1.5
+    gen = torch.nn.Linear(8, 8).to(dev)
+    dist.broadcast(gen.weight.data, 0)
+    dist.broadcast(gen.bias.data, 0)
+    snap = torch.cat([p.detach().reshape(-1) for p in gen.parameters()])
+    with torch.no_grad():
+        for p in gen.parameters():
+            p.add_(float(rank + 1))
+    head = torch.nn.Linear(8, 2).to(dev)
+    head(torch.ones(1, 8, device=dev) * (rank + 1)).sum().backward()
+    exchange_step2(list(gen.parameters()), snap, list(head.parameters()), world)
+    delta = (torch.cat([p.detach().reshape(-1) for p in gen.parameters()]) - snap).mean().item()
+    if rank == 0:
+        q.put((tr.flat.grad.cpu().numpy(), model.backbone.layer2[1].bn2.running_var.cpu().numpy(), delta,
+               head.weight.grad.mean().item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _single(train_bn):
+    from zs3_b200.parallel import DataParallelTrainer
+    from zs3_b200.utils.loss import SegmentationLosses
+    dev = torch.device("cuda", 0)
+    model = _build(train_bn, dev)
+    tr = DataParallelTrainer(model, SegmentationLosses(weight=None, cuda=True).build_loss("ce"), world_size=1)
+    x, t = _data()
+    tr._begin_step()
+    tr._forward_loss(x.to(dev), t.to(dev)).backward()
+    torch.cuda.synchronize()
+    return tr.flat.grad.cpu(), model.backbone.layer2[1].bn2.running_var.cpu()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one box (gpurun --gpus 2)")
+@pytest.mark.parametrize("train_bn", [False, True], ids=["frozen_bn", "sync_bn"])
+def test_two_ranks_reproduce_the_single_rank_global_batch(train_bn):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, train_bn, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g2, rv2, delta, hg = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g1, rv1 = _single(train_bn)
+    g2 = torch.from_numpy(g2)
+    rel = float(torch.linalg.norm(g2.double() - g1.double()) / torch.linalg.norm(g1.double()))
+    print(f"{'sync' if train_bn else 'frozen'} BN: 2 ranks x 4 vs 1 rank x 8, flat gradient rel-L2 = {rel:.3e}")
+    assert rel < 3e-2
+    if train_bn:   # the synchronised statistics are the global batch's: same running buffers as the single rank
+        assert float((torch.from_numpy(rv2) - rv1).abs().max() / rv1.abs().max()) < 2e-3
+    assert abs(delta - 1.5) < 1e-5 and abs(hg - 1.5) < 1e-5

@@ -116,6 +116,7 @@ class BnApplyArgs(C.Structure):
         ("mean_out", C.c_void_p), ("invstd_out", C.c_void_p), ("scale_out", C.c_void_p), ("shift_out", C.c_void_p),
         ("reset_sum", C.c_void_p), ("reset_sqsum", C.c_void_p), ("reset_count", C.c_int),
         ("relu_mask_out", C.c_void_p),
+        ("sync_clamp", C.c_int),
     ]
 
 
@@ -134,6 +135,7 @@ class BnBwdArgs(C.Structure):
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("C_real", C.c_int), ("param_accumulate", C.c_int),
         ("reset_sum_dz", C.c_void_p), ("reset_sum_dzx", C.c_void_p), ("reset_count", C.c_int),
         ("relu_mask", C.c_void_p),
+        ("stat_count", C.c_longlong),
     ]
 
 

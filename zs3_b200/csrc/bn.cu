@@ -130,6 +130,7 @@ struct ApplyP {
   double* reset_a; double* reset_b;  // the OTHER statistics buffer, zeroed for the next layer
   int reset_count;
   unsigned char* relu_bits;  // optional [M][C/8] ReLU bit mask for the backward
+  int sync_clamp;            // invstd = rsqrt(max(var, eps)) (reference SyncBN) instead of rsqrt(var + eps)
 };
 
 __device__ __forceinline__ void apply_one(const ApplyP& p, long long m, int c, const float (&sc)[8],
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyP p) {
         const double mean = p.stat_sum[ch] * p.inv_count;
         const double dvar = fma(-mean, mean, p.stat_sqsum[ch] * p.inv_count);
         const float var = fmaxf((float)dvar, 0.f);
-        is = rsqrtf(var + p.eps);
+        is = p.sync_clamp ? rsqrtf(fmaxf(var, p.eps)) : rsqrtf(var + p.eps);
         mu = (float)mean;
         s = (p.gamma ? p.gamma[ch] : 1.f) * is;
         b = (p.beta ? p.beta[ch] : 0.f) - mu * s;
@@ -276,6 +277,7 @@ struct BwdP {
   int rows_per_block;  // pixel rows handled concurrently by one CTA
   double* reset_a; double* reset_b; int reset_count;  // the other sums buffer, zeroed by the apply phase
   const unsigned char* relu_bits;  // relu == 3
+  long long stat_count;            // divisor of the batch sums (0: M); Synchronised BatchNorm passes the global count
 };
 
 // the "forward activation" operand of make_dz: the saved output row (relu == 1), the ReLU mask byte (relu == 3) or nothing
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdP p) {
   // per-channel coefficients once per CTA (thread t -> channel t, t+256, ...), through shared memory; CTA 0 also
   // writes the affine-parameter gradients
   {
-    const float inv_m = 1.f / (float)p.M;
+    const float inv_m = 1.f / (float)(p.stat_count > 0 ? p.stat_count : p.M);
     for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
       const float scl = p.scale[ch];
       float B = 0.f, Cc = 0.f;
@@ -709,6 +711,7 @@ extern "C" int zs3_bn_apply(const zs3_bn_apply_args* a, void* stream) {
   p.mean_out = a->mean_out; p.invstd_out = a->invstd_out; p.scale_out = a->scale_out; p.shift_out = a->shift_out;
   p.reset_a = a->reset_sum; p.reset_b = a->reset_sqsum; p.reset_count = a->reset_count;
   p.relu_bits = a->relu ? a->relu_mask_out : nullptr;
+  p.sync_clamp = a->sync_clamp;
   ZS3_CHECK_ARG(a->C <= 2048, "bn_apply: C=%d > 2048", a->C);
   p.rows_per_block = 256 / (a->C / 8) > 0 ? 256 / (a->C / 8) : 1;
   const size_t smem = a->stat_sum ? (size_t)2 * a->C * sizeof(float) : 0;
@@ -740,6 +743,7 @@ static int fill_bwd(const zs3_bn_bwd_args* a, BwdP& p, const char* who) {
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.C_real = a->C_real; p.param_acc = a->param_accumulate;
   p.reset_a = a->reset_sum_dz; p.reset_b = a->reset_sum_dzx; p.reset_count = a->reset_count;
   p.relu_bits = a->relu_mask;
+  p.stat_count = a->stat_count;
   p.rows_per_block = 1;
   return ZS3_OK;
 }

@@ -13,6 +13,7 @@ import torch
 
 from . import _lib as L
 from . import kernels as K
+from .modeling.sync_batchnorm import batchnorm as SBN
 
 _SCRATCH = {}
 PENDING_BATCH_COUNTERS = []  # num_batches_tracked buffers to bump (one fused foreach add per model forward)
@@ -98,6 +99,10 @@ class _StatBuffers:
         self.dirty[self.cur] = max(self.dirty[self.cur], c)
         b = self.buf[self.cur]
         return b[0, :c], b[1, :c]
+
+    def current_buffer(self):
+        """the whole [2, 2048] fp64 buffer `current()` hands out views of (one contiguous 32 KB all-reduce message)"""
+        return self.buf[self.cur]
 
     def flip(self):
         """returns (sum, sqsum, count) of the other buffer to be zeroed by this layer's bn_apply, then switches"""
@@ -235,7 +240,7 @@ def _bn_forward_coeffs(bn, stats, count, cs):
 class _Saved:
     """what a conv->BN->act forward keeps for its backward"""
     __slots__ = ("conv", "bn", "relu", "p", "training", "ranges", "has_res", "geom", "flops_per_cin", "mask_from_y",
-                 "y", "out", "mean", "invstd", "scale", "shift", "xs", "relu_bits")
+                 "y", "out", "mean", "invstd", "scale", "shift", "xs", "relu_bits", "sync_w")
 
 
 def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, channels, need_backward=True):
@@ -283,6 +288,9 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
     if stats is not None and not fuse_stats:
         K.bn_stats(y, stats)
     n, ho, wo, _ = y.shape
+    sync_w = SBN.sync_world(bn) if training else 1
+    if sync_w > 1:
+        SBN.all_reduce_stats(sb.current_buffer())   # (sum, sum of squares) over all ranks, before the fused finalize
     seed = off = 0
     p = float(drop_p) if (drop_p and drop_training) else 0.0
     if p > 0 and keep_mask is None:
@@ -295,10 +303,10 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
         scale, shift, mean, invstd = coef[0], coef[1], coef[2], coef[3]
         if bn.num_batches_tracked is not None:
             PENDING_BATCH_COUNTERS.append(bn.num_batches_tracked)
-        fin = dict(stats=stats, count=n * ho * wo, gamma=bn.weight.detach() if bn.weight is not None else None,
+        fin = dict(stats=stats, count=n * ho * wo * sync_w, gamma=bn.weight.detach() if bn.weight is not None else None,
                    beta=bn.bias.detach() if bn.bias is not None else None, eps=bn.eps,
                    momentum=bn.momentum if bn.momentum is not None else 0.1, running_mean=bn.running_mean,
-                   running_var=bn.running_var, coef=coef, c_real=cout, reset=sb.flip())
+                   running_var=bn.running_var, coef=coef, c_real=cout, reset=sb.flip(), sync_clamp=sync_w > 1)
     else:
         scale, shift, mean, invstd = _bn_forward_coeffs(bn, None, n * ho * wo, cout_p)
     # residual joins (out = relu(bn(y) + x)): the backward needs the ReLU mask twice; keep it as one bit per element
@@ -311,6 +319,7 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
                      offset_dev=_RngState.device_counter if (p > 0 and keep_mask is None) else None, finalize=fin,
                      relu_mask=relu_bits)
     sv = _Saved()
+    sv.sync_w = sync_w
     sv.relu_bits = relu_bits
     sv.conv, sv.bn, sv.relu, sv.p, sv.training = conv, bn, relu, p, training
     sv.ranges, sv.has_res = ranges, residual is not None
@@ -342,6 +351,7 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
     dres = torch.empty_like(dout) if sv.has_res else None
     bb = _BwdSumBuffers.get(dev)
     sums = bb.current(cout_p)
+    sync = (SBN.all_reduce_stats, bb.current_buffer(), sv.sync_w) if (sv.training and sv.sync_w > 1) else None
     # strided 3x3: write dy zero-inserted so that the data gradient is a stride-1 conv (see conv_igemm.cu)
     zero_insert = stride > 1 and R > 1
     n, ho, wo, _ = y.shape
@@ -353,7 +363,7 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
     dy = K.bn_backward(dout, sv.out, y, sv.mean, sv.invstd, sv.scale, sv.relu, grad_scale=1.0 / (1.0 - sv.p),
                        training=sv.training, dres=dres, dgamma=dgamma, dbeta=dbeta, sums=sums, reset=bb.flip(),
                        param_accumulate=direct_affine, scatter=None if dy_dense_needed else scatter,
-                       shift=sv.shift if sv.mask_from_y else None, relu_mask=getattr(sv, "relu_bits", None))
+                       shift=sv.shift if sv.mask_from_y else None, relu_mask=getattr(sv, "relu_bits", None), sync=sync)
     if direct_affine:
         dgamma = dbeta = None  # already added to bn.weight.grad / bn.bias.grad
     dy_z = dy
@@ -615,13 +625,16 @@ class Stem(torch.autograd.Function):
             stats = sb.current(cout_p)
             y = K.conv_fprop([(cols, wp)], 1, 1, 1, 0, 1, cout_p, flops=fl)
             K.bn_stats(y, stats)  # K = 192: far too short to hide the statistics in the conv epilogue
+            sync_w = SBN.sync_world(bn)
+            if sync_w > 1:
+                SBN.all_reduce_stats(sb.current_buffer())
             coef = torch.empty((4, cout_p), dtype=torch.float32, device=x.device)
             scale, shift, mean, invstd = coef[0], coef[1], coef[2], coef[3]
             if bn.num_batches_tracked is not None:
                 PENDING_BATCH_COUNTERS.append(bn.num_batches_tracked)
-            fin = dict(stats=stats, count=n * ho * wo, gamma=bn.weight.detach(), beta=bn.bias.detach(), eps=bn.eps,
+            fin = dict(stats=stats, count=n * ho * wo * sync_w, gamma=bn.weight.detach(), beta=bn.bias.detach(), eps=bn.eps,
                        momentum=bn.momentum if bn.momentum is not None else 0.1, running_mean=bn.running_mean,
-                       running_var=bn.running_var, coef=coef, c_real=cout, reset=sb.flip())
+                       running_var=bn.running_var, coef=coef, c_real=cout, reset=sb.flip(), sync_clamp=sync_w > 1)
             a = K.bn_apply(y, scale, shift, True, finalize=fin)
         else:
             y = K.conv_fprop([(cols, wp)], 1, 1, 1, 0, 1, cout_p, flops=fl)
@@ -630,6 +643,7 @@ class Stem(torch.autograd.Function):
         k, ps, pp = pool.kernel_size, pool.stride, pool.padding
         out, arg = K.maxpool_fwd(a, k, ps, pp)
         ctx.conv, ctx.bn, ctx.training, ctx.krsc = conv, bn, training, krsc
+        ctx.sync_w = SBN.sync_world(bn) if training else 1
         ctx.pool = (k, ps, pp)
         ctx.dims = (kreal, kpad, cout, cout_p)
         ctx.flops = fl
@@ -647,8 +661,9 @@ class Stem(torch.autograd.Function):
         dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
         dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
         sc = _scratch64(dev, "bwd")
+        sync = (SBN.all_reduce_stats, sc, ctx.sync_w) if ctx.sync_w > 1 else None
         dy = K.bn_backward(da, a, y, mean, invstd, scale, True, training=ctx.training, dgamma=dgamma, dbeta=dbeta,
-                           scratch=sc[:2 * cout_p].view(2, cout_p))
+                           scratch=sc[:2 * cout_p].view(2, cout_p), sync=sync)
         gbuf = _direct_grad_buffer(conv.weight) if ctx.krsc else None
         if gbuf is not None:
             # KRSC memory of the [cout,3,7,7] gradient is exactly the [cout][147] GEMM weight gradient

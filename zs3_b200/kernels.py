@@ -243,6 +243,7 @@ def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0,
         if f.get("reset") is not None:
             a.reset_sum, a.reset_sqsum = f["reset"][0].data_ptr(), f["reset"][1].data_ptr()
             a.reset_count = int(f["reset"][2])
+        a.sync_clamp = int(bool(f.get("sync_clamp", False)))
     else:
         a.scale, a.shift = scale.data_ptr(), shift.data_ptr()
     a.M, a.C = n * h * w, cs
@@ -265,7 +266,7 @@ def bn_apply(y, scale, shift, relu, residual=None, out=None, drop_p=0.0, seed=0,
 
 def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, training=True, dres=None,
                 dres_accumulate=False, dgamma=None, dbeta=None, param_accumulate=False, scatter=None, dy=None,
-                scratch=None, shift=None, sums=None, reset=None, relu_mask=None):
+                scratch=None, shift=None, sums=None, reset=None, relu_mask=None, sync=None):
     """Two-phase BatchNorm(+ReLU/+Dropout) backward.  Returns dy (bf16, same layout as y unless scatter).
     With `shift` given (plain conv->BN->ReLU layers) the ReLU mask is recomputed from y instead of read from `out`."""
     _chk_act(dout, "bn_backward dout")
@@ -310,6 +311,22 @@ def bn_backward(dout, out, y, mean, invstd, scale, relu, grad_scale=1.0, trainin
         a.reset_sum_dz, a.reset_sum_dzx, a.reset_count = reset[0].data_ptr(), reset[1].data_ptr(), int(reset[2])
     st = L.stream_ptr()
     L.check(L.lib().zs3_bn_bwd_reduce(C.byref(a), st), "zs3_bn_bwd_reduce")
+    if sync is not None:
+        # Synchronised BatchNorm: sync = (all_reduce, buffer holding sum_dz / sum_dzx, world size).  dy needs the sums
+        # over ALL ranks (divided by the global count); dgamma / dbeta keep the rank-local sums (they join the step's
+        # gradient all-reduce), so they are taken from the buffer before it is reduced.
+        all_reduce, buf, world = sync
+        if dgamma is not None:
+            c_real = dgamma.numel()
+            if param_accumulate:
+                dgamma.add_(scratch[1][:c_real].float())
+                dbeta.add_(scratch[0][:c_real].float())
+            else:
+                dgamma.copy_(scratch[1][:c_real])
+                dbeta.copy_(scratch[0][:c_real])
+            a.dgamma, a.dbeta = None, None
+        all_reduce(buf)
+        a.stat_count = n * h * w * world
     L.check(L.lib().zs3_bn_bwd_apply(C.byref(a), st), "zs3_bn_bwd_apply")
     return dy
 

@@ -213,9 +213,21 @@ class DataParallelTrainer:
     """step-1 training step of zs3/base_trainer.py:16-20 (zero_grad, forward, CE, backward, SGD) for one rank."""
 
     def __init__(self, model, criterion, lr=0.007, momentum=0.9, weight_decay=5e-4, nesterov=False, world_size=1,
-                 use_cuda_graph=False, fuse_loss=True):
+                 use_cuda_graph=False, fuse_loss=True, sync_bn=False):
+        """sync_bn: synchronise the training-mode statistics of every SynchronizedBatchNorm2d over the ranks (the
+        reference enables its SyncBN whenever it trains on more than one GPU, train_pascal.py:279); default False =
+        rank-local statistics.  The per-layer statistic all-reduces sit between kernels, so sync_bn runs eagerly."""
         self.model, self.criterion, self.world = model, criterion, world_size
         self.fuse_loss = fuse_loss
+        self.sync_bn = bool(sync_bn) and world_size > 1
+        from .modeling.sync_batchnorm.batchnorm import enable_sync
+        enable_sync(world_size if self.sync_bn else 1)
+        if self.sync_bn and os.environ.get("ZS3_SYNCBN_GRAPH", "0") != "1":
+            use_cuda_graph = False
+        # Loss scaling.  Every rank's criterion divides by ITS batch size and weight sum (loss.py:43-44), the reference's
+        # DataParallel evaluates ONE criterion on the gathered global batch (train_pascal.py:90-93 + base_trainer.py:18):
+        # sum_r grad(L_r) = world^2 * grad(L_global) for equally sized shards, hence 1/world^2 on the summed gradient.
+        self.grad_scale = 1.0 / float(world_size * world_size)
         self.use_cuda_graph, self.graph, self.graph_tail = use_cuda_graph, None, None
         groups = [list(model.get_1x_lr_params()), list(model.get_10x_lr_params())]
         self.flat = FlatParams(groups)
@@ -352,7 +364,7 @@ class DataParallelTrainer:
             early.wait()
             for w in late:
                 w.wait()
-        self.opt.step(grad_scale=1.0 / self.world)
+        self.opt.step(grad_scale=self.grad_scale)
 
     def _forward_loss(self, image, target):
         """criterion(model(image), target) (base_trainer.py:17-18).  When the criterion is this package's

@@ -178,7 +178,7 @@ class ZS3StepFused(ZS3Step):
         from . import kernels as K
         from . import parity as P
         upd = self.updater
-        dev = emb_map.device
+        dev = src.device
         hw, kin = fh * fw, self.embed_dim + self.noise_dim
         x = torch.zeros((1, fh, fw, K.cpad(kin)), dtype=torch.float32, device=dev)
         xv = x.view(hw, -1)
@@ -210,6 +210,10 @@ class ZS3StepFused(ZS3Step):
 
     def _extra_classifier_backward(self, model, state):
         """hook between the classifier's backward and optimizer.step() (used by ZS3StepGCN)"""
+
+    def _generator_params(self):
+        """every generator parameter this runner trains (their per-iteration delta is averaged over the ranks)"""
+        return list(self.updater.params)
 
     def _classifier_loss(self, model, features, image, target):
         """criterion(forward_class_prediction(features, input_size), target).  When the criterion is this package's
@@ -317,7 +321,7 @@ class ZS3StepFused(ZS3Step):
         mark("plan+index")
         gen_snapshot = None
         if self.world_size > 1:
-            gen_snapshot = torch.cat([p.detach().reshape(-1) for p in self.updater.params])
+            gen_snapshot = torch.cat([p.detach().reshape(-1) for p in self._generator_params()])
         fake_features = torch.zeros(real_features.shape, device=dev)
         fake_by_image = {}
         queue, keep, owners, loss_chunks = [], [], [e[1] for e in upd], []
@@ -395,7 +399,7 @@ class ZS3StepFused(ZS3Step):
         if self.world_size > 1:
             from .parallel import exchange_step2
             head = [p for g in self.optimizer.param_groups for p in g["params"] if p.grad is not None]
-            exchange_step2(self.updater.params, gen_snapshot, head, self.world_size)
+            exchange_step2(self._generator_params(), gen_snapshot, head, self.world_size)
         self.optimizer.step()
         mark("classifier")
         g_losses = torch.cat(loss_chunks).tolist() if loss_chunks else []
@@ -429,6 +433,9 @@ class ZS3StepGCN(ZS3StepFused):
         self.gcn_noise_fn = gcn_noise_fn      # optional: n -> [n, noise_dim] (tests); default torch.rand on the device
         self.gcn_mask_fn = gcn_mask_fn        # optional: n -> [n, hidden] Dropout keep mask of the graph generator (tests)
         self.last_gcn_losses = []
+
+    def _generator_params(self):
+        return list(self.updater.params) + list(self.generator_gcn.parameters())
 
     def _extra_classifier_backward(self, model, state):
         from . import graph as ZG
