@@ -259,9 +259,13 @@ def test_gcn_context_step_matches_oracle():
     assert len(step.last_gcn_losses) == len(ref["gcn_losses"]) > 0
     assert np.allclose([v.item() for v in step.last_gcn_losses], ref["gcn_losses"], rtol=1e-3)
     for k, p in gen_gcn.state_dict().items():
-        # Adam normalises every element's step to ~lr: elements whose gradient is at rounding level take a +-lr step of
-        # either sign (first B200 run: 6e-4 on gcn1.weight with graphs of 3-9 nodes); the losses above pin the arithmetic
-        assert rel_l2(p.cpu(), ref["gcn_generator"][k]) < 2e-3, k
+        # Adam normalises every element's step to ~lr: an element whose gradient is at rounding level takes a +-lr step of
+        # either sign (graphs of 3-9 nodes leave many such elements; a flipped bias element moves by 4 % of its 0.01 init).
+        # The losses above pin the arithmetic; here the accumulated UPDATE must point the same way as the oracle's.
+        upd, upd_ref = p.cpu() - gcn_state[k], ref["gcn_generator"][k] - gcn_state[k]
+        cos = float((upd * upd_ref).sum() / (upd.norm() * upd_ref.norm() + 1e-30))
+        print(f"  gcn generator {k}: update cosine {cos:.4f}, weights rel_l2 {rel_l2(p.cpu(), ref['gcn_generator'][k]):.2e}")
+        assert cos > 0.9 and rel_l2(p.cpu(), ref["gcn_generator"][k]) < 5e-2, k
     assert abs(loss.item() - ref["loss"]) < 2e-2 * abs(ref["loss"])
     assert rel_l2(model.decoder.pred_conv.weight.detach().cpu(), ref["pred_conv.weight"]) < 2e-2
 
