@@ -46,6 +46,8 @@ class ConvArgs(C.Structure):
         ("ep_scale", C.c_void_p), ("ep_shift", C.c_void_p), ("ep_residual", C.c_void_p),
         ("ep_res_cstride", C.c_int), ("ep_relu", C.c_int),
         ("w_forward_layout", C.c_int),
+        ("pre_scale", C.c_void_p * ZS3_MAX_SEGMENTS), ("pre_shift", C.c_void_p * ZS3_MAX_SEGMENTS),
+        ("pre_relu", C.c_int),
     ]
 
 

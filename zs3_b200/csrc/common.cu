@@ -64,7 +64,7 @@ static int ensure_driver() {
 }
 
 int encode_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C, int pad_lo, int upper_corner,
-                       int stride, int channels_per_pixel, int pixels_per_column) {
+                       int stride, int channels_per_pixel, int pixels_per_column, int oob_nan) {
   int rc = ensure_driver();
   if (rc) return rc;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -75,7 +75,8 @@ int encode_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int W, 
   CUresult r = g_encode_im2col(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
                                lower, upper, (cuuint32_t)channels_per_pixel, (cuuint32_t)pixels_per_column, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               oob_nan ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeIm2col failed (%d): N=%d H=%d W=%d C=%d pad=%d upper=%d stride=%d cpp=%d ppc=%d",
               (int)r, N, H, W, C, pad_lo, upper_corner, stride, channels_per_pixel, pixels_per_column);
