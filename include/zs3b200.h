@@ -51,6 +51,8 @@ int zs3_device_supported(void);
 #define ZS3_STRUCT_ROW_SOURCE 10
 #define ZS3_STRUCT_BN_ACT_F32_ARGS 11
 #define ZS3_STRUCT_BN_BWD_F32_ARGS 12
+#define ZS3_STRUCT_AUG_ITEM 13
+#define ZS3_STRUCT_AUGMENT_ARGS 14
 unsigned long long zs3_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
@@ -459,6 +461,42 @@ int zs3_argmax_confusion(const float* logits, const float* target, int B, int C,
 /* Evaluator.add_batch(gt_image, pre_image) (metrics.py:79-81) for predictions computed elsewhere: pred [n] int32 */
 int zs3_confusion_from_pred(const int* pred, const float* target, long long n, int C, unsigned long long* conf,
                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Input transforms of a whole batch on the device (csrc/aug.cu).  Replaces the per-sample PIL pipeline of
+ * zs3/dataloaders/custom_transforms.py: RandomHorizontalFlip (:47-56), RandomScaleCrop (:69-104),
+ * RandomGaussianBlur (:58-66), FixScale (:107-124), Normalize (:8-27), ToTensor (:30-44), composed in
+ * zs3/dataloaders/datasets/pascal.py:120-144 (transform_tr / transform_val).  The caller makes the random
+ * draws (same order as the reference) and passes them per picture; results are bit-exact against Pillow.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const unsigned char* image; /* device: decoded picture, [h][w][3] RGB bytes (np.array(PIL image)) */
+  const unsigned char* label; /* device: [h][w] class ids (np.array(PIL mask)); may be NULL when out_label is NULL */
+  int w, h;                   /* decoded size */
+  int flip;                   /* RandomHorizontalFlip (:51): mirror the columns of picture and mask first */
+  int rw, rh;                 /* size after Image.resize: (ow, oh) of :83-90 / :115-122; (w, h) = no resize */
+  int x1, y1;                 /* crop origin (:98-101) in the resized picture, padded on the right / bottom to the
+                                 output size (:93-96); 0, 0 for transform_val */
+  float blur_radius;          /* ImageFilter.GaussianBlur(radius) of :62-63; <= 0: no blur */
+} zs3_aug_item;
+
+typedef struct {
+  const zs3_aug_item* items;      /* device copy of the n items (read by the kernels) */
+  const zs3_aug_item* items_host; /* host copy of the same n items (validated by the call; not retained) */
+  int n;
+  int max_src_h;                  /* >= every item's h: row capacity of the horizontal-pass scratch */
+  int out_w, out_h;               /* crop_size x crop_size (transform_tr) or the resized size (transform_val) */
+  int fill_label;                 /* RandomScaleCrop fill (255): label value of the padding; the picture pads with 0 */
+  const float* lut;               /* device [3][256]: Normalize applied to every byte value, per channel */
+  float* out_image;               /* device [n][3][out_h][out_w] float32 (ToTensor's CHW) */
+  float* out_label;               /* device [n][out_h][out_w] float32 class ids; NULL = pictures only */
+  void* workspace; unsigned long long workspace_bytes; /* >= zs3_augment_workspace_size(...), 16-byte aligned */
+} zs3_augment_args;
+
+unsigned long long zs3_augment_workspace_size(int n, int max_src_h, int out_w, int out_h);
+/* five launches on `stream` (plan, horizontal pass, vertical pass + labels, and the two blur groups when any item is
+ * blurred); no allocation, no synchronisation; down-scaling by more than 8x per axis is rejected */
+int zs3_augment_batch(const zs3_augment_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fp32-grade parity mode (forward only; csrc/parity.cu).  An fp32 convolution is emulated on the bf16 tensor

@@ -134,3 +134,30 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert lib.zs3_argmax_confusion(p, p, 1, 65, 10, p, p, None) == -1 and "1 <= C <= 64" in err()
     assert lib.zs3_argmax_confusion(p, None, 1, 21, 10, None, None, None) == -1 and "nothing to compute" in err()
     assert lib.zs3_confusion_from_pred(None, p, 10, 21, p, None) == -1
+
+
+def test_augment_entry_point_validates_arguments_without_a_gpu():
+    import ctypes as C
+    from zs3_b200 import _lib
+    lib = _lib.lib()
+    err = lambda: lib.zs3_last_error().decode()  # noqa: E731
+    assert lib.zs3_augment_batch(None, None) == -1 and "null args" in err()
+    a = _lib.AugmentArgs()
+    assert lib.zs3_augment_batch(C.byref(a), None) == -1 and "bad dims" in err()
+    assert lib.zs3_augment_workspace_size(0, 10, 10, 10) == 0
+    need = lib.zs3_augment_workspace_size(16, 500, 513, 513)
+    assert 16 * (500 + 513) * 513 * 3 <= need < 16 * (500 + 513) * 513 * 3 + 16 * (1026 * 20 + 8) * 4 + 64
+    buf = (C.c_float * 64)()
+    p = C.addressof(buf)
+    items = (_lib.AugItem * 1)()
+    a.n, a.max_src_h, a.out_w, a.out_h, a.fill_label = 1, 50, 33, 33, 255
+    a.items, a.items_host, a.lut, a.out_image, a.out_label, a.workspace = p, items, p, p, p, p
+    items[0] = _lib.AugItem(p, p, 40, 50, 0, 4, 50, 0, 0, -1.0)
+    assert lib.zs3_augment_batch(C.byref(a), None) == -1 and "8x" in err()
+    items[0] = _lib.AugItem(p, None, 40, 50, 0, 40, 50, 0, 0, -1.0)
+    assert lib.zs3_augment_batch(C.byref(a), None) == -1 and "label map missing" in err()
+    items[0] = _lib.AugItem(p, p, 40, 60, 0, 40, 60, 0, 0, -1.0)
+    assert lib.zs3_augment_batch(C.byref(a), None) == -1 and "max_src_h" in err()
+    items[0] = _lib.AugItem(p, p, 40, 50, 0, 40, 50, 0, 0, -1.0)
+    a.workspace_bytes = 64
+    assert lib.zs3_augment_batch(C.byref(a), None) == -1 and "workspace" in err()

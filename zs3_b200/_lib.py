@@ -98,6 +98,9 @@ def _declare(lib):
     lib.zs3_gmmn_train_workspace_size.restype = C.c_ulonglong
     lib.zs3_gmmn_train_workspace_size.argtypes = [i, i, i, i]
     sigs["zs3_gmmn_train_workspace_size"] = [i, i, i, i]
+    lib.zs3_augment_workspace_size.restype = C.c_ulonglong
+    lib.zs3_augment_workspace_size.argtypes = [i, i, i, i]
+    sigs["zs3_augment_workspace_size"] = [i, i, i, i]
     return sigs
 
 
@@ -177,6 +180,22 @@ class ComponentsArgs(C.Structure):
         ("B", C.c_int), ("h", C.c_int), ("w", C.c_int), ("max_nodes", C.c_int),
         ("n_nodes", C.c_void_p), ("node_label", C.c_void_p), ("node_seed", C.c_void_p), ("node_map", C.c_void_p),
         ("adj", C.c_void_p),
+    ]
+
+
+class AugItem(C.Structure):
+    _fields_ = [
+        ("image", C.c_void_p), ("label", C.c_void_p), ("w", C.c_int), ("h", C.c_int), ("flip", C.c_int),
+        ("rw", C.c_int), ("rh", C.c_int), ("x1", C.c_int), ("y1", C.c_int), ("blur_radius", C.c_float),
+    ]
+
+
+class AugmentArgs(C.Structure):
+    _fields_ = [
+        ("items", C.c_void_p), ("items_host", C.POINTER(AugItem)), ("n", C.c_int), ("max_src_h", C.c_int),
+        ("out_w", C.c_int), ("out_h", C.c_int), ("fill_label", C.c_int),
+        ("lut", C.c_void_p), ("out_image", C.c_void_p), ("out_label", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_ulonglong),
     ]
 
 
@@ -260,6 +279,7 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_concat2": [vp, i, vp, i, vp, ll, vp],
         "zs3_gmmn_train_fused": [C.POINTER(GmmnTrainArgs), vp],
         "zs3_label_components": [C.POINTER(ComponentsArgs), vp],
+        "zs3_augment_batch": [C.POINTER(AugmentArgs), vp],
         "zs3_argmax_confusion": [vp, vp, i, i, ll, vp, vp, vp],
         "zs3_confusion_from_pred": [vp, vp, ll, i, vp, vp],
         "zs3_split3_f32": [vp, vp, vp, vp, ll, vp],
@@ -284,7 +304,8 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
 
 # ids of include/zs3b200.h (ZS3_STRUCT_*) -> ctypes mirror; checked against zs3_sizeof() when the library loads
 STRUCT_IDS = {1: ConvArgs, 2: WgradArgs, 3: BnApplyArgs, 4: BnBwdArgs, 5: SgemmArgs, 6: GmmnItem, 7: GmmnTrainArgs,
-              8: ComponentsArgs, 9: ConvSegment, 10: RowSource, 11: BnActF32Args, 12: BnBwdF32Args}
+              8: ComponentsArgs, 9: ConvSegment, 10: RowSource, 11: BnActF32Args, 12: BnBwdF32Args,
+              13: AugItem, 14: AugmentArgs}
 
 
 def lib():

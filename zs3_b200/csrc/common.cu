@@ -187,6 +187,8 @@ unsigned long long zs3_sizeof(int which) {
     case ZS3_STRUCT_ROW_SOURCE: return sizeof(zs3_row_source);
     case ZS3_STRUCT_BN_ACT_F32_ARGS: return sizeof(zs3_bn_act_f32_args);
     case ZS3_STRUCT_BN_BWD_F32_ARGS: return sizeof(zs3_bn_bwd_f32_args);
+    case ZS3_STRUCT_AUG_ITEM: return sizeof(zs3_aug_item);
+    case ZS3_STRUCT_AUGMENT_ARGS: return sizeof(zs3_augment_args);
     default: return 0;
   }
 }
