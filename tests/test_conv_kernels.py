@@ -32,6 +32,15 @@ CONV_CASES = [
     (2, 65, 65, 128, 256, 1, 2, 0, 1),
     (3, 20, 20, 48, 21, 3, 1, 1, 1),      # channel padding on both sides
     (16, 33, 33, 256, 256, 3, 1, 1, 1),   # layer3 conv2 shape at full batch
+    # filter rows that lie in the zero padding for whole tiles are skipped (valid_filter_rows): ASPP dilations at 33x33,
+    # a dilation larger than the map (OS8 ASPP: only the centre row ever touches a pixel), tiles straddling two images,
+    # maps so small that one 128-pixel tile spans several images, a strided 3x3
+    (5, 33, 33, 64, 256, 3, 1, 18, 18),
+    (3, 33, 33, 128, 64, 3, 1, 6, 6),
+    (2, 17, 17, 64, 64, 3, 1, 24, 24),
+    (9, 5, 5, 64, 64, 3, 1, 4, 4),
+    (7, 9, 9, 64, 128, 3, 1, 3, 3),
+    (3, 33, 33, 64, 64, 3, 2, 8, 8),
 ]
 
 
@@ -202,6 +211,9 @@ def test_wgrad_direct_into_krsc_grad_and_krsc_pack(case):
     (2, 33, 33, 256, 64, 1, 1, 0, 1),
     (3, 20, 20, 48, 21, 3, 1, 1, 1),
     (2, 17, 17, 1024, 256, 1, 1, 0, 1),
+    (5, 33, 33, 64, 256, 3, 1, 18, 18),   # culled filter rows in the data gradient
+    (2, 17, 17, 64, 64, 3, 1, 24, 24),
+    (9, 5, 5, 64, 64, 3, 1, 4, 4),
 ])
 def test_dgrad_from_forward_packed_weights(case):
     """data gradient straight from the forward-packed weights (MN-major B tiles, taps flipped in the kernel)"""

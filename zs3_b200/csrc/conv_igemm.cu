@@ -51,6 +51,9 @@ struct FpropParams {
   int num_m_tiles, num_n_tiles;
   int num_m_groups;  // ceil(num_m_tiles / cluster size): the CTAs of a cluster take consecutive m-tiles of one n-tile
   int kb_per_tile;   // total k-blocks per output tile
+  int kb_per_row;    // k-blocks per filter row r (kb_per_tile / R)
+  int cull;          // skip the filter rows whose taps lie in the zero padding for EVERY pixel of a tile
+  int H, Ho;         // input / output rows (tap culling)
   void* y;
   long long y_cstride;
   // output pixel (n,p,q) is stored at pixel index n*y_img + p*y_row + q*y_pix of y
@@ -81,6 +84,40 @@ struct FpropSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
   static_assert(2 * MAX_STAT_CH * 4 >= STAGING_BYTES, "statistics region must hold the second staging set");
 };
+
+// Filter rows r whose taps touch at least one real input row for some output pixel of the tile starting at pixel m0
+// (bit r of the result).  A filter row outside that set reads nothing but zero padding for the whole tile -- at 33x33
+// with dilation 12/18 (ASPP, aspp.py:57-80) or 4/8 (layer4's multi-grid blocks) that is up to a third of the k-blocks
+// of a tile -- so the producer does not fetch it and the MMA issuer does not multiply it.  Output row op reads input
+// row op*stride - pad + r*dil; the tile covers rows [op0, Ho) of its first image, every row of the images in between
+// and rows [0, op1] of its last image.
+__device__ __forceinline__ uint32_t valid_filter_rows(const FpropParams& p, int m0) {
+  const uint32_t all = (1u << p.R) - 1u;
+  if (!p.cull) return all;
+  int m_last = m0 + BLOCK_M;
+  if (m_last > p.M) m_last = p.M;
+  m_last -= 1;
+  if (m_last < m0) return 1u;  // a tile past the last pixel (cluster padding): nothing but TMA zero fill
+  const int img0 = m0 / p.HoWo, img1 = m_last / p.HoWo;
+  const int op0 = (m0 - img0 * p.HoWo) / p.Wo, op1 = (m_last - img1 * p.HoWo) / p.Wo;
+  uint32_t mask = 0;
+  for (int r = 0; r < p.R; ++r) {
+    const int t = p.pad - r * p.dil;
+    const int lo = t > 0 ? (t + p.stride - 1) / p.stride : 0;  // first output row whose tap r is inside the input
+    const int u = p.H - 1 + t;
+    int hi = u >= 0 ? u / p.stride : -1;                       // last such output row
+    if (hi > p.Ho - 1) hi = p.Ho - 1;
+    bool v;
+    if (img0 == img1)
+      v = (lo > op0 ? lo : op0) <= (hi < op1 ? hi : op1);
+    else if (img1 - img0 >= 2)
+      v = lo <= hi;
+    else
+      v = ((lo > op0 ? lo : op0) <= hi) || (lo <= (hi < op1 ? hi : op1));
+    mask |= (v ? 1u : 0u) << r;
+  }
+  return mask ? mask : 1u;
+}
 
 // Column sums over the 32 lanes of a warp: lane j ends up with sum over lanes of v[j].
 // Recursive halving: 31 shuffles instead of 32*5.
@@ -179,9 +216,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
         const int oq = rem - op * p.Wo;
         const int base_w = oq * p.stride - p.pad;
         const int base_h = op * p.stride - p.pad;
+        const uint32_t rows = valid_filter_rows(p, m0);
         for (int s = 0; s < p.num_segments; ++s) {
           const FpropSegment& sg = p.seg[s];
           for (int r = 0; r < p.R; ++r) {
+            if (!((rows >> r) & 1u)) continue;
             for (int q = 0; q < p.S; ++q) {
               const int tap = r * p.S + q;
               for (int cb = 0; cb < sg.num_cblk; ++cb) {
@@ -226,7 +265,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
         mbar_wait(&acc_empty[as], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < p.kb_per_tile; ++kb) {
+        // the issuer only needs the NUMBER of k-blocks the producer fetches for this tile
+        const int m_tile_i = (g / p.num_n_tiles) * csize + crank;
+        const int nkb = p.cull ? __popc(valid_filter_rows(p, m_tile_i * BLOCK_M)) * p.kb_per_row : p.kb_per_tile;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -1040,6 +1082,34 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   p.num_m_groups = ceil_div(m_tiles_total, csize);
   p.num_n_tiles = ceil_div(a->cout_pad, BN);
   p.kb_per_tile = kb;
+  p.kb_per_row = kb / a->R;
+  p.H = a->H;
+  p.Ho = a->Ho;
+  {
+    // ZS3_TAP_CULL=0 multiplies the zero padding like any other tap (A/B knob, profiles/r02_tap_culling.md)
+    static int cull_pref = -1;
+    if (cull_pref < 0) {
+      const char* env = getenv("ZS3_TAP_CULL");
+      cull_pref = env ? atoi(env) : 1;
+    }
+    // clusters run their CTAs in lock step on a shared weight stage: every CTA must fetch the same k-blocks.
+    // Only worth the per-tile index arithmetic when a noticeable share of the (output row, filter row) pairs reads
+    // padding: dilated 3x3 at 33x33 (layer4 d >= 4, ASPP) qualify, the pad-1 convs do not.
+    p.cull = 0;
+    if (cull_pref && a->R > 1 && a->R <= 16 && csize == 1) {
+      long long skippable = 0;
+      for (int r = 0; r < a->R; ++r) {
+        const int t = a->pad - r * a->dil;
+        const int lo = t > 0 ? (t + a->stride - 1) / a->stride : 0;
+        const int u = a->H - 1 + t;
+        int hi = u >= 0 ? u / a->stride : -1;
+        if (hi > a->Ho - 1) hi = a->Ho - 1;
+        const int valid = hi >= lo ? hi - lo + 1 : 0;
+        skippable += a->Ho - (valid < a->Ho ? valid : a->Ho);
+      }
+      p.cull = (cull_pref >= 2 || skippable * 20 >= (long long)a->R * a->Ho) ? 1 : 0;  // >= 5 % (2 = always, for tests)
+    }
+  }
   p.y = a->y;
   p.y_cstride = a->y_cstride;
   if (a->y_sp_stride > 1) {

@@ -140,9 +140,20 @@ class FusedSGD:
         self.lr_dev.copy_(torch.tensor(self._lrs, dtype=torch.float32), non_blocking=True)
 
     def step(self, grad_scale=1.0):
+        self.step_span(0, self.flat.flat.numel(), grad_scale)
+        self.finish_step()
+
+    def step_span(self, lo, hi, grad_scale=1.0):
+        """the update of the flat elements [lo, hi) only (each parameter group's part with its own learning rate): lets
+        the data-parallel runtime update the parameters whose gradients are already reduced while the rest of the
+        backward still runs; finish_step() closes the iteration once every span has been issued"""
         for gi, (a, b) in enumerate(self.flat.group_ranges):
-            K.sgd_step(self.flat.flat[a:b], self.flat.grad[a:b], self.buf[a:b], self.lr_dev[gi:gi + 1], self.momentum,
-                       self.weight_decay, self.nesterov, False, grad_scale)  # buf starts at 0: mom*0 + d == torch's first-step buf = d
+            a, b = max(a, lo), min(b, hi)
+            if b > a:
+                K.sgd_step(self.flat.flat[a:b], self.flat.grad[a:b], self.buf[a:b], self.lr_dev[gi:gi + 1], self.momentum,
+                           self.weight_decay, self.nesterov, False, grad_scale)  # buf starts at 0: mom*0 + d == torch's first-step buf = d
+
+    def finish_step(self):
         self.steps += 1
         ZF.invalidate_weight_caches()
 
@@ -246,16 +257,13 @@ class DataParallelTrainer:
                                                       m.weight.data_ptr())
         # parameters above the backbone cut (layer3 .. decoder): one contiguous range of the flat buffers, reduced
         # while the rest of the backward still runs (see _finish_distributed)
-        # Status: OFF unless ZS3_DP_CUT=1.  The first version failed its 2-GPU run (profiles/r01_dp_cut_failure.md):
-        # stage 1 used backward(inputs=[cut tensors]), which executes the nodes that PRODUCED the cut tensors, and the
-        # cut named low_level_feat, which is upstream of layer2's output.  cut_backward() now captures the cut
-        # gradients with torch.autograd.grad and the backbone hands the decoder an alias of low_level_feat; the
-        # two-stage logic is CPU-tested (tests/test_parallel_cpu.py) but not re-validated on GPUs, so the default is
-        # the flow measured in profiles/r01_bench_dp{2,4,8}.json: the whole backward from the graph, then ONE
-        # all-reduce over the flat gradient buffer.
-        self.early_range, self.early_params = None, []
+        # Status: ON (ZS3_DP_CUT=0 restores one all-reduce after the whole backward).  The round-1 version failed its
+        # first 2-GPU run (profiles/r01_dp_cut_failure.md); cut_backward() now captures the cut gradients with
+        # torch.autograd.grad and the backbone hands the decoder an alias of low_level_feat.  Validated on 2x B200
+        # (tests/test_multigpu_gpu.py: gradients equal the plain flow to 2e-8; profiles/r02_dp_cut.md: A/B bench).
+        self.early_range, self.early_params, self._opt_stream = None, [], None
         bb = getattr(model, "backbone", None)
-        if world_size > 1 and bb is not None and hasattr(bb, "layer3") and os.environ.get("ZS3_DP_CUT", "0") == "1":
+        if world_size > 1 and bb is not None and hasattr(bb, "layer3") and os.environ.get("ZS3_DP_CUT", "1") == "1":
             first = next(iter(bb.layer3.parameters()), None)
             if first is not None and first.grad is not None:
                 a = (first.grad.data_ptr() - self.flat.grad.data_ptr()) // self.flat.grad.element_size()
@@ -355,16 +363,25 @@ class DataParallelTrainer:
         buffer) are reduced on NCCL's stream WHILE the tail of the backward runs; the small remainder follows."""
         if tail is None:
             dist.all_reduce(self.flat.grad)
-        else:
-            a, b = self.early_range
-            early = dist.all_reduce(self.flat.grad[a:b], async_op=True)
-            tail()
-            late = [dist.all_reduce(self.flat.grad[lo:hi], async_op=True)
-                    for lo, hi in ((0, a), (b, self.flat.grad.numel())) if hi > lo]
+            self.opt.step(grad_scale=self.grad_scale)
+            return
+        a, b = self.early_range
+        main = torch.cuda.current_stream()
+        early = dist.all_reduce(self.flat.grad[a:b], async_op=True)
+        tail()
+        # the parameters above the cut (97 % of them) are updated on a side stream as soon as their all-reduce has
+        # landed, concurrently with the tail of the backward, which only reads the weights BELOW the cut
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream()
+        with torch.cuda.stream(self._opt_stream):
             early.wait()
-            for w in late:
-                w.wait()
-        self.opt.step(grad_scale=self.grad_scale)
+            self.opt.step_span(a, b, self.grad_scale)
+        for lo, hi in ((0, a), (b, self.flat.grad.numel())):
+            if hi > lo:
+                dist.all_reduce(self.flat.grad[lo:hi])
+                self.opt.step_span(lo, hi, self.grad_scale)
+        main.wait_stream(self._opt_stream)
+        self.opt.finish_step()
 
     def _forward_loss(self, image, target):
         """criterion(model(image), target) (base_trainer.py:17-18).  When the criterion is this package's
