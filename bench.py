@@ -609,6 +609,13 @@ def run_ours(args):
         except Exception as e:
             config5 = {"error": repr(e)[:300]}
 
+    input_transforms = None
+    if rank == 0 and world == 1 and not args.no_transforms:
+        try:
+            input_transforms = input_transforms_rate(dev)
+        except Exception as e:
+            input_transforms = {"error": repr(e)[:300]}
+
     if rank == 0:
         sampler.join(timeout=2)
         line = {
@@ -632,6 +639,7 @@ def run_ours(args):
             "forward_only": forward_only,
             "step2": step2,
             "config5": config5,
+            "input_transforms": input_transforms,
             "library_baseline": library_baseline,
             "parity_mode": parity_mode,
             "numerics_vs_fp64": numerics,
@@ -641,6 +649,63 @@ def run_ours(args):
     phase("done")
     if world > 1:
         dist.destroy_process_group()
+
+
+def input_transforms_rate(dev, n=16, reps=20):
+    """the training input transforms of one batch (custom_transforms.py via datasets/pascal.py:120-134) on
+    the device, bit-exact against Pillow: device-resident rate, end to end from host bytes, HBM roofline of the five
+    launches, and the same Pillow calls on one host thread (the reference's per-worker path)."""
+    import importlib.util
+    import random
+    spec = importlib.util.spec_from_file_location("augment_bench", os.path.join(ROOT, "tools", "augment_bench.py"))
+    AB = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(AB)
+    from zs3_b200.dataloaders.gpu_transforms import PASCAL_MEAN, PASCAL_STD, GpuTransforms
+    t = GpuTransforms(513, 513, device=dev)
+    samples = AB.pictures(n)
+    random.seed(1)
+    params = [t.draw_train(lab.shape[1], lab.shape[0]) for _, lab in samples]
+    staged = t.stage(samples, params)
+    out = t.launch(staged, 513, 513)
+    t0 = time.perf_counter()
+    px, py = AB.pillow_batch(samples, params, 513, PASCAL_MEAN, PASCAL_STD)
+    cpu_s = time.perf_counter() - t0
+    exact = bool(torch.equal(out["image"].cpu(), px) and torch.equal(out["label"].cpu(), py))
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_ms = 0.0
+    for _ in range(reps):
+        flush.zero_()                       # > L2: the sources are read from HBM in every timed launch group
+        e0.record()
+        t.launch(staged, 513, 513)
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms += e0.elapsed_time(e1)
+    dev_ms /= reps
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o = t.run(samples, params, 513, 513)
+        float(o["label"][0, 0, 0].item())   # D2H read of a result
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    src = sum(a.size + b.size for a, b in samples)
+    outb = n * 513 * 513 * 4 * 4
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = float(peaks.get("hbm_gbs", 0) or 0) or 6500.0   # measured copy bandwidth; else the profiling guide's fallback
+    ach = (src + outb) / (dev_ms * 1e-3) / 1e9
+    return {"workload": f"transform_tr of {n} VOC-like pictures (~500x375 RGB + label map) -> [n,3,513,513] float32 + "
+                        f"[n,513,513] float32; {int(sum(p['blur_radius'] >= 0 for p in params))} of {n} blurred",
+            "value": n / (dev_ms * 1e-3), "unit": "pictures/sec", "ms_per_batch": dev_ms, "gpu_launches_per_batch": 5,
+            "bit_exact_vs_pillow": exact,
+            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "pictures/sec", "ms_per_batch": e2e_ms,
+                    "h2d_bytes_per_step": int(t.h2d_bytes), "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if hbm else None,
+                         "traffic": None, "algorithmic_bytes": int(src + outb),
+                         "note": "five launches timed together; byte-granular integer work, latency- not bandwidth-bound "
+                                 "at this size (profiles/r02_augment.md)"},
+            "cpu_baseline": {"value": n / cpu_s, "unit": "pictures/sec", "cores": 1, "kind": "reference",
+                             "sample": f"the Pillow calls of custom_transforms.py:47-104 + Normalize/ToTensor on the same {n} "
+                                       f"pictures with the same draws, one host thread ({cpu_s:.2f} s)"}}
 
 
 def step2_inputs(B, HW, dev=None):
@@ -949,6 +1014,7 @@ def main():
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU arms")
     ap.add_argument("--no-parity", action="store_true", help="skip the split-precision (tolerance-meeting) training mode")
     ap.add_argument("--no-numerics", action="store_true", help="skip the distance-to-fp64 table")
+    ap.add_argument("--no-transforms", action="store_true", help="skip the device input-transform measurement")
     ap.add_argument("--layer-table", default="", help="write a per-conv-shape timing table (markdown) to this path")
     ap.add_argument("--mode", default="graph", choices=["eager", "graph"],
                     help="graph: capture the whole training step in one CUDA graph and replay it")

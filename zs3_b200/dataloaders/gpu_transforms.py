@@ -78,9 +78,9 @@ class GpuTransforms:
         return dict(flip=0, rw=ow, rh=oh, x1=0, y1=0, blur_radius=-1.0)
 
     # ---- device side
-    def run(self, arrays, params, out_w, out_h, want_label=True):
-        """arrays: list of (image uint8 [h,w,3], label uint8 [h,w]); params: list of dicts (draw_train / fix_scale)."""
-        lib = L.lib()
+    def stage(self, arrays, params):
+        """pack the pictures, label maps and the item table into one pinned buffer and start its (single) H2D copy;
+        returns the staged batch for launch()"""
         n = len(arrays)
         sizes = [a[0].size + a[1].size for a in arrays]
         offs = np.concatenate([[0], np.cumsum([(s + 15) // 16 * 16 for s in sizes])]).astype(np.int64)
@@ -98,20 +98,30 @@ class GpuTransforms:
                                  p["blur_radius"])
         item_off = int(offs[-1])
         host[item_off:item_off + C.sizeof(items)] = np.frombuffer(items, dtype=np.uint8)
-        dev.copy_(staging, non_blocking=True)                       # one H2D: pictures, label maps and the item table
-        max_h = max(a[1].shape[0] for a in arrays)
-        need = lib.zs3_augment_workspace_size(n, max_h, out_w, out_h)
+        dev.copy_(staging, non_blocking=True)
+        self.h2d_bytes = staging.numel()
+        return dict(dev=dev, items=items, item_ptr=base + item_off, n=n, max_h=max(a[1].shape[0] for a in arrays),
+                    staging=staging)
+
+    def launch(self, staged, out_w, out_h, want_label=True):
+        """the five launches of zs3_augment_batch on the current stream"""
+        lib = L.lib()
+        n = staged["n"]
+        need = lib.zs3_augment_workspace_size(n, staged["max_h"], out_w, out_h)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         image = torch.empty(n, 3, out_h, out_w, dtype=torch.float32, device=self.device)
         label = torch.empty(n, out_h, out_w, dtype=torch.float32, device=self.device) if want_label else None
-        a = L.AugmentArgs(base + item_off, items, n, max_h, out_w, out_h, self.fill, self.lut.data_ptr(),
-                          image.data_ptr(), label.data_ptr() if want_label else None, self._ws.data_ptr(),
-                          self._ws.numel())
+        a = L.AugmentArgs(staged["item_ptr"], staged["items"], n, staged["max_h"], out_w, out_h, self.fill,
+                          self.lut.data_ptr(), image.data_ptr(), label.data_ptr() if want_label else None,
+                          self._ws.data_ptr(), self._ws.numel())
         L.check(lib.zs3_augment_batch(C.byref(a), L.stream_ptr()), "zs3_augment_batch")
-        dev.record_stream(torch.cuda.current_stream())
-        self.h2d_bytes = staging.numel()
+        staged["dev"].record_stream(torch.cuda.current_stream())
         return {"image": image, "label": label}
+
+    def run(self, arrays, params, out_w, out_h, want_label=True):
+        """arrays: list of (image uint8 [h,w,3], label uint8 [h,w]); params: list of dicts (draw_train / fix_scale)."""
+        return self.launch(self.stage(arrays, params), out_w, out_h, want_label)
 
     def transform_tr(self, samples, rng=_random):
         arrays = [_as_bytes(s) for s in samples]
