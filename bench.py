@@ -545,6 +545,11 @@ def run_ours(args):
                 forward_only["train_mode_bn_cuda_graph"] = {"error": repr(e)[:200]}
         model.eval()                                      # running statistics: BN/ReLU/residual folded into the convs
         forward_only["eval_mode_bn_fused_epilogue"] = time_forward()
+        if world == 1:
+            try:
+                forward_only["eval_mode_bn_fused_epilogue_cuda_graph"] = time_forward_graph()
+            except Exception as e:  # reported, never fatal
+                forward_only["eval_mode_bn_fused_epilogue_cuda_graph"] = {"error": repr(e)[:200]}
         model.train()
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)

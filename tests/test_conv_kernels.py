@@ -248,3 +248,37 @@ def test_inference_epilogue_folds_bn_residual_relu():
                       epilogue=(scale, shift, None, False))
     ref2 = F.conv2d(x, w, padding=2, dilation=2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     assert rel_l2(y2.permute(0, 3, 1, 2), ref2) < TOL_F32_OUT
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, Cin, Cout, R, dil, residual, relu
+    (2, 33, 128, 256, 3, 2, True, True),
+    (3, 17, 64, 64, 1, 1, True, True),       # 64-column tiles, rows past M in the last tile
+    (2, 33, 256, 128, 1, 1, False, True),
+    (1, 20, 64, 512, 1, 1, True, False),     # two n-tiles, residual without ReLU
+    (2, 33, 64, 48, 3, 1, False, False),     # channel padding: the padded output channels stay zero
+    (16, 33, 256, 1024, 1, 1, True, True),   # layer3 conv3 at full batch: several tiles per CTA
+])
+def test_inference_epilogue_hot_variant(case):
+    """frozen / eval-mode BatchNorm (+ residual, + ReLU) folded into the pipelined TMA-store epilogue (MODE 3)"""
+    from zs3_b200 import kernels as K
+    N, H, Cin, Cout, R, dil, with_res, relu = case
+    pad = dil * (R - 1) // 2
+    x, w = _mk(N, H, H, Cin, Cout, R)
+    cin_p, cout_p = K.cpad(Cin), K.cpad(Cout)
+    g = torch.Generator().manual_seed(4)
+    scale = torch.zeros(cout_p).cuda()
+    shift = torch.zeros(cout_p).cuda()
+    scale[:Cout] = (torch.rand(Cout, generator=g) + 0.5).cuda()
+    shift[:Cout] = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, Cout, H, H, generator=g).to(torch.bfloat16).float().cuda() if with_res else None
+    ref = F.conv2d(x, w, padding=pad, dilation=dil) * scale[:Cout].view(1, -1, 1, 1) + shift[:Cout].view(1, -1, 1, 1)
+    if with_res:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    y = K.conv_fprop([(K.nchw_to_nhwc(x, cin_p), K.pack_weight(w, cout_p, cin_p))], R, R, 1, pad, dil, cout_p,
+                     epilogue=(scale, shift, K.nchw_to_nhwc(res, cout_p) if with_res else None, relu))
+    assert rel_l2(y[..., :Cout].permute(0, 3, 1, 2).float(), ref) < TOL_BF16_OUT
+    if cout_p > Cout:
+        assert y[..., Cout:].abs().max().item() == 0.0

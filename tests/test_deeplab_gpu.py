@@ -160,8 +160,11 @@ def test_frozen_bn_training_has_gradients(small_input):
 
 def test_trainer_fused_loss_matches_unfused(small_input):
     """The training runtime fuses the final x4 upsample into the loss (DeepLab.forward_scores +
-    SegmentationLosses.UpsampledCrossEntropyLoss); same loss (1e-5 rel) and same parameter gradients (bf16-rounding
-    level, 2e-2 rel-L2 over the whole flat gradient) as criterion(model(image), target)."""
+    SegmentationLosses.UpsampledCrossEntropyLoss).  Both loss paths are evaluated on the SAME class scores of one forward
+    pass (two train-mode forwards of the random-init network are not comparable: fp64 atomics order the batch statistics
+    differently and the network amplifies a last-bit difference ~1e3x): same loss (1e-5 rel) and the same gradient
+    with respect to the scores, hence the same parameter gradients; the full backward of the fused path is finite."""
+    from zs3_b200 import functional as ZF
     from zs3_b200.modeling.deeplab import DeepLab
     from zs3_b200.parallel import DataParallelTrainer
     from zs3_b200.utils.loss import SegmentationLosses
@@ -170,23 +173,30 @@ def test_trainer_fused_loss_matches_unfused(small_input):
     model.aspp.dropout.p = 0.0
     model.decoder.last_conv[3].p = 0.0
     model.decoder.last_conv[7].p = 0.0
-    crit = SegmentationLosses(weight=None, cuda=True).build_loss("ce")
+    owner = SegmentationLosses(weight=None, cuda=True)
+    crit = owner.build_loss("ce")
     trainer = DataParallelTrainer(model, crit)
     image = small_input.cuda()
     target = torch.randint(0, 21, (2, 65, 65), generator=torch.Generator().manual_seed(12)).float().cuda()
     target[:, :3] = 255
-    results = []
-    for fuse in (True, False):
-        trainer.fuse_loss = fuse
-        trainer.flat.zero_grad()
-        loss = trainer._forward_loss(image, target)
-        loss.backward()
-        torch.cuda.synchronize()
-        results.append((loss.item(), trainer.flat.grad.clone()))
-    (l_f, g_f), (l_u, g_u) = results
-    print(f"fused loss {l_f:.6f} unfused {l_u:.6f} grad rel_l2 {rel_l2(g_f, g_u):.3e}")
-    assert abs(l_f - l_u) < 1e-5 * abs(l_u)
-    assert rel_l2(g_f, g_u) < 2e-2
+    trainer._begin_step()      # zero_grad + refresh of the bf16 weight shadow, as every real step does
+    scores = model.forward_scores(image)
+    l_f = owner.UpsampledCrossEntropyLoss(scores, model.num_classes, target)
+    l_u = crit(ZF.UpsampleLogits.apply(scores, model.num_classes, 65, 65), target)
+    (g_f,) = torch.autograd.grad(l_f, scores, retain_graph=True)
+    (g_u,) = torch.autograd.grad(l_u, scores, retain_graph=True)
+    print(f"fused loss {l_f.item():.6f} unfused {l_u.item():.6f} d/dscores rel_l2 {rel_l2(g_f.float(), g_u.float()):.3e}")
+    assert abs(l_f.item() - l_u.item()) < 1e-5 * abs(l_u.item())
+    assert rel_l2(g_f.float(), g_u.float()) < 4e-3       # both gradients are rounded to bf16 once
+    # the trainer's own entry takes the fused path and its whole backward is finite and non-trivial
+    trainer._begin_step()
+    loss = trainer._forward_loss(image, target)
+    loss.backward()
+    torch.cuda.synchronize()
+    bad = [n for n, p in model.named_parameters() if not torch.isfinite(p.grad).all()]
+    assert not bad, f"non-finite gradients: {bad[:8]} ({len(bad)} parameters)"
+    assert abs(loss.item() - l_f.item()) < 5e-2 * abs(l_f.item())
+    assert float(trainer.flat.grad.abs().max()) > 0
 
 
 def test_reference_api_surface():

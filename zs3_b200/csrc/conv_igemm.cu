@@ -140,7 +140,10 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
 //   1  same + BatchNorm batch statistics kept in REGISTERS across the CTA's tiles (needs one n-tile per CTA, i.e.
 //      gridDim.x % num_n_tiles == 0) and flushed once at the end;
 //   2  generic: bias, fp32 / strided / read-modify-write outputs, the folded inference epilogue, statistics through
-//      per-CTA shared-memory partials.
+//      per-CTA shared-memory partials;
+//   3  variant 0 + the folded inference epilogue (frozen / eval-mode BatchNorm: out = relu?(acc*scale[n] + shift[n]
+//      (+ residual))) on the pipelined TMEM-read / staged TMA-store path: the frozen-backbone feature extraction of
+//      ZS3Net's step 2 (train_pascal_GMMN.py:154-157) and validation run every conv -> BN -> ReLU layer as this ONE kernel.
 template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   using L = FpropSmem<BN, STAGES>;
@@ -331,6 +334,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
         for (int ci = 0; ci < CHUNKS; ++ci) {
           const int n = n_tile * BN + (half + 2 * ci) * 32;
           uint32_t(&raw)[32] = raw2[ci & 1];
+          uint4 rres[4];
+          if constexpr (MODE == 3) {
+            // the residual row segment of this chunk (64 contiguous bytes per lane) is requested before the TMEM read
+            // is waited for, so both latencies overlap
+            if (p.ep_res != nullptr && valid && n < p.cout_pad) {
+              const uint4* rp =
+                  reinterpret_cast<const uint4*>(p.ep_res + (long long)(m_tile * BLOCK_M + row) * p.ep_res_cs + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rres[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
           tmem_ld_wait_for(raw);
           if (ci + 1 < CHUNKS) {
             tmem_ld_32x32(tacc + (ci + 1) * 64, raw2[(ci + 1) & 1]);
@@ -340,6 +357,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_fprop_kernel(const __grid
             if (lane == 0) mbar_arrive(&acc_empty[as]);
           }
           if (n >= p.cout_pad) continue;  // warp-uniform
+          if constexpr (MODE == 3) {
+            const float4* sc4 = reinterpret_cast<const float4*>(p.ep_scale + n);
+            const float4* sh4 = reinterpret_cast<const float4*>(p.ep_shift + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 a = __ldg(sc4 + j), b = __ldg(sh4 + j);  // same address in every lane: one broadcast each
+              raw[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(raw[4 * j + 0]), a.x, b.x));
+              raw[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(raw[4 * j + 1]), a.y, b.y));
+              raw[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(raw[4 * j + 2]), a.z, b.z));
+              raw[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(raw[4 * j + 3]), a.w, b.w));
+            }
+            if (p.ep_res != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                raw[8 * j + 0] = __float_as_uint(__uint_as_float(raw[8 * j + 0]) + bf16_lo(rres[j].x));
+                raw[8 * j + 1] = __float_as_uint(__uint_as_float(raw[8 * j + 1]) + bf16_hi(rres[j].x));
+                raw[8 * j + 2] = __float_as_uint(__uint_as_float(raw[8 * j + 2]) + bf16_lo(rres[j].y));
+                raw[8 * j + 3] = __float_as_uint(__uint_as_float(raw[8 * j + 3]) + bf16_hi(rres[j].y));
+                raw[8 * j + 4] = __float_as_uint(__uint_as_float(raw[8 * j + 4]) + bf16_lo(rres[j].z));
+                raw[8 * j + 5] = __float_as_uint(__uint_as_float(raw[8 * j + 5]) + bf16_hi(rres[j].z));
+                raw[8 * j + 6] = __float_as_uint(__uint_as_float(raw[8 * j + 6]) + bf16_lo(rres[j].w));
+                raw[8 * j + 7] = __float_as_uint(__uint_as_float(raw[8 * j + 7]) + bf16_hi(rres[j].w));
+              }
+            }
+            if (p.ep_relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(fmaxf(__uint_as_float(raw[j]), 0.f));
+            }
+          }
           if (MODE == 1 && !valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) raw[j] = 0u;  // rows past M must not reach the batch statistics
@@ -921,6 +967,16 @@ static int num_sms() {
 template <int BN, int STAGES, int MODE>
 static int launch_fprop_mode(const FpropParams& p, int csize, int clusters, cudaStream_t st);
 
+// ZS3_FOLD_HOT=0 sends the folded inference epilogue back to the generic variant (A/B knob, profiles/r02_*)
+static bool fold_hot_enabled() {
+  static int pref = -1;
+  if (pref < 0) {
+    const char* env = getenv("ZS3_FOLD_HOT");
+    pref = env ? atoi(env) : 1;
+  }
+  return pref != 0;
+}
+
 // epilogue variant + grid: see conv_fprop_kernel.  The register-statistics variant needs every CTA to stay on one
 // n-tile, i.e. a grid that is a multiple of num_n_tiles (148 already is for 1, 2 and 4 n-tiles; 8 n-tiles run on 144).
 template <int BN, int STAGES>
@@ -928,6 +984,10 @@ static int launch_fprop(const FpropParams& p, int csize, cudaStream_t st) {
   const int groups = p.num_m_groups * p.num_n_tiles;
   const int max_clusters = num_sms() / csize;
   int clusters = groups < max_clusters ? groups : max_clusters;
+  // the folded inference epilogue on the hot path: dense bf16 output, residual rows addressed by the output pixel index
+  if (p.use_tma_store && p.bias == nullptr && p.ep_scale != nullptr && p.stat_sum == nullptr && !p.accumulate &&
+      fold_hot_enabled())
+    return launch_fprop_mode<BN, STAGES, 3>(p, csize, clusters, st);
   const bool hot = p.use_tma_store && p.bias == nullptr && p.ep_scale == nullptr;
   if (!hot) return launch_fprop_mode<BN, STAGES, 2>(p, csize, clusters, st);
   if (p.stat_sum == nullptr) return launch_fprop_mode<BN, STAGES, 0>(p, csize, clusters, st);

@@ -331,6 +331,17 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
     return out, sv
 
 
+_DEBUG_FINITE = os.environ.get("ZS3_DEBUG_FINITE", "0") == "1"
+
+
+def _check_finite(what, t, sv):
+    """debug aid (ZS3_DEBUG_FINITE=1): name the first tensor of a backward that holds a non-finite value"""
+    if _DEBUG_FINITE and t is not None and not bool(torch.isfinite(t.float()).all()):
+        bad = (~torch.isfinite(t.float())).nonzero()
+        raise FloatingPointError(f"{what} of {sv.conv} holds {bad.shape[0]} non-finite values, first at {bad[0].tolist()}, "
+                                 f"shape {tuple(t.shape)}")
+
+
 def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None):
     """Backward of cba_forward.  need_dx: per-segment flags.  dx_into: optional per-segment (tensor, accumulate)
     targets the data gradient is written (or added) into -- how a residual join is summed without an extra kernel.
@@ -366,6 +377,10 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
                        shift=sv.shift if sv.mask_from_y else None, relu_mask=getattr(sv, "relu_bits", None), sync=sync)
     if direct_affine:
         dgamma = dbeta = None  # already added to bn.weight.grad / bn.bias.grad
+    if _DEBUG_FINITE:
+        for nm, t in (("dout", dout), ("saved y", y), ("saved out", sv.out), ("mean", sv.mean), ("invstd", sv.invstd),
+                      ("scale", sv.scale), ("bn-backward sums", sums[0]), ("dy", dy), ("dres", dres)):
+            _check_finite(nm, t, sv)
     dy_z = dy
     if dy_dense_needed:
         # both layouts are needed: dense for wgrad, zero-inserted for dgrad
@@ -396,6 +411,7 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
                 dx = K.conv_fprop([(_pad_to(dy_z, h_in + 2 * pad - dil * (R - 1), w_in + 2 * pad - dil * (S - 1)), wt)],
                                   R, S, 1, dil * (R - 1) - pad, dil, cin_p, out=tgt, accumulate=acc, flops=fl,
                                   kind="conv_dgrad", w_forward_layout=True)
+            _check_finite(f"dx[{i}] (accumulate={acc})", dx, sv)
             dxs.append(dx)
         else:
             dxs.append(None)

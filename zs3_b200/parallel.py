@@ -247,6 +247,7 @@ class DataParallelTrainer:
         # bf16 shadow of the flat parameter buffer: conv weights are KRSC, so a layer's slice of the shadow is its
         # packed forward weight [cout][R*S][cin] (layers with channel padding keep their own packed copies)
         self.shadow = torch.empty(self.flat.flat.numel(), dtype=torch.bfloat16, device=self.flat.flat.device)
+        K.cast_f32_to_bf16(self.flat.flat, self.shadow)   # valid from construction on; _begin_step refreshes it per step
         base = self.flat.flat.data_ptr()
         for m in model.modules():
             if isinstance(m, torch.nn.Conv2d) and K.is_krsc(m.weight):
@@ -277,6 +278,7 @@ class DataParallelTrainer:
             dist.broadcast(self.flat.flat, 0)
             for b in model.buffers():
                 dist.broadcast(b, 0)
+            K.cast_f32_to_bf16(self.flat.flat, self.shadow)
 
     def train_step(self, image, target):
         """One optimisation step; returns the (device) loss tensor.  With use_cuda_graph the step is captured once
