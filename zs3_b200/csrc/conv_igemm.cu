@@ -1221,6 +1221,73 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
   return launch_fprop<64, 8>(p, csize, st);
 }
 
+// Output-tile shape of the weight gradient.  The grid is (output tiles) x (pixel splits), one wave of CTAs; every CTA
+// ends with an fp32 reduce-add of its whole tile into dW, so the split-K reduction moves splits x |dW| bytes through
+// the L2 atomic units.  On the 33x33 layers (17 k pixels, 1 MB of dW) the largest tile (256 x 256) leaves 4-9 output
+// tiles and therefore 16-37 splits: 37 MB of reduce traffic per launch (22-29 us measured, profiles/r02_layer_table.md).
+// Smaller tiles re-read the operands more often but cut the splits; the choice is made by a three-term model (operand
+// bytes per CTA at the L2->SM rate, MMA time, total reduce bytes at the L2 reduce rate).  In practice it moves the
+// 1x1 1024<->256 layers of layer3 to 128 x 128 tiles (9 splits instead of 37) and leaves everything else on the
+// largest tile.  ZS3_WGRAD_TILE=<MB>x<CN> pins the tile (experiments).
+static void choose_wgrad_tile(long long M, int cout_pad, int cin_pad, int taps, int k_splits_arg, int* MB, int* CN) {
+  static int pin_mb = -1, pin_cn = 0;
+  if (pin_mb < 0) {
+    pin_mb = 0;
+    const char* env = getenv("ZS3_WGRAD_TILE");
+    if (env) {
+      int mb = 0, cn = 0;
+      if (sscanf(env, "%dx%d", &mb, &cn) == 2 && (mb == 1 || mb == 2) && (cn == 64 || cn == 128 || cn == 256)) {
+        pin_mb = mb;
+        pin_cn = cn;
+      }
+    }
+  }
+  const int max_cn = cin_pad >= 256 ? 256 : (cin_pad >= 128 ? 128 : 64);
+  const int max_mb = cout_pad >= 256 ? 2 : 1;
+  if (pin_mb > 0) {
+    *MB = pin_mb <= max_mb ? pin_mb : max_mb;
+    *CN = pin_cn <= max_cn ? pin_cn : max_cn;
+    return;
+  }
+  // rates fitted to four B200 measurements (3x3 256->256 and 1x1 1024->256 at 33x33, tiles 256x256 and 128x128,
+  // profiles/r02_wgrad_tile.md): T = operand bytes per CTA / kLoad + total reduce bytes / kReduce + const
+  const double kLoadBytesPerUs = 97e3;    // L2 -> one SM, TMA operand stream
+  const double kMacPerUs = 4096.0 * 1900; // one SM, dense bf16
+  const double kReduceBytesPerUs = 4.0e6; // all SMs -> L2 fp32 reduce-add
+  const long long pblocks = (M + WG_BLOCK_P - 1) / WG_BLOCK_P;
+  double best = 1e30, t_default = 1e30;
+  int best_mb = max_mb, best_cn = max_cn;
+  for (int mb = 1; mb <= max_mb; ++mb) {
+    for (int cn = 64; cn <= max_cn; cn *= 2) {
+      const long long tiles = (long long)ceil_div(cout_pad, 128 * mb) * ceil_div(cin_pad, cn) * taps;
+      long long ks = k_splits_arg > 0 ? k_splits_arg : num_sms() / tiles;
+      if (ks < 1) ks = 1;
+      const long long max_ks = pblocks / 4 > 0 ? pblocks / 4 : 1;
+      if (ks > max_ks) ks = max_ks;
+      const double waves = (double)((tiles * ks + num_sms() - 1) / num_sms());
+      const double px = (double)((pblocks + ks - 1) / ks) * WG_BLOCK_P;
+      const double t_load = px * (128.0 * mb + cn) * 2.0 / kLoadBytesPerUs;
+      const double t_mma = px * 128.0 * mb * cn / kMacPerUs;
+      const double t_red = (double)tiles * ks * (128.0 * mb * cn * 4.0) / kReduceBytesPerUs;
+      const double t = waves * ((t_load > t_mma ? t_load : t_mma) + 1.5) + t_red;
+      if (mb == max_mb && cn == max_cn) t_default = t;
+      if (t < best) {
+        best = t;
+        best_mb = mb;
+        best_cn = cn;
+      }
+    }
+  }
+  // the largest tile is the measured default; leave it only for a predicted gain of at least 10 %
+  if (best < 0.9 * t_default) {
+    *MB = best_mb;
+    *CN = best_cn;
+  } else {
+    *MB = max_mb;
+    *CN = max_cn;
+  }
+}
+
 extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   ZS3_CHECK_ARG(a != nullptr, "conv_wgrad: null args");
   ZS3_CHECK_ARG(a->cout_pad > 0 && a->cout_pad % 64 == 0 && a->cin_pad > 0 && a->cin_pad % 64 == 0,
@@ -1235,7 +1302,9 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   ZS3_CHECK_ARG(M > 0 && M < (1ll << 31), "conv_wgrad: bad pixel count");
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  const int CN = a->cin_pad >= 256 ? 256 : (a->cin_pad >= 128 ? 128 : 64);
+  int CN = a->cin_pad >= 256 ? 256 : (a->cin_pad >= 128 ? 128 : 64);
+  int MB = a->cout_pad >= 256 ? 2 : 1;  // 256 output channels per CTA when the layer has them
+  choose_wgrad_tile(M, a->cout_pad, a->cin_pad, a->R * a->S, a->k_splits, &MB, &CN);
   int rc = encode_tiled2d_bf16(&p.dy, a->dy, M, a->cout_pad, a->dy_cstride, WG_BLOCK_P, 64);
   if (rc) return rc;
   rc = encode_im2col_bf16(&p.x, a->x, a->N, a->H, a->W, a->x_cstride, a->pad, a->pad - (a->S - 1) * a->dil, a->stride,
@@ -1251,7 +1320,6 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   p.S = a->S;
   p.cout_pad = a->cout_pad;
   p.cin_pad = a->cin_pad;
-  const int MB = a->cout_pad >= 256 ? 2 : 1;  // 256 output channels per CTA when the layer has them
   p.num_co_tiles = ceil_div(a->cout_pad, 128 * MB);
   p.num_ci_tiles = ceil_div(a->cin_pad, CN);
   p.pblocks_total = (int)ceil_div_ll(M, WG_BLOCK_P);
