@@ -474,11 +474,11 @@ def run_ours(args):
         ach = fl_all / (ms_all * 1e-3) / 1e12
         # DRAM bytes per conv launch from the committed ncu capture of the same step (bench.py cannot run under ncu)
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 tj = json.load(fh)
-            traffic, traffic_src = tj.get("conv_dram_bytes_per_launch_avg"), "profiles/r01_conv_traffic.json: " + tj.get("source", "")
+            traffic, traffic_src = tj.get("conv_dram_bytes_per_launch_avg"), "profiles/r02_conv_traffic.json: " + tj.get("source", "")
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_unit": "bytes per conv launch (average over the step's conv launches)",
                     "traffic_source": traffic_src, "kernel": "conv_fprop_kernel/conv_wgrad_kernel (tcgen05 implicit GEMM; fprop+dgrad+wgrad)",
