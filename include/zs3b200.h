@@ -321,6 +321,14 @@ int zs3_upsample_ce_fwd(const void* x, const float* target, const float* weight,
 int zs3_upsample_ce_bwd(const void* x, const float* target, const float* weight, int N, int C, int Hi, int Wi, int cs,
                         int Ho, int Wo, int ignore_index, float div, const double* accum2, const float* grad_out,
                         void* dx, void* stream);
+/* the same backward for the exact x4 geometry of DeepLab (Ho == 4*(Hi-1)+1, Wo == 4*(Wi-1)+1, Wo <= 544): one softmax
+ * evaluation per output pixel, shared-memory accumulation without atomics, two fp32 partials per input row combined in
+ * a fixed order (deterministic).  Returns ZS3_ERR_UNSUPPORTED for any other geometry.  workspace (16-byte aligned) >=
+ * zs3_upsample4_ce_bwd_workspace_size(N, C, Hi, Wi) bytes. */
+unsigned long long zs3_upsample4_ce_bwd_workspace_size(int N, int C, int Hi, int Wi);
+int zs3_upsample4_ce_bwd(const void* x, const float* target, const float* weight, int N, int C, int Hi, int Wi, int cs,
+                         int Ho, int Wo, int ignore_index, float div, const double* accum2, const float* grad_out,
+                         void* dx, void* workspace, unsigned long long workspace_bytes, void* stream);
 
 /* torch.optim.SGD (zs3/train_pascal.py:55-60) and torch.optim.Adam (zs3/train_pascal_GMMN.py:65-67) over one
  * flat fp32 buffer; grad_scale multiplies the gradient first (1/world_size after the NCCL all-reduce). */

@@ -110,14 +110,19 @@ def test_cross_entropy(C, weighted):
     assert abs(l2.item() - r2.item()) < 1e-5 * abs(r2.item())
 
 
+@pytest.mark.parametrize("x4", [True, False], ids=["x4_fast_path", "generic"])
 @pytest.mark.parametrize("C,hi,ho,weighted", [(21, 33, 129, False), (21, 17, 65, True), (5, 9, 33, True), (21, 129, 513, False),
-                                              (60, 17, 65, True), (60, 129, 513, False), (33, 33, 129, True)])
-def test_fused_upsample_cross_entropy(C, hi, ho, weighted):
+                                              (60, 17, 65, True), (60, 129, 513, False), (33, 33, 129, True),
+                                              (21, 20, 65, True), (7, 2, 5, False)])
+def test_fused_upsample_cross_entropy(C, hi, ho, weighted, x4, monkeypatch):
     """loss = CE(interpolate(scores)) straight from the low-resolution NHWC bf16 scores (training-loss fusion) against
     torch's interpolate + cross_entropy in fp32 on the same bf16-representable scores; tolerances: loss 1e-5 rel,
     d loss / d scores 4e-3 rel-L2 (the gradient is stored in bf16, 2^-9 per element)."""
     from zs3_b200 import kernels as K
     from zs3_b200.utils.loss import SegmentationLosses
+    # the backward has two kernels: the exact-x4 geometry of DeepLab (one softmax per output pixel, deterministic
+    # combine) and the generic one; (20 -> 65) is not x4 and always takes the generic kernel
+    monkeypatch.setenv("ZS3_CE_BWD_X4", "1" if x4 else "0")
     g = torch.Generator().manual_seed(11)
     N = 2
     x = _bf(torch.randn(N, C, hi, hi, generator=g) * 2).cuda().requires_grad_(True)

@@ -98,6 +98,9 @@ def _declare(lib):
     lib.zs3_gmmn_train_workspace_size.restype = C.c_ulonglong
     lib.zs3_gmmn_train_workspace_size.argtypes = [i, i, i, i]
     sigs["zs3_gmmn_train_workspace_size"] = [i, i, i, i]
+    lib.zs3_upsample4_ce_bwd_workspace_size.restype = C.c_ulonglong
+    lib.zs3_upsample4_ce_bwd_workspace_size.argtypes = [i, i, i, i]
+    sigs["zs3_upsample4_ce_bwd_workspace_size"] = [i, i, i, i]
     lib.zs3_augment_workspace_size.restype = C.c_ulonglong
     lib.zs3_augment_workspace_size.argtypes = [i, i, i, i]
     sigs["zs3_augment_workspace_size"] = [i, i, i, i]
@@ -265,6 +268,7 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_ce_bwd": [vp, vp, vp, i, i, ll, i, f, vp, vp, vp, vp],
         "zs3_upsample_ce_fwd": [vp, vp, vp, i, i, i, i, i, i, i, i, f, vp, vp, vp],
         "zs3_upsample_ce_bwd": [vp, vp, vp, i, i, i, i, i, i, i, i, f, vp, vp, vp, vp],
+        "zs3_upsample4_ce_bwd": [vp, vp, vp, i, i, i, i, i, i, i, i, f, vp, vp, vp, vp, C.c_ulonglong, vp],
         "zs3_cast_f32_to_bf16": [vp, vp, ll, vp],
         "zs3_sgd_step": [vp, vp, vp, ll, f, f, f, i, i, f, vp],
         "zs3_sgd_step_lrdev": [vp, vp, vp, ll, vp, f, f, i, i, f, vp],

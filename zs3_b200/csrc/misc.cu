@@ -527,8 +527,7 @@ __global__ void __launch_bounds__(640) upsample_ce_bwd_kernel(const __nv_bfloat1
   extern __shared__ float smem_f[];
   const int ldi = Wi + 1, ldo = Wo + 1;
   float* xs = smem_f;                 // [3][C][Wi+1]: input rows h-1, h, h+1
-  float* bl = xs + 3 * C * ldi;       // [C][Wi+1]: the two input rows of the current output row, blended vertically
-  float* v = smem_f;                  // [C][Wo+1]: ALIASES xs/bl (only written after the row loop is done with them)
+  float* v = smem_f;                  // [C][Wo+1]: ALIASES xs (only written after the row loop is done with it)
   const int fl_words = max(4 * C * ldi, C * ldo);
   unsigned char* tg = reinterpret_cast<unsigned char*>(smem_f + fl_words);  // [max_rows][Wo] labels (255 = no gradient)
   const int h = blockIdx.x % Hi, n = blockIdx.x / Hi;
@@ -555,52 +554,71 @@ __global__ void __launch_bounds__(640) upsample_ce_bwd_kernel(const __nv_bfloat1
   float acc[MAXC];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    int y0, y1; float ly;
-    bl_coord(oh_lo + r, sh, Hi, y0, y1, ly);
-    const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
-    if (wy == 0.f) continue;  // CTA-uniform
-    __syncthreads();          // xs staged (first pass) / previous row's readers of bl are done
-    const float* s0 = xs + (y0 - (h - 1)) * C * ldi;
-    const float* s1 = xs + (y1 - (h - 1)) * C * ldi;
-    for (int i = threadIdx.x; i < C * Wi; i += blockDim.x) {
-      const int c = i / Wi, w = i - c * Wi;
-      bl[c * ldi + w] = (1.f - ly) * s0[c * ldi + w] + ly * s1[c * ldi + w];
-    }
-    __syncthreads();
-    if (ow >= Wo) continue;
-    const int t = tg[r * Wo + ow];
-    if (t == 255) continue;
-    float lg[KEEP ? MAXC : 1];
-    float mx = -INFINITY;
+  __syncthreads();  // xs and tg staged
+  // No block-wide step inside the row loop: every thread blends its own two input columns vertically in registers
+  // (same order as the forward: vertical into fp32, then horizontal), so the warps of the CTA run the ~7 contributing
+  // output rows independently.  (The first version staged the vertically blended row in shared memory behind two
+  // __syncthreads per output row; with one 17-warp CTA per SM -- 96 registers x 544 threads -- that serialisation made
+  // this kernel 0.64 ms of the 18.4 ms step, profiles/r02_launches_step.md.)
+  if (ow < Wo) {
+    for (int r = 0; r < rows; ++r) {
+      int y0, y1; float ly;
+      bl_coord(oh_lo + r, sh, Hi, y0, y1, ly);
+      const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
+      if (wy == 0.f) continue;  // CTA-uniform
+      const int t = tg[r * Wo + ow];
+      if (t == 255) continue;
+      const float* s0 = xs + (y0 - (h - 1)) * C * ldi;
+      const float* s1 = xs + (y1 - (h - 1)) * C * ldi;
+      const float my = 1.f - ly, mxw = 1.f - lx;
+      float lg[KEEP ? MAXC : 1];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      if (c < C) {
-        const float l = (1.f - lx) * bl[c * ldi + x0] + lx * bl[c * ldi + x1];
-        if (KEEP) lg[c] = l;
-        mx = fmaxf(mx, l);
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          const float a = my * s0[c * ldi + x0] + ly * s1[c * ldi + x0];
+          const float b = my * s0[c * ldi + x1] + ly * s1[c * ldi + x1];
+          const float l = mxw * a + lx * b;
+          if (KEEP) lg[c] = l;
+          mx = fmaxf(mx, l);
+        }
       }
-    }
-    float s = 0.f;
+      float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      if (c < C) {
-        const float e = __expf((KEEP ? lg[c] : (1.f - lx) * bl[c * ldi + x0] + lx * bl[c * ldi + x1]) - mx);
-        if (KEEP) lg[c] = e;
-        s += e;
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          float l;
+          if (KEEP) {
+            l = lg[c];
+          } else {
+            const float a = my * s0[c * ldi + x0] + ly * s1[c * ldi + x0];
+            const float b = my * s0[c * ldi + x1] + ly * s1[c * ldi + x1];
+            l = mxw * a + lx * b;
+          }
+          const float e = __expf(l - mx);
+          if (KEEP) lg[c] = e;
+          s += e;
+        }
       }
-    }
-    const float coef = wy * g * (weight ? weight[t] : 1.f);
-    const float inv = coef / s;
+      const float coef = wy * g * (weight ? weight[t] : 1.f);
+      const float inv = coef / s;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      if (c < C) {
-        const float e = KEEP ? lg[c] : __expf((1.f - lx) * bl[c * ldi + x0] + lx * bl[c * ldi + x1] - mx);
-        acc[c] += e * inv - (c == t ? coef : 0.f);
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          float e;
+          if (KEEP) {
+            e = lg[c];
+          } else {
+            const float a = my * s0[c * ldi + x0] + ly * s1[c * ldi + x0];
+            const float b = my * s0[c * ldi + x1] + ly * s1[c * ldi + x1];
+            e = __expf(mxw * a + lx * b - mx);
+          }
+          acc[c] += e * inv - (c == t ? coef : 0.f);
+        }
       }
     }
   }
-  __syncthreads();  // every reader of xs / bl is done: v (same shared memory) may be written
+  __syncthreads();  // every reader of xs is done: v (same shared memory) may be written
   if (ow < Wo) {
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
@@ -623,6 +641,122 @@ __global__ void __launch_bounds__(640) upsample_ce_bwd_kernel(const __nv_bfloat1
       }
     }
     out[(long long)w * cs + c] = __float2bfloat16(a);
+  }
+}
+
+// ---- x4 fast path of the fused upsample + cross-entropy backward (DeepLab: 129 -> 513, 17 -> 65: Ho = 4(Hi-1)+1).
+// With the exact 1/4 scale, output row oh blends input rows y0 = oh/4 and y0+1 with ly = (oh%4)/4 and output column ow
+// blends columns x0 = ow/4 and x0+1 with lx = (ow%4)/4.  One CTA per input-row INTERVAL h (output rows 4h .. 4h+3), one
+// thread per output column: the softmax of every output pixel is evaluated exactly ONCE (the generic kernel above
+// evaluates it from both neighbouring input rows), nothing persists in registers across rows (plain loops over the
+// classes, online softmax), the four output columns of an input interval are reduced with a two-step butterfly per class
+// and lane j of the quad accumulates into plane j of four per-CTA shared-memory planes -- A0/A1: input row h, columns
+// x0 / x0+1; B0/B1: input row h+1 -- each address owned by exactly one thread (no atomics).  Interval h leaves its sums for row h in pa and for row h+1 in pb; the combine
+// kernel adds the two partials of every input row in a fixed order: deterministic, no read-modify-write in HBM.
+__global__ void __launch_bounds__(544, 2) upsample4_ce_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                  const float* __restrict__ target,
+                                                                  const float* __restrict__ weight, int C, int Hi, int Wi,
+                                                                  int cs, int Ho, int Wo, int ignore,
+                                                                  const double* __restrict__ accum, float div,
+                                                                  const float* __restrict__ gout, float* __restrict__ pa,
+                                                                  float* __restrict__ pb, int pc) {
+  extern __shared__ float smem_f[];
+  const int ldi = Wi + 1, plane = C * ldi;
+  float* xs0 = smem_f;            // [C][Wi+1] input row h
+  float* xs1 = xs0 + plane;       // input row h+1 (row h again for the last interval)
+  float* bl = xs1 + plane;        // the two rows blended for the current output row
+  float* acc = bl + plane;        // four planes: A0, B0, A1, B1
+  const int h = blockIdx.x % Hi, n = blockIdx.x / Hi;
+  const int h1 = min(h + 1, Hi - 1);
+  for (int i = threadIdx.x; i < Wi * C; i += blockDim.x) {
+    const int c = i % C, w = i / C;
+    xs0[c * ldi + w] = __bfloat162float(x[(((long long)n * Hi + h) * Wi + w) * cs + c]);
+    xs1[c * ldi + w] = __bfloat162float(x[(((long long)n * Hi + h1) * Wi + w) * cs + c]);
+  }
+  for (int i = threadIdx.x; i < 4 * plane; i += blockDim.x) acc[i] = 0.f;
+  const float g = gout[0] / ((float)accum[1] * div);
+  const int ow = threadIdx.x;
+  const bool col = ow < Wo;
+  const int x0 = min(ow >> 2, Wi - 1), x1 = min(x0 + 1, Wi - 1);
+  const float lx = col ? 0.25f * (float)(ow & 3) : 0.f;
+  // after the butterfly every lane of a quad holds both sums; lane j of the quad owns plane j:
+  //   0: A0 (row h, column x0)   1: B0 (row h+1, column x0)   2: A1 (row h, column x0+1)   3: B1 (row h+1, column x0+1)
+  const int q = ow & 3;
+  const bool mine = (ow & ~3) < Wo && (q < 2 || x0 + 1 < Wi);
+  float* my = acc + q * plane + (q < 2 ? x0 : x0 + 1);
+  for (int r = 0; r < 4; ++r) {
+    const int oh = 4 * h + r;
+    if (oh >= Ho) break;  // CTA-uniform (last interval: one row)
+    const float ly = 0.25f * (float)r;
+    __syncthreads();      // staging done (r = 0) / the previous row's readers of bl are done
+    for (int i = threadIdx.x; i < plane; i += blockDim.x) bl[i] = (1.f - ly) * xs0[i] + ly * xs1[i];
+    __syncthreads();
+    int t = 255;
+    if (col) {
+      const int tv = (int)__ldg(target + ((long long)n * Ho + oh) * Wo + ow);
+      t = (tv == ignore || tv < 0 || tv >= C) ? 255 : tv;
+    }
+    const float* b0 = bl + x0;
+    const float* b1 = bl + x1;
+    float mx = -INFINITY, s = 0.f;
+    if (t != 255) {  // online softmax: one pass for the maximum and the normaliser
+#pragma unroll 4
+      for (int c = 0; c < C; ++c) {
+        const float l = (1.f - lx) * b0[c * ldi] + lx * b1[c * ldi];
+        if (l > mx) {
+          s *= __expf(mx - l);
+          mx = l;
+        }
+        s += __expf(l - mx);
+      }
+    }
+    const float coef = t != 255 ? g * (weight ? weight[t] : 1.f) : 0.f;
+    const float inv = t != 255 ? coef / s : 0.f;
+    const float wq = (q & 1) ? ly : 1.f - ly;  // planes 1 and 3 belong to input row h+1
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      float d = 0.f;
+      if (t != 255) {
+        const float l = (1.f - lx) * b0[c * ldi] + lx * b1[c * ldi];
+        d = __expf(l - mx) * inv - (c == t ? coef : 0.f);
+      }
+      float u0 = (1.f - lx) * d, u1 = lx * d;
+      u0 += __shfl_xor_sync(0xffffffffu, u0, 1);
+      u1 += __shfl_xor_sync(0xffffffffu, u1, 1);
+      u0 += __shfl_xor_sync(0xffffffffu, u0, 2);
+      u1 += __shfl_xor_sync(0xffffffffu, u1, 2);
+      if (mine) my[c * ldi] += wq * (q < 2 ? u0 : u1);
+    }
+  }
+  __syncthreads();
+  const float* A0 = acc;
+  const float* B0 = acc + plane;
+  const float* A1 = acc + 2 * plane;
+  const float* B1 = acc + 3 * plane;
+  float* oa = pa + ((long long)n * Hi + h) * Wi * pc;
+  float* ob = pb + ((long long)n * Hi + h1) * Wi * pc;
+  const bool has_b = h + 1 < Hi;
+  for (int i = threadIdx.x; i < Wi * C; i += blockDim.x) {
+    const int c = i % C, w = i / C;
+    oa[(long long)w * pc + c] = A0[c * ldi + w] + A1[c * ldi + w];
+    if (has_b) ob[(long long)w * pc + c] = B0[c * ldi + w] + B1[c * ldi + w];
+  }
+}
+
+// dx[n][h][w][c] = pa[n][h][w][c] + pb[n][h][w][c] (row 0 has no pb), padding channels zero
+__global__ void upsample4_ce_combine_kernel(const float* __restrict__ pa, const float* __restrict__ pb,
+                                            __nv_bfloat16* __restrict__ dx, long long pixels, int Hi, int Wi, int C, int pc,
+                                            int cs) {
+  const long long total = pixels * cs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long px = i / cs;
+    const int c = (int)(i - px * cs);
+    float v = 0.f;
+    if (c < C) {
+      v = pa[px * pc + c];
+      if ((px / Wi) % Hi != 0) v += pb[px * pc + c];
+    }
+    dx[i] = __float2bfloat16(v);
   }
 }
 
@@ -842,6 +976,44 @@ extern "C" int zs3_upsample_ce_bwd(const void* x, const float* target, const flo
                                                                       grad_out, BF(dx), max_rows);
   }
   ZS3_CHECK_LAUNCH("upsample_ce_bwd");
+  return ZS3_OK;
+}
+
+extern "C" unsigned long long zs3_upsample4_ce_bwd_workspace_size(int N, int C, int Hi, int Wi) {
+  if (N <= 0 || C <= 0 || Hi <= 0 || Wi <= 0) return 0;
+  const unsigned long long pc = (unsigned long long)((C + 3) / 4 * 4);
+  return 2ull * N * Hi * Wi * pc * sizeof(float);
+}
+
+/* x4 fast path of zs3_upsample_ce_bwd (Ho == 4*(Hi-1)+1, Wo == 4*(Wi-1)+1, Wo <= 544); returns ZS3_ERR_UNSUPPORTED for
+ * other geometries (the caller then uses zs3_upsample_ce_bwd).  workspace: zs3_upsample4_ce_bwd_workspace_size bytes. */
+extern "C" int zs3_upsample4_ce_bwd(const void* x, const float* target, const float* weight, int N, int C, int Hi, int Wi,
+                                    int cs, int Ho, int Wo, int ignore_index, float div, const double* accum2,
+                                    const float* grad_out, void* dx, void* workspace, unsigned long long workspace_bytes,
+                                    void* stream) {
+  ZS3_CHECK_ARG(x && target && accum2 && grad_out && dx && workspace && C > 0 && C <= cs && C <= CE_MAX_C,
+                "upsample4_ce_bwd: bad args (C <= %d)", CE_MAX_C);
+  if (Ho != 4 * (Hi - 1) + 1 || Wo != 4 * (Wi - 1) + 1 || Wo > 544 || Hi < 2 || Wi < 2) {
+    zs3::set_error("upsample4_ce_bwd: geometry %dx%d -> %dx%d is not an exact x4 upsample", Hi, Wi, Ho, Wo);
+    return ZS3_ERR_UNSUPPORTED;
+  }
+  ZS3_CHECK_ARG(workspace_bytes >= zs3_upsample4_ce_bwd_workspace_size(N, C, Hi, Wi) &&
+                    (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                "upsample4_ce_bwd: workspace too small or misaligned");
+  const int pc = (C + 3) / 4 * 4;
+  const size_t smem = (size_t)7 * C * (Wi + 1) * sizeof(float);
+  ZS3_CHECK_ARG(smem <= 224 * 1024, "upsample4_ce_bwd: %d classes x %d columns do not fit in shared memory", C, Wi);
+  float* pa = static_cast<float*>(workspace);
+  float* pb = pa + (size_t)N * Hi * Wi * pc;
+  const int threads = ((Wo + 31) / 32) * 32;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(upsample4_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  upsample4_ce_bwd_kernel<<<N * Hi, threads, smem, ST(stream)>>>(CBF(x), target, weight, C, Hi, Wi, cs, Ho, Wo, ignore_index,
+                                                                 accum2, div, grad_out, pa, pb, pc);
+  ZS3_CHECK_LAUNCH("upsample4_ce_bwd");
+  const long long pixels = (long long)N * Hi * Wi;
+  upsample4_ce_combine_kernel<<<ew_blocks(pixels * cs, 256), 256, 0, ST(stream)>>>(pa, pb, BF(dx), pixels, Hi, Wi, C, pc, cs);
+  ZS3_CHECK_LAUNCH("upsample4_ce_bwd(combine)");
   return ZS3_OK;
 }
 

@@ -57,6 +57,14 @@ class UpsampleCrossEntropy(torch.autograd.Function):
         n, hi, wi, cs = x.shape
         dx = torch.empty_like(x)
         gout = gout.contiguous().float()
+        if (ho == 4 * (hi - 1) + 1 and wo == 4 * (wi - 1) + 1 and wo <= 544 and hi >= 2 and wi >= 2
+                and 7 * c * (wi + 1) * 4 <= 224 * 1024 and os.environ.get("ZS3_CE_BWD_X4", "1") == "1"):
+            # DeepLab's exact x4 geometry: one softmax per output pixel, deterministic two-partial combine
+            ws = torch.empty(L.lib().zs3_upsample4_ce_bwd_workspace_size(n, c, hi, wi), dtype=torch.uint8, device=x.device)
+            L.check(L.lib().zs3_upsample4_ce_bwd(L.ptr(x), L.ptr(target), L.ptr(wt), n, c, hi, wi, cs, ho, wo, ignore, div,
+                                                 L.ptr(accum), L.ptr(gout), L.ptr(dx), L.ptr(ws), ws.numel(),
+                                                 L.stream_ptr()), "zs3_upsample4_ce_bwd")
+            return dx, None, None, None, None, None
         L.check(L.lib().zs3_upsample_ce_bwd(L.ptr(x), L.ptr(target), L.ptr(wt), n, c, hi, wi, cs, ho, wo, ignore, div,
                                             L.ptr(accum), L.ptr(gout), L.ptr(dx), L.stream_ptr()), "zs3_upsample_ce_bwd")
         return dx, None, None, None, None, None
