@@ -75,12 +75,19 @@ __global__ void __launch_bounds__(256) stem_im2col_krsc_kernel(const float* __re
   const int Wp = W + 2 * pad;
   const int p = blockIdx.x % Ho, n = blockIdx.x / Ho;
   const int K = C * R * R, SC = R * C;
-  for (int i = threadIdx.x; i < C * R * Wp; i += blockDim.x) {
-    const int wv = i % Wp, cr = i / Wp;
+  // one (channel, filter row) source line at a time, consecutive threads on consecutive columns: coalesced reads and
+  // no per-element index arithmetic (the first version derived (c, r, w) from a flat index with three divisions per
+  // element, which made the staging loop 6x the instruction count of the im2col expansion itself)
+  for (int cr = 0; cr < C * R; ++cr) {
     const int r = cr % R, c = cr / R;
-    const int ih = p * stride - pad + r, iw = wv - pad;
-    rows[(r * Wp + wv) * C + c] =
-        (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + (((long long)n * C + c) * H + ih) * W + iw) : 0.f;
+    const int ih = p * stride - pad + r;
+    const bool row_ok = ih >= 0 && ih < H;
+    const float* src = x + (((long long)n * C + c) * H + (row_ok ? ih : 0)) * W;
+    float* dst = rows + (long long)r * Wp * C + c;
+    for (int wv = threadIdx.x; wv < Wp; wv += blockDim.x) {
+      const int iw = wv - pad;
+      dst[wv * C] = (row_ok && iw >= 0 && iw < W) ? __ldg(src + iw) : 0.f;
+    }
   }
   __syncthreads();
   const int groups = kpad >> 3;                 // 8-column groups per pixel
@@ -107,16 +114,18 @@ __global__ void __launch_bounds__(256) stem_im2col_krsc_kernel(const float* __re
 
 // --------------------------------------------------------------------------------- max-pool
 // first maximum in row-major window order wins (ATen max_pool2d semantics); argmax stores the window slot.
+// IdxT = int when the flat item count fits in 31 bits (always on this path): the index arithmetic is 32-bit divisions
+// instead of emulated 64-bit ones, which were most of the instructions of these map kernels.
+template <typename IdxT>
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    unsigned char* __restrict__ arg, int N, int H, int W, int C, int Ho, int Wo, int k,
                                    int stride, int pad) {
   const int vpc = C >> 3;
-  const long long total = (long long)N * Ho * Wo * vpc;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IdxT total = (IdxT)N * Ho * Wo * vpc;
+  for (IdxT i = blockIdx.x * (IdxT)blockDim.x + threadIdx.x; i < total; i += (IdxT)gridDim.x * blockDim.x) {
     const int c = (int)(i % vpc) << 3;
-    const long long m = i / vpc;
-    const int q = (int)(m % Wo), p = (int)((m / Wo) % Ho), n = (int)(m / ((long long)Wo * Ho));
+    const IdxT m = i / vpc;
+    const int q = (int)(m % Wo), p = (int)((m / Wo) % Ho), n = (int)(m / ((IdxT)Wo * Ho));
     float best[8];
     int bi[8];
 #pragma unroll
@@ -143,11 +152,14 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 }
 
 // gather form: every input pixel sums the output gradients of the windows that selected it.  One CTA per input row:
-// the (at most 8) output rows whose windows cover it are resolved once, the inner loop is 32-bit arithmetic only.
+// the (at most 8) output rows whose windows cover it are resolved once and STAGED in shared memory (gradient row +
+// argmax-slot row, coalesced 16-byte copies), so every output pixel is fetched once per CTA instead of once per input
+// pixel it covers (k/stride * k/stride times through L1/L2 in the first version: 187 us for the 135 MB stem gradient).
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                           const unsigned char* __restrict__ arg,
                                                           __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C,
-                                                          int Ho, int Wo, int k, int stride, int pad) {
+                                                          int Ho, int Wo, int k, int stride, int pad, int max_rows) {
+  extern __shared__ __align__(16) unsigned char mp_smem[];
   const int vpc = C >> 3;
   const int h = blockIdx.x % H, n = blockIdx.x / H;
   int prow[8], rsel[8], np = 0;
@@ -155,30 +167,40 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
     const int t = h + pad - r;
     if (t < 0 || t % stride) continue;
     const int p = t / stride;
-    if (p < Ho && np < 8) {
+    if (p < Ho && np < max_rows) {
       prow[np] = p;
       rsel[np] = r;
       ++np;
     }
   }
+  const int row_bytes_g = Wo * C * 2, row_bytes_a = Wo * C;                       // multiples of 16 and 8 (C % 8 == 0)
+  uint4* sg = reinterpret_cast<uint4*>(mp_smem);                                   // [max_rows][Wo*C] bf16
+  uint2* sa = reinterpret_cast<uint2*>(mp_smem + (size_t)max_rows * row_bytes_g);  // [max_rows][Wo*C] bytes
+  for (int a = 0; a < np; ++a) {
+    const long long obase = ((long long)n * Ho + prow[a]) * Wo * C;
+    const uint4* gsrc = reinterpret_cast<const uint4*>(dy + obase);
+    const uint2* asrc = reinterpret_cast<const uint2*>(arg + obase);
+    for (int i = threadIdx.x; i < row_bytes_g / 16; i += blockDim.x) sg[a * (row_bytes_g / 16) + i] = gsrc[i];
+    for (int i = threadIdx.x; i < row_bytes_a / 8; i += blockDim.x) sa[a * (row_bytes_a / 8) + i] = asrc[i];
+  }
+  __syncthreads();
   const int rowlen = W * vpc;
   __nv_bfloat16* drow = dx + ((long long)n * H + h) * W * C;
   for (int i = threadIdx.x; i < rowlen; i += blockDim.x) {
-    const int w = i / vpc, c = (i - w * vpc) << 3;
+    const int w = i / vpc, cv = i - w * vpc;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int a = 0; a < np; ++a) {
-      const long long obase = ((long long)n * Ho + prow[a]) * Wo;
-      for (int s = 0; s < k; ++s) {
-        const int u = w + pad - s;
-        if (u < 0 || u % stride) continue;
-        const int q = u / stride;
-        if (q >= Wo) continue;
-        const long long mo = (obase + q) * C + c;
-        const uint2 sel2 = *reinterpret_cast<const uint2*>(arg + mo);
+    for (int s = 0; s < k; ++s) {
+      const int u = w + pad - s;
+      if (u < 0 || u % stride) continue;
+      const int q = u / stride;
+      if (q >= Wo) continue;
+      for (int a = 0; a < np; ++a) {
+        const int e = q * vpc + cv;  // 8-channel group index inside the staged row
+        const uint2 sel2 = sa[a * (row_bytes_a / 8) + e];
         float g[8];
-        unpack8m(*reinterpret_cast<const uint4*>(dy + mo), g);
+        unpack8m(sg[a * (row_bytes_g / 16) + e], g);
         const unsigned slot = (unsigned)(rsel[a] * k + s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -187,7 +209,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
         }
       }
     }
-    *reinterpret_cast<uint4*>(drow + (long long)w * C + c) = pack8m(acc);
+    *reinterpret_cast<uint4*>(drow + (long long)w * C + (cv << 3)) = pack8m(acc);
   }
 }
 
@@ -200,15 +222,15 @@ __device__ __forceinline__ void bl_coord(int o, float scale, int in_size, int& i
   l1 = r - i0;
 }
 
+template <typename IdxT>
 __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int Hi,
                                     int Wi, int Ho, int Wo, int C, int x_cs, int y_cs, float sh, float sw) {
   const int vpc = C >> 3;
-  const long long total = (long long)N * Ho * Wo * vpc;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IdxT total = (IdxT)N * Ho * Wo * vpc;
+  for (IdxT i = blockIdx.x * (IdxT)blockDim.x + threadIdx.x; i < total; i += (IdxT)gridDim.x * blockDim.x) {
     const int c = (int)(i % vpc) << 3;
-    const long long m = i / vpc;
-    const int ow = (int)(m % Wo), oh = (int)((m / Wo) % Ho), n = (int)(m / ((long long)Wo * Ho));
+    const IdxT m = i / vpc;
+    const int ow = (int)(m % Wo), oh = (int)((m / Wo) % Ho), n = (int)(m / ((IdxT)Wo * Ho));
     int y0, y1, x0, x1;
     float ly, lx;
     bl_coord(oh, sh, Hi, y0, y1, ly);
@@ -227,17 +249,17 @@ __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 }
 
 // gather form of the transpose: dx[h][w] = sum over the output pixels whose stencil touches (h,w)
+template <typename IdxT>
 __global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
                                     int Hi, int Wi, int Ho, int Wo, int C, int dy_cs, int dx_cs, float sh, float sw,
                                     int accumulate) {
   const int vpc = C >> 3;
-  const long long total = (long long)N * Hi * Wi * vpc;
+  const IdxT total = (IdxT)N * Hi * Wi * vpc;
   const float ish = sh > 0.f ? 1.f / sh : 0.f, isw = sw > 0.f ? 1.f / sw : 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  for (IdxT i = blockIdx.x * (IdxT)blockDim.x + threadIdx.x; i < total; i += (IdxT)gridDim.x * blockDim.x) {
     const int c = (int)(i % vpc) << 3;
-    const long long m = i / vpc;
-    const int w = (int)(m % Wi), h = (int)((m / Wi) % Hi), n = (int)(m / ((long long)Wi * Hi));
+    const IdxT m = i / vpc;
+    const int w = (int)(m % Wi), h = (int)((m / Wi) % Hi), n = (int)(m / ((IdxT)Wi * Hi));
     int oh_lo = sh > 0.f ? (int)floorf((h - 1) * ish) - 1 : 0, oh_hi = sh > 0.f ? (int)ceilf((h + 1) * ish) + 1 : Ho - 1;
     int ow_lo = sw > 0.f ? (int)floorf((w - 1) * isw) - 1 : 0, ow_hi = sw > 0.f ? (int)ceilf((w + 1) * isw) + 1 : Wo - 1;
     oh_lo = max(oh_lo, 0); oh_hi = min(oh_hi, Ho - 1);
@@ -743,20 +765,33 @@ __global__ void __launch_bounds__(544, 2) upsample4_ce_bwd_kernel(const __nv_bfl
   }
 }
 
-// dx[n][h][w][c] = pa[n][h][w][c] + pb[n][h][w][c] (row 0 has no pb), padding channels zero
+// dx[n][h][w][c] = pa[n][h][w][c] + pb[n][h][w][c] (row 0 has no pb), padding channels zero.  One thread per 8
+// channels: float4 partial loads (pc % 4 == 0), one 16-byte store.
 __global__ void upsample4_ce_combine_kernel(const float* __restrict__ pa, const float* __restrict__ pb,
-                                            __nv_bfloat16* __restrict__ dx, long long pixels, int Hi, int Wi, int C, int pc,
+                                            __nv_bfloat16* __restrict__ dx, int pixels, int Hi, int Wi, int C, int pc,
                                             int cs) {
-  const long long total = pixels * cs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long px = i / cs;
-    const int c = (int)(i - px * cs);
-    float v = 0.f;
-    if (c < C) {
-      v = pa[px * pc + c];
-      if ((px / Wi) % Hi != 0) v += pb[px * pc + c];
+  const int vpc = cs >> 3;
+  const int total = pixels * vpc;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int px = i / vpc, c0 = (i - px * vpc) << 3;
+    const bool with_b = (px / Wi) % Hi != 0;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + j < pc) {  // pc is a multiple of 4: the whole vector is inside the partial row
+        a = *reinterpret_cast<const float4*>(pa + (long long)px * pc + c0 + j);
+        if (with_b) {
+          const float4 b = *reinterpret_cast<const float4*>(pb + (long long)px * pc + c0 + j);
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+      }
+      v[j] = c0 + j < C ? a.x : 0.f;
+      v[j + 1] = c0 + j + 1 < C ? a.y : 0.f;
+      v[j + 2] = c0 + j + 2 < C ? a.z : 0.f;
+      v[j + 3] = c0 + j + 3 < C ? a.w : 0.f;
     }
-    dx[i] = __float2bfloat16(v);
+    *reinterpret_cast<uint4*>(dx + (long long)px * cs + c0) = pack8m(v);
   }
 }
 
@@ -833,8 +868,13 @@ extern "C" int zs3_stem_im2col(const float* x, void* cols, int N, int C, int H, 
 extern "C" int zs3_maxpool_fwd(const void* x, void* y, unsigned char* argmax, int N, int H, int W, int C, int Ho,
                                int Wo, int k, int stride, int pad, void* stream) {
   ZS3_CHECK_ARG(x && y && argmax && C % 8 == 0 && k * k <= 255, "maxpool_fwd: bad args");
-  maxpool_fwd_kernel<<<ew_blocks((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(x), BF(y), argmax, N, H, W, C, Ho, Wo, k, stride, pad);
+  const long long items = (long long)N * Ho * Wo * (C / 8);
+  if (items * 2 < (1ll << 31) && (long long)N * H * W * C < (1ll << 31))
+    maxpool_fwd_kernel<int><<<ew_blocks(items, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), argmax, N, H, W, C, Ho, Wo, k,
+                                                                         stride, pad);
+  else
+    maxpool_fwd_kernel<long long><<<ew_blocks(items, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), argmax, N, H, W, C, Ho, Wo,
+                                                                               k, stride, pad);
   ZS3_CHECK_LAUNCH("maxpool_fwd");
   return ZS3_OK;
 }
@@ -843,7 +883,13 @@ extern "C" int zs3_maxpool_bwd(const void* dy, const unsigned char* argmax, void
                                int Ho, int Wo, int k, int stride, int pad, void* stream) {
   ZS3_CHECK_ARG(dy && dx && argmax && C % 8 == 0, "maxpool_bwd: bad args");
   ZS3_CHECK_ARG(k >= 1 && k <= 8 && stride >= 1, "maxpool_bwd: kernel size %d outside [1, 8]", k);
-  maxpool_bwd_kernel<<<N * H, 256, 0, ST(stream)>>>(CBF(dy), argmax, BF(dx), N, H, W, C, Ho, Wo, k, stride, pad);
+  // output rows whose windows can cover one input row: ceil(k / stride), staged in shared memory (gradient + slots)
+  const int max_rows = (k + stride - 1) / stride < 8 ? (k + stride - 1) / stride : 8;
+  const size_t smem = (size_t)max_rows * Wo * C * 3;
+  ZS3_CHECK_ARG(smem <= 200 * 1024, "maxpool_bwd: %d output rows of %d x %d do not fit in shared memory", max_rows, Wo, C);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(maxpool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  maxpool_bwd_kernel<<<N * H, 256, smem, ST(stream)>>>(CBF(dy), argmax, BF(dx), N, H, W, C, Ho, Wo, k, stride, pad, max_rows);
   ZS3_CHECK_LAUNCH("maxpool_bwd");
   return ZS3_OK;
 }
@@ -853,8 +899,13 @@ static float bl_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (flo
 extern "C" int zs3_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int x_cs,
                                 int y_cs, void* stream) {
   ZS3_CHECK_ARG(x && y && C % 8 == 0 && x_cs % 8 == 0 && y_cs % 8 == 0 && x_cs >= C && y_cs >= C, "bilinear_fwd: bad args");
-  bilinear_fwd_kernel<<<ew_blocks((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(x), BF(y), N, Hi, Wi, Ho, Wo, C, x_cs, y_cs, bl_scale(Hi, Ho), bl_scale(Wi, Wo));
+  const long long items = (long long)N * Ho * Wo * (C / 8);
+  if (items * 2 < (1ll << 31) && (long long)N * Ho * Wo * y_cs < (1ll << 31))
+    bilinear_fwd_kernel<int><<<ew_blocks(items, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), N, Hi, Wi, Ho, Wo, C, x_cs, y_cs,
+                                                                          bl_scale(Hi, Ho), bl_scale(Wi, Wo));
+  else
+    bilinear_fwd_kernel<long long><<<ew_blocks(items, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), N, Hi, Wi, Ho, Wo, C, x_cs,
+                                                                                y_cs, bl_scale(Hi, Ho), bl_scale(Wi, Wo));
   ZS3_CHECK_LAUNCH("bilinear_fwd");
   return ZS3_OK;
 }
@@ -862,8 +913,13 @@ extern "C" int zs3_bilinear_fwd(const void* x, void* y, int N, int Hi, int Wi, i
 extern "C" int zs3_bilinear_bwd(const void* dy, void* dx, int N, int Hi, int Wi, int Ho, int Wo, int C, int dy_cs,
                                 int dx_cs, int accumulate, void* stream) {
   ZS3_CHECK_ARG(dy && dx && C % 8 == 0 && dy_cs % 8 == 0 && dx_cs % 8 == 0, "bilinear_bwd: bad args");
-  bilinear_bwd_kernel<<<ew_blocks((long long)N * Hi * Wi * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(dy), BF(dx), N, Hi, Wi, Ho, Wo, C, dy_cs, dx_cs, bl_scale(Hi, Ho), bl_scale(Wi, Wo), accumulate);
+  const long long items = (long long)N * Hi * Wi * (C / 8);
+  if (items * 2 < (1ll << 31) && (long long)N * Hi * Wi * dx_cs < (1ll << 31))
+    bilinear_bwd_kernel<int><<<ew_blocks(items, 256), 256, 0, ST(stream)>>>(
+        CBF(dy), BF(dx), N, Hi, Wi, Ho, Wo, C, dy_cs, dx_cs, bl_scale(Hi, Ho), bl_scale(Wi, Wo), accumulate);
+  else
+    bilinear_bwd_kernel<long long><<<ew_blocks(items, 256), 256, 0, ST(stream)>>>(
+        CBF(dy), BF(dx), N, Hi, Wi, Ho, Wo, C, dy_cs, dx_cs, bl_scale(Hi, Ho), bl_scale(Wi, Wo), accumulate);
   ZS3_CHECK_LAUNCH("bilinear_bwd");
   return ZS3_OK;
 }
@@ -1012,7 +1068,9 @@ extern "C" int zs3_upsample4_ce_bwd(const void* x, const float* target, const fl
                                                                  accum2, div, grad_out, pa, pb, pc);
   ZS3_CHECK_LAUNCH("upsample4_ce_bwd");
   const long long pixels = (long long)N * Hi * Wi;
-  upsample4_ce_combine_kernel<<<ew_blocks(pixels * cs, 256), 256, 0, ST(stream)>>>(pa, pb, BF(dx), pixels, Hi, Wi, C, pc, cs);
+  ZS3_CHECK_ARG(cs % 8 == 0 && pixels * (cs / 8) < (1ll << 31), "upsample4_ce_bwd: bad channel stride / too many pixels");
+  upsample4_ce_combine_kernel<<<ew_blocks(pixels * (cs / 8), 256), 256, 0, ST(stream)>>>(pa, pb, BF(dx), (int)pixels, Hi, Wi,
+                                                                                          C, pc, cs);
   ZS3_CHECK_LAUNCH("upsample4_ce_bwd(combine)");
   return ZS3_OK;
 }
