@@ -886,6 +886,41 @@ def step2_rate(dev, B, HW, steps, warmup=3, baselines=True, world=1, rank=0):
     except Exception as e:
         res["roofline"] = {"error": repr(e)[:200]}
     if baselines:
+        # ---- the loop as the UNCHANGED reference trainer drives it (train_pascal_GMMN.py:164-268) on this repo's modules:
+        # per (image, class) a host-side torch.rand of [n_c, 300] + its H2D copy, boolean-mask gathers, .item() syncs
+        try:
+            from zs3_b200.step2 import ZS3Step
+            import copy
+            gen_u = copy.deepcopy(gen)
+            ustep = ZS3Step(model, gen_u, crit, crit_g, opt, torch.optim.Adam(gen_u.parameters(), lr=2e-4), seen, unseen)
+            ustep.training_step(image, target, embedding)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, _, gl = ustep.training_step(image, target, embedding)
+            torch.cuda.synchronize()
+            dt_u = time.perf_counter() - t0
+            lab = torch.nn.functional.interpolate(target[:, None], size=(129, 129), mode="nearest")[:, 0] if HW == 513 else None
+            t0 = time.perf_counter()
+            n_draw = 0
+            if lab is not None:     # the host noise draws of that loop alone (train_pascal_GMMN.py:216-218)
+                for i in range(B):
+                    for c in torch.unique(lab[i]).tolist():
+                        if c != 255:
+                            n_c = int((lab[i] == c).sum())
+                            torch.rand((n_c, 300)).to(dev)
+                            n_draw += n_c
+                torch.cuda.synchronize()
+            dt_z = time.perf_counter() - t0
+            res["unchanged_trainer_loop"] = {
+                "value": B / dt_u, "unit": "images/sec", "ms_per_step": dt_u * 1e3, "generator_updates": len(gl),
+                "host_noise_draw_ms_per_step": dt_z * 1e3, "noise_rows_per_step": n_draw,
+                "what": "ZS3Step: the reference's per-(image, class) Python loop on this repo's modules (generator, MMD loss, "
+                        "backward, torch Adam called one by one); the loop's own host work -- torch.rand((n_c, 300)) on the "
+                        "CPU + H2D per class, boolean-mask gathers, .item() per update -- is part of the trainer, not of the "
+                        "modules"}
+            del ustep, gen_u
+        except Exception as e:
+            res["unchanged_trainer_loop"] = {"error": repr(e)[:200]}
         # ---- the same iteration on stock PyTorch on this GPU (the reference's own path) and on the host cores
         try:
             dt, nupd = min((oracle_step2_iteration(dev, image, target, embedding, (seen, unseen)) for _ in range(2)),
@@ -973,11 +1008,20 @@ def config5_rate(dev, B, HW, steps, warmup=3, world=1, rank=0):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
+    seg = None
+    try:   # per-segment host / device milliseconds of one more step (not timed above)
+        step.profile = {}
+        step.training_step(image, target, class_embeddings=table)
+        torch.cuda.synchronize()
+        seg = {k: {a: round(b, 3) for a, b in v.items()} for k, v in step.profile_summary().items()}
+        step.profile = None
+    except Exception as e:
+        seg = {"error": repr(e)[:200]}
     res = {"workload": f"Pascal-Context (60 logits) ZS3Net + GCN-context step (BASELINE configs[4]), bs={B}/GPU {HW}x{HW}, "
                        f"{world} GPU(s), 4-10 classes and 5-40 clusters per image, unseen {unseen}, GCN_weight 0.1",
            "value": world * B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps, "n_gpus": world,
            "generator_updates_per_step": len(g_losses), "graph_generator_updates_per_step": len(step.last_gcn_losses),
-           "final_loss": float(loss.item())}
+           "final_loss": float(loss.item()), "segments_ms": seg}
     del step, model, gen, gen_gcn
     torch.cuda.empty_cache()
     return res

@@ -338,9 +338,23 @@ def check(rc, what=""):
         raise Zs3NativeError(f"{what} failed with code {rc}: {msg}")
 
 
+_raw_stream = None
+
+
 def stream_ptr():
-    import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's CURRENT stream on the current device (follows torch.cuda.stream(...) and graph capture).
+    Called once per kernel launch: torch.cuda.current_stream() costs ~19 us of Python per call (measured on the box:
+    3 ms per config-5 step, tools/profile_config5_host.py), the raw accessor well under 1 us."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
+        get_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        get_dev = getattr(torch._C, "_cuda_getDevice", None)
+        if get_stream is not None and get_dev is not None:
+            _raw_stream = lambda: get_stream(get_dev())  # noqa: E731
+        else:
+            _raw_stream = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    return C.c_void_p(_raw_stream())
 
 
 def ptr(t):

@@ -75,6 +75,35 @@ class ZS3Step:
         return loss, generator_loss_batch, g_losses
 
 
+class _PinnedRing:
+    """Small host->device uploads (index lists of a step's plan) through a ring of pinned buffers: a pageable
+    `torch.tensor(list).to(device)` blocks the host until the stream has drained (4 ms per step while the feature graph
+    runs, tools/profile_config5_host.py); a pinned non_blocking copy is just enqueued.  A slot is reused only after the
+    copy that last read it has executed (event)."""
+
+    def __init__(self, slots=4, capacity=1 << 16):
+        self.buf = [torch.empty(capacity, dtype=torch.int64).pin_memory() for _ in range(slots)]
+        self.done = [None] * slots
+        self.k = 0
+
+    def upload(self, values, dev):
+        """values: list of Python ints -> int64 device tensor"""
+        n = len(values)
+        if n > self.buf[0].numel():
+            return torch.tensor(values, dtype=torch.int64).to(dev)
+        k = self.k
+        self.k = (k + 1) % len(self.buf)
+        if self.done[k] is not None:
+            self.done[k].synchronize()
+        host = self.buf[k][:n]
+        host.copy_(torch.tensor(values, dtype=torch.int64))
+        out = host.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.done[k] = ev
+        return out
+
+
 class ZS3StepFused(ZS3Step):
     """Same iteration as `ZS3Step`, with the per-(image, class) generator updates executed by the fused
     work-list kernel (`zs3_gmmn_train_fused`, csrc/gmmn_fused.cu) instead of ~65 launches + 2 host syncs each.
@@ -118,6 +147,7 @@ class ZS3StepFused(ZS3Step):
         sigma = getattr(getattr(self.criterion_generator, "__self__", None), "sigma", None) or (2, 5, 10, 20, 40, 80)
         self.updater = FusedGeneratorUpdater(self.generator, self.optimizer_generator, sigma=sigma)
         self._src_index = {}
+        self._ring = None
 
     def _nearest_source_index(self, in_hw, out_hw, dev):
         """flat source-pixel index of every destination pixel under F.interpolate(mode='nearest') (`:175-195`),
@@ -302,9 +332,15 @@ class ZS3StepFused(ZS3Step):
         upd = [e for e in plan if e[0] == "item"]
         rows = self.batch_size_generator
         if upd:
-            base = torch.tensor([e[1] * hw + e[3] for e in upd], dtype=torch.int64).to(dev)
+            if self._ring is None and dev.type == "cuda":
+                self._ring = _PinnedRing()
+            up = (lambda v: self._ring.upload(v, dev)) if self._ring is not None else \
+                (lambda v: torch.tensor(v, dtype=torch.int64).to(dev))
+            # one upload for the three index lists of the plan: [base | n_c | image]
+            packed = up([e[1] * hw + e[3] for e in upd] + [e[2] for e in upd] + [e[1] for e in upd])
+            base, n_c_i, img_of = packed[:len(upd)], packed[len(upd):2 * len(upd)], packed[2 * len(upd):]
             if self._device_index:   # floor(u * n_c), u ~ U[0,1): uniform over the class's pixels, with replacement
-                n_c_all = torch.tensor([e[2] for e in upd], dtype=torch.float32).to(dev)
+                n_c_all = n_c_i.to(torch.float32)
                 u = torch.rand((len(upd), rows), device=dev)
                 ridx_all = torch.minimum((u * n_c_all[:, None]).floor(), n_c_all[:, None] - 1).to(torch.int32)
             else:
@@ -314,7 +350,6 @@ class ZS3StepFused(ZS3Step):
             if table is None:
                 spix_all = src[pix_all.long()].contiguous()                              # same pixels, input grid
             else:   # rows of the class table: the label of each sampled pixel (constant per update)
-                img_of = torch.tensor([e[1] for e in upd], dtype=torch.int64).to(dev)
                 spix_all = tg[img_of[:, None], pix_all.long()].to(torch.int32).contiguous()
             z_all = torch.rand((len(upd), rows, self.noise_dim), device=dev) if self._device_noise else None
 
