@@ -406,9 +406,15 @@ typedef struct {
   zs3_row_source real;   /* [rows][feat]      real decoder features of the sampled pixels */
   const unsigned char* keep_mask; /* optional Dropout keep mask [*][hidden] (bytes); NULL = counter-based RNG */
   const int* keep_rows;  /* optional row gather for keep_mask (and the RNG's row key) */
-  int rows;              /* M = N = number of sampled rows, 1..128 (batch_size_generator) */
-  int reserved;
+  const float* adj;      /* optional [rows][rows] row-major adjacency: the graph generator of config 5 (GMMNnetwork_GCN,
+                            zs3/modeling/gmmn.py:52-67; pygcn GraphConvolution = adj @ (x @ W) + b): both layers multiply by
+                            it, the rows are the image's cluster nodes (train_context_GMMN_GCNcontext.py:400-419); NULL = MLP */
+  float* out;            /* optional [rows][feat] dense: the generated features of this item (the reference keeps them as
+                            classifier inputs for images holding an unseen class, `:421-428`) */
+  int rows;              /* M = N = number of sampled rows, 1..128 (batch_size_generator / number of nodes) */
+  int flags;             /* ZS3_GMMN_FORWARD_ONLY: generate `out` and stop (no loss, no backward, no Adam step) */
 } zs3_gmmn_item;
+#define ZS3_GMMN_FORWARD_ONLY 1
 
 typedef struct {
   const zs3_gmmn_item* items; /* DEVICE array [n_items] */
@@ -430,6 +436,8 @@ typedef struct {
   void* workspace; unsigned long long workspace_bytes; /* >= zs3_gmmn_train_workspace_size(...), 16-byte aligned */
   unsigned long long* phase_stamps; /* optional [n_items][8]: %globaltimer (ns) at the start of each update and after
                                        each of its six phases, written by CTA 0 (profiling aid); NULL = off */
+  int weights_in_out;         /* 0: nn.Linear layout, w1 [hidden][in], w2 [feat][hidden] (GMMNnetwork);
+                                 1: pygcn layout, w1 [in][hidden], w2 [hidden][feat] (GMMNnetwork_GCN's gcn1/gcn2.weight) */
 } zs3_gmmn_train_args;
 
 unsigned long long zs3_gmmn_train_workspace_size(int embed_dim, int noise_dim, int hidden, int feat);

@@ -205,8 +205,11 @@ def test_image_level_generation_on_tensor_cores_matches_per_class_generator():
     assert rel_l2(fake.cpu(), cpu) < 1e-4
 
 
-def test_gcn_context_step_matches_oracle():
-    """config 5 (zs3/train_context_GMMN_GCNcontext.py:270-460): ZS3StepGCN on the CUDA modules vs oracle step2(gcn=...)"""
+@pytest.mark.parametrize("fused_gcn", [True, False], ids=["gcn_fused_work_list", "gcn_modules"])
+def test_gcn_context_step_matches_oracle(fused_gcn):
+    """config 5 (zs3/train_context_GMMN_GCNcontext.py:270-460): ZS3StepGCN on the CUDA modules vs oracle step2(gcn=...);
+    the graph-generator updates either as ONE work list of the fused kernel (items carry the adjacency matrix; default)
+    or call by call through the GMMNnetwork_GCN module"""
     import zs3_oracle as O
     import zs3_step2_oracle as S
     from zs3.modeling.deeplab import DeepLab
@@ -246,6 +249,9 @@ def test_gcn_context_step_matches_oracle():
                       noise_fn=rp.noise, index_fn=rp.index, mask_fn=rp.mask, generator_gcn=gen_gcn,
                       optimizer_generator_gcn=torch.optim.Adam(gen_gcn.parameters(), lr=2e-4), gcn_weight=0.1,
                       gcn_noise_fn=rp_gcn.noise, gcn_mask_fn=rp_gcn.mask)
+    assert step.updater_gcn is not None and step.updater_gcn.graph
+    if not fused_gcn:
+        step.updater_gcn = None
     with torch.no_grad():
         real = model.forward_before_class_prediction(image.cuda())
         real = real / real.std()

@@ -154,8 +154,8 @@ class RowSource(C.Structure):
 class GmmnItem(C.Structure):
     _fields_ = [
         ("emb", RowSource), ("noise", RowSource), ("real", RowSource),
-        ("keep_mask", C.c_void_p), ("keep_rows", C.c_void_p),
-        ("rows", C.c_int), ("reserved", C.c_int),
+        ("keep_mask", C.c_void_p), ("keep_rows", C.c_void_p), ("adj", C.c_void_p), ("out", C.c_void_p),
+        ("rows", C.c_int), ("flags", C.c_int),
     ]
 
 
@@ -174,6 +174,7 @@ class GmmnTrainArgs(C.Structure):
         ("losses", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_ulonglong),
         ("phase_stamps", C.c_void_p),
+        ("weights_in_out", C.c_int),
     ]
 
 

@@ -17,6 +17,11 @@
 //   P1 Hd = dropout(leaky(Xin W1^T + b1)) + gather of item w+1 (idle CTAs)     P4 dY_i = 1/loss * sum_j P_ij (x_j - x_i)
 //   P2 Y  = Hd W2^T + b2  -> X[0:B]                 P5 dH  = (dY W2) * f'(Hd)
 //   P3 P_ij, loss^2 partials (difference form)      P6 dW1, db1, dW2, db2 -> Adam in the epilogue
+// Graph generator (config 5, GMMNnetwork_GCN, zs3/modeling/gmmn.py:52-67): an item with an adjacency matrix A runs both
+// layers as pygcn GraphConvolutions, A (x W) + b: P1 / P2 then produce the products without bias, two extra phases
+// multiply by A (P1b applies bias, LeakyReLU, Dropout; P2b the bias), and the backward inserts dT2 = A^T dY before P5
+// and dT1 = A^T dZ1 before P6 (weights stored [in][out]: `weights_in_out`).  Items flagged ZS3_GMMN_FORWARD_ONLY stop
+// after the forward (features of images holding an unseen class, train_context_GMMN_GCNcontext.py:421-428).
 // fp32 SIMT on purpose (the MMD exponent cancels catastrophically in reduced precision); the whole
 // iteration is 90 MFMA -- the cost is latency (6 barriers + operand staging), not arithmetic.
 //
@@ -70,6 +75,11 @@ struct FusedP {
   float* P;       // [2*FMAXB][2*FMAXB]
   float* dY;      // [FMAXB][F]
   float* dH;      // [FMAXB][H]
+  float* T1;      // [FMAXB][H]  graph items: Xin W1 before the adjacency product
+  float* T2;      // [FMAXB][F]  graph items: Hd W2 before the adjacency product
+  float* dT2;     // [FMAXB][F]  graph items: A^T dY
+  float* dT1;     // [FMAXB][H]  graph items: A^T dZ1
+  int w_in_out;   // weights stored [in][out] (pygcn) instead of [out][in] (nn.Linear)
   double* lossp;  // [128] per-tile partial sums of loss^2 (P3: 16 x 8 tiles at most)
   unsigned* barrier;
   unsigned long long* stamps;  // optional [n_items][8] %globaltimer at the phase boundaries
@@ -324,12 +334,13 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
   }
   grid_barrier(p.barrier, bar_target);
 
+  int n_updates = 0;  // Adam steps taken so far in this launch (forward-only items take none)
   for (int w = 0; w < p.n_items; ++w) {
     __syncthreads();
     if (threadIdx.x == 0) {
       sh_item[0] = p.items[w];
       if (w + 1 < p.n_items) sh_item[1] = p.items[w + 1];
-      const double t = (double)(p.step0 + w + 1);
+      const double t = (double)(p.step0 + n_updates + 1);
       sh_scalar[1] = (float)(1.0 - pow((double)p.beta1, t));
       sh_scalar[2] = (float)sqrt(1.0 - pow((double)p.beta2, t));
     }
@@ -337,14 +348,45 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
     phase_stamp(p.stamps, w, 0);
     const zs3_gmmn_item& it = sh_item[0];
     const int B = min(it.rows, FMAXB), L = 2 * B;
+    const float* adj = it.adj;                    // graph item: both layers are A (x W) + b
+    const bool fwd_only = (it.flags & ZS3_GMMN_FORWARD_ONLY) != 0;
     float* Xin = p.Xin + (size_t)(w & 1) * FMAXB * K1;
     float* X = p.X + (size_t)(w & 1) * 2 * FMAXB * F;
     const int tL = (L + FT - 1) / FT, tH = (H + FT - 1) / FT, tF = (F + FT - 1) / FT;
     const int tK1 = (K1 + FT - 1) / FT;
     const int tBr = (B + FTR - 1) / FTR, tLr = (L + FTR - 1) / FTR;  // row tiles of P1-P5
+    // weight operands: element (out j, in k) of W1 / W2 in either storage order
+    const Opnd W1_jk = p.w_in_out ? Opnd{p.W1, H, 0} : Opnd{p.W1, K1, 1};   // (h, k1)
+    const Opnd W2_jk = p.w_in_out ? Opnd{p.W2, F, 0} : Opnd{p.W2, H, 1};    // (f, h)
+    const Opnd W2_kj = p.w_in_out ? Opnd{p.W2, F, 1} : Opnd{p.W2, H, 0};    // (h, f): reduction over f
 
-    // ---- P1: Hd = dropout(leaky(Xin W1^T + b1)); the CTAs without a tile gather the rows of item w+1 into the
-    //          other Xin / X buffers (last read in P6 of item w-1, i.e. before the previous grid barrier)
+    // epilogue of the hidden layer: bias, LeakyReLU, Dropout -> Hd
+    auto hidden_epilogue = [&](int i, int j, float v) {
+      v += __ldcg(p.b1 + j);
+      v = v > 0.f ? v : v * p.slope;
+      if (p.drop_p > 0.f) {
+        const long long krow = it.keep_rows ? (long long)__ldg(it.keep_rows + i) : (long long)i;
+        bool keep;
+        if (it.keep_mask) {
+          keep = __ldg(it.keep_mask + krow * H + j) != 0;
+        } else {
+          const uint64_t idx = (uint64_t)krow * (uint64_t)H + (uint64_t)j;
+          const uint64_t hsh = splitmix64f(p.seed ^ splitmix64f(p.offset + ((uint64_t)w << 40) + (idx >> 2)));
+          keep = ((uint32_t)(hsh >> (16 * (idx & 3))) & 0xFFFFu) >= thresh;
+        }
+        v = keep ? v * ks : 0.f;
+      }
+      p.Hd[(long long)i * H + j] = v;
+    };
+    auto output_epilogue = [&](int i, int j, float v) {
+      v += __ldcg(p.b2 + j);
+      X[(long long)i * F + j] = v;
+      if (it.out) it.out[(long long)i * F + j] = v;
+    };
+
+    // ---- P1: Hd = dropout(leaky(Xin W1^T + b1)) (graph items: T1 = Xin W1 only); the CTAs without a tile gather the
+    //          rows of item w+1 into the other Xin / X buffers (last read in P6 of item w-1, i.e. before the previous
+    //          grid barrier)
     const int ng = (w + 1 < p.n_items) ? (min(sh_item[1].rows, FMAXB) + FGATHER_ROWS - 1) / FGATHER_ROWS : 0;
     for (int u = blockIdx.x; u < tBr * tH + ng; u += gridDim.x) {
       if (u >= tBr * tH) {
@@ -353,37 +395,44 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
         continue;
       }
       const int i0 = (u / tH) * FTR, j0 = (u % tH) * FT;
-      tile32<OP_DOT, FTR>(sm, Opnd{Xin, K1, 1}, i0, B, Opnd{p.W1, K1, 1}, j0, H, K1, nullptr, 0,
-                     [&](int i, int j, float v) {
-                       v += __ldcg(p.b1 + j);
-                       v = v > 0.f ? v : v * p.slope;
-                       if (p.drop_p > 0.f) {
-                         const long long krow = it.keep_rows ? (long long)__ldg(it.keep_rows + i) : (long long)i;
-                         bool keep;
-                         if (it.keep_mask) {
-                           keep = __ldg(it.keep_mask + krow * H + j) != 0;
-                         } else {
-                           const uint64_t idx = (uint64_t)krow * (uint64_t)H + (uint64_t)j;
-                           const uint64_t hsh =
-                               splitmix64f(p.seed ^ splitmix64f(p.offset + ((uint64_t)w << 40) + (idx >> 2)));
-                           keep = ((uint32_t)(hsh >> (16 * (idx & 3))) & 0xFFFFu) >= thresh;
-                         }
-                         v = keep ? v * ks : 0.f;
-                       }
-                       p.Hd[(long long)i * H + j] = v;
-                     });
+      if (adj)
+        tile32<OP_DOT, FTR>(sm, Opnd{Xin, K1, 1}, i0, B, W1_jk, j0, H, K1, nullptr, 0,
+                            [&](int i, int j, float v) { p.T1[(long long)i * H + j] = v; });
+      else
+        tile32<OP_DOT, FTR>(sm, Opnd{Xin, K1, 1}, i0, B, W1_jk, j0, H, K1, nullptr, 0, hidden_epilogue);
     }
     grid_barrier(p.barrier, bar_target);
+    if (adj) {  // ---- P1b: Hd = dropout(leaky(A T1 + b1))
+      for (int u = blockIdx.x; u < tBr * tH; u += gridDim.x) {
+        const int i0 = (u / tH) * FTR, j0 = (u % tH) * FT;
+        tile32<OP_DOT, FTR>(sm, Opnd{adj, B, 1}, i0, B, Opnd{p.T1, H, 0}, j0, H, B, nullptr, 0, hidden_epilogue);
+      }
+      grid_barrier(p.barrier, bar_target);
+    }
     phase_stamp(p.stamps, w, 1);
 
-    // ---- P2: Y = Hd W2^T + b2 -> X[0:B]
+    // ---- P2: Y = Hd W2^T + b2 -> X[0:B] (graph items: T2 = Hd W2, then P2b: Y = A T2 + b2)
     for (int u = blockIdx.x; u < tBr * tF; u += gridDim.x) {
       const int i0 = (u / tF) * FTR, j0 = (u % tF) * FT;
-      tile32<OP_DOT, FTR>(sm, Opnd{p.Hd, H, 1}, i0, B, Opnd{p.W2, H, 1}, j0, F, H, nullptr, 0,
-                     [&](int i, int j, float v) { X[(long long)i * F + j] = v + __ldcg(p.b2 + j); });
+      if (adj)
+        tile32<OP_DOT, FTR>(sm, Opnd{p.Hd, H, 1}, i0, B, W2_jk, j0, F, H, nullptr, 0,
+                            [&](int i, int j, float v) { p.T2[(long long)i * F + j] = v; });
+      else
+        tile32<OP_DOT, FTR>(sm, Opnd{p.Hd, H, 1}, i0, B, W2_jk, j0, F, H, nullptr, 0, output_epilogue);
     }
     grid_barrier(p.barrier, bar_target);
+    if (adj) {
+      for (int u = blockIdx.x; u < tBr * tF; u += gridDim.x) {
+        const int i0 = (u / tF) * FTR, j0 = (u % tF) * FT;
+        tile32<OP_DOT, FTR>(sm, Opnd{adj, B, 1}, i0, B, Opnd{p.T2, F, 0}, j0, F, B, nullptr, 0, output_epilogue);
+      }
+      grid_barrier(p.barrier, bar_target);
+    }
     phase_stamp(p.stamps, w, 2);
+    if (fwd_only) {  // uniform over the grid: every CTA skips the same barriers
+      if (blockIdx.x == 0 && threadIdx.x == 0) p.losses[w] = 0.f;
+      continue;
+    }
 
     // ---- P3: P_ij = s_i s_j sum_sigma exp(e_ij/sigma)/sigma, loss^2 partial per tile; e_ij = -|x_i - x_j|^2 / 2.
     // get_scale_matrix quirk (loss.py:92-97): the FIRST N rows carry +1/N, the last M rows -1/M (M = N = B here).
@@ -441,20 +490,38 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
       }
     }
     grid_barrier(p.barrier, bar_target);
+    if (adj) {  // ---- P4b: dT2 = A^T dY (gradient of T2 = Hd W2 through Y = A T2 + b2)
+      for (int u = blockIdx.x; u < tBr * tF; u += gridDim.x) {
+        const int i0 = (u / tF) * FTR, j0 = (u % tF) * FT;
+        tile32<OP_DOT, FTR>(sm, Opnd{adj, B, 0}, i0, B, Opnd{p.dY, F, 0}, j0, F, B, nullptr, 0,
+                            [&](int i, int j, float v) { p.dT2[(long long)i * F + j] = v; });
+      }
+      grid_barrier(p.barrier, bar_target);
+    }
     phase_stamp(p.stamps, w, 4);
+    const float* G2 = adj ? p.dT2 : p.dY;   // gradient of the output layer's matrix product
 
-    // ---- P5: dH = (dY W2) * d/dh[dropout(leaky(h))], reconstructed from the forward output Hd
+    // ---- P5: dZ1 = (G2 W2) * d/dh[dropout(leaky(h))], reconstructed from the forward output Hd
     for (int u = blockIdx.x; u < tBr * tH; u += gridDim.x) {
       const int i0 = (u / tH) * FTR, j0 = (u % tH) * FT;
-      tile32<OP_DOT, FTR>(sm, Opnd{p.dY, F, 1}, i0, B, Opnd{p.W2, H, 0}, j0, H, F, nullptr, 0, [&](int i, int j, float v) {
+      tile32<OP_DOT, FTR>(sm, Opnd{G2, F, 1}, i0, B, W2_kj, j0, H, F, nullptr, 0, [&](int i, int j, float v) {
         const float hv = __ldcg(p.Hd + (long long)i * H + j);
         p.dH[(long long)i * H + j] = v * (hv > 0.f ? ks : (hv < 0.f ? p.slope * ks : 0.f));
       });
     }
     grid_barrier(p.barrier, bar_target);
+    if (adj) {  // ---- P5b: dT1 = A^T dZ1
+      for (int u = blockIdx.x; u < tBr * tH; u += gridDim.x) {
+        const int i0 = (u / tH) * FTR, j0 = (u % tH) * FT;
+        tile32<OP_DOT, FTR>(sm, Opnd{adj, B, 0}, i0, B, Opnd{p.dH, H, 0}, j0, H, B, nullptr, 0,
+                            [&](int i, int j, float v) { p.dT1[(long long)i * H + j] = v; });
+      }
+      grid_barrier(p.barrier, bar_target);
+    }
     phase_stamp(p.stamps, w, 5);
+    const float* G1 = adj ? p.dT1 : p.dH;   // gradient of the hidden layer's matrix product
 
-    // ---- P6: dW1 = dH^T Xin, dW2 = dY^T Hd, db1, db2 -> Adam
+    // ---- P6: dW1 = G1^T Xin, dW2 = G2^T Hd, db1 = colsum(dZ1), db2 = colsum(dY) -> Adam
     {
       const float bc1 = sh_scalar[1], bc2s = sh_scalar[2];
       const int n1 = tH * tK1, n2 = tF * tH;
@@ -479,29 +546,32 @@ __global__ void __launch_bounds__(FTHREADS) gmmn_train_fused_kernel(const FusedP
         } else if (u < 2 + n1) {
           const int t = u - 2;
           const int i0 = (t / tK1) * FT, j0 = (t % tK1) * FT;
-          tile32<OP_DOT, FT>(sm, Opnd{p.dH, H, 0}, i0, H, Opnd{Xin, K1, 0}, j0, K1, B, nullptr, 0,
+          tile32<OP_DOT, FT>(sm, Opnd{G1, H, 0}, i0, H, Opnd{Xin, K1, 0}, j0, K1, B, nullptr, 0,
                          [&](int i, int j, float v) {
-                           apply_grad(p, p.W1, p.mW1, p.vW1, p.gW1, (long long)i * K1 + j, v, bc1, bc2s);
+                           apply_grad(p, p.W1, p.mW1, p.vW1, p.gW1,
+                                      p.w_in_out ? (long long)j * H + i : (long long)i * K1 + j, v, bc1, bc2s);
                          });
         } else {
           const int t = u - 2 - n1;
           const int i0 = (t / tH) * FT, j0 = (t % tH) * FT;
-          tile32<OP_DOT, FT>(sm, Opnd{p.dY, F, 0}, i0, F, Opnd{p.Hd, H, 0}, j0, H, B, nullptr, 0,
+          tile32<OP_DOT, FT>(sm, Opnd{G2, F, 0}, i0, F, Opnd{p.Hd, H, 0}, j0, H, B, nullptr, 0,
                          [&](int i, int j, float v) {
-                           apply_grad(p, p.W2, p.mW2, p.vW2, p.gW2, (long long)i * H + j, v, bc1, bc2s);
+                           apply_grad(p, p.W2, p.mW2, p.vW2, p.gW2,
+                                      p.w_in_out ? (long long)j * F + i : (long long)i * H + j, v, bc1, bc2s);
                          });
         }
       }
     }
     grid_barrier(p.barrier, bar_target);
     phase_stamp(p.stamps, w, 6);
+    ++n_updates;
   }
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct FusedLayout {
-  size_t xin, x, hd, pm, dy, dh, lossp, barrier, total;
+  size_t xin, x, hd, pm, dy, dh, t1, t2, dt2, dt1, lossp, barrier, total;
 };
 
 static FusedLayout fused_layout(int E, int Z, int H, int F) {
@@ -513,6 +583,10 @@ static FusedLayout fused_layout(int E, int Z, int H, int F) {
   l.pm = o; o += align256(sizeof(float) * 4 * FMAXB * FMAXB);
   l.dy = o; o += align256(sizeof(float) * FMAXB * (size_t)F);
   l.dh = o; o += align256(sizeof(float) * FMAXB * (size_t)H);
+  l.t1 = o; o += align256(sizeof(float) * FMAXB * (size_t)H);
+  l.t2 = o; o += align256(sizeof(float) * FMAXB * (size_t)F);
+  l.dt2 = o; o += align256(sizeof(float) * FMAXB * (size_t)F);
+  l.dt1 = o; o += align256(sizeof(float) * FMAXB * (size_t)H);
   l.lossp = o; o += align256(sizeof(double) * 128);
   l.barrier = o; o += 256;
   l.total = o;
@@ -579,6 +653,11 @@ extern "C" int zs3_gmmn_train_fused(const zs3_gmmn_train_args* a, void* stream) 
   p.P = reinterpret_cast<float*>(ws + l.pm);
   p.dY = reinterpret_cast<float*>(ws + l.dy);
   p.dH = reinterpret_cast<float*>(ws + l.dh);
+  p.T1 = reinterpret_cast<float*>(ws + l.t1);
+  p.T2 = reinterpret_cast<float*>(ws + l.t2);
+  p.dT2 = reinterpret_cast<float*>(ws + l.dt2);
+  p.dT1 = reinterpret_cast<float*>(ws + l.dt1);
+  p.w_in_out = a->weights_in_out ? 1 : 0;
   p.lossp = reinterpret_cast<double*>(ws + l.lossp);
   p.barrier = reinterpret_cast<unsigned*>(ws + l.barrier);
   p.stamps = a->phase_stamps;

@@ -30,8 +30,13 @@ def row_source(t, rows=None, row_stride=None, col_stride=None):
     return s
 
 
-def pack_item(emb, noise, real, rows, keep_mask=None, keep_rows=None):
-    """emb / noise / real: zs3_row_source; keep_mask: uint8 [*, hidden] contiguous or None; keep_rows: int32 or None"""
+FORWARD_ONLY = 1   # ZS3_GMMN_FORWARD_ONLY
+
+
+def pack_item(emb, noise, real, rows, keep_mask=None, keep_rows=None, adj=None, out=None, forward_only=False):
+    """emb / noise / real: zs3_row_source; keep_mask: uint8 [*, hidden] contiguous or None; keep_rows: int32 or None;
+    adj: fp32 [rows, rows] contiguous adjacency (graph generator) or None; out: fp32 [rows, feat] contiguous tensor that
+    receives the generated features, or None; forward_only: generate `out` and stop (no loss / backward / Adam)."""
     if not 1 <= int(rows) <= MAX_ROWS:
         raise ValueError(f"a generator update samples 1..{MAX_ROWS} rows, got {rows}")
     it = L.GmmnItem()
@@ -40,7 +45,18 @@ def pack_item(emb, noise, real, rows, keep_mask=None, keep_rows=None):
         raise TypeError("keep_mask is a contiguous uint8 tensor")
     it.keep_mask = None if keep_mask is None else keep_mask.data_ptr()
     it.keep_rows = None if keep_rows is None else keep_rows.data_ptr()
+    if adj is not None:
+        if adj.dtype != torch.float32 or not adj.is_contiguous() or tuple(adj.shape) != (int(rows), int(rows)):
+            raise TypeError("adj is a contiguous fp32 [rows, rows] tensor")
+        it.adj = adj.data_ptr()
+    if out is not None:
+        if out.dtype != torch.float32 or not out.is_contiguous() or out.shape[0] != int(rows):
+            raise TypeError("out is a contiguous fp32 [rows, feat] tensor")
+        it.out = out.data_ptr()
+    if forward_only and out is None:
+        raise ValueError("a forward-only item needs an `out` tensor")
     it.rows = int(rows)
+    it.flags = FORWARD_ONLY if forward_only else 0
     return it
 
 
@@ -86,7 +102,7 @@ def pack_items_vectorized(images, rows, emb, emb_rows, noise, real, real_rows, k
 
 def pack_args(items_ptr, n_items, dims, params, sigma, losses, workspace, *, adam=None, grads=None, lr=2e-4,
               betas=(0.9, 0.999), eps=1e-8, step0=0, slope=0.2, drop_p=0.5, seed=0, offset=0, max_rows=MAX_ROWS,
-              phase_stamps=None):
+              phase_stamps=None, weights_in_out=False):
     """dims = (embed_dim, noise_dim, hidden, feat); params = (w1, b1, w2, b2) fp32 contiguous tensors;
     adam = ([exp_avg x4], [exp_avg_sq x4]) for in-place Adam, or grads = [g x4] for gradient output."""
     a = L.GmmnTrainArgs()
@@ -113,6 +129,7 @@ def pack_args(items_ptr, n_items, dims, params, sigma, losses, workspace, *, ada
     a.losses = losses.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     a.phase_stamps = None if phase_stamps is None else phase_stamps.data_ptr()   # int64 [n_items, 8]
+    a.weights_in_out = 1 if weights_in_out else 0   # pygcn GraphConvolution weights are [in, out]
     return a
 
 
@@ -129,21 +146,31 @@ def _launch_seed(calls):
 
 
 class FusedGeneratorUpdater:
-    """Runs work lists of generator updates for a `GMMNnetwork` (hidden_size > 0) and its torch.optim.Adam.
+    """Runs work lists of generator updates for a `GMMNnetwork` (hidden_size > 0) or a `GMMNnetwork_GCN` (items then
+    carry the image's adjacency matrix) and its torch.optim.Adam.
     The Adam state (`exp_avg`, `exp_avg_sq`, `step`) stays in `optimizer.state`, so checkpoints and a later
     `optimizer.step()` keep working."""
 
     def __init__(self, generator, optimizer, sigma=(2, 5, 10, 20, 40, 80)):
-        model = generator.model
-        if not isinstance(model, torch.nn.Sequential) or len(model) != 4:
-            raise NotImplementedError("the fused update covers the one-hidden-layer generator (gmmn.py:17-21)")
-        if getattr(generator, "semantic_reconstruction", False):
-            raise NotImplementedError("semantic_reconstruction has a second output; use the unfused modules")
         self.generator, self.optimizer, self.sigma = generator, optimizer, tuple(float(s) for s in sigma)
-        self.lin1, self.act, self.drop, self.lin2 = model[0], model[1], model[2], model[3]
-        self.params = (self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias)
-        self.hidden, self.in_dim = self.lin1.weight.shape
-        self.feat = self.lin2.weight.shape[0]
+        if hasattr(generator, "gcn1") and hasattr(generator, "gcn2"):
+            # GMMNnetwork_GCN (gmmn.py:52-67): two GraphConvolutions, weights [in, out]; items carry the adjacency
+            self.graph = True
+            self.lin1, self.act, self.drop, self.lin2 = generator.gcn1, generator.relu, generator.dropout, generator.gcn2
+            self.params = (self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias)
+            self.in_dim, self.hidden = self.lin1.weight.shape
+            self.feat = self.lin2.weight.shape[1]
+        else:
+            self.graph = False
+            model = generator.model
+            if not isinstance(model, torch.nn.Sequential) or len(model) != 4:
+                raise NotImplementedError("the fused update covers the one-hidden-layer generator (gmmn.py:17-21)")
+            if getattr(generator, "semantic_reconstruction", False):
+                raise NotImplementedError("semantic_reconstruction has a second output; use the unfused modules")
+            self.lin1, self.act, self.drop, self.lin2 = model[0], model[1], model[2], model[3]
+            self.params = (self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias)
+            self.hidden, self.in_dim = self.lin1.weight.shape
+            self.feat = self.lin2.weight.shape[0]
         if not isinstance(optimizer, torch.optim.Adam):
             raise NotImplementedError("the fused update implements torch.optim.Adam (train_pascal_GMMN.py:65-67)")
         if len(optimizer.param_groups) != 1:
@@ -199,14 +226,11 @@ class FusedGeneratorUpdater:
                       tuple(p.data for p in self.params), self.sigma, losses, self._workspace, adam=(ms, vs),
                       lr=float(g["lr"]), betas=tuple(g["betas"]), eps=float(g["eps"]), step0=step,
                       slope=float(self.act.negative_slope), drop_p=float(self.drop.p) if training else 0.0,
-                      seed=_launch_seed(self._calls), offset=0, phase_stamps=phase_stamps)
+                      seed=_launch_seed(self._calls), offset=0, phase_stamps=phase_stamps, weights_in_out=self.graph)
         L.check(lib.zs3_gmmn_train_fused(C.byref(a), L.stream_ptr()), "zs3_gmmn_train_fused")
+        n_upd = n if isinstance(items, np.ndarray) else sum(1 for it in items if not (it.flags & FORWARD_ONLY))
         for p in self.params:
-            st = self.optimizer.state[p]
-            if torch.is_tensor(st["step"]):
-                st["step"] += n
-            else:
-                st["step"] += n
+            self.optimizer.state[p]["step"] += n_upd      # forward-only items take no Adam step
         del keepalive  # the caller's tensors were only needed until the launch was enqueued (stream-ordered allocator)
         return losses
 
@@ -227,6 +251,6 @@ class FusedGeneratorUpdater:
                       tuple(p.data for p in self.params), self.sigma, losses, self._workspace, grads=grads,
                       slope=float(self.act.negative_slope),
                       drop_p=float(self.drop.p) if self.generator.training else 0.0,
-                      seed=_launch_seed(self._calls), offset=0)
+                      seed=_launch_seed(self._calls), offset=0, weights_in_out=self.graph)
         L.check(lib.zs3_gmmn_train_fused(C.byref(a), L.stream_ptr()), "zs3_gmmn_train_fused")
         return losses[0], grads

@@ -468,6 +468,18 @@ class ZS3StepGCN(ZS3StepFused):
         self.gcn_noise_fn = gcn_noise_fn      # optional: n -> [n, noise_dim] (tests); default torch.rand on the device
         self.gcn_mask_fn = gcn_mask_fn        # optional: n -> [n, hidden] Dropout keep mask of the graph generator (tests)
         self.last_gcn_losses = []
+        # the graph-generator updates of a batch run as ONE work list of the fused kernel (items carry the adjacency
+        # matrix) when the generator is this package's GMMNnetwork_GCN with a plain Adam; anything else (stand-in
+        # modules in the CPU tests, other optimizers, > 128 nodes) takes the module path, one call at a time
+        self.updater_gcn = None
+        try:
+            from .gmmn_fused import FusedGeneratorUpdater
+            sigma = getattr(getattr(self.criterion_generator, "__self__", None), "sigma", None) or (2, 5, 10, 20, 40, 80)
+            self.updater_gcn = FusedGeneratorUpdater(generator_gcn, optimizer_generator_gcn, sigma=sigma)
+            if not self.updater_gcn.graph:
+                self.updater_gcn = None
+        except (NotImplementedError, ValueError, AttributeError, TypeError):
+            self.updater_gcn = None
 
     def _generator_params(self):
         return list(self.updater.params) + list(self.generator_gcn.parameters())
@@ -481,6 +493,18 @@ class ZS3StepGCN(ZS3StepFused):
         n_nodes, node_label, node_seed, adj, _ = ZG.label_components(labels.float(), fh, fw, max_nodes=self.max_nodes)
         counts = n_nodes.tolist()                                                   # one sync for the batch
         feats, targets, self.last_gcn_losses = [], [], []
+        from . import gmmn_fused as GF
+        fused = self.updater_gcn is not None and real.is_cuda
+        queue, keep, queued_updates = [], [], []
+
+        def flush():
+            if queue:
+                losses = self.updater_gcn.run(list(queue), self.embed_dim, self.noise_dim, keepalive=list(keep))
+                self.last_gcn_losses += [losses[k] for k in queued_updates]
+                queue.clear()
+                keep.clear()
+                queued_updates.clear()
+
         for i, n in enumerate(counts):
             if n > self.max_nodes:
                 raise RuntimeError(f"image {i}: {n} clusters exceed max_nodes={self.max_nodes}")
@@ -495,19 +519,36 @@ class ZS3StepGCN(ZS3StepFused):
             real_n = real[i].reshape(fd, -1)[:, seeds].t().contiguous()             # seed features `:72-74`
             z = (torch.rand((n, self.noise_dim), device=dev) if self.gcn_noise_fn is None
                  else self.gcn_noise_fn(n).to(dev).float())                         # `:404`
+            has_unseen = state["image_has_unseen"][i]
+            keep_real = self.real_seen_features and not has_unseen
+            if fused and n <= GF.MAX_ROWS:
+                # one item of the fused work list: forward (both graph convolutions), MMD loss, backward, Adam -- or the
+                # forward alone for an image holding an unseen class (`:413-428`)
+                adj_i = adj[i, :n, :n].contiguous()
+                m8 = None if self.gcn_mask_fn is None else self.gcn_mask_fn(n).to(dev).to(torch.uint8).contiguous()
+                out = None if keep_real else torch.empty((n, fd), dtype=torch.float32, device=dev)
+                z = z.contiguous()
+                queue.append(GF.pack_item(GF.row_source(emb_n), GF.row_source(z), GF.row_source(real_n), n, keep_mask=m8,
+                                          adj=adj_i, out=out, forward_only=has_unseen))
+                keep.extend([emb_n, z, real_n, adj_i, m8, out])
+                if not has_unseen:
+                    queued_updates.append(len(queue) - 1)
+                feats.append(real_n if keep_real else out)
+                continue
+            flush()                                                                 # keep the updates in image order
             self.optimizer_generator_gcn.zero_grad()                                # `:402`
             if self.gcn_mask_fn is not None:
                 fake_n = self.generator_gcn(emb_n, z, adj[i, :n, :n].contiguous(),
                                             keep_mask=self.gcn_mask_fn(n).to(dev).to(torch.uint8).contiguous())
             else:
                 fake_n = self.generator_gcn(emb_n, z, adj[i, :n, :n].contiguous())  # `:407-409`
-            if not state["image_has_unseen"][i]:                                    # `:413-419`
+            if not has_unseen:                                                      # `:413-419`
                 g_loss = self.criterion_generator(fake_n, real_n)
                 g_loss.backward()
                 self.optimizer_generator_gcn.step()
                 self.last_gcn_losses.append(g_loss.detach())
-            keep_real = self.real_seen_features and not state["image_has_unseen"][i]
             feats.append(real_n if keep_real else fake_n.detach())                  # `:421-428`
+        flush()
         if not feats:
             return
         x = torch.cat(feats, 0)                                                     # [N, fd]
