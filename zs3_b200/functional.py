@@ -341,6 +341,45 @@ def cba_forward(conv, bn, relu, drop_p, drop_training, keep_mask, residual, xs, 
 
 _DEBUG_FINITE = os.environ.get("ZS3_DEBUG_FINITE", "0") == "1"
 
+# Weight-gradient kernels on a side stream.  In the backward of a layer the data gradient is on the critical path (the
+# next layer's BatchNorm backward needs it), the weight gradient is not: it only has to be done before the optimizer.
+# The BatchNorm-backward kernels that follow are HBM-bound, use no shared memory and leave the tensor cores idle, so a
+# weight-gradient kernel (tensor-bound, one smem-heavy CTA per SM) can run under them.  ZS3_WGRAD_STREAM=1 forks every
+# in-place weight-gradient launch to one side stream (ordered after everything enqueued so far) and joins it at the end
+# of the backward pass (autograd engine callback), also inside CUDA-graph capture.
+_WGRAD_SIDE = {"on": os.environ.get("ZS3_WGRAD_STREAM", "0") == "1", "stream": None, "pending": False}
+
+
+def join_wgrad_stream():
+    """make the current stream wait for the weight-gradient kernels forked by _wgrad_async (no-op when none pending)"""
+    st = _WGRAD_SIDE
+    if st["pending"]:
+        torch.cuda.current_stream().wait_stream(st["stream"])
+        st["pending"] = False
+
+
+def _wgrad_async(tensors, fn):
+    """run fn() -- launches of weight-gradient kernels that READ `tensors` and reduce into persistent .grad buffers --
+    on the side stream when enabled, else inline"""
+    st = _WGRAD_SIDE
+    if not st["on"] or not tensors[0].is_cuda:
+        fn()
+        return
+    if st["stream"] is None:
+        st["stream"] = torch.cuda.Stream()
+    side = st["stream"]
+    side.wait_stream(torch.cuda.current_stream())      # the operands (and the data gradient launched before) are enqueued
+    with torch.cuda.stream(side):
+        fn()
+    for t in tensors:
+        t.record_stream(side)                          # the allocator must not hand these blocks out before the kernel ran
+    if not st["pending"]:
+        st["pending"] = True
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(join_wgrad_stream)
+        except RuntimeError:                            # not inside a backward pass: the caller joins explicitly
+            pass
+
 
 def _check_finite(what, t, sv):
     """debug aid (ZS3_DEBUG_FINITE=1): name the first tensor of a backward that holds a non-finite value"""
@@ -424,8 +463,9 @@ def cba_backward(sv, dout, need_dx, need_w=True, need_affine=True, dx_into=None)
         else:
             dxs.append(None)
         if need_w and gbuf is not None:
-            K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, dw=gbuf, flops=sv.flops_per_cin * c_real,
-                         dw_view=(conv.in_channels, ci0, cout, c_real))
+            _wgrad_async([x, dy], lambda x=x, ci0=ci0, c_real=c_real, cin_p=cin_p: K.conv_wgrad(
+                x, dy, R, S, stride, pad, dil, cin_p, cout_p, dw=gbuf, flops=sv.flops_per_cin * c_real,
+                dw_view=(conv.in_channels, ci0, cout, c_real)))
         elif need_w:
             dw = K.conv_wgrad(x, dy, R, S, stride, pad, dil, cin_p, cout_p, flops=sv.flops_per_cin * c_real)
             K.unpack_wgrad(dw, dweight, ci0, c_real, accumulate=False)
