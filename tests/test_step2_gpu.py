@@ -205,6 +205,58 @@ def test_image_level_generation_on_tensor_cores_matches_per_class_generator():
     assert rel_l2(fake.cpu(), cpu) < 1e-4
 
 
+def test_step2_iteration_at_full_resolution_matches_oracle():
+    """BASELINE configs[2] geometry: 513x513 inputs, 129x129 feature grid, classes covering up to 16.6 k pixels, one image
+    holding an unseen class (image-level generation on the tensor cores is NOT used here: the injected Dropout masks keep
+    the per-class generator path), bs=4 so that the CPU oracle and the 1.3 GB embedding map stay within seconds.  The
+    decoder features are injected on both sides; everything downstream (label down-sampling, per-class gathers, 128-row
+    sampling, fused generator updates, classifier loss with the fused x4 upsample, SGD) runs at full size."""
+    import zs3_oracle as O
+    import zs3_step2_oracle as S
+    from zs3.modeling.deeplab import DeepLab
+    from zs3.modeling.gmmn import GMMNnetwork
+    from zs3.utils.loss import GMMNLoss, SegmentationLosses
+    from zs3_b200.step2 import ZS3StepFused
+    B, HW, C, fh = 4, 513, 21, 129
+    unseen, seen = [10, 14], [c for c in range(21) if c not in (10, 14)]
+    target = _labels(B, HW, [[0, 3, 7, 12], [0, 14, 5], [2, 9], [1, 4, 6, 8, 20]], seed=6)
+    emb_table = torch.randn(C, 300, generator=torch.Generator().manual_seed(8)) * 0.06
+    embedding = emb_table[target.clamp(max=C - 1).long()].permute(0, 3, 1, 2).contiguous()
+    image = torch.zeros(B, 3, HW, HW)
+    real = torch.relu(torch.randn(B, 256, fh, fh, generator=torch.Generator().manual_seed(2)))
+    st = O.init_deeplab_state(seed=1)
+    gst = O.init_gmmn_state(seed=3)
+    model = DeepLab(num_classes=C, sync_bn=True, freeze_bn=True, pretrained=False)
+    model.load_state_dict(st)
+    model = model.cuda().train()
+    model.freeze_bn()
+    gen = GMMNnetwork(300, 300, 256, 256)
+    gen.load_state_dict(gst)
+    gen = gen.cuda().train()
+    cw = torch.ones(C)
+    cw[unseen] = 100.0
+    crit = SegmentationLosses(weight=cw.cuda(), cuda=True).build_loss("ce")
+    crit_g = GMMNLoss(sigma=[2, 5, 10, 20, 40, 80], cuda=True).build_loss()
+    opt = torch.optim.SGD([{"params": model.get_1x_lr_params(), "lr": 0.007},
+                           {"params": model.get_10x_lr_params(), "lr": 0.07}], momentum=0.9, weight_decay=5e-4)
+    rp = Replay(123)
+    step = ZS3StepFused(model, gen, crit, crit_g, opt, torch.optim.Adam(gen.parameters(), lr=2e-4), seen, unseen,
+                        noise_fn=rp.noise, index_fn=rp.index, mask_fn=rp.mask)
+    loss, glb, g_losses = step.training_step(image.cuda(), target.cuda(), embedding.cuda(), real_features=real.cuda())
+    torch.cuda.synchronize()
+    rp.reset()
+    sub = {k: v for k, v in st.items() if k.startswith("decoder.pred_conv")}
+    ref = S.step2(sub, gst, real, target, embedding, (HW, HW), set(seen), set(unseen), rp.noise, rp.index, rp.mask, cw)
+    print("full-resolution g_losses gpu", np.round(g_losses, 5), "oracle", np.round(ref["g_losses"], 5))
+    assert len(g_losses) == len(ref["g_losses"]) >= 9            # images 0, 2, 3: 4 + 2 + 5 classes minus ignore rows
+    assert np.allclose(g_losses, ref["g_losses"], rtol=1e-3)
+    assert abs(glb - ref["generator_loss_batch"]) < 1e-3 * abs(ref["generator_loss_batch"])
+    for k, p in gen.state_dict().items():
+        assert rel_l2(p.cpu(), ref["generator"][k]) < 1e-4, k
+    assert abs(loss.item() - ref["loss"]) < 2e-2 * abs(ref["loss"])
+    assert rel_l2(model.decoder.pred_conv.weight.detach().cpu(), ref["pred_conv.weight"]) < 2e-2
+
+
 @pytest.mark.parametrize("fused_gcn", [True, False], ids=["gcn_fused_work_list", "gcn_modules"])
 def test_gcn_context_step_matches_oracle(fused_gcn):
     """config 5 (zs3/train_context_GMMN_GCNcontext.py:270-460): ZS3StepGCN on the CUDA modules vs oracle step2(gcn=...);
