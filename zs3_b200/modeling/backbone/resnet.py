@@ -33,7 +33,7 @@ class Bottleneck(nn.Module):
         return ZF.bottleneck(self, x)
 
 
-_DP_CUT = os.environ.get("ZS3_DP_CUT", "0") == "1"
+_DP_CUT = os.environ.get("ZS3_DP_CUT", "1") == "1"   # same default as parallel.DataParallelTrainer
 
 class ResNet(nn.Module):
     """stem + 4 residual stages; returns (stage-4 features, stage-1 'low level' features), reference resnet.py:56-226"""
@@ -79,7 +79,7 @@ class ResNet(nn.Module):
         # the activations that separate {stem, layer1, layer2} from the rest of the network: the data-parallel
         # runtime cuts the backward pass here to overlap the gradient all-reduce of everything above the cut
         # (97 % of the parameters) with the backward of everything below it
-        # (opt-in, ZS3_DP_CUT=1, see parallel.py.  The decoder then consumes an ALIAS of layer1's output:
+        # (default; ZS3_DP_CUT=0 disables it, see parallel.py.  The decoder then consumes an ALIAS of layer1's output:
         # low_level_feat itself is upstream of x, and a cut must be an antichain -- with the alias, the decoder's
         # gradient arrives at a node of its own.)
         self.last_cut = None

@@ -263,6 +263,7 @@ class DataParallelTrainer:
         # torch.autograd.grad and the backbone hands the decoder an alias of low_level_feat.  Validated on 2x B200
         # (tests/test_multigpu_gpu.py: gradients equal the plain flow to 2e-8; profiles/r02_dp_cut.md: A/B bench).
         self.early_range, self.early_params, self._opt_stream = None, [], None
+        self.segment_events = None   # set to [] to collect (start, head done, tail done, step done) events per step
         bb = getattr(model, "backbone", None)
         if world_size > 1 and bb is not None and hasattr(bb, "layer3") and os.environ.get("ZS3_DP_CUT", "1") == "1":
             first = next(iter(bb.layer3.parameters()), None)
@@ -291,9 +292,25 @@ class DataParallelTrainer:
             self._capture(image, target)
         self.static_image.copy_(image, non_blocking=True)
         self.static_target.copy_(target, non_blocking=True)
+        marks = self.segment_events
+        if marks is not None:      # debug aid (tools/scale_probe.py): CUDA events around the segments of a step
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         self.graph.replay()
+        if marks is not None:
+            ev[1].record()
         if self.world > 1:
-            self._finish_distributed(self.graph_tail.replay if self.graph_tail is not None else None)
+            tail = self.graph_tail.replay if self.graph_tail is not None else None
+            if marks is not None and tail is not None:
+                def tail():   # noqa: F811
+                    self.graph_tail.replay()
+                    ev[2].record()
+            self._finish_distributed(tail)
+        if marks is not None:
+            if self.world == 1 or self.graph_tail is None:
+                ev[2].record()
+            ev[3].record()
+            marks.append(ev)
         return self.static_loss
 
     def _capture(self, image, target):
