@@ -82,8 +82,9 @@ class ResNet(nn.Module):
         # (default; ZS3_DP_CUT=0 disables it, see parallel.py.  The decoder then consumes an ALIAS of layer1's output:
         # low_level_feat itself is upstream of x, and a cut must be an antichain -- with the alias, the decoder's
         # gradient arrives at a node of its own.)
+        # Only a multi-rank DataParallelTrainer asks for it (it sets `expose_cut`): single-GPU graphs stay without the alias.
         self.last_cut = None
-        if _DP_CUT:
+        if _DP_CUT and getattr(self, "expose_cut", False):
             low_level_feat = low_level_feat.view_as(low_level_feat)
             self.last_cut = (x, low_level_feat)
         x = self.layer4(self.layer3(x))

@@ -274,6 +274,7 @@ class DataParallelTrainer:
                 early_n = sum(p.numel() for p in self.early_params)
                 if 0 < a and a + early_n == self.flat.grad.numel():  # layout is [stem, layer1, layer2 | the rest]
                     self.early_range = (a, self.flat.grad.numel())
+                    bb.expose_cut = True   # the backbone publishes the cut activations (backbone/resnet.py: last_cut)
         if world_size > 1:
             # identical replicas: broadcast rank 0's weights and BN buffers once
             dist.broadcast(self.flat.flat, 0)
