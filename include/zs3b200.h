@@ -593,6 +593,10 @@ int zs3_bilinear_bwd_f32(const float* dy, float* dx, int N, int Hi, int Wi, int 
 int zs3_spatial_broadcast_acc_f32(const float* x, float* y, int N, int HW, int C, float scale, int accumulate,
                                   void* stream);
 
+/* debug / tests: the output tile (MB x 128 output channels, CN input channels) zs3_conv_wgrad picks for a layer of M
+ * output pixels (host-side cost model, no device work) */
+int zs3_debug_wgrad_tile(long long M, int cout_pad, int cin_pad, int taps, int* mb, int* cn);
+
 /* debug: one im2col TMA load dumped raw (tests/test_tma_probe.py) */
 int zs3_debug_im2col_probe(const void* x, int N, int H, int W, int C, int pad, int upper, int stride, int cpp, int ppc,
                            int c, int w, int h, int n, int off_w, int off_h, void* out, void* stream);

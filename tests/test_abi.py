@@ -161,3 +161,29 @@ def test_augment_entry_point_validates_arguments_without_a_gpu():
     items[0] = _lib.AugItem(p, p, 40, 50, 0, 40, 50, 0, 0, -1.0)
     a.workspace_bytes = 64
     assert lib.zs3_augment_batch(C.byref(a), None) == -1 and "workspace" in err()
+
+
+def test_wgrad_tile_cost_model_choices_without_a_gpu():
+    """host-side tile choice of zs3_conv_wgrad (csrc/conv_igemm.cu choose_wgrad_tile): layer3's 1x1 1024<->256 layers at
+    33x33 move to 128 x 128 tiles (9 pixel splits instead of 37), every other shape of the network keeps the largest
+    tile (profiles/r02_wgrad_tile.md); ZS3_WGRAD_TILE is not set in the test environment"""
+    import ctypes as C
+    import os
+    from zs3_b200 import _lib
+    assert "ZS3_WGRAD_TILE" not in os.environ
+    lib = _lib.lib()
+
+    def tile(M, cout, cin, taps):
+        mb, cn = C.c_int(0), C.c_int(0)
+        assert lib.zs3_debug_wgrad_tile(M, cout, cin, taps, C.byref(mb), C.byref(cn)) == 0
+        return mb.value, cn.value
+
+    m33, m65, m129 = 16 * 33 * 33, 16 * 65 * 65, 16 * 129 * 129
+    for cout, cin in ((256, 1024), (1024, 256)):
+        mb, cn = tile(m33, cout, cin, 1)
+        assert 128 * mb * cn < 256 * 256, (cout, cin, mb, cn)     # a smaller tile than the default: fewer pixel splits
+    assert tile(m33, 256, 256, 9) == (2, 256)                     # 3x3 256->256 at 33x33: measured slower on small tiles
+    assert tile(m129, 256, 256, 9) == (2, 256) and tile(m129, 256, 320, 9) == (2, 256)     # decoder
+    assert tile(m33, 256, 2048, 9) == (2, 256) and tile(m33, 512, 512, 9) == (2, 256)      # ASPP, layer4
+    assert tile(m129, 64, 64, 9) == (1, 64) and tile(m65, 128, 128, 9) == (1, 128)         # layer1 / layer2 3x3
+    assert lib.zs3_debug_wgrad_tile(0, 256, 256, 1, None, None) == -1

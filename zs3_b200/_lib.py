@@ -284,6 +284,7 @@ def _EXTRA_SIGS(vp, i, ll, f, d):
         "zs3_concat2": [vp, i, vp, i, vp, ll, vp],
         "zs3_gmmn_train_fused": [C.POINTER(GmmnTrainArgs), vp],
         "zs3_label_components": [C.POINTER(ComponentsArgs), vp],
+        "zs3_debug_wgrad_tile": [ll, i, i, i, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "zs3_augment_batch": [C.POINTER(AugmentArgs), vp],
         "zs3_argmax_confusion": [vp, vp, i, i, ll, vp, vp, vp],
         "zs3_confusion_from_pred": [vp, vp, ll, i, vp, vp],

@@ -1376,6 +1376,15 @@ extern "C" int zs3_conv_wgrad(const zs3_wgrad_args* a, void* stream) {
   return launch_wgrad<64, 8, 1>(p, st);
 }
 
+extern "C" int zs3_debug_wgrad_tile(long long M, int cout_pad, int cin_pad, int taps, int* mb, int* cn) {
+  ZS3_CHECK_ARG(M > 0 && cout_pad > 0 && cout_pad % 64 == 0 && cin_pad > 0 && cin_pad % 64 == 0 && taps > 0 && mb && cn,
+                "debug_wgrad_tile: bad args");
+  *cn = cin_pad >= 256 ? 256 : (cin_pad >= 128 ? 128 : 64);
+  *mb = cout_pad >= 256 ? 2 : 1;
+  choose_wgrad_tile(M, cout_pad, cin_pad, taps, 0, mb, cn);
+  return ZS3_OK;
+}
+
 extern "C" int zs3_pack_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int ci_begin, int ci_count,
                                void* dst_bf16, int cout_pad, int cin_pad, int mode, void* stream) {
   ZS3_CHECK_ARG(w_oihw && dst_bf16, "pack_weight: null pointer");
