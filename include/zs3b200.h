@@ -102,12 +102,12 @@ typedef struct {
   int w_forward_layout; /* 1 (data-gradient mode): seg[i].w is the FORWARD-packed weight of the layer being
                            differentiated, [seg.cin_pad = forward cout][R*S][cout_pad = forward cin]; the kernel reads it
                            as MN-major B tiles and flips the taps itself, so no transposed copy has to be packed */
-  /* operand prologue: segment i is the RAW (pre-normalisation) output y of a conv -> BatchNorm -> ReLU layer and the
-   * activation relu?(y * pre_scale[i][c] + pre_shift[i][c]) is applied to every A tile in shared memory between the
-   * TMA load and the MMA (4 transform warps), so that layer's normalised output never makes a round trip through HBM
-   * (resnet.py:36-42: bn1/relu -> conv2, bn2/relu -> conv3).  [cin_pad] fp32 each (zs3_bn_finalize), NULL = segment is
-   * used as is.  Zero padding survives because the im2col map of such a segment fills out-of-bounds elements with NaN
-   * and max(NaN, 0) = 0: pre_relu must be 1 whenever the conv pads (R*S > 1).  Not available in data-gradient mode. */
+  /* RESERVED (must be NULL / 0; zs3_conv_fprop rejects anything else): operand prologue.  Planned meaning: segment i is the
+   * RAW (pre-normalisation) output y of a conv -> BatchNorm -> ReLU layer and relu?(y * pre_scale[i][c] + pre_shift[i][c])
+   * is applied to every A tile in shared memory between the TMA load and the MMA, so that layer's normalised output never
+   * makes a round trip through HBM (resnet.py:36-42: bn1/relu -> conv2, bn2/relu -> conv3).  The transform stage is not
+   * built (only 27 % of the BatchNorm elements have a single consumer); the fields keep the struct
+   * layout stable for it. */
   const float* pre_scale[ZS3_MAX_SEGMENTS];
   const float* pre_shift[ZS3_MAX_SEGMENTS];
   int pre_relu;

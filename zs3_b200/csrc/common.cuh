@@ -65,8 +65,9 @@ static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 
 
 // bf16, SWIZZLE_128B tensor maps.  All return 0 on success.
 // im2col map over an NHWC activation tensor [N][H][W][C] (C = channel stride, elements).
-// oob_nan: out-of-bounds elements (zero padding, rows past the tensor) are filled with NaN instead of zero -- used when
-// an activation (scale*x + shift, ReLU) is applied to the tile in shared memory: max(NaN, 0) = 0 restores the padding
+// oob_nan (reserved, no caller passes it yet): out-of-bounds elements (zero padding, rows past the tensor) are filled with
+// NaN instead of zero -- meant for an operand prologue that applies max(scale*x + shift, 0) in shared memory, where
+// max(NaN, 0) = 0 restores the padding
 int encode_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C, int pad_lo, int upper_corner,
                        int stride, int channels_per_pixel, int pixels_per_column, int oob_nan = 0);
 // tiled 2-D map over a row-major [rows][cols] bf16 matrix with row stride ld (elements); box = [box_rows][box_cols].

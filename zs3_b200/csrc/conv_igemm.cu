@@ -1079,6 +1079,9 @@ extern "C" int zs3_conv_fprop(const zs3_conv_args* a, void* stream) {
                 MAX_STAT_CH);
   const long long M = (long long)a->N * a->Ho * a->Wo;
   ZS3_CHECK_ARG(M < (1ll << 31), "conv_fprop: too many output pixels");
+  for (int s = 0; s < ZS3_MAX_SEGMENTS; ++s)
+    ZS3_CHECK_ARG(a->pre_scale[s] == nullptr && a->pre_shift[s] == nullptr && a->pre_relu == 0,
+                  "conv_fprop: the operand prologue (pre_scale / pre_shift / pre_relu) is reserved and not implemented");
 
   FpropParams p;
   memset(&p, 0, sizeof(p));
