@@ -111,6 +111,25 @@ def cpu_reference_step_rate(batch, hw, steps, warmup, threads):
     return batch / s, s
 
 
+def cpu_reference_forward_configs0(threads, repeats=7):
+    """BASELINE configs[0] / SURVEY 8d config 1: the reference's forward on 1 x 3 x 513 x 513, eval mode, no_grad, on the
+    host cores: median of `repeats` after one warm-up (oracle restatement = the reference's arithmetic)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zs3_oracle as O
+    torch.set_num_threads(threads)
+    st = O.init_deeplab_state(seed=1)
+    x = torch.randn(1, 3, 513, 513, generator=torch.Generator().manual_seed(1))
+    times = []
+    with torch.no_grad():
+        for it in range(repeats + 1):
+            t0 = time.perf_counter()
+            O.deeplab_forward(st, x, training=False)
+            if it:
+                times.append(time.perf_counter() - t0)
+    times.sort()
+    return times[len(times) // 2]
+
+
 def cpu_threads():
     """threads for the CPU arm: all host cores up to 32 -- measured on the 128-core B200 host, oneDNN's conv backward
     at 513x513 gets SLOWER beyond a few dozen threads (61 s/step at 128 threads vs ~3 s at 8 on the build box)"""
@@ -560,6 +579,33 @@ def run_ours(args):
         cpu_baseline = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                         "sample": f"2 steps of bs=2 {HW}x{HW} fwd+CE+bwd+SGD with the oracle port on {cores} threads "
                                   f"({s:.2f} s/step; host has {os.cpu_count()} cores)"}
+        try:   # BASELINE configs[0]: the reference's CPU forward on one 513x513 image, and the same forward on the GPU
+            t_cpu = cpu_reference_forward_configs0(cores)
+            cfg0 = {"workload": "DeepLabv3+ ResNet-101 forward, 1x3x513x513, eval mode (BASELINE configs[0])",
+                    "cpu_reference_forward_ms": t_cpu * 1e3, "cpu_images_per_sec": 1.0 / t_cpu, "cores": cores,
+                    "how": "median of 7 after 1 warm-up, oracle port (the reference's arithmetic), no_grad"}
+            try:
+                model.eval()
+                x1 = devb[0][0][:1].contiguous()
+                with torch.no_grad():
+                    for _ in range(3):
+                        model(x1)
+                    torch.cuda.synchronize()
+                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    g0.record()
+                    for _ in range(10):
+                        model(x1)
+                    g1.record()
+                    torch.cuda.synchronize()
+                cfg0["zs3_b200_forward_ms"] = g0.elapsed_time(g1) / 10
+                cfg0["zs3_b200_note"] = "eager launches, batch 1 (latency-bound: ~350 launches for one image)"
+            except Exception as e:
+                cfg0["zs3_b200_forward_ms"] = {"error": repr(e)[:200]}
+            finally:
+                model.train()
+            cpu_baseline["configs0"] = cfg0
+        except Exception as e:
+            cpu_baseline["configs0"] = {"error": repr(e)[:200]}
 
     # ---- BASELINE configs[2]: the ZS3Net step-2 iteration (feature extraction + generator updates + classifier)
     step2 = None
