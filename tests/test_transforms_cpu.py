@@ -144,3 +144,20 @@ def test_kernel_source_matches_reference_on_the_host(emul):
     x, y = run_emulated(emul, [(GOLD[f"val{i}_img"], GOLD[f"val{i}_lab"])],
                         [dict(flip=False, ow=ow, oh=oh, x1=0, y1=0, radius=-1.0)], ow, oh)
     assert np.array_equal(x[0], GOLD[f"val{i}_x"]) and np.array_equal(y[0], GOLD[f"val{i}_y"])
+
+
+def test_oracle_matches_pillow_directly_on_random_cases():
+    """beyond the committed golden vectors: the numpy restatement against the installed Pillow itself (the reference's
+    dependency) on seeded random sizes -- resize BILINEAR / NEAREST incl. > 2x down-scaling, GaussianBlur radii in [0, 3)"""
+    PIL = pytest.importorskip("PIL")
+    from PIL import Image, ImageFilter
+    rs = np.random.RandomState(17)
+    for _ in range(25):
+        h, w = int(rs.randint(3, 80)), int(rs.randint(3, 80))
+        oh, ow = int(rs.randint(2, 100)), int(rs.randint(2, 100))
+        img, lab = synth(rs, h, w)
+        assert np.array_equal(np.array(Image.fromarray(img).resize((ow, oh), Image.BILINEAR)), TO.resize_bilinear(img, ow, oh))
+        assert np.array_equal(np.array(Image.fromarray(lab).resize((ow, oh), Image.NEAREST)), TO.resize_nearest(lab, ow, oh))
+        r = float(rs.rand() * (3.0 if rs.rand() < 0.3 else 1.0))
+        assert np.array_equal(np.array(Image.fromarray(img).filter(ImageFilter.GaussianBlur(radius=r))), TO.gaussian_blur(img, r))
+    assert PIL.__version__
