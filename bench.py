@@ -676,6 +676,11 @@ def run_ours(args):
             "config": {"workload": "DeepLabv3+ ResNet-101 fwd+bwd+SGD, bs=16/GPU 513x513 synthetic (BASELINE configs[1])",
                        "num_classes": NUM_CLASSES, "per_gpu_batch": B, "global_batch": B * world, "input": f"{HW}x{HW}",
                        "parallelism": f"dp{world}", "bn": "rank-local batch statistics", "launch_mode": args.mode,
+                       "dp_exchange": (None if world == 1 else
+                                       "two-stage backward: the all-reduce of the gradients above the backbone cut and "
+                                       "their SGD update overlap the backward tail, then a 6 MB all-reduce"
+                                       if getattr(trainer, "early_range", None) is not None else
+                                       "one all-reduce of the flat gradient buffer after the backward"),
                        "l2_policy": "inputs+activations per step (>6 GB) exceed the 126 MB L2; 2 alternating input batches",
                        "optimizer": "fused SGD momentum 0.9 wd 5e-4, lr 0.007/0.07",
                        "loss": "weighted CE with ignore_index, /batch; final x4 bilinear upsample fused into the loss "
